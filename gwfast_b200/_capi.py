@@ -1,0 +1,86 @@
+"""ctypes mirror of ``include/gwfast_b200.h`` and loader of ``lib/libgwfast_b200.so``.
+
+The library is the product: there is no Python/numpy fallback.  If it cannot be loaded (not built, wrong
+arch) every entry point of the package raises :class:`EngineUnavailable`.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'lib', 'libgwfast_b200.so')
+
+GWF_TAYLORF2, GWF_IMRPHENOMD, GWF_IMRPHENOMD_NRTIDALV2, GWF_IMRPHENOMHM = 0, 1, 2, 3
+GWF_MODEL_TIDAL, GWF_MODEL_3P5PN_SPINHO, GWF_MODEL_PHIREF_VLSO, GWF_MODEL_QUADMON_TID = 1, 2, 4, 8
+GWF_MODEL_KERR_ISCO, GWF_MODEL_NO_FCUT, GWF_MODEL_HAS_FREF, GWF_MODEL_LAMBDA_GIVEN = 16, 32, 64, 128
+GWF_OPT_M1M2, GWF_OPT_CHIS_CHIA, GWF_OPT_LIN_GRID = 1, 2, 4
+GWF_NPARAM_IN = 13
+# order of gwf_events.p[]
+EVENT_KEYS = ('Mc', 'eta', 'dL', 'theta', 'phi', 'iota', 'psi', 'tcoal', 'Phicoal', 'chi1z', 'chi2z', 'Lambda1', 'Lambda2')
+
+
+class gwf_model(C.Structure):
+    _fields_ = [('id', C.c_int32), ('flags', C.c_int32), ('fcutPar', C.c_double), ('fRef', C.c_double)]
+
+
+class gwf_detector(C.Structure):
+    _fields_ = [('lat_rad', C.c_double), ('long_rad', C.c_double), ('xax_rad', C.c_double), ('shape', C.c_int32),
+                ('use_earth_motion', C.c_int32), ('no_motion', C.c_int32), ('psd', C.c_int32), ('fmin', C.c_double),
+                ('fmax', C.c_double)]
+
+
+class gwf_events(C.Structure):
+    _fields_ = [('p', C.c_void_p * GWF_NPARAM_IN)]
+
+
+class gwf_opts(C.Structure):
+    _fields_ = [('res', C.c_int32), ('flags', C.c_int32), ('per_arm', C.c_int32), ('reserved', C.c_int32)]
+
+
+class EngineUnavailable(RuntimeError):
+    pass
+
+
+class EngineError(RuntimeError):
+    pass
+
+
+# every symbol include/gwfast_b200.h declares (tests check that the library exports all of them)
+SYMBOLS = ('gwf_version', 'gwf_last_error', 'gwf_num_params', 'gwf_num_arms', 'gwf_workspace_bytes', 'gwf_psd_create',
+           'gwf_psd_destroy', 'gwf_set_qnm_tables', 'gwf_fisher', 'gwf_snr', 'gwf_unpack_fisher', 'gwf_waveform')
+
+_lib = None
+
+
+def load():
+    """Load the shared library (once) and declare the prototypes."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise EngineUnavailable('%s not built: run `python -c "import __graft_entry__ as g; g.build()"` '
+                                '(there is no CPU fallback)' % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    vp, i32, i64, dbl = C.c_void_p, C.c_int32, C.c_int64, C.c_double
+    P = C.POINTER
+    lib.gwf_version.restype = C.c_int
+    lib.gwf_last_error.restype = C.c_char_p
+    lib.gwf_num_params.argtypes = [P(gwf_model)]
+    lib.gwf_num_arms.argtypes = [P(gwf_detector), i32]
+    lib.gwf_workspace_bytes.argtypes = [P(gwf_model), i64]
+    lib.gwf_workspace_bytes.restype = C.c_size_t
+    lib.gwf_psd_create.argtypes = [P(dbl), P(dbl), i32, P(vp)]
+    lib.gwf_psd_destroy.argtypes = [vp]
+    lib.gwf_psd_destroy.restype = None
+    lib.gwf_set_qnm_tables.argtypes = [P(dbl), P(dbl), P(dbl), i32]
+    common = [P(gwf_model), P(gwf_detector), i32, P(vp), i32, P(gwf_events), i64, P(gwf_opts)]
+    lib.gwf_fisher.argtypes = common + [vp, vp, vp, C.c_size_t, vp]
+    lib.gwf_snr.argtypes = common + [vp, vp, C.c_size_t, vp]
+    lib.gwf_unpack_fisher.argtypes = [vp, i64, i32, vp, vp]
+    lib.gwf_waveform.argtypes = [P(gwf_model), P(gwf_events), i64, vp, i32, i32, vp, vp, vp, vp, vp, C.c_size_t, vp]
+    _lib = lib
+    return lib
+
+
+def check(rc, what):
+    if rc != 0:
+        raise EngineError('%s failed (%d): %s' % (what, rc, load().gwf_last_error().decode()))

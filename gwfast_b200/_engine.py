@@ -1,0 +1,188 @@
+"""Device plumbing between the gwfast-style Python classes and ``libgwfast_b200.so``.
+
+torch is used for what it is good at here -- device/pinned memory with caching allocators, streams, and (in
+``parallel.py``) ``torch.distributed`` -- and for nothing numerical: every O(N*res) operation is a hand-written
+CUDA kernel behind the C ABI (``include/gwfast_b200.h``).  There is no CPU path: without the library or without a
+CUDA device every call raises :class:`EngineUnavailable`.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _capi as K
+from ._capi import EngineUnavailable, EngineError  # noqa: F401
+from . import gwfastGlobals as glob
+
+CHUNK_EVENTS = 1 << 18     # events per launch group: bounds the coefficient-record workspace (~2.2 KB/event)
+
+_state = None
+launch_count = 0           # kernels launched through this module (bench.py reports it as gpu_launches)
+
+
+class _State:
+    def __init__(self):
+        try:
+            import torch
+        except ImportError as e:  # pragma: no cover
+            raise EngineUnavailable('torch is required for device memory and streams') from e
+        self.torch = torch
+        self.lib = K.load()
+        if not torch.cuda.is_available():
+            raise EngineUnavailable('no CUDA device visible: gwfast_b200 has no CPU fallback')
+        self.device = torch.device('cuda', torch.cuda.current_device())
+        torch.cuda.init()
+        torch.zeros(1, device=self.device)   # make sure the primary context exists before the library's first call
+        dp = C.POINTER(C.c_double)
+        tabs = [np.ascontiguousarray(np.loadtxt(os.path.join(glob.WFfilesPath, 'QNMData_%s.txt' % k))) for k in ('a', 'fring', 'fdamp')]
+        K.check(self.lib.gwf_set_qnm_tables(tabs[0].ctypes.data_as(dp), tabs[1].ctypes.data_as(dp), tabs[2].ctypes.data_as(dp), len(tabs[0])),
+                'gwf_set_qnm_tables')
+        self.psds = {}
+        self.workspace = None
+
+
+def state():
+    global _state
+    if _state is None:
+        _state = _State()
+    return _state
+
+
+def psd_handle(freq, S):
+    """device PSD table for (strainFreq, noiseCurve); cached on the arrays' content."""
+    st = state()
+    freq = np.ascontiguousarray(freq, dtype=np.float64)
+    S = np.ascontiguousarray(S, dtype=np.float64)
+    key = (freq.shape[0], hash(freq.tobytes()), hash(S.tobytes()))
+    h = st.psds.get(key)
+    if h is None:
+        dp = C.POINTER(C.c_double)
+        out = C.c_void_p()
+        K.check(st.lib.gwf_psd_create(freq.ctypes.data_as(dp), S.ctypes.data_as(dp), freq.shape[0], C.byref(out)), 'gwf_psd_create')
+        h = out.value
+        st.psds[key] = h
+    return h
+
+
+def _workspace(st, nbytes):
+    if st.workspace is None or st.workspace.numel() < nbytes:
+        st.workspace = st.torch.empty(int(nbytes), dtype=st.torch.uint8, device=st.device)
+    return st.workspace
+
+
+def _upload(st, ev, n, keys):
+    """events dict -> one pinned staging buffer -> one H2D copy; returns (device tensor, gwf_events, bytes)."""
+    torch = st.torch
+    present = [k for k in keys if k in ev]
+    host = torch.empty((len(present), n), dtype=torch.float64, pin_memory=True)
+    hnp = host.numpy()
+    for i, k in enumerate(present):
+        a = np.asarray(ev[k])
+        if a.shape != (n,):
+            a = np.broadcast_to(np.real(a).astype(np.float64, copy=False), (n,))
+        hnp[i] = np.real(a)
+    dev = host.to(st.device, non_blocking=True)
+    evs = K.gwf_events()
+    base, stride = dev.data_ptr(), n * 8
+    for i, k in enumerate(K.EVENT_KEYS):
+        evs.p[i] = base + present.index(k) * stride if k in present else None
+    return dev, host, evs, host.numel() * 8
+
+
+def _call_arrays(dets, psd_handles):
+    darr = (K.gwf_detector * len(dets))(*dets)
+    parr = (C.c_void_p * len(psd_handles))(*psd_handles)
+    return darr, parr
+
+
+def fisher(model, dets, psd_handles, ev, n, res, flags, per_arm, want_snr2=True, keep_on_device=False):
+    """Run gwf_fisher (+ gwf_unpack_fisher) on the current device.
+
+    Returns ``(F, snr2, io)`` with ``F`` of shape ``(npass, nP, nP, n)`` and ``snr2`` ``(npass, n)`` as numpy arrays
+    (or device tensors if ``keep_on_device``); ``io`` = (h2d_bytes, d2h_bytes).
+    """
+    global launch_count
+    st = state()
+    torch = st.torch
+    lib = st.lib
+    nP = lib.gwf_num_params(C.byref(model))
+    if nP < 0:
+        raise EngineError('unknown model')
+    npack = nP * (nP + 1) // 2
+    darr, parr = _call_arrays(dets, psd_handles)
+    npass = lib.gwf_num_arms(darr, len(dets)) if per_arm else 1
+    stream = torch.cuda.current_stream(st.device)
+    sp = C.c_void_p(stream.cuda_stream)
+    full = torch.empty((npass, nP, nP, n), dtype=torch.float64, device=st.device)
+    snr2 = torch.empty((npass, n), dtype=torch.float64, device=st.device)
+    opts = K.gwf_opts(int(res), int(flags), int(bool(per_arm)), 0)
+    h2d = 0
+    keep = []
+    for lo in range(0, n, CHUNK_EVENTS):
+        m = min(CHUNK_EVENTS, n - lo)
+        sub = ev if (lo == 0 and m == n) else {k: np.asarray(v)[lo:lo + m] for k, v in ev.items() if k in K.EVENT_KEYS}
+        dev_ev, host_ev, evs, nb = _upload(st, sub, m, K.EVENT_KEYS)
+        h2d += nb
+        ws = _workspace(st, lib.gwf_workspace_bytes(C.byref(model), m))
+        packed = torch.empty((npass, m, npack), dtype=torch.float64, device=st.device)
+        s2 = torch.empty((npass, m), dtype=torch.float64, device=st.device)
+        K.check(lib.gwf_fisher(C.byref(model), darr, len(dets), parr, len(psd_handles), C.byref(evs), m, C.byref(opts),
+                               C.c_void_p(packed.data_ptr()), C.c_void_p(s2.data_ptr()), C.c_void_p(ws.data_ptr()), ws.numel(), sp),
+                'gwf_fisher')
+        launch_count += 1 + npass
+        if m == n:
+            for p in range(npass):
+                K.check(lib.gwf_unpack_fisher(C.c_void_p(packed[p].data_ptr()), m, nP, C.c_void_p(full[p].data_ptr()), sp), 'gwf_unpack_fisher')
+                launch_count += 1
+            snr2 = s2
+        else:
+            tmp = torch.empty((npass, nP, nP, m), dtype=torch.float64, device=st.device)
+            for p in range(npass):
+                K.check(lib.gwf_unpack_fisher(C.c_void_p(packed[p].data_ptr()), m, nP, C.c_void_p(tmp[p].data_ptr()), sp), 'gwf_unpack_fisher')
+                launch_count += 1
+            full[..., lo:lo + m] = tmp
+            snr2[:, lo:lo + m] = s2
+        keep.append((dev_ev, host_ev, packed))
+    if keep_on_device:
+        return full, snr2, (h2d, 0)
+    out_f = torch.empty(full.shape, dtype=torch.float64, pin_memory=True)
+    out_s = torch.empty(snr2.shape, dtype=torch.float64, pin_memory=True)
+    out_f.copy_(full, non_blocking=True)
+    out_s.copy_(snr2, non_blocking=True)
+    stream.synchronize()
+    return out_f.numpy(), out_s.numpy(), (h2d, (out_f.numel() + out_s.numel()) * 8)
+
+
+def snr(model, dets, psd_handles, ev, n, res, flags=0, keep_on_device=False):
+    """Run gwf_snr: per-arm integrals 4*int (Ap^2+Ac^2)/Sn df, shape (n_arms, n)."""
+    global launch_count
+    st = state()
+    torch = st.torch
+    lib = st.lib
+    darr, parr = _call_arrays(dets, psd_handles)
+    narms = lib.gwf_num_arms(darr, len(dets))
+    stream = torch.cuda.current_stream(st.device)
+    sp = C.c_void_p(stream.cuda_stream)
+    out = torch.empty((narms, n), dtype=torch.float64, device=st.device)
+    opts = K.gwf_opts(int(res), int(flags), 0, 0)
+    h2d = 0
+    keep = []
+    for lo in range(0, n, CHUNK_EVENTS):
+        m = min(CHUNK_EVENTS, n - lo)
+        sub = ev if (lo == 0 and m == n) else {k: np.asarray(v)[lo:lo + m] for k, v in ev.items() if k in K.EVENT_KEYS}
+        dev_ev, host_ev, evs, nb = _upload(st, sub, m, K.EVENT_KEYS)
+        h2d += nb
+        ws = _workspace(st, lib.gwf_workspace_bytes(C.byref(model), m))
+        part = out if m == n else torch.empty((narms, m), dtype=torch.float64, device=st.device)
+        K.check(lib.gwf_snr(C.byref(model), darr, len(dets), parr, len(psd_handles), C.byref(evs), m, C.byref(opts),
+                            C.c_void_p(part.data_ptr()), C.c_void_p(ws.data_ptr()), ws.numel(), sp), 'gwf_snr')
+        launch_count += 2
+        if m != n:
+            out[:, lo:lo + m] = part
+        keep.append((dev_ev, host_ev, part))
+    if keep_on_device:
+        return out, (h2d, 0)
+    host = torch.empty(out.shape, dtype=torch.float64, pin_memory=True)
+    host.copy_(out, non_blocking=True)
+    stream.synchronize()
+    return host.numpy(), (h2d, host.numel() * 8)

@@ -1,0 +1,174 @@
+// Per-(event, frequency) work of the fused Fisher/SNR path, independent of the thread mapping:
+// frequency grid + trapezoid weights (gwfast/signal.py:715-723, 884-901, 929), model dispatch, detector loop.
+#pragma once
+#include "detector.cuh"
+#include "model_phenomd.cuh"
+#include "model_tf2.cuh"
+
+namespace gwf {
+
+// ------------------------------------------------------------------ model traits
+template <int MODEL, int NT> struct ModelTraits;
+
+template <int NT> struct ModelTraits<kTaylorF2, NT> {
+    typedef TF2Rec<NT> Rec;
+    static GWF_HD void prologue(Rec& r, const EventIn& e, const ModelCfg& cfg, int opt_flags, const QnmTables&, const double*, int) {
+        const Intrinsic<NT> p = seed_intrinsic<NT>(e, opt_flags, (cfg.flags & kFlagTidal) != 0);
+        tf2_prologue(r, p, e.dL, cfg);
+    }
+    // waveform at f: amplitude, d ln A, d Phi and (if need_tau) d t_noloc
+    static GWF_HD void eval(const Rec& r, const ModelCfg&, int, double f, bool need_tau, PointWf<NT>& w) {
+        VPow p;
+        p.set(r.s * f);
+        double phi;
+        tf2_phase(r, p, phi, w.phi_d);
+        const double f16 = rsqrt(cbrt(f));          // f^(-1/6)
+        const double f76 = f16 / f;                  // f^(-7/6)
+        w.A = r.C * f76;
+#pragma unroll
+        for (int j = 0; j < NT; ++j) w.lnA_d[j] = r.lnC_d[j];
+        w.dtn[0] = w.dtn[1] = 0.;
+        w.tau = 0.;
+        if (need_tau) {
+            double tau, dtau[2];
+            tau_eval(r.tau, p.vm1, p.lpx3, r.lam, tau, dtau);
+            w.tau = tau;
+            w.dtn[0] = -dtau[0] / kDay;
+            w.dtn[1] = -dtau[1] / kDay;
+        }
+    }
+};
+
+template <int NT> struct ModelTraits<kPhenomD, NT> {
+    typedef PhenomDRec<NT> Rec;
+    static GWF_HD void prologue(Rec& r, const EventIn& e, const ModelCfg& cfg, int opt_flags, const QnmTables& q, const double* fmin_g, int ng) {
+        const Intrinsic<NT> p = seed_intrinsic<NT>(e, opt_flags, false);
+        phenomd_prologue(r, p, e.dL, q, fmin_g, ng, cfg);
+    }
+    static GWF_HD void eval(const Rec& r, const ModelCfg& cfg, int g, double f, bool need_tau, PointWf<NT>& w) {
+        XPow p;
+        p.set(r.s * f);
+        const bool cut = !(cfg.flags & kFlagNoFcut);
+        double phi;
+        phenomd_phase(r, g, p, cut, phi, w.phi_d);
+        phenomd_amp(r, p, cut, w.A, w.lnA_d);
+        w.dtn[0] = w.dtn[1] = 0.;
+        w.tau = 0.;
+        if (need_tau) {
+            double tau, dtau[2];
+            const double cpm1 = 0.68278406325529568146702083315816;   // pi^(-1/3)
+            tau_eval(r.tau, p.xm13 * cpm1, p.lpx3, r.lam, tau, dtau);
+            w.tau = tau;
+            w.dtn[0] = -dtau[0] / kDay;
+            w.dtn[1] = -dtau[1] / kDay;
+        }
+    }
+};
+
+// ------------------------------------------------------------------ frequency grid of one (event, group)
+struct Grid {
+    double fmin, fcut;
+    double l0, step;      // geom: log10 f_k = l0 + k*step ; lin: f_k = fmin + k*step
+    double hw_in, hw_lo, hw_hi;   // trapezoid half-widths: geom -> multiply f_k; lin -> absolute
+    int res, lin;
+    GWF_HD void set(double fmin_, double fcut_, int res_, bool lin_) {
+        fmin = fmin_; fcut = fcut_; res = res_; lin = lin_;
+        if (lin) {
+            step = (fcut - fmin) / (res - 1);
+            hw_in = step; hw_lo = hw_hi = 0.5 * step;
+            l0 = 0.;
+        } else {
+            // numpy.geomspace: 10**(log10(start) + k*(log10(stop)-log10(start))/(num-1)), end points overwritten
+            l0 = log10(fmin);
+            step = (log10(fcut) - l0) / (res - 1);
+            const double r = exp10(step);
+            hw_in = 0.5 * (r - 1.0 / r); hw_lo = 0.5 * (r - 1.0); hw_hi = 0.5 * (1.0 - 1.0 / r);
+        }
+    }
+    // f_k, the trapezoid weight w_k = (f_{k+1}-f_{k-1})/2 (one-sided at the ends; np.trapz, signal.py:929), log2 f_k
+    GWF_HD void point(int k, double& f, double& w, double& l2f) const {
+        if (lin) {
+            f = k == res - 1 ? fcut : fmin + k * step;
+            w = (k == 0 || k == res - 1) ? hw_lo : hw_in;
+            l2f = log2(f);
+        } else {
+            const double lf = fma((double)k, step, l0);
+            f = k == 0 ? fmin : (k == res - 1 ? fcut : exp10(lf));
+            w = f * (k == 0 ? hw_lo : (k == res - 1 ? hw_hi : hw_in));
+            l2f = lf * 3.3219280948873623478703194294893902;   // log2(10)
+        }
+    }
+};
+
+// ------------------------------------------------------------------ one frequency point of one grid group
+// acc: packed lower-triangular Fisher (NP(NP+1)/2), snr2: sum of 4 w |h|^2 / Sn over the arms of the pass
+template <int MODEL, int NT>
+GWF_HD void fisher_point(const typename ModelTraits<MODEL, NT>::Rec& rec, const ModelCfg& cfg, const EvGeom& geom, const NetworkDev& net, int g,
+                         bool group_rot, const Grid& grid, int k, double* __restrict__ acc, double& snr2) {
+    double f, wk, l2f;
+    grid.point(k, f, wk, l2f);
+    PointWf<NT> w;
+    ModelTraits<MODEL, NT>::eval(rec, cfg, g, f, group_rot, w);
+    const double tau = w.tau;
+    w.f = f;
+    if (!(w.A > 0.0)) return;             // beyond the model cut (or zero amplitude): no contribution
+    const double wA2 = 4.0 * wk * w.A * w.A;
+    // Earth-rotation phase common to the detectors of the group: 2 pi (tcoal - tau/86400), signal.py:449
+    double sBr = 0., cBr = 1.;
+    if (group_rot) sincos(2.0 * kPi * (geom.tcoal - tau / kDay), &sBr, &cBr);
+    double sBf, cBf;
+    sincos(2.0 * kPi * geom.tcoal, &sBf, &cBf);
+    for (int di = 0; di < net.ndet; ++di) {
+        const DetDev& d = net.det[di];
+        if (d.group != g || d.arm_begin == d.arm_end) continue;
+        const double Sn = psd_lookup(net.psd[d.psd], f, l2f);
+        DetPoint dp;
+        PointWf<NT> wd = w;
+        if (d.no_motion) {
+            det_point(d, geom, 1.0, 0.0, dp);
+            wd.dtn[0] = wd.dtn[1] = 0.;
+        } else if (d.use_rot) {
+            det_point(d, geom, cBr, sBr, dp);
+        } else {
+            det_point(d, geom, cBf, sBf, dp);
+            wd.dtn[0] = wd.dtn[1] = 0.;
+        }
+        const double wgt = wA2 / Sn;
+        for (int ai = d.arm_begin; ai < d.arm_end; ++ai) arm_rows_accumulate<NT>(wd, dp, d, net.arm[ai], geom, wgt, acc, snr2);
+    }
+}
+
+// value-only point for the SNR kernel: per-arm SNR^2 contributions (signal.py:725-767)
+template <int MODEL>
+GWF_HD void snr_point(const typename ModelTraits<MODEL, 4>::Rec& rec, const ModelCfg& cfg, const EvGeom& geom, const NetworkDev& net, int g,
+                      bool group_rot, const Grid& grid, int k, double* __restrict__ snr2_arm) {
+    double f, wk, l2f;
+    grid.point(k, f, wk, l2f);
+    PointWf<4> w;
+    ModelTraits<MODEL, 4>::eval(rec, cfg, g, f, group_rot, w);
+    const double tau = w.tau;
+    if (!(w.A > 0.0)) return;
+    const double wA2 = 4.0 * wk * w.A * w.A;
+    double sBr = 0., cBr = 1.;
+    if (group_rot) sincos(2.0 * kPi * (geom.tcoal - tau / kDay), &sBr, &cBr);
+    double sBf, cBf;
+    sincos(2.0 * kPi * geom.tcoal, &sBf, &cBf);
+    for (int di = 0; di < net.ndet; ++di) {
+        const DetDev& d = net.det[di];
+        if (d.group != g) continue;
+        const double Sn = psd_lookup(net.psd[d.psd], f, l2f);
+        DetPoint dp;
+        if (d.no_motion) det_point(d, geom, 1.0, 0.0, dp);
+        else if (d.use_rot) det_point(d, geom, cBr, sBr, dp);
+        else det_point(d, geom, cBf, sBf, dp);
+        const double wgt = wA2 / Sn;
+        for (int ai = d.arm_begin; ai < d.arm_end; ++ai) {
+            double Fp, Fc;
+            arm_pattern(dp, net.arm[ai], geom, Fp, Fc);
+            const double Gr = Fp * geom.K, Gi = Fc * geom.ci;
+            snr2_arm[net.arm[ai].out] = fma(wgt * net.arm[ai].weight, Gr * Gr + Gi * Gi, snr2_arm[net.arm[ai].out]);
+        }
+    }
+}
+
+}  // namespace gwf

@@ -1,0 +1,399 @@
+// libgwfast_b200.so -- kernels and C ABI (include/gwfast_b200.h).  sm_100a, FP64 throughout.
+//
+// Launch structure for one gwf_fisher call:
+//   K1  prologue_kernel   one thread per event: dual-number evaluation of every f-independent quantity
+//                         -> coefficient record (HBM, ~2 KB/event, read once by K2)
+//   K2  fisher_kernel     one warp per event, lanes = frequency samples; per sample: waveform amplitude and
+//                         tangents by basis expansion against the record (staged in shared memory), detector
+//                         geometry + analytic derivative rows per arm, packed Gram accumulated in FP64 registers;
+//                         butterfly reduction over the warp; one packed Fisher (+ SNR^2) written per event.
+// The derivative strain never exists in memory (the reference materialises (nP,N,res) complex128 per arm,
+// gwfast/signal.py:917-922).
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <algorithm>
+#include <cmath>
+
+#include "../../include/gwfast_b200.h"
+#include "fisher_core.cuh"
+#include "host_build.h"
+
+namespace gwf {
+
+#define GWF_CUDA(call)                                                                              \
+    do {                                                                                            \
+        cudaError_t e_ = (call);                                                                    \
+        if (e_ != cudaSuccess) return fail(GWF_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
+    } while (0)
+
+struct EventsDev {
+    const double* p[GWF_NPARAM_IN];
+};
+__device__ __forceinline__ EventIn load_event(const EventsDev& ev, long long e) {
+    EventIn in;
+    in.Mc = ev.p[0][e]; in.eta = ev.p[1][e]; in.dL = ev.p[2][e]; in.theta = ev.p[3][e]; in.phi = ev.p[4][e];
+    in.iota = ev.p[5][e]; in.psi = ev.p[6][e]; in.tcoal = ev.p[7][e]; in.Phicoal = ev.p[8][e];
+    in.chi1z = ev.p[9][e]; in.chi2z = ev.p[10][e];
+    in.Lambda1 = ev.p[11] ? ev.p[11][e] : 0.0;
+    in.Lambda2 = ev.p[12] ? ev.p[12][e] : 0.0;
+    return in;
+}
+
+struct GroupInfo {
+    int n;
+    double fmin[kMaxGroups];
+};
+
+// ------------------------------------------------------------------------------------------- K1
+template <int MODEL, int NT>
+__global__ void __launch_bounds__(128) prologue_kernel(EventsDev ev, long long n, ModelCfg cfg, int opt_flags, QnmTables q, GroupInfo gi,
+                                                      typename ModelTraits<MODEL, NT>::Rec* __restrict__ recs) {
+    const long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    const EventIn in = load_event(ev, e);
+    ModelTraits<MODEL, NT>::prologue(recs[e], in, cfg, opt_flags, q, gi.fmin, gi.n);
+}
+
+// ------------------------------------------------------------------------------------------- K2
+constexpr int kFisherThreads = 256;
+constexpr int kWarpsPerCta = kFisherThreads / 32;
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+template <int MODEL, int NT>
+__global__ void __launch_bounds__(kFisherThreads, 1)
+fisher_kernel(const typename ModelTraits<MODEL, NT>::Rec* __restrict__ recs, EventsDev ev, long long n, int res, int lin, ModelCfg cfg,
+              const __grid_constant__ NetworkDev net, double* __restrict__ out, double* __restrict__ snr2_out) {
+    typedef typename ModelTraits<MODEL, NT>::Rec Rec;
+    constexpr int NP = NT + 7, NPACK = NP * (NP + 1) / 2;
+    constexpr int kRecDoubles = (int)(sizeof(Rec) / sizeof(double));
+    extern __shared__ double smem[];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    double* mine = smem + (size_t)wid * kRecDoubles;
+    const Rec& rec = *reinterpret_cast<const Rec*>(mine);
+    const long long nwarps = (long long)gridDim.x * kWarpsPerCta;
+    for (long long e = (long long)blockIdx.x * kWarpsPerCta + wid; e < n; e += nwarps) {
+        // stage the event's coefficient record in shared memory (coalesced 8-byte loads, read by broadcast)
+        const double* src = reinterpret_cast<const double*>(recs + e);
+        __syncwarp();
+        for (int i = lane; i < kRecDoubles; i += 32) mine[i] = __ldg(src + i);
+        __syncwarp();
+        EvGeom geom;
+        geom.set(load_event(ev, e));
+        double acc[NPACK];
+#pragma unroll
+        for (int p = 0; p < NPACK; ++p) acc[p] = 0.0;
+        double snr2 = 0.0;
+        for (int g = 0; g < net.ngroups; ++g) {
+            double fcut = rec.fcut_hz;
+            if (net.group_fmax[g] > 0.0 && fcut > net.group_fmax[g]) fcut = net.group_fmax[g];   // signal.py:717-718
+            Grid grid;
+            grid.set(net.group_fmin[g], fcut, res, lin != 0);
+            const bool rot = net.group_rot[g] != 0;
+            for (int k = lane; k < res; k += 32) fisher_point<MODEL, NT>(rec, cfg, geom, net, g, rot, grid, k, acc, snr2);
+        }
+#pragma unroll
+        for (int p = 0; p < NPACK; ++p) acc[p] = warp_sum(acc[p]);
+        snr2 = warp_sum(snr2);
+        if (lane == 0) {
+            double* o = out + e * NPACK;
+#pragma unroll
+            for (int p = 0; p < NPACK; ++p) o[p] = acc[p];
+            if (snr2_out) snr2_out[e] = snr2;
+        }
+    }
+}
+
+// SNR: per-arm integrals, value-only
+template <int MODEL>
+__global__ void __launch_bounds__(kFisherThreads, 2)
+snr_kernel(const typename ModelTraits<MODEL, 4>::Rec* __restrict__ recs, EventsDev ev, long long n, int res, int lin, ModelCfg cfg,
+           const __grid_constant__ NetworkDev net, int narm_out, double* __restrict__ snr2_arm) {
+    typedef typename ModelTraits<MODEL, 4>::Rec Rec;
+    constexpr int kRecDoubles = (int)(sizeof(Rec) / sizeof(double));
+    extern __shared__ double smem[];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    double* mine = smem + (size_t)wid * kRecDoubles;
+    const Rec& rec = *reinterpret_cast<const Rec*>(mine);
+    const long long nwarps = (long long)gridDim.x * kWarpsPerCta;
+    for (long long e = (long long)blockIdx.x * kWarpsPerCta + wid; e < n; e += nwarps) {
+        const double* src = reinterpret_cast<const double*>(recs + e);
+        __syncwarp();
+        for (int i = lane; i < kRecDoubles; i += 32) mine[i] = __ldg(src + i);
+        __syncwarp();
+        EvGeom geom;
+        geom.set(load_event(ev, e));
+        double s2[kMaxArms];
+#pragma unroll
+        for (int a = 0; a < kMaxArms; ++a) s2[a] = 0.0;
+        for (int g = 0; g < net.ngroups; ++g) {
+            double fcut = rec.fcut_hz;
+            if (net.group_fmax[g] > 0.0 && fcut > net.group_fmax[g]) fcut = net.group_fmax[g];
+            Grid grid;
+            grid.set(net.group_fmin[g], fcut, res, lin != 0);
+            const bool rot = net.group_rot[g] != 0;
+            for (int k = lane; k < res; k += 32) snr_point<MODEL>(rec, cfg, geom, net, g, rot, grid, k, s2);
+        }
+        for (int a = 0; a < narm_out; ++a) {
+            const double v = warp_sum(s2[a]);
+            if (lane == 0) snr2_arm[(long long)a * n + e] = v;
+        }
+    }
+}
+
+__global__ void unpack_kernel(const double* __restrict__ packed, long long n, int nP, double* __restrict__ full) {
+    const long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    const int npack = nP * (nP + 1) / 2;
+    const double* src = packed + e * npack;
+    for (int i = 0; i < nP; ++i)
+        for (int j = 0; j <= i; ++j) {
+            const double v = src[tri(i, j)];
+            full[((long long)i * nP + j) * n + e] = v;
+            full[((long long)j * nP + i) * n + e] = v;
+        }
+}
+
+// ------------------------------------------------------------------------------------------- host side
+static QnmTables g_qnm = {nullptr, nullptr, nullptr, 0};
+
+static int collect_psds(const gwf_psd* const* psds, int npsd, PsdDev* out) {
+    if (npsd < 1 || npsd > kMaxPsd) return fail(GWF_ERR_ARG, "number of PSD tables must be in [1, 8]");
+    for (int i = 0; i < npsd; ++i) {
+        if (!psds[i]) return fail(GWF_ERR_ARG, "null PSD handle");
+        out[i] = reinterpret_cast<const PsdHost*>(psds[i])->dev;
+    }
+    return GWF_OK;
+}
+
+template <int MODEL, int NT>
+static int run_fisher(const gwf_model* model, const gwf_detector* dets, int ndet, const gwf_psd* const* psds, int npsd, const EventsDev& ev,
+                      long long n, const gwf_opts* opts, double* fisher, double* snr2, void* ws, size_t ws_bytes, cudaStream_t st) {
+    typedef typename ModelTraits<MODEL, NT>::Rec Rec;
+    constexpr int NP = NT + 7, NPACK = NP * (NP + 1) / 2;
+    if (ws_bytes < sizeof(Rec) * (size_t)n) return fail(GWF_ERR_WORKSPACE, "workspace too small");
+    Rec* recs = reinterpret_cast<Rec*>(ws);
+    ModelCfg cfg = {model->id, model->flags, model->fcutPar, model->fRef};
+    NetworkDev net;
+    PsdDev pd[kMaxPsd];
+    int rc = collect_psds(psds, npsd, pd);
+    if (rc) return rc;
+    rc = build_network(dets, ndet, pd, npsd, -1, false, net);
+    if (rc) return rc;
+    GroupInfo gi;
+    gi.n = net.ngroups;
+    for (int g = 0; g < kMaxGroups; ++g) gi.fmin[g] = net.group_fmin[g];
+    const int pb = 128;
+    prologue_kernel<MODEL, NT><<<(unsigned)((n + pb - 1) / pb), pb, 0, st>>>(ev, n, cfg, opts->flags, g_qnm, gi, recs);
+    GWF_CUDA(cudaGetLastError());
+    int dev = 0, sms = 0;
+    GWF_CUDA(cudaGetDevice(&dev));
+    GWF_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const size_t shmem = sizeof(Rec) * kWarpsPerCta;
+    auto kern = fisher_kernel<MODEL, NT>;
+    GWF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem));
+    int per_sm = 1;
+    GWF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kFisherThreads, shmem));
+    if (per_sm < 1) per_sm = 1;
+    const long long want = (n + kWarpsPerCta - 1) / kWarpsPerCta;
+    const unsigned grid = (unsigned)std::min<long long>(want, (long long)sms * per_sm);
+    const int lin = (opts->flags & GWF_OPT_LIN_GRID) ? 1 : 0;
+    const int npass = opts->per_arm ? gwf_num_arms(dets, ndet) : 1;
+    for (int pass = 0; pass < npass; ++pass) {
+        if (opts->per_arm) {
+            rc = build_network(dets, ndet, pd, npsd, pass, false, net);
+            if (rc) return rc;
+        }
+        kern<<<grid, kFisherThreads, shmem, st>>>(recs, ev, n, opts->res, lin, cfg, net, fisher + (size_t)pass * n * NPACK,
+                                                  snr2 ? snr2 + (size_t)pass * n : nullptr);
+        GWF_CUDA(cudaGetLastError());
+    }
+    return GWF_OK;
+}
+
+template <int MODEL>
+static int run_snr(const gwf_model* model, const gwf_detector* dets, int ndet, const gwf_psd* const* psds, int npsd, const EventsDev& ev,
+                   long long n, const gwf_opts* opts, double* snr2_arm, void* ws, size_t ws_bytes, cudaStream_t st) {
+    typedef typename ModelTraits<MODEL, 4>::Rec Rec;
+    if (ws_bytes < sizeof(Rec) * (size_t)n) return fail(GWF_ERR_WORKSPACE, "workspace too small");
+    Rec* recs = reinterpret_cast<Rec*>(ws);
+    ModelCfg cfg = {model->id, model->flags, model->fcutPar, model->fRef};
+    NetworkDev net;
+    PsdDev pd[kMaxPsd];
+    int rc = collect_psds(psds, npsd, pd);
+    if (rc) return rc;
+    rc = build_network(dets, ndet, pd, npsd, -1, true, net);
+    if (rc) return rc;
+    GroupInfo gi;
+    gi.n = net.ngroups;
+    for (int g = 0; g < kMaxGroups; ++g) gi.fmin[g] = net.group_fmin[g];
+    const int pb = 128;
+    // SNRInteg hands the dict entries straight to the waveform: no Fisher re-parametrisation (signal.py:715-726)
+    prologue_kernel<MODEL, 4><<<(unsigned)((n + pb - 1) / pb), pb, 0, st>>>(ev, n, cfg, 0, g_qnm, gi, recs);
+    GWF_CUDA(cudaGetLastError());
+    int dev = 0, sms = 0;
+    GWF_CUDA(cudaGetDevice(&dev));
+    GWF_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const size_t shmem = sizeof(Rec) * kWarpsPerCta;
+    auto kern = snr_kernel<MODEL>;
+    GWF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem));
+    int per_sm = 1;
+    GWF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kFisherThreads, shmem));
+    if (per_sm < 1) per_sm = 1;
+    const long long want = (n + kWarpsPerCta - 1) / kWarpsPerCta;
+    const unsigned grid = (unsigned)std::min<long long>(want, (long long)sms * per_sm);
+    const int lin = (opts->flags & GWF_OPT_LIN_GRID) ? 1 : 0;
+    kern<<<grid, kFisherThreads, shmem, st>>>(recs, ev, n, opts->res, lin, cfg, net, net.narms, snr2_arm);
+    GWF_CUDA(cudaGetLastError());
+    return GWF_OK;
+}
+
+}  // namespace gwf
+
+using namespace gwf;
+
+extern "C" {
+
+int gwf_version(void) { return GWF_VERSION; }
+const char* gwf_last_error(void) { return g_err.c_str(); }
+
+int gwf_num_params(const gwf_model* model) {
+    if (!model) return GWF_ERR_ARG;
+    const int nt = model_nt(*model);
+    return nt < 0 ? GWF_ERR_ARG : nt + 7;
+}
+
+int gwf_num_arms(const gwf_detector* dets, int32_t ndet) {
+    int n = 0;
+    for (int i = 0; i < ndet; ++i) n += dets[i].shape == 0 ? 1 : 3;
+    return n;
+}
+
+size_t gwf_workspace_bytes(const gwf_model* model, int64_t n) {
+    if (!model || n < 0) return 0;
+    size_t rec = 0;
+    switch (model->id) {
+        case GWF_TAYLORF2: rec = std::max(sizeof(TF2Rec<4>), sizeof(TF2Rec<6>)); break;
+        case GWF_IMRPHENOMD: rec = sizeof(PhenomDRec<4>); break;
+        default: rec = 0;
+    }
+    return rec * (size_t)n;
+}
+
+int gwf_psd_create(const double* f, const double* S, int32_t n, gwf_psd** out) {
+    if (!out) return fail(GWF_ERR_ARG, "gwf_psd_create: null output");
+    std::vector<double4> tab;
+    std::vector<int> bucket;
+    PsdHost* h = new PsdHost;
+    int rc = build_psd_tables(f, S, n, tab, bucket, h->dev);
+    if (rc) { delete h; return rc; }
+    if (cudaMalloc(&h->tab, sizeof(double4) * tab.size()) != cudaSuccess || cudaMalloc(&h->bucket, sizeof(int) * bucket.size()) != cudaSuccess) {
+        delete h;
+        return fail(GWF_ERR_CUDA, "gwf_psd_create: cudaMalloc failed");
+    }
+    GWF_CUDA(cudaMemcpy(h->tab, tab.data(), sizeof(double4) * tab.size(), cudaMemcpyHostToDevice));
+    GWF_CUDA(cudaMemcpy(h->bucket, bucket.data(), sizeof(int) * bucket.size(), cudaMemcpyHostToDevice));
+    h->dev.tab = h->tab;
+    h->dev.bucket = h->bucket;
+    *out = reinterpret_cast<gwf_psd*>(h);
+    return GWF_OK;
+}
+
+void gwf_psd_destroy(gwf_psd* psd) {
+    if (!psd) return;
+    PsdHost* h = reinterpret_cast<PsdHost*>(psd);
+    cudaFree(h->tab);
+    cudaFree(h->bucket);
+    delete h;
+}
+
+int gwf_set_qnm_tables(const double* a, const double* fring, const double* fdamp, int32_t n) {
+    if (!a || !fring || !fdamp || n < 2) return fail(GWF_ERR_ARG, "gwf_set_qnm_tables: bad arguments");
+    double* buf = nullptr;
+    GWF_CUDA(cudaMalloc(&buf, sizeof(double) * 3 * n));
+    GWF_CUDA(cudaMemcpy(buf, a, sizeof(double) * n, cudaMemcpyHostToDevice));
+    GWF_CUDA(cudaMemcpy(buf + n, fring, sizeof(double) * n, cudaMemcpyHostToDevice));
+    GWF_CUDA(cudaMemcpy(buf + 2 * n, fdamp, sizeof(double) * n, cudaMemcpyHostToDevice));
+    if (g_qnm.a) cudaFree(const_cast<double*>(g_qnm.a));
+    g_qnm.a = buf;
+    g_qnm.fring = buf + n;
+    g_qnm.fdamp = buf + 2 * n;
+    g_qnm.n = n;
+    return GWF_OK;
+}
+
+static int check_common(const gwf_model* model, const gwf_detector* dets, const gwf_psd* const* psds, const gwf_events* events, int64_t n,
+                        const gwf_opts* opts) {
+    if (!model || !dets || !psds || !events || !opts) return fail(GWF_ERR_ARG, "null argument");
+    if (n < 0) return fail(GWF_ERR_ARG, "negative event count");
+    if (opts->res < 2) return fail(GWF_ERR_ARG, "res must be at least 2");
+    for (int i = 0; i < 11; ++i)
+        if (!events->p[i] && n > 0) return fail(GWF_ERR_ARG, "missing event parameter array");
+    if ((model->id == GWF_IMRPHENOMD || model->id == GWF_IMRPHENOMD_NRTIDALV2) && !g_qnm.a)
+        return fail(GWF_ERR_ARG, "QNM tables not set (gwf_set_qnm_tables)");
+    return GWF_OK;
+}
+
+int gwf_fisher(const gwf_model* model, const gwf_detector* dets, int32_t ndet, const gwf_psd* const* psds, int32_t npsd, const gwf_events* events,
+               int64_t n, const gwf_opts* opts, double* fisher_packed, double* snr2, void* workspace, size_t workspace_bytes, void* stream) {
+    int rc = check_common(model, dets, psds, events, n, opts);
+    if (rc) return rc;
+    if (!fisher_packed) return fail(GWF_ERR_ARG, "null output");
+    if (n == 0) return GWF_OK;
+    EventsDev ev;
+    for (int i = 0; i < GWF_NPARAM_IN; ++i) ev.p[i] = events->p[i];
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    switch (model->id) {
+        case GWF_TAYLORF2:
+            if (model->flags & GWF_MODEL_TIDAL) {
+                if (!ev.p[11] || !ev.p[12]) return fail(GWF_ERR_ARG, "tidal model needs Lambda1, Lambda2");
+                return run_fisher<kTaylorF2, 6>(model, dets, ndet, psds, npsd, ev, n, opts, fisher_packed, snr2, workspace, workspace_bytes, st);
+            }
+            return run_fisher<kTaylorF2, 4>(model, dets, ndet, psds, npsd, ev, n, opts, fisher_packed, snr2, workspace, workspace_bytes, st);
+        case GWF_IMRPHENOMD:
+            return run_fisher<kPhenomD, 4>(model, dets, ndet, psds, npsd, ev, n, opts, fisher_packed, snr2, workspace, workspace_bytes, st);
+        default:
+            return fail(GWF_ERR_UNSUPPORTED, "model not built yet");
+    }
+}
+
+int gwf_snr(const gwf_model* model, const gwf_detector* dets, int32_t ndet, const gwf_psd* const* psds, int32_t npsd, const gwf_events* events,
+            int64_t n, const gwf_opts* opts, double* snr2_arm, void* workspace, size_t workspace_bytes, void* stream) {
+    int rc = check_common(model, dets, psds, events, n, opts);
+    if (rc) return rc;
+    if (!snr2_arm) return fail(GWF_ERR_ARG, "null output");
+    if (n == 0) return GWF_OK;
+    EventsDev ev;
+    for (int i = 0; i < GWF_NPARAM_IN; ++i) ev.p[i] = events->p[i];
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    switch (model->id) {
+        case GWF_TAYLORF2:
+            return run_snr<kTaylorF2>(model, dets, ndet, psds, npsd, ev, n, opts, snr2_arm, workspace, workspace_bytes, st);
+        case GWF_IMRPHENOMD:
+            return run_snr<kPhenomD>(model, dets, ndet, psds, npsd, ev, n, opts, snr2_arm, workspace, workspace_bytes, st);
+        default:
+            return fail(GWF_ERR_UNSUPPORTED, "model not built yet");
+    }
+}
+
+int gwf_unpack_fisher(const double* packed, int64_t n, int32_t nP, double* full, void* stream) {
+    if (!packed || !full || nP < 1) return fail(GWF_ERR_ARG, "gwf_unpack_fisher: bad arguments");
+    if (n == 0) return GWF_OK;
+    const int tb = 256;
+    unpack_kernel<<<(unsigned)((n + tb - 1) / tb), tb, 0, reinterpret_cast<cudaStream_t>(stream)>>>(packed, n, nP, full);
+    GWF_CUDA(cudaGetLastError());
+    return GWF_OK;
+}
+
+int gwf_waveform(const gwf_model*, const gwf_events*, int64_t, const double*, int32_t, int32_t, double*, double*, double*, double*, void*, size_t,
+                 void*) {
+    return fail(GWF_ERR_UNSUPPORTED, "gwf_waveform: not built yet");
+}
+
+}  // extern "C"

@@ -1,0 +1,220 @@
+"""``GWSignal`` with the reference's constructor, attributes, keyword arguments, side effects and return shapes
+(gwfast/signal.py:37-1098).  The numerical work of ``SNRInteg`` / ``FisherMatr`` -- frequency grid, PSD
+interpolation, waveform, detector projection, derivatives, inner products -- is one fused CUDA launch per call
+(``gwf_snr`` / ``gwf_fisher``); this file only keeps the host-side contract: dict mutation, error messages,
+duty-cycle masks drawn from numpy's global RNG, ``return_all`` shapes.
+"""
+import numpy as onp
+
+from . import gwfastUtils as utils
+from . import _capi as K
+from . import _engine
+
+
+def _fill_spins(wf_model, evParams, verbose):
+    """signal.py:694-704 / 824-834: add chi1z, chi2z from chiS, chiA (mutates the dict)."""
+    if 'chi1z' not in evParams:
+        try:
+            if verbose:
+                print('Adding chi1z, chi2z from chiS, chiA')
+            evParams['chi1z'] = evParams['chiS'] + evParams['chiA']
+            evParams['chi2z'] = evParams['chiS'] - evParams['chiA']
+        except KeyError:
+            raise ValueError('Two among chi1z, chi2z and chiS, chiA have to be provided.')
+
+
+def _num_events(evParams):
+    return len(onp.atleast_1d(evParams['Mc']))
+
+
+def _engine_events(wf_model, evParams, lambdas=None):
+    """the arrays the engine consumes (never mutates the caller's dict)."""
+    ev = {k: evParams[k] for k in K.EVENT_KEYS[:11]}
+    if wf_model.is_tidal:
+        L1, L2 = lambdas if lambdas is not None else (evParams['Lambda1'], evParams['Lambda2'])
+        ev['Lambda1'], ev['Lambda2'] = L1, L2
+    return ev
+
+
+def hot_snr(signals, evParams, res):
+    """per-arm SNR^2 for a list of GWSignal sharing one waveform model: ONE launch for the whole list.
+
+    Returns (snr2_arm (n_arms, N), arm_slices) where arm_slices[i] is the slice of arms of signals[i].
+    """
+    wf = signals[0].wf_model
+    n = _num_events(evParams)
+    dets, handles, slices, a0 = [], [], [], 0
+    for s in signals:
+        dets.append(s._detector_struct(len(handles)))
+        handles.append(s._psd_handle())
+        na = 1 if s.detector_shape == 'L' else 3
+        slices.append(slice(a0, a0 + na))
+        a0 += na
+    out, io = _engine.snr(wf._descriptor(evParams), dets, handles, _engine_events(wf, evParams), n, res)
+    return out, slices, io
+
+
+def hot_fisher(signals, evParams, lambdas, res, spacing, use_m1m2, use_chi1chi2, per_arm):
+    """Fisher matrices for a list of GWSignal sharing one waveform model: ONE prologue + one launch per block."""
+    wf = signals[0].wf_model
+    n = _num_events(evParams)
+    flags = 0
+    if use_m1m2:
+        flags |= K.GWF_OPT_M1M2
+    if not use_chi1chi2:
+        flags |= K.GWF_OPT_CHIS_CHIA
+    if spacing == 'lin':
+        flags |= K.GWF_OPT_LIN_GRID
+    elif spacing != 'geom':
+        raise ValueError("spacing has to be 'geom' or 'lin'")
+    dets, handles = [], []
+    for s in signals:
+        dets.append(s._detector_struct(len(handles)))
+        handles.append(s._psd_handle())
+    F, snr2, io = _engine.fisher(wf._descriptor(evParams), dets, handles, _engine_events(wf, evParams, lambdas), n, res, flags, per_arm)
+    return F, snr2, io
+
+
+class GWSignal(object):
+    """Single detector (L-shaped or triangular); see gwfast/signal.py:37-160 for the parameters."""
+
+    def __init__(self, wf_model, psd_path=None, detector_shape='T', det_lat=40.44, det_long=9.45, det_xax=0., verbose=True,
+                 is_ASD=True, useEarthMotion=False, noMotion=False, fmin=2., fmax=None, IntTablePath=None, DutyFactor=None,
+                 compute2arms=True, jitCompileDerivs=False):
+        if (detector_shape != 'L') and (detector_shape != 'T'):
+            raise ValueError('Enter valid detector configuration')
+        if psd_path is None:
+            raise ValueError('Enter a valid PSD or ASD path')
+        if verbose:
+            print(('Using ASD from file %s ' if is_ASD else 'Using PSD from file %s ') % psd_path)
+        if useEarthMotion and (wf_model.objType == 'BBH') and verbose:
+            print('WARNING: the motion of Earth gives a negligible contribution for BBH signals, consider switching it off to make the code run faster')
+        if (not useEarthMotion) and (wf_model.objType in ('BNS', 'NSBH')) and verbose:
+            print('WARNING: the motion of Earth gives a relevant contribution for %s signals, consider switching it on' % wf_model.objType)
+        self.wf_model = wf_model
+        self.psd_base_path = ('/').join(psd_path.split('/')[:-1])
+        self.psd_file_name = psd_path.split('/')[-1]
+        self.verbose = verbose
+        self.detector_shape = detector_shape
+        self.det_lat_rad = det_lat * onp.pi / 180.
+        self.det_long_rad = det_long * onp.pi / 180.
+        self.det_xax_rad = det_xax * onp.pi / 180.
+        self.IntTablePath = IntTablePath
+        self.DutyFactor = DutyFactor
+        noise = onp.loadtxt(psd_path, usecols=(0, 1))
+        self.strainFreq = noise[:, 0]
+        self.noiseCurve = noise[:, 1] ** 2 if is_ASD else noise[:, 1]
+        self.useEarthMotion = useEarthMotion
+        self.noMotion = noMotion
+        if self.noMotion and self.useEarthMotion:
+            print('noMotion and useEarthMotion are True. switching off useEarthMotion ')
+            self.useEarthMotion = False
+        self.fmin = fmin
+        self.fmax = fmax
+        self.angbtwArms = 0.5 * onp.pi if detector_shape == 'L' else onp.pi / 3.
+        self.IntegInterpArr = None
+        self.compute2arms = compute2arms
+        onp.random.seed(None)
+        self.seedUse = onp.random.randint(2 ** 32 - 1, size=1)
+        self.jitCompileDerivs = jitCompileDerivs   # accepted for compatibility; there is nothing to jit
+        self._psd = None
+
+    # ------------------------------------------------------------------ engine hooks
+    def _psd_handle(self):
+        if self._psd is None:
+            self._psd = _engine.psd_handle(self.strainFreq, self.noiseCurve)
+        return self._psd
+
+    def _detector_struct(self, psd_index):
+        return K.gwf_detector(self.det_lat_rad, self.det_long_rad, self.det_xax_rad, 0 if self.detector_shape == 'L' else 1,
+                              int(bool(self.useEarthMotion)), int(bool(self.noMotion)), psd_index, float(self.fmin),
+                              float(self.fmax) if self.fmax is not None else 0.)
+
+    def _clear_cache(self):
+        pass
+
+    def _update_seed(self, seed=None):
+        """signal.py:221-232."""
+        onp.random.seed(None)
+        self.seedUse = onp.random.randint(2 ** 32 - 1, size=1) if seed is None else seed
+
+    def _narms(self):
+        return 1 if self.detector_shape == 'L' else 3
+
+    def _duty_masks(self, n):
+        """one Bernoulli mask per arm from numpy's global RNG, drawn in the reference's order (signal.py:729-762)."""
+        return [onp.random.choice([0, 1], n, p=[1. - self.DutyFactor, self.DutyFactor]) for _ in range(self._narms())]
+
+    # ------------------------------------------------------------------ SNR
+    def _prepare_snr(self, evParams):
+        utils.check_evparams(evParams)
+        _fill_spins(self.wf_model, evParams, self.verbose)
+        if self.wf_model.is_tidal and 'Lambda1' not in evParams:
+            try:
+                evParams['Lambda1'], evParams['Lambda2'] = utils.Lam12_from_Lamt_delLam(evParams['LambdaTilde'], evParams['deltaLambda'], evParams['eta'])
+            except KeyError:
+                raise ValueError('Two among Lambda1, Lambda2 and LambdaTilde and deltaLambda have to be provided.')
+
+    def _snr_from_arms(self, s2, n, return_all):
+        """s2: (narms, N) per-arm 4*int(...)  ->  the reference's return value (signal.py:767-777)."""
+        if self.DutyFactor is not None:
+            s2 = s2 * onp.array(self._duty_masks(n))
+        if self.detector_shape == 'T':
+            return onp.sqrt(s2) if return_all else onp.sqrt(s2.sum(axis=0))
+        return onp.sqrt(s2[0])
+
+    def SNRInteg(self, evParams, res=1000, return_all=False):
+        """SNR of the event(s), shape (N,) ((3, N) for a triangle with ``return_all``); signal.py:658-777."""
+        if self.DutyFactor is not None:
+            onp.random.seed(self.seedUse)
+        self._prepare_snr(evParams)
+        s2, _, _ = hot_snr([self], evParams, res)
+        return self._snr_from_arms(s2, _num_events(evParams), return_all)
+
+    # ------------------------------------------------------------------ Fisher
+    def _prepare_fisher(self, evParams, res, df, computeDerivFinDiff, return_derivatives, return_SNR_derivatives):
+        """host-side part of signal.py:812-898; returns (Lambda1, Lambda2) locals (not written to the dict) and res."""
+        utils.check_evparams(evParams)
+        _fill_spins(self.wf_model, evParams, self.verbose)
+        lambdas = None
+        if self.wf_model.is_tidal:
+            try:
+                lambdas = (evParams['Lambda1'], evParams['Lambda2'])
+            except KeyError:
+                try:
+                    lambdas = utils.Lam12_from_Lamt_delLam(evParams['LambdaTilde'], evParams['deltaLambda'], evParams['eta'])
+                except KeyError:
+                    raise ValueError('Two among Lambda1, Lambda2 and LambdaTilde and deltaLambda have to be provided.')
+        if computeDerivFinDiff:
+            raise NotImplementedError('finite-difference derivatives (numdifftools) are only used by the LAL/TEOBResumS wrappers of the reference; '
+                                      'this engine always differentiates exactly')
+        if return_derivatives or return_SNR_derivatives:
+            raise NotImplementedError('return_derivatives / return_SNR_derivatives are not built yet (the derivative strain never leaves the GPU registers)')
+        if res is None and df is not None:
+            fcut = self.wf_model.fcut(**evParams)
+            if self.fmax is not None:
+                fcut = onp.where(fcut > self.fmax, self.fmax, fcut)
+            res = onp.amax(onp.floor(onp.real(1 + (fcut - self.fmin) / df)))      # signal.py:890-892
+        elif res is None and df is None:
+            raise ValueError('Provide either resolution in frequency or step size.')
+        return lambdas, int(res)
+
+    def FisherMatr(self, evParams, res=1000, df=None, spacing='geom', use_m1m2=False, use_chi1chi2=True, use_prec_ang=True,
+                   computeDerivFinDiff=False, computeAnalyticalDeriv=True, return_all=False, return_derivatives=False,
+                   return_SNR_derivatives=False, **kwargs):
+        """Fisher matrix, shape (nParams, nParams, N) (list per arm with ``return_all``); signal.py:782-1098.
+
+        ``computeAnalyticalDeriv`` is accepted for compatibility: the engine's derivatives are exact either way.
+        """
+        if self.DutyFactor is not None:
+            onp.random.seed(self.seedUse)
+        lambdas, res = self._prepare_fisher(evParams, res, df, computeDerivFinDiff, return_derivatives, return_SNR_derivatives)
+        n = _num_events(evParams)
+        per_arm = return_all or (self.DutyFactor is not None)
+        F, _, _ = hot_fisher([self], evParams, lambdas, res, spacing, use_m1m2, use_chi1chi2, per_arm)
+        if self.DutyFactor is not None:
+            masks = self._duty_masks(n)
+            F = F * onp.array(masks)[:, None, None, :]
+        if return_all:
+            return [F[i] for i in range(F.shape[0])]
+        return F.sum(axis=0) if F.shape[0] > 1 else F[0]

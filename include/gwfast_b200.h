@@ -1,0 +1,128 @@
+/* gwfast_b200 -- C ABI of the B200-native Fisher/SNR engine (libgwfast_b200.so).
+ *
+ * The reference (CosmoStatGW/gwfast) has no FFI layer: the hot path sits behind Python methods.  Each entry
+ * point below names the reference method whose numerical work it replaces; the Python classes in
+ * gwfast_b200/{waveforms,signal,network}.py keep the reference's names and call these through ctypes
+ * (INTEGRATION.md shows the stub).  Conventions:
+ *   - plain C types only; every array pointer is a DEVICE pointer unless the name ends in _host;
+ *   - all arithmetic is FP64; events are SoA (one array of length N per parameter);
+ *   - calls are stream-ordered on `stream` (a cudaStream_t passed as void*), never synchronise, and allocate
+ *     nothing: the caller passes the workspace (gwf_workspace_bytes);
+ *   - return 0 on success, a negative gwf_status otherwise; gwf_last_error() gives the text.
+ */
+#ifndef GWFAST_B200_H
+#define GWFAST_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GWF_VERSION 100 /* 0.1.0 */
+
+typedef enum {
+    GWF_OK = 0,
+    GWF_ERR_ARG = -1,        /* invalid argument (null pointer, bad id, too many detectors ...) */
+    GWF_ERR_UNSUPPORTED = -2, /* combination not built (e.g. eccentric TaylorF2) */
+    GWF_ERR_CUDA = -3,       /* a CUDA runtime call failed */
+    GWF_ERR_WORKSPACE = -4   /* workspace too small */
+} gwf_status;
+
+/* waveform models: gwfast/waveforms.py classes at :697, :959, :1339, :1838 */
+typedef enum { GWF_TAYLORF2 = 0, GWF_IMRPHENOMD = 1, GWF_IMRPHENOMD_NRTIDALV2 = 2, GWF_IMRPHENOMHM = 3 } gwf_model_id;
+
+/* gwf_model.flags -- constructor options of the reference classes that change the arithmetic */
+#define GWF_MODEL_TIDAL 1          /* TaylorF2_RestrictedPN(is_tidal=True)            waveforms.py:850-855 */
+#define GWF_MODEL_3P5PN_SPINHO 2   /* TaylorF2_RestrictedPN(use_3p5PN_SpinHO=True)    waveforms.py:808-812 */
+#define GWF_MODEL_PHIREF_VLSO 4    /* TaylorF2_RestrictedPN(phiref_vlso=True)         waveforms.py:796-802 */
+#define GWF_MODEL_QUADMON_TID 8    /* TaylorF2_RestrictedPN(use_QuadMonTid=True)      waveforms.py:774-782 */
+#define GWF_MODEL_KERR_ISCO 16     /* TaylorF2_RestrictedPN(which_ISCO='Kerr')        waveforms.py:922-953 */
+#define GWF_MODEL_NO_FCUT 32       /* WaveFormModel(apply_fcut=False)                 waveforms.py:1142-1153 */
+#define GWF_MODEL_HAS_FREF 64      /* IMRPhenomD(fRef=...)                            waveforms.py:1139-1141 */
+#define GWF_MODEL_LAMBDA_GIVEN 128 /* events carried Lambda1/Lambda2 when fcut() ran  signal.py:884 (SURVEY A-20) */
+
+typedef struct {
+    int32_t id;      /* gwf_model_id */
+    int32_t flags;   /* GWF_MODEL_* */
+    double fcutPar;  /* WaveFormModel.fcutPar (waveforms.py:75) */
+    double fRef;     /* Hz, used if GWF_MODEL_HAS_FREF */
+} gwf_model;
+
+/* one GWSignal (gwfast/signal.py:68-160) */
+typedef struct {
+    double lat_rad, long_rad, xax_rad; /* det_lat_rad, det_long_rad, det_xax_rad (signal.py:113-116) */
+    int32_t shape;                     /* 0 = 'L', 1 = 'T' (signal.py:144-147) */
+    int32_t use_earth_motion;          /* useEarthMotion (signal.py:136) */
+    int32_t no_motion;                 /* noMotion (signal.py:137) */
+    int32_t psd;                       /* index into the psds[] array passed with the call */
+    double fmin, fmax;                 /* Hz; fmax <= 0 means None (signal.py:141-142) */
+} gwf_detector;
+
+/* PSD table on the device: built once per GWSignal from strainFreq/noiseCurve (signal.py:122-130) */
+typedef struct gwf_psd gwf_psd;
+int gwf_psd_create(const double* freq_host, const double* psd_host, int32_t n, gwf_psd** out);
+void gwf_psd_destroy(gwf_psd* psd);
+
+/* QNM ringdown tables WFfiles/QNMData_{a,fring,fdamp}.txt (waveforms.py:988-990); host arrays, copied once */
+int gwf_set_qnm_tables(const double* a_host, const double* fring_host, const double* fdamp_host, int32_t n);
+
+/* the events dict as device SoA; order of p[]:
+ * Mc eta dL theta phi iota psi tcoal Phicoal chi1z chi2z Lambda1 Lambda2 (p[11], p[12] may be NULL for BBH) */
+#define GWF_NPARAM_IN 13
+typedef struct {
+    const double* p[GWF_NPARAM_IN];
+} gwf_events;
+
+/* gwf_opts.flags -- keyword arguments of GWSignal.FisherMatr (signal.py:782-786) */
+#define GWF_OPT_M1M2 1       /* use_m1m2=True      */
+#define GWF_OPT_CHIS_CHIA 2  /* use_chi1chi2=False */
+#define GWF_OPT_LIN_GRID 4   /* spacing='lin'      */
+typedef struct {
+    int32_t res;    /* frequency samples per event (res=1000) */
+    int32_t flags;  /* GWF_OPT_* */
+    int32_t per_arm; /* 0: one Fisher summed over the whole network (DetNet.FisherMatr default, network.py:118);
+                        1: one Fisher per arm, triangle arms in the order 0, 60 deg, -(1+2) (return_all=True) */
+    int32_t reserved;
+} gwf_opts;
+
+int gwf_version(void);
+const char* gwf_last_error(void);
+
+/* number of Fisher parameters (WaveFormModel.nParams, waveforms.py:87-124) and of arms (1 per L, 3 per T) */
+int gwf_num_params(const gwf_model* model);
+int gwf_num_arms(const gwf_detector* dets, int32_t ndet);
+
+/* bytes of device workspace needed by gwf_fisher / gwf_snr for n events */
+size_t gwf_workspace_bytes(const gwf_model* model, int64_t n);
+
+/* Replaces DetNet.FisherMatr / GWSignal.FisherMatr (network.py:84-123, signal.py:782-1098) including
+ * _SignalDerivatives + _AnalyticalDerivatives (signal.py:1102-1584).
+ *   fisher_packed: per_arm=0 -> [n][nP(nP+1)/2], per_arm=1 -> [n_arms][n][nP(nP+1)/2]; lower triangle, row-major,
+ *                  rows/cols in ParNums order (waveforms.py:78-147)
+ *   snr2:          same leading shape, [n] per block: 4 int |h|^2/Sn df of the arms in the block
+ *                  (= SNR^2 for the non-HM models; may be NULL) */
+int gwf_fisher(const gwf_model* model, const gwf_detector* dets, int32_t ndet, const gwf_psd* const* psds, int32_t npsd,
+               const gwf_events* events, int64_t n, const gwf_opts* opts, double* fisher_packed, double* snr2,
+               void* workspace, size_t workspace_bytes, void* stream);
+
+/* Replaces DetNet.SNR / GWSignal.SNRInteg (network.py:53-81, signal.py:658-777).
+ *   snr2_arm: [n_arms][n], the per-arm integrals 4 int (Ap^2+Ac^2)/Sn df (SNR_arm = sqrt of it) */
+int gwf_snr(const gwf_model* model, const gwf_detector* dets, int32_t ndet, const gwf_psd* const* psds, int32_t npsd,
+            const gwf_events* events, int64_t n, const gwf_opts* opts, double* snr2_arm,
+            void* workspace, size_t workspace_bytes, void* stream);
+
+/* packed lower triangle [n][nP(nP+1)/2] -> the reference's (nP, nP, N) layout, event axis fastest (signal.py:924) */
+int gwf_unpack_fisher(const double* packed, int64_t n, int32_t nP, double* full, void* stream);
+
+/* Replaces WaveFormModel.Phi / Ampl / tau_star / fcut evaluated on a user grid (waveforms.py:149-199).
+ *   f: [res][n] if f_is_2d else [res]; outputs [res][n] (any may be NULL); fcut_out: [n] */
+int gwf_waveform(const gwf_model* model, const gwf_events* events, int64_t n, const double* f, int32_t res, int32_t f_is_2d,
+                 double* phi_out, double* ampl_out, double* tau_out, double* fcut_out,
+                 void* workspace, size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GWFAST_B200_H */

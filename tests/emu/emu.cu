@@ -1,0 +1,135 @@
+// CPU emulation harness for the device math (TEST INFRASTRUCTURE, never shipped or loaded by gwfast_b200).
+//
+// The per-event prologue and the per-(event, frequency) point functions of gwfast_b200/csrc are written as
+// __host__ __device__ code; this file drives exactly those functions in a plain double loop on the host so that
+// `pytest -m "not gpu"` can check the formulas against the oracle in a container that has no GPU.  It does not
+// exercise the kernels' thread mapping, shared-memory staging or warp reductions -- the `-m gpu` tests do.
+#include <vector>
+#include <cstring>
+#include "../../gwfast_b200/csrc/fisher_core.cuh"
+#include "../../gwfast_b200/csrc/host_build.h"
+
+using namespace gwf;
+
+struct EmuPsd {
+    std::vector<double4> tab;
+    std::vector<int> bucket;
+    PsdDev dev;
+};
+
+static QnmTables g_q = {nullptr, nullptr, nullptr, 0};
+static std::vector<double> g_qbuf;
+
+template <int MODEL, int NT>
+static int emu_run(const gwf_model* model, const gwf_detector* dets, int ndet, const PsdDev* pd, int npsd, const double* const* ev, long long n,
+                   const gwf_opts* opts, double* fisher, double* snr2) {
+    typedef typename ModelTraits<MODEL, NT>::Rec Rec;
+    constexpr int NP = NT + 7, NPACK = NP * (NP + 1) / 2;
+    ModelCfg cfg = {model->id, model->flags, model->fcutPar, model->fRef};
+    const int npass = opts->per_arm ? gwf_num_arms(dets, ndet) : 1;
+    for (int pass = 0; pass < npass; ++pass) {
+        NetworkDev net;
+        int rc = build_network(dets, ndet, pd, npsd, opts->per_arm ? pass : -1, false, net);
+        if (rc) return rc;
+        for (long long e = 0; e < n; ++e) {
+            EventIn in;
+            in.Mc = ev[0][e]; in.eta = ev[1][e]; in.dL = ev[2][e]; in.theta = ev[3][e]; in.phi = ev[4][e]; in.iota = ev[5][e];
+            in.psi = ev[6][e]; in.tcoal = ev[7][e]; in.Phicoal = ev[8][e]; in.chi1z = ev[9][e]; in.chi2z = ev[10][e];
+            in.Lambda1 = ev[11] ? ev[11][e] : 0.; in.Lambda2 = ev[12] ? ev[12][e] : 0.;
+            Rec rec;
+            ModelTraits<MODEL, NT>::prologue(rec, in, cfg, opts->flags, g_q, net.group_fmin, net.ngroups);
+            EvGeom geom;
+            geom.set(in);
+            double acc[NPACK];
+            for (int p = 0; p < NPACK; ++p) acc[p] = 0.;
+            double s2 = 0.;
+            for (int g = 0; g < net.ngroups; ++g) {
+                double fcut = rec.fcut_hz;
+                if (net.group_fmax[g] > 0.0 && fcut > net.group_fmax[g]) fcut = net.group_fmax[g];
+                Grid grid;
+                grid.set(net.group_fmin[g], fcut, opts->res, (opts->flags & GWF_OPT_LIN_GRID) != 0);
+                for (int k = 0; k < opts->res; ++k) fisher_point<MODEL, NT>(rec, cfg, geom, net, g, net.group_rot[g] != 0, grid, k, acc, s2);
+            }
+            std::memcpy(fisher + ((size_t)pass * n + e) * NPACK, acc, sizeof(acc));
+            if (snr2) snr2[(size_t)pass * n + e] = s2;
+        }
+    }
+    return 0;
+}
+
+template <int MODEL>
+static int emu_run_snr(const gwf_model* model, const gwf_detector* dets, int ndet, const PsdDev* pd, int npsd, const double* const* ev, long long n,
+                       const gwf_opts* opts, double* snr2_arm) {
+    typedef typename ModelTraits<MODEL, 4>::Rec Rec;
+    ModelCfg cfg = {model->id, model->flags, model->fcutPar, model->fRef};
+    NetworkDev net;
+    int rc = build_network(dets, ndet, pd, npsd, -1, true, net);
+    if (rc) return rc;
+    for (long long e = 0; e < n; ++e) {
+        EventIn in;
+        in.Mc = ev[0][e]; in.eta = ev[1][e]; in.dL = ev[2][e]; in.theta = ev[3][e]; in.phi = ev[4][e]; in.iota = ev[5][e];
+        in.psi = ev[6][e]; in.tcoal = ev[7][e]; in.Phicoal = ev[8][e]; in.chi1z = ev[9][e]; in.chi2z = ev[10][e];
+        in.Lambda1 = ev[11] ? ev[11][e] : 0.; in.Lambda2 = ev[12] ? ev[12][e] : 0.;
+        Rec rec;
+        ModelTraits<MODEL, 4>::prologue(rec, in, cfg, 0, g_q, net.group_fmin, net.ngroups);
+        EvGeom geom;
+        geom.set(in);
+        double s2[kMaxArms] = {0};
+        for (int g = 0; g < net.ngroups; ++g) {
+            double fcut = rec.fcut_hz;
+            if (net.group_fmax[g] > 0.0 && fcut > net.group_fmax[g]) fcut = net.group_fmax[g];
+            Grid grid;
+            grid.set(net.group_fmin[g], fcut, opts->res, (opts->flags & GWF_OPT_LIN_GRID) != 0);
+            for (int k = 0; k < opts->res; ++k) snr_point<MODEL>(rec, cfg, geom, net, g, net.group_rot[g] != 0, grid, k, s2);
+        }
+        for (int a = 0; a < net.narms; ++a) snr2_arm[(size_t)a * n + e] = s2[a];
+    }
+    return 0;
+}
+
+extern "C" {
+
+int gwf_num_arms(const gwf_detector* dets, int32_t ndet) {
+    int n = 0;
+    for (int i = 0; i < ndet; ++i) n += dets[i].shape == 0 ? 1 : 3;
+    return n;
+}
+
+const char* emu_last_error(void) { return g_err.c_str(); }
+
+int emu_set_qnm(const double* a, const double* fr, const double* fd, int n) {
+    g_qbuf.assign(a, a + n);
+    g_qbuf.insert(g_qbuf.end(), fr, fr + n);
+    g_qbuf.insert(g_qbuf.end(), fd, fd + n);
+    g_q.a = g_qbuf.data(); g_q.fring = g_qbuf.data() + n; g_q.fdamp = g_qbuf.data() + 2 * n; g_q.n = n;
+    return 0;
+}
+
+// psd_f/psd_S: concatenated host tables, psd_n[i] rows each
+int emu_fisher(const gwf_model* model, const gwf_detector* dets, int ndet, const double* const* psd_f, const double* const* psd_S, const int* psd_n,
+               int npsd, const double* const* ev, long long n, const gwf_opts* opts, double* fisher, double* snr2, int snr_mode) {
+    std::vector<EmuPsd> P(npsd);
+    PsdDev pd[kMaxPsd];
+    for (int i = 0; i < npsd; ++i) {
+        int rc = build_psd_tables(psd_f[i], psd_S[i], psd_n[i], P[i].tab, P[i].bucket, P[i].dev);
+        if (rc) return rc;
+        P[i].dev.tab = P[i].tab.data();
+        P[i].dev.bucket = P[i].bucket.data();
+        pd[i] = P[i].dev;
+    }
+    if (snr_mode) {
+        switch (model->id) {
+            case GWF_TAYLORF2: return emu_run_snr<kTaylorF2>(model, dets, ndet, pd, npsd, ev, n, opts, fisher);
+            case GWF_IMRPHENOMD: return emu_run_snr<kPhenomD>(model, dets, ndet, pd, npsd, ev, n, opts, fisher);
+        }
+        return -2;
+    }
+    switch (model->id) {
+        case GWF_TAYLORF2:
+            if (model->flags & GWF_MODEL_TIDAL) return emu_run<kTaylorF2, 6>(model, dets, ndet, pd, npsd, ev, n, opts, fisher, snr2);
+            return emu_run<kTaylorF2, 4>(model, dets, ndet, pd, npsd, ev, n, opts, fisher, snr2);
+        case GWF_IMRPHENOMD: return emu_run<kPhenomD, 4>(model, dets, ndet, pd, npsd, ev, n, opts, fisher, snr2);
+    }
+    return -2;
+}
+}

@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_HERE, 'lib', 'libgwfast_b200.so')
 GWF_TAYLORF2, GWF_IMRPHENOMD, GWF_IMRPHENOMD_NRTIDALV2, GWF_IMRPHENOMHM = 0, 1, 2, 3
 GWF_MODEL_TIDAL, GWF_MODEL_3P5PN_SPINHO, GWF_MODEL_PHIREF_VLSO, GWF_MODEL_QUADMON_TID = 1, 2, 4, 8
 GWF_MODEL_KERR_ISCO, GWF_MODEL_NO_FCUT, GWF_MODEL_HAS_FREF, GWF_MODEL_LAMBDA_GIVEN = 16, 32, 64, 128
-GWF_OPT_M1M2, GWF_OPT_CHIS_CHIA, GWF_OPT_LIN_GRID = 1, 2, 4
+GWF_OPT_M1M2, GWF_OPT_CHIS_CHIA, GWF_OPT_LIN_GRID, GWF_OPT_REUSE_WORKSPACE = 1, 2, 4, 8
 GWF_NPARAM_IN = 13
 # order of gwf_events.p[]
 EVENT_KEYS = ('Mc', 'eta', 'dL', 'theta', 'phi', 'iota', 'psi', 'tcoal', 'Phicoal', 'chi1z', 'chi2z', 'Lambda1', 'Lambda2')
@@ -46,7 +46,7 @@ class EngineError(RuntimeError):
 
 # every symbol include/gwfast_b200.h declares (tests check that the library exports all of them)
 SYMBOLS = ('gwf_version', 'gwf_last_error', 'gwf_num_params', 'gwf_num_arms', 'gwf_workspace_bytes', 'gwf_psd_create',
-           'gwf_psd_destroy', 'gwf_set_qnm_tables', 'gwf_fisher', 'gwf_snr', 'gwf_unpack_fisher', 'gwf_waveform')
+           'gwf_psd_destroy', 'gwf_set_qnm_tables', 'gwf_fisher', 'gwf_snr', 'gwf_unpack_fisher', 'gwf_waveform', 'gwf_fp64_peak')
 
 _lib = None
 
@@ -77,6 +77,7 @@ def load():
     lib.gwf_snr.argtypes = common + [vp, vp, C.c_size_t, vp]
     lib.gwf_unpack_fisher.argtypes = [vp, i64, i32, vp, vp]
     lib.gwf_waveform.argtypes = [P(gwf_model), P(gwf_events), i64, vp, i32, i32, vp, vp, vp, vp, vp, C.c_size_t, vp]
+    lib.gwf_fp64_peak.argtypes = [dbl, P(dbl), vp]
     _lib = lib
     return lib
 

@@ -147,6 +147,20 @@ snr_kernel(const typename ModelTraits<MODEL, 4>::Rec* __restrict__ recs, EventsD
     }
 }
 
+// FP64 FMA throughput probe: 8 independent chains per thread, all in registers
+__global__ void __launch_bounds__(256) dfma_kernel(double* out, int iters, double a, double b) {
+    double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+            x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+        }
+    }
+    const double s = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+    if (s == 12345.678) out[0] = s;
+}
+
 __global__ void unpack_kernel(const double* __restrict__ packed, long long n, int nP, double* __restrict__ full) {
     const long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (e >= n) return;
@@ -190,8 +204,10 @@ static int run_fisher(const gwf_model* model, const gwf_detector* dets, int ndet
     gi.n = net.ngroups;
     for (int g = 0; g < kMaxGroups; ++g) gi.fmin[g] = net.group_fmin[g];
     const int pb = 128;
-    prologue_kernel<MODEL, NT><<<(unsigned)((n + pb - 1) / pb), pb, 0, st>>>(ev, n, cfg, opts->flags, g_qnm, gi, recs);
-    GWF_CUDA(cudaGetLastError());
+    if (!(opts->flags & GWF_OPT_REUSE_WORKSPACE)) {
+        prologue_kernel<MODEL, NT><<<(unsigned)((n + pb - 1) / pb), pb, 0, st>>>(ev, n, cfg, opts->flags, g_qnm, gi, recs);
+        GWF_CUDA(cudaGetLastError());
+    }
     int dev = 0, sms = 0;
     GWF_CUDA(cudaGetDevice(&dev));
     GWF_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -388,6 +404,38 @@ int gwf_unpack_fisher(const double* packed, int64_t n, int32_t nP, double* full,
     const int tb = 256;
     unpack_kernel<<<(unsigned)((n + tb - 1) / tb), tb, 0, reinterpret_cast<cudaStream_t>(stream)>>>(packed, n, nP, full);
     GWF_CUDA(cudaGetLastError());
+    return GWF_OK;
+}
+
+int gwf_fp64_peak(double ms, double* tflops_out, void* stream) {
+    if (!tflops_out) return fail(GWF_ERR_ARG, "gwf_fp64_peak: null output");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    int dev = 0, sms = 0;
+    GWF_CUDA(cudaGetDevice(&dev));
+    GWF_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    double* out = nullptr;
+    GWF_CUDA(cudaMalloc(&out, sizeof(double)));
+    cudaEvent_t e0, e1;
+    GWF_CUDA(cudaEventCreate(&e0));
+    GWF_CUDA(cudaEventCreate(&e1));
+    const int blocks = sms * 8, threads = 256;
+    int iters = 2000;
+    double best = 0.0;
+    for (int rep = 0; rep < 6; ++rep) {
+        GWF_CUDA(cudaEventRecord(e0, st));
+        dfma_kernel<<<blocks, threads, 0, st>>>(out, iters, 1.0000001, 1e-9);
+        GWF_CUDA(cudaEventRecord(e1, st));
+        GWF_CUDA(cudaEventSynchronize(e1));
+        float t = 0.f;
+        GWF_CUDA(cudaEventElapsedTime(&t, e0, e1));
+        const double flops = 2.0 * 64.0 * iters * (double)blocks * threads;
+        if (rep > 0) best = std::max(best, flops / (t * 1e-3) * 1e-12);
+        if (t > 0.f) iters = (int)std::min(4.0e6, std::max(1000.0, iters * ms / t));
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(out);
+    *tflops_out = best;
     return GWF_OK;
 }
 

@@ -79,6 +79,8 @@ typedef struct {
 #define GWF_OPT_M1M2 1       /* use_m1m2=True      */
 #define GWF_OPT_CHIS_CHIA 2  /* use_chi1chi2=False */
 #define GWF_OPT_LIN_GRID 4   /* spacing='lin'      */
+#define GWF_OPT_REUSE_WORKSPACE 8 /* the workspace still holds the coefficient records of the previous gwf_fisher call on the
+                                     same events/model/options: skip the prologue kernel (used to time the main kernel alone) */
 typedef struct {
     int32_t res;    /* frequency samples per event (res=1000) */
     int32_t flags;  /* GWF_OPT_* */
@@ -121,6 +123,11 @@ int gwf_unpack_fisher(const double* packed, int64_t n, int32_t nP, double* full,
 int gwf_waveform(const gwf_model* model, const gwf_events* events, int64_t n, const double* f, int32_t res, int32_t f_is_2d,
                  double* phi_out, double* ampl_out, double* tau_out, double* fcut_out,
                  void* workspace, size_t workspace_bytes, void* stream);
+
+/* Diagnostics (no reference counterpart): sustained FP64 FMA throughput of the current device in TFLOP/s, measured with a
+ * register-resident DFMA chain kernel over ~`ms` milliseconds; used by bench.py as the measured FP64 roofline denominator.
+ * Synchronises the stream. */
+int gwf_fp64_peak(double ms, double* tflops_out, void* stream);
 
 #ifdef __cplusplus
 }

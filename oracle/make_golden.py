@@ -1,0 +1,175 @@
+"""Generate ``tests/golden/*.npz`` by running the UNMODIFIED reference (``/root/reference/gwfast``) under the
+numpy/dual shim (TEST INFRASTRUCTURE; container only -- the reference tree does not exist on the GPU box).
+
+    python -m oracle.make_golden            # all fixtures
+    python -m oracle.make_golden c2 init    # some
+
+Every fixture stores its inputs (events, configuration as a JSON string) next to the reference outputs, so the
+tests rebuild the same detector network with the engine (or the port) and compare.
+"""
+import json
+import os
+import sys
+import warnings
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from oracle import reference  # noqa: E402
+from gwfast_b200 import synthetic  # noqa: E402
+
+GOLD = os.path.join(ROOT, 'tests', 'golden')
+REF_PSDS = os.path.join(reference.REFERENCE_ROOT, 'psds')
+
+# the reference's own warm-up event, gwfast/signal.py:181-203
+INIT_EVENT = {'Mc': [77.23905294], 'Phicoal': [3.28297867], 'chi1z': [0.2018924], 'chi2z': [-0.68859213], 'dL': [22.68426174],
+              'eta': [0.20586622], 'iota': [4.48411048], 'phi': [0.90252645], 'psi': [3.11843169], 'Lambda1': [300.], 'Lambda2': [300.],
+              'tcoal': [0.], 'theta': [3.00702251]}
+# GW170817 as printed in notebooks/gwfast_tutorial.ipynb cell 10
+GW170817 = {'Mc': [1.19752182], 'dL': [0.04374755], 'theta': [1.97888033], 'phi': [3.44616], 'iota': [2.5450656], 'psi': [0.], 'tcoal': [0.43432288],
+            'eta': [0.24786618], 'Phicoal': [0.], 'chi1z': [0.00513614], 'chi2z': [0.00323515], 'Lambda1': [368.17802384], 'Lambda2': [586.54870315]}
+
+
+def _model(wf, spec):
+    return getattr(wf, spec['cls'])(**spec.get('kw', {}))
+
+
+def _copy(ev):
+    return {k: np.array(v, dtype=float) for k, v in ev.items()}
+
+
+def run_network(cfg, ev, want_all=True):
+    """cfg: dict(model=dict(cls, kw), network=name, rot, fmin, fmax, fisher_kw, res)."""
+    wf, sig, net, utils, glob = reference.load()
+    kw = {}
+    if cfg.get('fmax') is not None:
+        kw['fmax'] = cfg['fmax']
+    sigs = synthetic.build_network(sig.GWSignal, _model(wf, cfg['model']), cfg['network'], useEarthMotion=cfg['rot'], fmin=cfg['fmin'],
+                                   psd_root=REF_PSDS, **kw)
+    N = net.DetNet(sigs, verbose=False)
+    res = cfg.get('res', 1000)
+    fkw = dict(cfg.get('fisher_kw', {}))
+    out = {'snr': N.SNR(_copy(ev), res=res), 'fisher': N.FisherMatr(_copy(ev), res=res, **fkw)}
+    if want_all:
+        sa = N.SNR(_copy(ev), res=res, return_all=True)
+        fa = N.FisherMatr(_copy(ev), res=res, return_all=True, **fkw)
+        for k in sa:
+            out['snr__' + k] = sa[k]
+            out['fisher__' + k] = fa[k]
+    return out
+
+
+def save(name, cfg, ev, out, extra=None):
+    os.makedirs(GOLD, exist_ok=True)
+    data = {'config': np.array(json.dumps(cfg))}
+    data.update({'ev__' + k: np.asarray(v, dtype=float) for k, v in ev.items()})
+    data.update(out)
+    if extra:
+        data.update(extra)
+    path = os.path.join(GOLD, name + '.npz')
+    np.savez_compressed(path, **data)
+    print('wrote %s (%.1f KB)' % (path, os.path.getsize(path) / 1024.))
+
+
+def take(ev, n):
+    return {k: v[:n] for k, v in ev.items()}
+
+
+def fx_init():
+    """the 16-row table of SURVEY.md App. C: 4 models x L/T x rot on the reference's warm-up event."""
+    wf, sig, net, utils, glob = reference.load()
+    ev = {k: np.array(v) for k, v in INIT_EVENT.items()}
+    out = {}
+    psd = os.path.join(REF_PSDS, 'ET-0000A-18.txt')
+    for cls in ('TaylorF2_RestrictedPN', 'IMRPhenomD', 'IMRPhenomD_NRTidalv2', 'IMRPhenomHM'):
+        for shape in 'LT':
+            for rot in (0, 1):
+                s = sig.GWSignal(getattr(wf, cls)(), psd_path=psd, detector_shape=shape, det_lat=40.44, det_long=9.45, det_xax=0., verbose=False,
+                                 useEarthMotion=bool(rot), fmin=2.)
+                key = '%s__%s__%d' % (cls, shape, rot)
+                out['snr__' + key] = s.SNRInteg(_copy(ev), res=1000)
+                out['fisher__' + key] = s.FisherMatr(_copy(ev), res=1000)
+    save('init_event', dict(det_lat=40.44, det_long=9.45, det_xax=0., fmin=2., res=1000, psd='ET-0000A-18.txt'), ev, out)
+
+
+def fx_c1():
+    cfg = dict(model=dict(cls='TaylorF2_RestrictedPN'), network='ETSL', rot=True, fmin=2.)
+    ev = synthetic.bns_catalog(100, synthetic.SEEDS['C1'])
+    save('c1_tf2_bns_etsl', cfg, ev, run_network(cfg, ev))
+
+
+def fx_c1b():
+    cfg = dict(model=dict(cls='TaylorF2_RestrictedPN', kw=dict(is_tidal=True, use_3p5PN_SpinHO=True)), network='ET', rot=True, fmin=2.)
+    ev = take(synthetic.bns_catalog(100, synthetic.SEEDS['C1'] + 100, tidal=True), 32)
+    save('c1b_tf2tidal_et', cfg, ev, run_network(cfg, ev))
+    cfg = dict(model=dict(cls='TaylorF2_RestrictedPN', kw=dict(is_tidal=True, use_QuadMonTid=True, phiref_vlso=True, which_ISCO='Kerr')),
+               network='ETSL', rot=True, fmin=5.)
+    save('c1c_tf2_options_etsl', cfg, take(ev, 16), run_network(cfg, take(ev, 16)))
+
+
+def fx_c2():
+    cfg = dict(model=dict(cls='IMRPhenomD'), network='ET+2CE', rot=True, fmin=2.)
+    ev = take(synthetic.bbh_catalog(10000, synthetic.SEEDS['C2']), 64)
+    save('c2_phenomd_et2ce', cfg, ev, run_network(cfg, ev))
+
+
+def fx_variants():
+    ev = take(synthetic.bbh_catalog(10000, synthetic.SEEDS['C2']), 16)
+    for tag, cfg in (
+        ('m1m2_chisa', dict(model=dict(cls='IMRPhenomD', kw=dict(is_chi1chi2=False)), network='ET', rot=True, fmin=2.,
+                            fisher_kw=dict(use_m1m2=True, use_chi1chi2=False))),
+        ('lin_res400_fmax', dict(model=dict(cls='IMRPhenomD'), network='ET+2CE', rot=False, fmin=5., fmax=256., res=400, fisher_kw=dict(spacing='lin'))),
+        ('fref_nocut', dict(model=dict(cls='IMRPhenomD', kw=dict(fRef=20., apply_fcut=False)), network='ETSL', rot=False, fmin=2.)),
+        ('tf2_m1m2', dict(model=dict(cls='TaylorF2_RestrictedPN', kw=dict(use_3p5PN_SpinHO=True)), network='LVK-O4', rot=False, fmin=10.,
+                          fisher_kw=dict(use_m1m2=True))),
+    ):
+        save('var_' + tag, cfg, ev, run_network(cfg, ev))
+
+
+def fx_c3():
+    cfg = dict(model=dict(cls='IMRPhenomD_NRTidalv2'), network='ET+2CE', rot=True, fmin=2.)
+    ev = take(synthetic.bns_catalog(10000, synthetic.SEEDS['C3'], tidal=True), 32)
+    save('c3_nrtidal_et2ce', cfg, ev, run_network(cfg, ev))
+
+
+def fx_c4():
+    cfg = dict(model=dict(cls='IMRPhenomHM'), network='LVK-O4', rot=False, fmin=10.)
+    ev = take(synthetic.bbh_catalog(100000, synthetic.SEEDS['C4']), 32)
+    save('c4_phenomhm_lvk', cfg, ev, run_network(cfg, ev))
+    cfg = dict(model=dict(cls='IMRPhenomHM'), network='ET', rot=True, fmin=2.)
+    save('c4b_phenomhm_et', cfg, take(ev, 8), run_network(cfg, take(ev, 8)))
+
+
+def fx_gw170817():
+    """notebook known answers: network SNR 33.16 (cell 12), 1 - F[dL,dL]/(SNR/dL)^2 = 2.2e-16 (cell 15), fcut 1590.1/3433.5 Hz."""
+    wf, sig, net, utils, glob = reference.load()
+    files = {'L1': 'LVC_O1O2O3/2017-08-06_DCH_C02_L1_O2_Sensitivity_strain_asd.txt', 'H1': 'LVC_O1O2O3/2017-06-10_DCH_C02_H1_O2_Sensitivity_strain_asd.txt',
+             'Virgo': 'LVC_O1O2O3/Hrec_hoft_V1O2Repro2A_16384Hz.txt'}
+    ev = {k: np.array(v) for k, v in GW170817.items()}
+    sigs, extra = {}, {}
+    for d, rel in files.items():
+        s = glob.detectors[d]
+        sigs[d] = sig.GWSignal(wf.IMRPhenomD_NRTidalv2(), psd_path=os.path.join(REF_PSDS, rel), detector_shape=s['shape'], det_lat=s['lat'],
+                               det_long=s['long'], det_xax=s['xax'], verbose=False, useEarthMotion=False, fmin=10.)
+        extra['psd_f__' + d] = sigs[d].strainFreq
+        extra['psd_S__' + d] = sigs[d].noiseCurve
+    N = net.DetNet(sigs, verbose=False)
+    out = {'snr': N.SNR(_copy(ev)), 'fisher': N.FisherMatr(_copy(ev))}
+    out['tf2_fcut_schw'] = wf.TaylorF2_RestrictedPN().fcut(**ev)
+    out['tf2_fcut_kerr'] = wf.TaylorF2_RestrictedPN(which_ISCO='Kerr').fcut(**ev)
+    print('GW170817: SNR %.8f  1-F[dL,dL]dL^2/SNR^2 = %.2e  fcut %.8f %.8f' % (
+        out['snr'][0], 1 - out['fisher'][2, 2, 0] * ev['dL'][0] ** 2 / out['snr'][0] ** 2, out['tf2_fcut_schw'][0], out['tf2_fcut_kerr'][0]))
+    save('gw170817', dict(model=dict(cls='IMRPhenomD_NRTidalv2'), detectors=list(files), rot=False, fmin=10.), ev, out, extra)
+
+
+ALL = {'init': fx_init, 'c1': fx_c1, 'c1b': fx_c1b, 'c2': fx_c2, 'var': fx_variants, 'c3': fx_c3, 'c4': fx_c4, 'gw170817': fx_gw170817}
+
+if __name__ == '__main__':
+    warnings.filterwarnings('ignore')
+    if not reference.available():
+        sys.exit('the reference tree is not mounted; fixtures can only be generated in the build container')
+    for k in (sys.argv[1:] or list(ALL)):
+        ALL[k]()

@@ -51,8 +51,10 @@ struct NetworkDev {
     PsdDev psd[kMaxPsd];
 };
 
-// np.interp(f, strainFreq, noiseCurve, left=1., right=1.)  (signal.py:723, 901) with an O(1) bucket start.
-// l2f = log2(f) is supplied by the caller (known in closed form on a geometric grid).
+// np.interp(f, strainFreq, noiseCurve, left=1., right=1.)  (signal.py:723, 901).  The table row j is
+// (f_j, S_j, slope_j, f_{j+1}); a log2-bucket index gives the row in O(1) (each bucket holds at most a few nodes),
+// so the common case is one 32-byte row read by two 16-byte loads.  l2f = log2(f) comes from the caller (closed
+// form on a geometric grid).
 #ifdef __CUDA_ARCH__
 #define GWF_LDG(ptr) __ldg(ptr)
 #else
@@ -61,18 +63,21 @@ struct NetworkDev {
 GWF_HD double psd_lookup(const PsdDev& p, double f, double l2f) {
     if (!(f >= p.f_first) || f > p.f_last) return 1.0;
     int b = (int)((l2f - p.lo) * p.inv);
-    b = b < 1 ? 1 : (b > p.nb - 1 ? p.nb - 1 : b);
-    int lo = GWF_LDG(p.bucket + b - 1);                    // one bucket of slack on each side against rounding of l2f
-    int hi = (b + 2 < p.nb ? GWF_LDG(p.bucket + b + 2) : p.n - 2) + 1;
-    hi = hi > p.n - 1 ? p.n - 1 : hi;
-    // largest j in [lo, hi) with f_j <= f
-    while (hi - lo > 1) {
-        const int mid = (lo + hi) >> 1;
-        if (GWF_LDG(&p.tab[mid].x) <= f) lo = mid; else hi = mid;
+    b = b < 0 ? 0 : (b > p.nb - 1 ? p.nb - 1 : b);
+    int j = GWF_LDG(p.bucket + b);
+    const double2* row = reinterpret_cast<const double2*>(p.tab + j);
+    double2 fs = GWF_LDG(row), sn = GWF_LDG(row + 1);      // (f_j, S_j), (slope_j, f_{j+1})
+    while (f < fs.x && j > 0) {                            // rounding of l2f put us one bucket too high (rare)
+        --j;
+        row = reinterpret_cast<const double2*>(p.tab + j);
+        fs = GWF_LDG(row); sn = GWF_LDG(row + 1);
     }
-    const double2* row = reinterpret_cast<const double2*>(p.tab + lo);
-    const double2 fs = GWF_LDG(row), sl = GWF_LDG(row + 1);      // (f_j, S_j), (slope_j, 0): two 16-byte loads
-    return fma(sl.x, f - fs.x, fs.y);
+    while (f >= sn.y && j < p.n - 2) {                     // more than one node inside the bucket
+        ++j;
+        row = reinterpret_cast<const double2*>(p.tab + j);
+        fs = GWF_LDG(row); sn = GWF_LDG(row + 1);
+    }
+    return fma(sn.x, f - fs.x, fs.y);
 }
 
 // per-event sky / orientation constants
@@ -82,6 +87,7 @@ struct EvGeom {
     double c2psi, s2psi;
     double ci, si, K;            // cos iota, sin iota, (1 + cos^2 iota)/2
     double tcoal, inv_dL;
+    double cT, sT;               // cos/sin(2 pi tcoal): detectors that do not follow the Earth rotation
     GWF_HD void set(const EventIn& e) {
         // dec = pi/2 - theta (gwfastUtils.py:151-164): sin dec = cos theta, cos dec = sin theta
         const double dec = 0.5 * kPi - e.theta;
@@ -93,6 +99,31 @@ struct EvGeom {
         K = 0.5 * (1.0 + ci * ci);
         tcoal = e.tcoal;
         inv_dL = 1.0 / e.dL;
+        sincos(2.0 * kPi * e.tcoal, &sT, &cT);
+    }
+};
+
+constexpr double kInvDay = 1.0 / kDay;
+constexpr double kRc = kREarth / kClight;          // Earth radius in light-seconds
+
+// f-independent products of the event's sky position with one detector's site constants
+struct EvDet {
+    double cA, sA;                 // cos/sin(ra - lon)
+    double kc, k0;                 // Delta t      = -Rc (kc  c0 + k0 ),  kc  = cos(dec) cos(lat), k0  = sin(dec) sin(lat)
+    double kc_th, k0_th;           // d Delta t/d theta = -Rc (kc_th c0 + k0_th)
+    double p[5], q[4], pd[5], qd[4];   // a/b coefficient groups of signal.py:360-376 and their d/d(dec)
+    GWF_HD void set(const DetDev& d, const EvGeom& g) {
+        cA = g.cra * d.clon + g.sra * d.slon;
+        sA = g.sra * d.clon - g.cra * d.slon;
+        kc = g.cd * d.cl; k0 = g.sd * d.sl;
+        kc_th = g.sd * d.cl; k0_th = -g.cd * d.sl;
+        const double k3 = 3.0 - d.c2l, e3 = 3.0 - g.c2d;
+        p[0] = 0.0625 * k3 * e3; p[1] = 0.25 * d.s2l * g.s2d; p[2] = 0.75 * d.cl * d.cl * g.cd * g.cd;
+        p[3] = 0.25 * d.sl * e3; p[4] = 0.5 * d.cl * g.s2d;
+        q[0] = d.sl * g.sd; q[1] = d.cl * g.cd; q[2] = 0.25 * k3 * g.sd; q[3] = 0.5 * d.s2l * g.cd;
+        pd[0] = 0.125 * k3 * g.s2d; pd[1] = 0.5 * d.s2l * g.c2d; pd[2] = -0.75 * d.cl * d.cl * g.s2d;
+        pd[3] = 0.5 * d.sl * g.s2d; pd[4] = d.cl * g.c2d;
+        qd[0] = d.sl * g.cd; qd[1] = -d.cl * g.sd; qd[2] = 0.25 * k3 * g.cd; qd[3] = -0.5 * d.s2l * g.sd;
     }
 };
 
@@ -103,43 +134,31 @@ struct DetPoint {
     double dt;                    // Delta t [s]
 };
 
-// tn = detector-independent time in days BEFORE the Earth-centre->site delay; (cB, sB) = cos/sin(2 pi tn)
-GWF_HD void det_point(const DetDev& d, const EvGeom& g, double cB, double sB, DetPoint& o) {
-    const double Rc = kREarth / kClight;
-    // A = ra - lon
-    const double cA = g.cra * d.clon + g.sra * d.slon, sA = g.sra * d.clon - g.cra * d.slon;
+// (cB, sB) = cos/sin(2 pi tn), tn = time in days BEFORE the Earth-centre->site delay is added (signal.py:444-453)
+GWF_HD void det_point(const EvDet& e, double cB, double sB, DetPoint& o) {
     // ang0 = (ra - lon) - 2 pi tn
-    const double c0 = cA * cB + sA * sB, s0 = sA * cB - cA * sB;
-    o.dt = -Rc * (g.cd * d.cl * c0 + g.sd * d.sl);                       // signal.py:417-421
-    o.dt_th = -Rc * (g.sd * d.cl * c0 - g.cd * d.sl);                    // signal.py:1483-1491
-    o.dt_ph = Rc * g.cd * d.cl * s0;                                     // signal.py:1441-1448
-    o.dt_tn = -2.0 * kPi * Rc * g.cd * d.cl * s0;                        // signal.py:1527-1534
+    const double c0 = e.cA * cB + e.sA * sB, s0 = e.sA * cB - e.cA * sB;
+    o.dt = -kRc * (e.kc * c0 + e.k0);                                    // signal.py:417-421
+    o.dt_th = -kRc * (e.kc_th * c0 + e.k0_th);                           // signal.py:1483-1491
+    o.dt_ph = kRc * e.kc * s0;                                           // signal.py:1441-1448
+    o.dt_tn = -2.0 * kPi * o.dt_ph;                                      // signal.py:1527-1534
     // ang = ang0 - 2 pi dt/86400 ; the shift is ~1e-6 rad: 3rd-order Taylor is exact to 1e-24
-    const double del = 2.0 * kPi * o.dt / kDay;
+    const double del = (2.0 * kPi * kInvDay) * o.dt;
     const double cdl = 1.0 - 0.5 * del * del, sdl = del * (1.0 - del * del * (1. / 6.));
     const double c1 = c0 * cdl + s0 * sdl, s1 = s0 * cdl - c0 * sdl;
     const double c2 = c1 * c1 - s1 * s1, s2 = 2.0 * s1 * c1;
-    // signal.py:360-376 regrouped by (S2, C2)
-    const double k3 = 3.0 - d.c2l, e3 = 3.0 - g.c2d;
-    const double p1 = 0.0625 * k3 * e3, p2 = 0.25 * d.s2l * g.s2d, p3 = 0.75 * d.cl * d.cl * g.cd * g.cd;
-    const double p4 = 0.25 * d.sl * e3, p5 = 0.5 * d.cl * g.s2d;
-    const double q1 = d.sl * g.sd, q2 = d.cl * g.cd, q3 = 0.25 * k3 * g.sd, q4 = 0.5 * d.s2l * g.cd;
-    o.aS = p1 * c2 + p2 * c1 + p3;
-    o.aC = -(p4 * s2 + p5 * s1);
-    o.bC = q1 * c2 + q2 * c1;
-    o.bS = q3 * s2 + q4 * s1;
-    o.aS_g = -2.0 * p1 * s2 - p2 * s1;
-    o.aC_g = -(2.0 * p4 * c2 + p5 * c1);
-    o.bC_g = -2.0 * q1 * s2 - q2 * s1;
-    o.bS_g = 2.0 * q3 * c2 + q4 * c1;
-    // d/d(dec) of the p's and q's
-    const double p1d = 0.125 * k3 * g.s2d, p2d = 0.5 * d.s2l * g.c2d, p3d = -0.75 * d.cl * d.cl * g.s2d;
-    const double p4d = 0.5 * d.sl * g.s2d, p5d = d.cl * g.c2d;
-    const double q1d = d.sl * g.cd, q2d = -d.cl * g.sd, q3d = 0.25 * k3 * g.cd, q4d = -0.5 * d.s2l * g.sd;
-    o.aS_d = p1d * c2 + p2d * c1 + p3d;
-    o.aC_d = -(p4d * s2 + p5d * s1);
-    o.bC_d = q1d * c2 + q2d * c1;
-    o.bS_d = q3d * s2 + q4d * s1;
+    o.aS = e.p[0] * c2 + e.p[1] * c1 + e.p[2];
+    o.aC = -(e.p[3] * s2 + e.p[4] * s1);
+    o.bC = e.q[0] * c2 + e.q[1] * c1;
+    o.bS = e.q[2] * s2 + e.q[3] * s1;
+    o.aS_g = -2.0 * e.p[0] * s2 - e.p[1] * s1;
+    o.aC_g = -(2.0 * e.p[3] * c2 + e.p[4] * c1);
+    o.bC_g = -2.0 * e.q[0] * s2 - e.q[1] * s1;
+    o.bS_g = 2.0 * e.q[2] * c2 + e.q[3] * c1;
+    o.aS_d = e.pd[0] * c2 + e.pd[1] * c1 + e.pd[2];
+    o.aC_d = -(e.pd[3] * s2 + e.pd[4] * s1);
+    o.bC_d = e.qd[0] * c2 + e.qd[1] * c1;
+    o.bS_d = e.qd[2] * s2 + e.qd[3] * s1;
 }
 
 // value-only pattern functions of one arm (SNR path)
@@ -162,10 +181,36 @@ struct PointWf {
 // packed lower-triangular index
 GWF_HD constexpr int tri(int i, int j) { return i * (i + 1) / 2 + j; }
 
+// detector-level chain-rule factors shared by the arms of one detector at one frequency
+template <int NT>
+struct DetRows {
+    double ang_x[2], psi_x[NT];    // d ang / d slot (slots 0,1), d Psi / d slot
+    double ang_t, ph_t, ang_p, ph_p, ang_c, ph_c;
+    GWF_HD void set(const PointWf<NT>& w, const DetPoint& p, bool follows_rotation, bool no_motion) {
+        const double W2 = 2.0 * kPi * w.f, twopi = 2.0 * kPi;
+        const double tfac = no_motion ? 0.0 : fma(p.dt_tn, kInvDay, 1.0);          // d t / d t_noloc
+#pragma unroll
+        for (int j = 0; j < NT; ++j) psi_x[j] = -w.phi_d[j];
+        ang_x[0] = ang_x[1] = 0.;
+        if (follows_rotation) {
+            const double wd = W2 * p.dt_tn;
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                ang_x[j] = -twopi * w.dtn[j] * tfac;
+                psi_x[j] = fma(wd, w.dtn[j], psi_x[j]);
+            }
+        }
+        ang_t = -(twopi * kInvDay) * p.dt_th; ph_t = W2 * p.dt_th;                 // signal.py:1482-1523
+        ang_p = 1.0 - (twopi * kInvDay) * p.dt_ph; ph_p = W2 * p.dt_ph;            // signal.py:1439-1480
+        ang_c = -(twopi * kInvDay) * tfac;                                         // signal.py:1525-1565, per second (:920)
+        ph_c = no_motion ? W2 : W2 * tfac;
+    }
+};
+
 // rows of d h / d p (divided by A e^{i Psi}) for one arm and their weighted Gram; NP = NT + 7.
 // Row order = ParNums (waveforms.py:78): Mc eta dL theta phi iota psi tcoal Phicoal chi1z chi2z [LambdaTilde deltaLambda]
 template <int NT>
-GWF_HD void arm_rows_accumulate(const PointWf<NT>& w, const DetPoint& p, const DetDev& d, const ArmDev& a, const EvGeom& g, double wgt,
+GWF_HD void arm_rows_accumulate(const PointWf<NT>& w, const DetPoint& p, const DetRows<NT>& dr, const ArmDev& a, const EvGeom& g, double wgt,
                                 double* __restrict__ acc, double& snr2) {
     constexpr int NP = NT + 7;
     const double av = a.S2 * p.aS + a.C2 * p.aC, bv = a.C2 * p.bC + a.S2 * p.bS;
@@ -175,51 +220,32 @@ GWF_HD void arm_rows_accumulate(const PointWf<NT>& w, const DetPoint& p, const D
     const double Gr = Fp * g.K, Gi = Fc * g.ci;                                       // signal.py:463-464
     const double Ggr = (ag * g.c2psi + bg * g.s2psi) * g.K, Ggi = (bg * g.c2psi - ag * g.s2psi) * g.ci;
     const double Gdr = (ad * g.c2psi + bd * g.s2psi) * g.K, Gdi = (bd * g.c2psi - ad * g.s2psi) * g.ci;
-    const double W2 = 2.0 * kPi * w.f;
-    const double twopi = 2.0 * kPi;
-    const double tfac = d.no_motion ? 0.0 : 1.0 + p.dt_tn / kDay;       // d t / d t_noloc
     double ra[NP], rb[NP];
-    // intrinsic rows (AD rows of the reference, signal.py:1153-1189)
+    // intrinsic rows (the AD rows of the reference, signal.py:1153-1189)
 #pragma unroll
     for (int j = 0; j < NT; ++j) {
         const int row = j < 2 ? j : 7 + j;
-        double ang_x = 0., psi_x = -w.phi_d[j];
+        double re = fma(w.lnA_d[j], Gr, -Gi * dr.psi_x[j]), im = fma(w.lnA_d[j], Gi, Gr * dr.psi_x[j]);
         if (j < 2) {
-            ang_x = -twopi * w.dtn[j] * tfac;
-            psi_x = fma(W2 * p.dt_tn, w.dtn[j], psi_x);
+            re = fma(Ggr, dr.ang_x[j], re);
+            im = fma(Ggi, dr.ang_x[j], im);
         }
-        ra[row] = w.lnA_d[j] * Gr + Ggr * ang_x - Gi * psi_x;
-        rb[row] = w.lnA_d[j] * Gi + Ggi * ang_x + Gr * psi_x;
+        ra[row] = re;
+        rb[row] = im;
     }
-    // dL, signal.py:1576
-    ra[2] = -Gr * g.inv_dL;
+    ra[2] = -Gr * g.inv_dL;                                   // dL, signal.py:1576
     rb[2] = -Gi * g.inv_dL;
-    // theta, signal.py:1482-1523 (dec = pi/2 - theta)
-    {
-        const double ang_t = -twopi * p.dt_th / kDay, ph = W2 * p.dt_th;
-        ra[3] = Ggr * ang_t - Gdr - Gi * ph;
-        rb[3] = Ggi * ang_t - Gdi + Gr * ph;
-    }
-    // phi, signal.py:1439-1480
-    {
-        const double ang_p = 1.0 - twopi * p.dt_ph / kDay, ph = W2 * p.dt_ph;
-        ra[4] = Ggr * ang_p - Gi * ph;
-        rb[4] = Ggi * ang_p + Gr * ph;
-    }
-    // iota, signal.py:1567-1571
-    ra[5] = -Fp * g.ci * g.si;
+    ra[3] = fma(Ggr, dr.ang_t, -Gdr) - Gi * dr.ph_t;          // theta (dec = pi/2 - theta)
+    rb[3] = fma(Ggi, dr.ang_t, -Gdi) + Gr * dr.ph_t;
+    ra[4] = fma(Ggr, dr.ang_p, -Gi * dr.ph_p);                // phi
+    rb[4] = fma(Ggi, dr.ang_p, Gr * dr.ph_p);
+    ra[5] = -Fp * g.ci * g.si;                                // iota, signal.py:1567-1571
     rb[5] = -Fc * g.si;
-    // psi, signal.py:1432-1437
-    ra[6] = 2.0 * Fc * g.K;
+    ra[6] = 2.0 * Fc * g.K;                                   // psi, signal.py:1432-1437
     rb[6] = -2.0 * Fp * g.ci;
-    // tcoal, in 1/s (signal.py:1525-1565 and :920)
-    {
-        const double ang_c = -twopi * tfac / kDay, ph = W2 * (1.0 + (d.no_motion ? 0.0 : p.dt_tn / kDay));
-        ra[7] = Ggr * ang_c - Gi * ph;
-        rb[7] = Ggi * ang_c + Gr * ph;
-    }
-    // Phicoal, signal.py:1577
-    ra[8] = Gi;
+    ra[7] = fma(Ggr, dr.ang_c, -Gi * dr.ph_c);                // tcoal
+    rb[7] = fma(Ggi, dr.ang_c, Gr * dr.ph_c);
+    ra[8] = Gi;                                               // Phicoal, signal.py:1577
     rb[8] = -Gr;
     // 4 Re int conj(d_a h) d_b h / Sn df, signal.py:922-931
     const double wg = wgt * a.weight;

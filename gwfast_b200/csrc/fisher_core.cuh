@@ -33,8 +33,8 @@ template <int NT> struct ModelTraits<kTaylorF2, NT> {
             double tau, dtau[2];
             tau_eval(r.tau, p.vm1, p.lpx3, r.lam, tau, dtau);
             w.tau = tau;
-            w.dtn[0] = -dtau[0] / kDay;
-            w.dtn[1] = -dtau[1] / kDay;
+            w.dtn[0] = -dtau[0] * kInvDay;
+            w.dtn[1] = -dtau[1] * kInvDay;
         }
     }
 };
@@ -59,8 +59,8 @@ template <int NT> struct ModelTraits<kPhenomD, NT> {
             const double cpm1 = 0.68278406325529568146702083315816;   // pi^(-1/3)
             tau_eval(r.tau, p.xm13 * cpm1, p.lpx3, r.lam, tau, dtau);
             w.tau = tau;
-            w.dtn[0] = -dtau[0] / kDay;
-            w.dtn[1] = -dtau[1] / kDay;
+            w.dtn[0] = -dtau[0] * kInvDay;
+            w.dtn[1] = -dtau[1] * kInvDay;
         }
     }
 };
@@ -100,67 +100,69 @@ struct Grid {
     }
 };
 
+// ------------------------------------------------------------------ per-event detector scratch
+// EvDet for every detector, plus the (frequency independent) DetPoint of the detectors that do not follow the
+// Earth rotation.  Lives in shared memory, one block per warp (kernels) or on the stack (emulation).
+struct EventScratch {
+    EvDet ed[kMaxDet];
+    DetPoint fixed[kMaxDet];
+};
+// detector `di` of the network (called by lane di in the kernels)
+GWF_HD void scratch_set(EventScratch& s, const NetworkDev& net, const EvGeom& geom, int di) {
+    const DetDev& d = net.det[di];
+    s.ed[di].set(d, geom);
+    if (d.no_motion) det_point(s.ed[di], 1.0, 0.0, s.fixed[di]);            // t = 0, signal.py:444-446
+    else if (!d.use_rot) det_point(s.ed[di], geom.cT, geom.sT, s.fixed[di]);   // t = tcoal, signal.py:452
+}
+
 // ------------------------------------------------------------------ one frequency point of one grid group
 // acc: packed lower-triangular Fisher (NP(NP+1)/2), snr2: sum of 4 w |h|^2 / Sn over the arms of the pass
 template <int MODEL, int NT>
-GWF_HD void fisher_point(const typename ModelTraits<MODEL, NT>::Rec& rec, const ModelCfg& cfg, const EvGeom& geom, const NetworkDev& net, int g,
-                         bool group_rot, const Grid& grid, int k, double* __restrict__ acc, double& snr2) {
+GWF_HD void fisher_point(const typename ModelTraits<MODEL, NT>::Rec& rec, const ModelCfg& cfg, const EvGeom& geom, const NetworkDev& net,
+                         const EventScratch& sc, int g, bool group_rot, const Grid& grid, int k, double* __restrict__ acc, double& snr2) {
     double f, wk, l2f;
     grid.point(k, f, wk, l2f);
     PointWf<NT> w;
     ModelTraits<MODEL, NT>::eval(rec, cfg, g, f, group_rot, w);
-    const double tau = w.tau;
     w.f = f;
     if (!(w.A > 0.0)) return;             // beyond the model cut (or zero amplitude): no contribution
     const double wA2 = 4.0 * wk * w.A * w.A;
     // Earth-rotation phase common to the detectors of the group: 2 pi (tcoal - tau/86400), signal.py:449
     double sBr = 0., cBr = 1.;
-    if (group_rot) sincos(2.0 * kPi * (geom.tcoal - tau / kDay), &sBr, &cBr);
-    double sBf, cBf;
-    sincos(2.0 * kPi * geom.tcoal, &sBf, &cBf);
+    if (group_rot) sincos(2.0 * kPi * fma(-w.tau, kInvDay, geom.tcoal), &sBr, &cBr);
     for (int di = 0; di < net.ndet; ++di) {
         const DetDev& d = net.det[di];
         if (d.group != g || d.arm_begin == d.arm_end) continue;
         const double Sn = psd_lookup(net.psd[d.psd], f, l2f);
         DetPoint dp;
-        PointWf<NT> wd = w;
-        if (d.no_motion) {
-            det_point(d, geom, 1.0, 0.0, dp);
-            wd.dtn[0] = wd.dtn[1] = 0.;
-        } else if (d.use_rot) {
-            det_point(d, geom, cBr, sBr, dp);
-        } else {
-            det_point(d, geom, cBf, sBf, dp);
-            wd.dtn[0] = wd.dtn[1] = 0.;
-        }
+        if (d.use_rot) det_point(sc.ed[di], cBr, sBr, dp);
+        else dp = sc.fixed[di];
+        DetRows<NT> dr;
+        dr.set(w, dp, d.use_rot != 0, d.no_motion != 0);
         const double wgt = wA2 / Sn;
-        for (int ai = d.arm_begin; ai < d.arm_end; ++ai) arm_rows_accumulate<NT>(wd, dp, d, net.arm[ai], geom, wgt, acc, snr2);
+        for (int ai = d.arm_begin; ai < d.arm_end; ++ai) arm_rows_accumulate<NT>(w, dp, dr, net.arm[ai], geom, wgt, acc, snr2);
     }
 }
 
 // value-only point for the SNR kernel: per-arm SNR^2 contributions (signal.py:725-767)
 template <int MODEL>
-GWF_HD void snr_point(const typename ModelTraits<MODEL, 4>::Rec& rec, const ModelCfg& cfg, const EvGeom& geom, const NetworkDev& net, int g,
-                      bool group_rot, const Grid& grid, int k, double* __restrict__ snr2_arm) {
+GWF_HD void snr_point(const typename ModelTraits<MODEL, 4>::Rec& rec, const ModelCfg& cfg, const EvGeom& geom, const NetworkDev& net,
+                      const EventScratch& sc, int g, bool group_rot, const Grid& grid, int k, double* __restrict__ snr2_arm) {
     double f, wk, l2f;
     grid.point(k, f, wk, l2f);
     PointWf<4> w;
     ModelTraits<MODEL, 4>::eval(rec, cfg, g, f, group_rot, w);
-    const double tau = w.tau;
     if (!(w.A > 0.0)) return;
     const double wA2 = 4.0 * wk * w.A * w.A;
     double sBr = 0., cBr = 1.;
-    if (group_rot) sincos(2.0 * kPi * (geom.tcoal - tau / kDay), &sBr, &cBr);
-    double sBf, cBf;
-    sincos(2.0 * kPi * geom.tcoal, &sBf, &cBf);
+    if (group_rot) sincos(2.0 * kPi * fma(-w.tau, kInvDay, geom.tcoal), &sBr, &cBr);
     for (int di = 0; di < net.ndet; ++di) {
         const DetDev& d = net.det[di];
         if (d.group != g) continue;
         const double Sn = psd_lookup(net.psd[d.psd], f, l2f);
         DetPoint dp;
-        if (d.no_motion) det_point(d, geom, 1.0, 0.0, dp);
-        else if (d.use_rot) det_point(d, geom, cBr, sBr, dp);
-        else det_point(d, geom, cBf, sBf, dp);
+        if (d.use_rot) det_point(sc.ed[di], cBr, sBr, dp);
+        else dp = sc.fixed[di];
         const double wgt = wA2 / Sn;
         for (int ai = d.arm_begin; ai < d.arm_end; ++ai) {
             double Fp, Fc;

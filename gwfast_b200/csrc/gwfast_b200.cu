@@ -66,46 +66,98 @@ __device__ __forceinline__ double warp_sum(double v) {
     return v;
 }
 
+// Warp reduction of L per-lane accumulators by recursive halving: at every step a lane keeps one half of its
+// vector and sends the other half to its partner, so the whole reduction costs ~L shuffles instead of 5 L, and each
+// lane ends up owning ceil(L/32) fully reduced entries.  All indexing is compile-time (the vector stays in registers).
+__host__ __device__ constexpr int fold_half(int L) { return (L + 1) / 2; }
+template <int L>
+__device__ __forceinline__ void fold_step(double* v, bool upper, int offset) {
+    constexpr int H = fold_half(L);
+#pragma unroll
+    for (int i = 0; i < H; ++i) {
+        const double lo = v[i];
+        const double hi = (i + H < L) ? v[i + H] : 0.0;
+        const double recv = __shfl_xor_sync(0xffffffffu, upper ? lo : hi, offset);
+        v[i] = (upper ? hi : lo) + recv;
+    }
+}
+// after fold_all<L>, entry i (i < kFoldOut<L>) of lane `lane` holds the total of original index fold_index<L>(lane, i)
+// (or nothing if that index is >= L)
+template <int L> struct Fold {
+    static constexpr int L1 = fold_half(L), L2 = fold_half(L1), L3 = fold_half(L2), L4 = fold_half(L3), L5 = fold_half(L4);
+    static constexpr int kOut = L5;
+    static __device__ __forceinline__ void run(double* v, int lane) {
+        fold_step<L>(v, (lane & 16) != 0, 16);
+        fold_step<L1>(v, (lane & 8) != 0, 8);
+        fold_step<L2>(v, (lane & 4) != 0, 4);
+        fold_step<L3>(v, (lane & 2) != 0, 2);
+        fold_step<L4>(v, (lane & 1) != 0, 1);
+    }
+    // original index of final slot i, or -1 if the slot only ever held padding
+    static __device__ __forceinline__ int index(int lane, int i) {
+        int pos = i;
+        bool ok = true;
+        pos += (lane & 1) ? L5 : 0;  ok = ok && pos < L4;
+        pos += (lane & 2) ? L4 : 0;  ok = ok && pos < L3;
+        pos += (lane & 4) ? L3 : 0;  ok = ok && pos < L2;
+        pos += (lane & 8) ? L2 : 0;  ok = ok && pos < L1;
+        pos += (lane & 16) ? L1 : 0; ok = ok && pos < L;
+        return ok ? pos : -1;
+    }
+};
+
+// per-warp shared memory: the event's coefficient record followed by the detector scratch
+template <class Rec> struct WarpSmem {
+    Rec rec;
+    EventScratch sc;
+};
+
+template <class Rec>
+__device__ __forceinline__ void stage_event(WarpSmem<Rec>* mine, const Rec* recs, long long e, const NetworkDev& net, const EvGeom& geom, int lane) {
+    constexpr int kRecDoubles = (int)(sizeof(Rec) / sizeof(double));
+    const double* src = reinterpret_cast<const double*>(recs + e);
+    double* dst = reinterpret_cast<double*>(&mine->rec);
+    __syncwarp();
+    // coefficient record: coalesced 8-byte loads, later read by broadcast
+    for (int i = lane; i < kRecDoubles; i += 32) dst[i] = __ldg(src + i);
+    if (lane < net.ndet) scratch_set(mine->sc, net, geom, lane);
+    __syncwarp();
+}
+
 template <int MODEL, int NT>
 __global__ void __launch_bounds__(kFisherThreads, 1)
 fisher_kernel(const typename ModelTraits<MODEL, NT>::Rec* __restrict__ recs, EventsDev ev, long long n, int res, int lin, ModelCfg cfg,
               const __grid_constant__ NetworkDev net, double* __restrict__ out, double* __restrict__ snr2_out) {
     typedef typename ModelTraits<MODEL, NT>::Rec Rec;
     constexpr int NP = NT + 7, NPACK = NP * (NP + 1) / 2;
-    constexpr int kRecDoubles = (int)(sizeof(Rec) / sizeof(double));
-    extern __shared__ double smem[];
+    extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    double* mine = smem + (size_t)wid * kRecDoubles;
-    const Rec& rec = *reinterpret_cast<const Rec*>(mine);
+    WarpSmem<Rec>* mine = reinterpret_cast<WarpSmem<Rec>*>(smem_raw) + wid;
+    const Rec& rec = mine->rec;
     const long long nwarps = (long long)gridDim.x * kWarpsPerCta;
     for (long long e = (long long)blockIdx.x * kWarpsPerCta + wid; e < n; e += nwarps) {
-        // stage the event's coefficient record in shared memory (coalesced 8-byte loads, read by broadcast)
-        const double* src = reinterpret_cast<const double*>(recs + e);
-        __syncwarp();
-        for (int i = lane; i < kRecDoubles; i += 32) mine[i] = __ldg(src + i);
-        __syncwarp();
         EvGeom geom;
         geom.set(load_event(ev, e));
-        double acc[NPACK];
+        stage_event(mine, recs, e, net, geom, lane);
+        double acc[NPACK + 1];                 // packed Fisher, then the SNR^2 accumulator
 #pragma unroll
-        for (int p = 0; p < NPACK; ++p) acc[p] = 0.0;
-        double snr2 = 0.0;
+        for (int p = 0; p <= NPACK; ++p) acc[p] = 0.0;
         for (int g = 0; g < net.ngroups; ++g) {
             double fcut = rec.fcut_hz;
             if (net.group_fmax[g] > 0.0 && fcut > net.group_fmax[g]) fcut = net.group_fmax[g];   // signal.py:717-718
             Grid grid;
             grid.set(net.group_fmin[g], fcut, res, lin != 0);
             const bool rot = net.group_rot[g] != 0;
-            for (int k = lane; k < res; k += 32) fisher_point<MODEL, NT>(rec, cfg, geom, net, g, rot, grid, k, acc, snr2);
+            for (int k = lane; k < res; k += 32) fisher_point<MODEL, NT>(rec, cfg, geom, net, mine->sc, g, rot, grid, k, acc, acc[NPACK]);
         }
+        typedef Fold<NPACK + 1> F;
+        F::run(acc, lane);
+        double* o = out + e * NPACK;
 #pragma unroll
-        for (int p = 0; p < NPACK; ++p) acc[p] = warp_sum(acc[p]);
-        snr2 = warp_sum(snr2);
-        if (lane == 0) {
-            double* o = out + e * NPACK;
-#pragma unroll
-            for (int p = 0; p < NPACK; ++p) o[p] = acc[p];
-            if (snr2_out) snr2_out[e] = snr2;
+        for (int i = 0; i < F::kOut; ++i) {
+            const int idx = F::index(lane, i);
+            if (idx >= 0 && idx < NPACK) o[idx] = acc[i];
+            else if (idx == NPACK && snr2_out) snr2_out[e] = acc[i];
         }
     }
 }
@@ -116,19 +168,15 @@ __global__ void __launch_bounds__(kFisherThreads, 2)
 snr_kernel(const typename ModelTraits<MODEL, 4>::Rec* __restrict__ recs, EventsDev ev, long long n, int res, int lin, ModelCfg cfg,
            const __grid_constant__ NetworkDev net, int narm_out, double* __restrict__ snr2_arm) {
     typedef typename ModelTraits<MODEL, 4>::Rec Rec;
-    constexpr int kRecDoubles = (int)(sizeof(Rec) / sizeof(double));
-    extern __shared__ double smem[];
+    extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    double* mine = smem + (size_t)wid * kRecDoubles;
-    const Rec& rec = *reinterpret_cast<const Rec*>(mine);
+    WarpSmem<Rec>* mine = reinterpret_cast<WarpSmem<Rec>*>(smem_raw) + wid;
+    const Rec& rec = mine->rec;
     const long long nwarps = (long long)gridDim.x * kWarpsPerCta;
     for (long long e = (long long)blockIdx.x * kWarpsPerCta + wid; e < n; e += nwarps) {
-        const double* src = reinterpret_cast<const double*>(recs + e);
-        __syncwarp();
-        for (int i = lane; i < kRecDoubles; i += 32) mine[i] = __ldg(src + i);
-        __syncwarp();
         EvGeom geom;
         geom.set(load_event(ev, e));
+        stage_event(mine, recs, e, net, geom, lane);
         double s2[kMaxArms];
 #pragma unroll
         for (int a = 0; a < kMaxArms; ++a) s2[a] = 0.0;
@@ -138,7 +186,7 @@ snr_kernel(const typename ModelTraits<MODEL, 4>::Rec* __restrict__ recs, EventsD
             Grid grid;
             grid.set(net.group_fmin[g], fcut, res, lin != 0);
             const bool rot = net.group_rot[g] != 0;
-            for (int k = lane; k < res; k += 32) snr_point<MODEL>(rec, cfg, geom, net, g, rot, grid, k, s2);
+            for (int k = lane; k < res; k += 32) snr_point<MODEL>(rec, cfg, geom, net, mine->sc, g, rot, grid, k, s2);
         }
         for (int a = 0; a < narm_out; ++a) {
             const double v = warp_sum(s2[a]);
@@ -211,7 +259,7 @@ static int run_fisher(const gwf_model* model, const gwf_detector* dets, int ndet
     int dev = 0, sms = 0;
     GWF_CUDA(cudaGetDevice(&dev));
     GWF_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    const size_t shmem = sizeof(Rec) * kWarpsPerCta;
+    const size_t shmem = sizeof(WarpSmem<Rec>) * kWarpsPerCta;
     auto kern = fisher_kernel<MODEL, NT>;
     GWF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem));
     int per_sm = 1;
@@ -256,7 +304,7 @@ static int run_snr(const gwf_model* model, const gwf_detector* dets, int ndet, c
     int dev = 0, sms = 0;
     GWF_CUDA(cudaGetDevice(&dev));
     GWF_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    const size_t shmem = sizeof(Rec) * kWarpsPerCta;
+    const size_t shmem = sizeof(WarpSmem<Rec>) * kWarpsPerCta;
     auto kern = snr_kernel<MODEL>;
     GWF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem));
     int per_sm = 1;

@@ -27,9 +27,9 @@ static int build_psd_tables(const double* f, const double* S, int n, std::vector
     for (int i = 0; i < n; ++i) {
         // slope exactly as numpy's interp builds it: (fp[j+1]-fp[j])/(xp[j+1]-xp[j])
         const double slope = i + 1 < n ? (S[i + 1] - S[i]) / (f[i + 1] - f[i]) : 0.0;
-        tab[i] = make_double4(f[i], S[i], slope, 0.0);
+        tab[i] = make_double4(f[i], S[i], slope, i + 1 < n ? f[i + 1] : f[i]);
     }
-    const int nb = std::max(64, std::min(1 << 16, 2 * n));
+    const int nb = std::max(1024, std::min(1 << 17, 4 * n));
     const double lo = std::log2(f[0]), hi = std::log2(f[n - 1]);
     const double inv = nb / (hi - lo);
     bucket.resize(nb);

@@ -40,6 +40,8 @@ static int emu_run(const gwf_model* model, const gwf_detector* dets, int ndet, c
             ModelTraits<MODEL, NT>::prologue(rec, in, cfg, opts->flags, g_q, net.group_fmin, net.ngroups);
             EvGeom geom;
             geom.set(in);
+            EventScratch sc;
+            for (int di = 0; di < net.ndet; ++di) scratch_set(sc, net, geom, di);
             double acc[NPACK];
             for (int p = 0; p < NPACK; ++p) acc[p] = 0.;
             double s2 = 0.;
@@ -48,7 +50,7 @@ static int emu_run(const gwf_model* model, const gwf_detector* dets, int ndet, c
                 if (net.group_fmax[g] > 0.0 && fcut > net.group_fmax[g]) fcut = net.group_fmax[g];
                 Grid grid;
                 grid.set(net.group_fmin[g], fcut, opts->res, (opts->flags & GWF_OPT_LIN_GRID) != 0);
-                for (int k = 0; k < opts->res; ++k) fisher_point<MODEL, NT>(rec, cfg, geom, net, g, net.group_rot[g] != 0, grid, k, acc, s2);
+                for (int k = 0; k < opts->res; ++k) fisher_point<MODEL, NT>(rec, cfg, geom, net, sc, g, net.group_rot[g] != 0, grid, k, acc, s2);
             }
             std::memcpy(fisher + ((size_t)pass * n + e) * NPACK, acc, sizeof(acc));
             if (snr2) snr2[(size_t)pass * n + e] = s2;
@@ -74,13 +76,15 @@ static int emu_run_snr(const gwf_model* model, const gwf_detector* dets, int nde
         ModelTraits<MODEL, 4>::prologue(rec, in, cfg, 0, g_q, net.group_fmin, net.ngroups);
         EvGeom geom;
         geom.set(in);
+        EventScratch sc;
+        for (int di = 0; di < net.ndet; ++di) scratch_set(sc, net, geom, di);
         double s2[kMaxArms] = {0};
         for (int g = 0; g < net.ngroups; ++g) {
             double fcut = rec.fcut_hz;
             if (net.group_fmax[g] > 0.0 && fcut > net.group_fmax[g]) fcut = net.group_fmax[g];
             Grid grid;
             grid.set(net.group_fmin[g], fcut, opts->res, (opts->flags & GWF_OPT_LIN_GRID) != 0);
-            for (int k = 0; k < opts->res; ++k) snr_point<MODEL>(rec, cfg, geom, net, g, net.group_rot[g] != 0, grid, k, s2);
+            for (int k = 0; k < opts->res; ++k) snr_point<MODEL>(rec, cfg, geom, net, sc, g, net.group_rot[g] != 0, grid, k, s2);
         }
         for (int a = 0; a < net.narms; ++a) snr2_arm[(size_t)a * n + e] = s2[a];
     }

@@ -17,14 +17,12 @@ template <int NT> struct ModelTraits<kTaylorF2, NT> {
         tf2_prologue(r, p, e.dL, cfg);
     }
     // waveform at f: amplitude, d ln A, d Phi and (if need_tau) d t_noloc
-    static GWF_HD void eval(const Rec& r, const ModelCfg&, int, double f, bool need_tau, PointWf<NT>& w) {
+    static GWF_HD void eval(const Rec& r, const ModelCfg&, int, const FreqPoint& fp, bool need_tau, PointWf<NT>& w) {
         VPow p;
-        p.set(r.s * f);
+        p.set(r.sp, fp);
         double phi;
         tf2_phase(r, p, phi, w.phi_d);
-        const double f16 = rsqrt(cbrt(f));          // f^(-1/6)
-        const double f76 = f16 / f;                  // f^(-7/6)
-        w.A = r.C * f76;
+        w.A = r.C * fp.fm76;
 #pragma unroll
         for (int j = 0; j < NT; ++j) w.lnA_d[j] = r.lnC_d[j];
         w.dtn[0] = w.dtn[1] = 0.;
@@ -45,9 +43,9 @@ template <int NT> struct ModelTraits<kPhenomD, NT> {
         const Intrinsic<NT> p = seed_intrinsic<NT>(e, opt_flags, false);
         phenomd_prologue(r, p, e.dL, q, fmin_g, ng, cfg);
     }
-    static GWF_HD void eval(const Rec& r, const ModelCfg& cfg, int g, double f, bool need_tau, PointWf<NT>& w) {
+    static GWF_HD void eval(const Rec& r, const ModelCfg& cfg, int g, const FreqPoint& fp, bool need_tau, PointWf<NT>& w) {
         XPow p;
-        p.set(r.s * f);
+        p.set(r.s, r.sp, fp);
         const bool cut = !(cfg.flags & kFlagNoFcut);
         double phi;
         phenomd_phase(r, g, p, cut, phi, w.phi_d);
@@ -66,37 +64,56 @@ template <int NT> struct ModelTraits<kPhenomD, NT> {
 };
 
 // ------------------------------------------------------------------ frequency grid of one (event, group)
+// numpy.geomspace(fmin, fcut, res) (signal.py:721, 898): f_k = 10**(log10 fmin + k (log10 fcut - log10 fmin)/(res-1)) with
+// both end points overwritten exactly, or numpy.linspace for spacing='lin'.  A caller walks the grid with a fixed stride
+// (32 in the kernels): on the geometric grid the sample and its powers are advanced by multiplying with the constant
+// ratio of the stride, so no transcendental is evaluated per sample (the drift over res/stride <= 32 steps is < 1e-14).
 struct Grid {
     double fmin, fcut;
-    double l0, step;      // geom: log10 f_k = l0 + k*step ; lin: f_k = fmin + k*step
+    double l0, step;              // geom: log10 f_k = l0 + k*step ; lin: f_k = fmin + k*step
     double hw_in, hw_lo, hw_hi;   // trapezoid half-widths: geom -> multiply f_k; lin -> absolute
-    int res, lin;
-    GWF_HD void set(double fmin_, double fcut_, int res_, bool lin_) {
-        fmin = fmin_; fcut = fcut_; res = res_; lin = lin_;
+    double r, r13, rm13, rm76, dln;   // per-stride ratios of f, f^(1/3), f^(-1/3), f^(-7/6) and increment of ln f
+    int res, lin, stride;
+    GWF_HD void set(double fmin_, double fcut_, int res_, bool lin_, int stride_) {
+        fmin = fmin_; fcut = fcut_; res = res_; lin = lin_; stride = stride_;
         if (lin) {
             step = (fcut - fmin) / (res - 1);
             hw_in = step; hw_lo = hw_hi = 0.5 * step;
             l0 = 0.;
+            r = r13 = rm13 = rm76 = 1.; dln = 0.;
         } else {
-            // numpy.geomspace: 10**(log10(start) + k*(log10(stop)-log10(start))/(num-1)), end points overwritten
             l0 = log10(fmin);
             step = (log10(fcut) - l0) / (res - 1);
-            const double r = exp10(step);
-            hw_in = 0.5 * (r - 1.0 / r); hw_lo = 0.5 * (r - 1.0); hw_hi = 0.5 * (1.0 - 1.0 / r);
+            const double q = exp10(step);
+            hw_in = 0.5 * (q - 1.0 / q); hw_lo = 0.5 * (q - 1.0); hw_hi = 0.5 * (1.0 - 1.0 / q);
+            const double e = step * stride;                  // log10 of the stride ratio
+            r = exp10(e); r13 = exp10(e * (1. / 3.)); rm13 = 1.0 / r13; rm76 = exp10(e * (-7. / 6.));
+            dln = e * 2.3025850929940456840179914546843642;  // ln 10
         }
     }
-    // f_k, the trapezoid weight w_k = (f_{k+1}-f_{k-1})/2 (one-sided at the ends; np.trapz, signal.py:929), log2 f_k
-    GWF_HD void point(int k, double& f, double& w, double& l2f) const {
+    GWF_HD double freq(int k) const {
+        if (k == 0) return fmin;
+        if (k == res - 1) return fcut;
+        return lin ? fma((double)k, step, fmin) : exp10(fma((double)k, step, l0));
+    }
+    GWF_HD void weight(int k, FreqPoint& p) const {
+        const double hw = k == 0 ? hw_lo : (k == res - 1 ? hw_hi : hw_in);
+        p.w = lin ? hw : p.f * hw;      // np.trapz on this grid, signal.py:929
+    }
+    // first sample of a walk
+    GWF_HD void start(int k, FreqPoint& p) const {
+        p.from_f(freq(k));
+        weight(k, p);
+    }
+    // move from sample k - stride to sample k
+    GWF_HD void advance(int k, FreqPoint& p) const {
         if (lin) {
-            f = k == res - 1 ? fcut : fmin + k * step;
-            w = (k == 0 || k == res - 1) ? hw_lo : hw_in;
-            l2f = log2(f);
+            p.from_f(freq(k));
         } else {
-            const double lf = fma((double)k, step, l0);
-            f = k == 0 ? fmin : (k == res - 1 ? fcut : exp10(lf));
-            w = f * (k == 0 ? hw_lo : (k == res - 1 ? hw_hi : hw_in));
-            l2f = lf * 3.3219280948873623478703194294893902;   // log2(10)
+            p.f = k == res - 1 ? fcut : p.f * r;
+            p.f13 *= r13; p.fm13 *= rm13; p.fm76 *= rm76; p.lnf += dln;
         }
+        weight(k, p);
     }
 };
 
@@ -119,14 +136,13 @@ GWF_HD void scratch_set(EventScratch& s, const NetworkDev& net, const EvGeom& ge
 // acc: packed lower-triangular Fisher (NP(NP+1)/2), snr2: sum of 4 w |h|^2 / Sn over the arms of the pass
 template <int MODEL, int NT>
 GWF_HD void fisher_point(const typename ModelTraits<MODEL, NT>::Rec& rec, const ModelCfg& cfg, const EvGeom& geom, const NetworkDev& net,
-                         const EventScratch& sc, int g, bool group_rot, const Grid& grid, int k, double* __restrict__ acc, double& snr2) {
-    double f, wk, l2f;
-    grid.point(k, f, wk, l2f);
+                         const EventScratch& sc, int g, bool group_rot, const FreqPoint& fp, double* __restrict__ acc, double& snr2) {
+    const double f = fp.f, l2f = fp.lnf * 1.4426950408889634073599246810018921;   // log2 f
     PointWf<NT> w;
-    ModelTraits<MODEL, NT>::eval(rec, cfg, g, f, group_rot, w);
+    ModelTraits<MODEL, NT>::eval(rec, cfg, g, fp, group_rot, w);
     w.f = f;
     if (!(w.A > 0.0)) return;             // beyond the model cut (or zero amplitude): no contribution
-    const double wA2 = 4.0 * wk * w.A * w.A;
+    const double wA2 = 4.0 * fp.w * w.A * w.A;
     // Earth-rotation phase common to the detectors of the group: 2 pi (tcoal - tau/86400), signal.py:449
     double sBr = 0., cBr = 1.;
     if (group_rot) sincos(2.0 * kPi * fma(-w.tau, kInvDay, geom.tcoal), &sBr, &cBr);
@@ -147,13 +163,12 @@ GWF_HD void fisher_point(const typename ModelTraits<MODEL, NT>::Rec& rec, const 
 // value-only point for the SNR kernel: per-arm SNR^2 contributions (signal.py:725-767)
 template <int MODEL>
 GWF_HD void snr_point(const typename ModelTraits<MODEL, 4>::Rec& rec, const ModelCfg& cfg, const EvGeom& geom, const NetworkDev& net,
-                      const EventScratch& sc, int g, bool group_rot, const Grid& grid, int k, double* __restrict__ snr2_arm) {
-    double f, wk, l2f;
-    grid.point(k, f, wk, l2f);
+                      const EventScratch& sc, int g, bool group_rot, const FreqPoint& fp, double* __restrict__ snr2_arm) {
+    const double f = fp.f, l2f = fp.lnf * 1.4426950408889634073599246810018921;   // log2 f
     PointWf<4> w;
-    ModelTraits<MODEL, 4>::eval(rec, cfg, g, f, group_rot, w);
+    ModelTraits<MODEL, 4>::eval(rec, cfg, g, fp, group_rot, w);
     if (!(w.A > 0.0)) return;
-    const double wA2 = 4.0 * wk * w.A * w.A;
+    const double wA2 = 4.0 * fp.w * w.A * w.A;
     double sBr = 0., cBr = 1.;
     if (group_rot) sincos(2.0 * kPi * fma(-w.tau, kInvDay, geom.tcoal), &sBr, &cBr);
     for (int di = 0; di < net.ndet; ++di) {

@@ -146,9 +146,14 @@ fisher_kernel(const typename ModelTraits<MODEL, NT>::Rec* __restrict__ recs, Eve
             double fcut = rec.fcut_hz;
             if (net.group_fmax[g] > 0.0 && fcut > net.group_fmax[g]) fcut = net.group_fmax[g];   // signal.py:717-718
             Grid grid;
-            grid.set(net.group_fmin[g], fcut, res, lin != 0);
+            grid.set(net.group_fmin[g], fcut, res, lin != 0, 32);
             const bool rot = net.group_rot[g] != 0;
-            for (int k = lane; k < res; k += 32) fisher_point<MODEL, NT>(rec, cfg, geom, net, mine->sc, g, rot, grid, k, acc, acc[NPACK]);
+            FreqPoint fp;
+            if (lane < res) grid.start(lane, fp);
+            for (int k = lane; k < res; k += 32) {
+                if (k != lane) grid.advance(k, fp);
+                fisher_point<MODEL, NT>(rec, cfg, geom, net, mine->sc, g, rot, fp, acc, acc[NPACK]);
+            }
         }
         typedef Fold<NPACK + 1> F;
         F::run(acc, lane);
@@ -184,9 +189,14 @@ snr_kernel(const typename ModelTraits<MODEL, 4>::Rec* __restrict__ recs, EventsD
             double fcut = rec.fcut_hz;
             if (net.group_fmax[g] > 0.0 && fcut > net.group_fmax[g]) fcut = net.group_fmax[g];
             Grid grid;
-            grid.set(net.group_fmin[g], fcut, res, lin != 0);
+            grid.set(net.group_fmin[g], fcut, res, lin != 0, 32);
             const bool rot = net.group_rot[g] != 0;
-            for (int k = lane; k < res; k += 32) snr_point<MODEL>(rec, cfg, geom, net, mine->sc, g, rot, grid, k, s2);
+            FreqPoint fp;
+            if (lane < res) grid.start(lane, fp);
+            for (int k = lane; k < res; k += 32) {
+                if (k != lane) grid.advance(k, fp);
+                snr_point<MODEL>(rec, cfg, geom, net, mine->sc, g, rot, fp, s2);
+            }
         }
         for (int a = 0; a < narm_out; ++a) {
             const double v = warp_sum(s2[a]);

@@ -92,6 +92,33 @@ struct IntrinsicV {
     double Mc, eta, chi1, chi2, L1, L2;
 };
 
+// one sample of the frequency grid with the powers every model needs.  On a geometric grid these are advanced by
+// recurrence (a handful of multiplications per sample instead of exp10/cbrt/log/sqrt calls), see Grid in fisher_core.cuh.
+struct FreqPoint {
+    double f;      // Hz
+    double f13;    // f^(1/3)
+    double fm13;   // f^(-1/3)
+    double fm76;   // f^(-7/6)
+    double lnf;    // ln f
+    double w;      // trapezoid weight (f_{k+1} - f_{k-1})/2, one-sided at the ends
+    GWF_HD void from_f(double f_) {
+        f = f_;
+        f13 = cbrt(f_);
+        fm13 = 1.0 / f13;
+        fm76 = fm13 * fm13 * fm13 * sqrt(fm13);
+        lnf = log(f_);
+    }
+};
+// per-event scale s (x = s f) in the same powers
+struct ScalePow {
+    double s13, sm13, lps3;   // s^(1/3), s^(-1/3), ln(pi s)/3
+    GWF_HD void set(double s) {
+        s13 = cbrt(s);
+        sm13 = 1.0 / s13;
+        lps3 = log(kPi * s) * (1. / 3.);
+    }
+};
+
 // waveform quantities at one frequency: amplitude, d(ln A), phase tangent (value optional)
 template <int NT>
 struct WfPoint {

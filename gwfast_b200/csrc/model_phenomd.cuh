@@ -59,10 +59,12 @@ constexpr int kAInt = 5;    // (x - 0.014)^k, k=0..4
 template <int NT>
 struct PhenomDRec {
     double s;                 // x = s f      (s = M GMsun/c^3)
+    ScalePow sp;              // powers of s used to build x^(1/3), x^(-1/3), ln(pi x)/3 from the grid's f-powers
     double lam[NT];           // d ln s / d slot
     double fcut_hz;           // model cut frequency in Hz (before the detector's fmax clip)
     double x_mrd, x_peak;     // phase int->MRD join (fring/2), amplitude int->MRD join (fpeak)
     double C, lnC_d[NT];      // overall amplitude factor 2 sqrt(5/64pi) M^2 GMsun_c2_Gpc GMsun_c3/dL * amp0, and d ln C
+    double C76;               // C * s^(-7/6): A = C76 f^(-7/6) ampIMR(x)
     double pc[kMaxGroups][1 + NT];   // per grid group: t0*xRef - phiRef  (xRef = s*fmin unless fRef given)
     double pins[kPIns][1 + NT];
     double pint[kPInt][1 + NT];
@@ -204,6 +206,7 @@ GWF_HD void phenomd_fill(PhenomDRec<NT>& r, const PhenomDCore<NT>& c, const Dual
     typedef Dual<NT> D;
     const D s = M * kGMsunC3;
     r.s = s.v;
+    r.sp.set(s.v);
 #pragma unroll
     for (int j = 0; j < NT; ++j) r.lam[j] = s.d[j] / s.v;
     r.fcut_hz = kMfCut / s.v;                                 // waveforms.py:1333
@@ -213,6 +216,7 @@ GWF_HD void phenomd_fill(PhenomDRec<NT>& r, const PhenomDCore<NT>& c, const Dual
     const D amp0 = dsqrt(2.0 * c.eta / 3.0) * pow(kPi, -1. / 6.);
     const D Cc = 2. * sqrt(5. / (64. * kPi)) * M * kGMsunC2Gpc * M * kGMsunC3 / dL * amp0;
     r.C = Cc.v;
+    r.C76 = Cc.v * (r.sp.sm13 * r.sp.sm13 * r.sp.sm13 * sqrt(r.sp.sm13));
 #pragma unroll
     for (int j = 0; j < NT; ++j) r.lnC_d[j] = Cc.d[j] / Cc.v;
     const bool apply_cut = !(cfg.flags & kFlagNoFcut);
@@ -290,12 +294,14 @@ GWF_HD void expand(const double (*c)[1 + NT], const double* b, const double* bx,
 // powers of x shared by the regions
 struct XPow {
     double x, x13, x23, xm13, lpx3;   // x^(1/3), x^(2/3), x^(-1/3), log(pi x)/3
-    GWF_HD void set(double x_) {
-        x = x_;
-        x13 = cbrt(x);
+    double fm76;                      // f^(-7/6)
+    GWF_HD void set(double s, const ScalePow& sp, const FreqPoint& fp) {
+        x = s * fp.f;
+        x13 = sp.s13 * fp.f13;
         x23 = x13 * x13;
-        xm13 = 1.0 / x13;
-        lpx3 = log(kPi * x) * (1. / 3.);
+        xm13 = sp.sm13 * fp.fm13;
+        lpx3 = fma(fp.lnf, 1. / 3., sp.lps3);
+        fm76 = fp.fm76;
     }
 };
 
@@ -314,12 +320,12 @@ GWF_HD void phenomd_phase(const PhenomDRec<NT>& r, int g, const XPow& p, bool ap
                                   -5. / 3. * xm53, x, 4. / 3. * x43, 5. / 3. * x53, 2. * x2};
         expand<kPIns, NT>(r.pins, b, bx, v, d, dx);
     } else if (x < r.x_mrd) {
-        const double xm1 = 1.0 / x, xm3 = xm1 * xm1 * xm1, lx = log(x);
+        const double xm1 = p.xm13 * p.xm13 * p.xm13, xm3 = xm1 * xm1 * xm1, lx = 3.0 * p.lpx3 - 1.1447298858494001741434273513530587;   // ln x = ln(pi x) - ln pi
         const double b[kPInt] = {1., x, xm3, lx, p.x23};
         const double bx[kPInt] = {0., x, -3. * xm3, 1., 2. / 3. * p.x23};
         expand<kPInt, NT>(r.pint, b, bx, v, d, dx);
     } else if (!apply_cut || x < kMfCut) {
-        const double xm1 = 1.0 / x, sx = sqrt(x), x34 = sx * sqrt(sx);
+        const double xm1 = p.xm13 * p.xm13 * p.xm13, sx = sqrt(x), x34 = sx * sqrt(sx);
         const double b[kPMrd] = {1., x, xm1, x34, p.x23};
         const double bx[kPMrd] = {0., x, -xm1, 0.75 * x34, 2. / 3. * p.x23};
         expand<kPMrd, NT>(r.pmrd, b, bx, v, d, dx);
@@ -376,9 +382,8 @@ GWF_HD void phenomd_amp(const PhenomDRec<NT>& r, const XPow& p, bool apply_cut, 
         for (int j = 0; j < NT; ++j) lnA_d[j] = 0.;
         return;
     }
-    // A = C x^(-7/6) v
-    const double xm76 = p.xm13 * p.xm13 * p.xm13 * sqrt(p.xm13);
-    A = r.C * xm76 * v;
+    // A = C x^(-7/6) v = C76 f^(-7/6) v
+    A = r.C76 * p.fm76 * v;
     const double iv = 1.0 / v;
 #pragma unroll
     for (int j = 0; j < NT; ++j) lnA_d[j] = r.lnC_d[j] + (dx * iv - 7. / 6.) * r.lam[j] + d[j] * iv;

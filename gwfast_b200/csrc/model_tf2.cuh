@@ -10,6 +10,7 @@ constexpr int kTF2 = 11;   // v^-5, v^-3, v^-2, v^-1, 1, log v, v, v log v, v^2,
 template <int NT>
 struct TF2Rec {
     double s;
+    ScalePow sp;
     double lam[NT];
     double fcut_hz;
     double C, lnC_d[NT];          // A = C f^(-7/6)
@@ -58,6 +59,7 @@ GWF_HD void tf2_prologue(TF2Rec<NT>& r, const Intrinsic<NT>& p, double dL, const
     const D M = p.Mc / dpow(p.eta, 3. / 5.);
     const D s = M * kGMsunC3;
     r.s = s.v;
+    r.sp.set(s.v);
 #pragma unroll
     for (int j = 0; j < NT; ++j) r.lam[j] = s.d[j] / s.v;
     r.fcut_hz = (cfg.flags & kFlagKerrISCO) ? tf2_fcut_kerr(p.Mc.v, p.eta.v, p.chi1.v, p.chi2.v) : cfg.fcutPar / M.v;   // waveforms.py:918-953
@@ -98,11 +100,12 @@ GWF_HD void tf2_prologue(TF2Rec<NT>& r, const Intrinsic<NT>& p, double dL, const
 // v-powers at x
 struct VPow {
     double v, vm1, lv, lpx3;
-    GWF_HD void set(double x) {
-        const double px = kPi * x;
-        v = cbrt(px);
-        vm1 = 1.0 / v;
-        lpx3 = log(px) * (1. / 3.);
+    GWF_HD void set(const ScalePow& sp, const FreqPoint& fp) {
+        const double cp = 1.4645918875615232630201425272637904;      // pi^(1/3)
+        const double cpm = 0.68278406325529568146702083315816;       // pi^(-1/3)
+        v = cp * sp.s13 * fp.f13;
+        vm1 = cpm * sp.sm13 * fp.fm13;
+        lpx3 = fma(fp.lnf, 1. / 3., sp.lps3);
         lv = lpx3;          // log v = log(pi x)/3
     }
 };

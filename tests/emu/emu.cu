@@ -49,8 +49,16 @@ static int emu_run(const gwf_model* model, const gwf_detector* dets, int ndet, c
                 double fcut = rec.fcut_hz;
                 if (net.group_fmax[g] > 0.0 && fcut > net.group_fmax[g]) fcut = net.group_fmax[g];
                 Grid grid;
-                grid.set(net.group_fmin[g], fcut, opts->res, (opts->flags & GWF_OPT_LIN_GRID) != 0);
-                for (int k = 0; k < opts->res; ++k) fisher_point<MODEL, NT>(rec, cfg, geom, net, sc, g, net.group_rot[g] != 0, grid, k, acc, s2);
+                grid.set(net.group_fmin[g], fcut, opts->res, (opts->flags & GWF_OPT_LIN_GRID) != 0, 32);
+                // same walk as the kernels: 32 interleaved strided walks ("lanes")
+                for (int lane = 0; lane < 32 && lane < opts->res; ++lane) {
+                    FreqPoint fp;
+                    grid.start(lane, fp);
+                    for (int k = lane; k < opts->res; k += 32) {
+                        if (k != lane) grid.advance(k, fp);
+                        fisher_point<MODEL, NT>(rec, cfg, geom, net, sc, g, net.group_rot[g] != 0, fp, acc, s2);
+                    }
+                }
             }
             std::memcpy(fisher + ((size_t)pass * n + e) * NPACK, acc, sizeof(acc));
             if (snr2) snr2[(size_t)pass * n + e] = s2;
@@ -83,8 +91,15 @@ static int emu_run_snr(const gwf_model* model, const gwf_detector* dets, int nde
             double fcut = rec.fcut_hz;
             if (net.group_fmax[g] > 0.0 && fcut > net.group_fmax[g]) fcut = net.group_fmax[g];
             Grid grid;
-            grid.set(net.group_fmin[g], fcut, opts->res, (opts->flags & GWF_OPT_LIN_GRID) != 0);
-            for (int k = 0; k < opts->res; ++k) snr_point<MODEL>(rec, cfg, geom, net, sc, g, net.group_rot[g] != 0, grid, k, s2);
+            grid.set(net.group_fmin[g], fcut, opts->res, (opts->flags & GWF_OPT_LIN_GRID) != 0, 32);
+            for (int lane = 0; lane < 32 && lane < opts->res; ++lane) {
+                FreqPoint fp;
+                grid.start(lane, fp);
+                for (int k = lane; k < opts->res; k += 32) {
+                    if (k != lane) grid.advance(k, fp);
+                    snr_point<MODEL>(rec, cfg, geom, net, sc, g, net.group_rot[g] != 0, fp, s2);
+                }
+            }
         }
         for (int a = 0; a < net.narms; ++a) snr2_arm[(size_t)a * n + e] = s2[a];
     }

@@ -4,6 +4,7 @@
 #include "detector.cuh"
 #include "model_phenomd.cuh"
 #include "model_tf2.cuh"
+#include "model_nrtidal.cuh"
 
 namespace gwf {
 
@@ -56,6 +57,64 @@ template <int NT> struct ModelTraits<kPhenomD, NT> {
             double tau, dtau[2];
             const double cpm1 = 0.68278406325529568146702083315816;   // pi^(-1/3)
             tau_eval(r.tau, p.xm13 * cpm1, p.lpx3, r.lam, tau, dtau);
+            w.tau = tau;
+            w.dtn[0] = -dtau[0] * kInvDay;
+            w.dtn[1] = -dtau[1] * kInvDay;
+        }
+    }
+};
+
+template <int NT> struct ModelTraits<kNRTidalv2, NT> {
+    typedef NRTidalRec<NT> Rec;
+    static GWF_HD void prologue(Rec& r, const EventIn& e, const ModelCfg& cfg, int opt_flags, const QnmTables& q, const double* fmin_g, int ng) {
+        // NT = 6: Fisher parametrisation (Lambda re-mapped through LambdaTilde/deltaLambda); NT = 4: SNR path, dict values as they are
+        const Intrinsic<NT> p = seed_intrinsic<NT>(e, opt_flags, NT >= 6);
+        nrtidal_prologue(r, p, e.dL, q, fmin_g, ng, cfg, NT < 6 || (cfg.flags & kFlagLambdaGiven) != 0);
+    }
+    static GWF_HD void eval(const Rec& r, const ModelCfg& cfg, int g, const FreqPoint& fp, bool need_tau, PointWf<NT>& w) {
+        const PhenomDRec<NT>& d = r.d;
+        XPow p;
+        p.set(d.s, d.sp, fp);
+        w.dtn[0] = w.dtn[1] = 0.;
+        w.tau = 0.;
+        const double cp = 1.4645918875615232630201425272637904;      // pi^(1/3)
+        const double p13 = cp * p.x13;
+        // amplitude: C [x^(-7/6) ampIMR + kam Q] T, waveforms.py:1724
+        double T, Ty;
+        nrt_taper(p.x, r.ym[0], T, Ty);
+        double v, dv[NT];
+        const bool inside = phenomd_amp_core(d, p, true, v, dv);
+        if (T == 0.0) {
+            w.A = 0.;
+            return;
+        }
+        double Q, xQp;
+        nrt_amp_shape(p13, p.lpx3, Q, xQp);
+        const double xm76 = r.sm76 * fp.fm76;
+        const double B = fma(xm76, v, r.kam[0] * Q);
+        w.A = d.C * B * T;
+        if (w.A == 0.0) return;
+        const double iB = 1.0 / B, tT = Ty / T;
+#pragma unroll
+        for (int j = 0; j < NT; ++j) {
+            const double dB = xm76 * (dv[j] - (7. / 6.) * d.lam[j] * v) + r.kam[1 + j] * Q + r.kam[0] * xQp * d.lam[j];
+            w.lnA_d[j] = d.lnC_d[j] + dB * iB + tT * r.ym[1 + j];
+        }
+        (void)inside;
+        // phase: PhenomD regions (+ SS/SSS folded into the x^(2/3) slots) + Pade tidal term, all inside the cut (waveforms.py:1570)
+        const bool cut = !(cfg.flags & kFlagNoFcut);
+        double phi;
+        phenomd_phase(d, g, p, cut, phi, w.phi_d);
+        if (!cut || p.x < kMfCut) {
+            double R, xRp;
+            nrt_phase_shape(p13, R, xRp);
+#pragma unroll
+            for (int j = 0; j < NT; ++j) w.phi_d[j] += r.kph[1 + j] * R + r.kph[0] * xRp * d.lam[j];
+        }
+        if (need_tau) {
+            double tau, dtau[2];
+            const double cpm1 = 0.68278406325529568146702083315816;   // pi^(-1/3)
+            tau_eval(d.tau, p.xm13 * cpm1, p.lpx3, d.lam, tau, dtau);
             w.tau = tau;
             w.dtn[0] = -dtau[0] * kInvDay;
             w.dtn[1] = -dtau[1] * kInvDay;
@@ -141,7 +200,7 @@ GWF_HD void fisher_point(const typename ModelTraits<MODEL, NT>::Rec& rec, const 
     PointWf<NT> w;
     ModelTraits<MODEL, NT>::eval(rec, cfg, g, fp, group_rot, w);
     w.f = f;
-    if (!(w.A > 0.0)) return;             // beyond the model cut (or zero amplitude): no contribution
+    if (w.A == 0.0) return;               // beyond the model cut / taper: no contribution
     const double wA2 = 4.0 * fp.w * w.A * w.A;
     // Earth-rotation phase common to the detectors of the group: 2 pi (tcoal - tau/86400), signal.py:449
     double sBr = 0., cBr = 1.;
@@ -167,7 +226,7 @@ GWF_HD void snr_point(const typename ModelTraits<MODEL, 4>::Rec& rec, const Mode
     const double f = fp.f, l2f = fp.lnf * 1.4426950408889634073599246810018921;   // log2 f
     PointWf<4> w;
     ModelTraits<MODEL, 4>::eval(rec, cfg, g, fp, group_rot, w);
-    if (!(w.A > 0.0)) return;
+    if (w.A == 0.0) return;
     const double wA2 = 4.0 * fp.w * w.A * w.A;
     double sBr = 0., cBr = 1.;
     if (group_rot) sincos(2.0 * kPi * fma(-w.tau, kInvDay, geom.tcoal), &sBr, &cBr);

@@ -355,6 +355,7 @@ size_t gwf_workspace_bytes(const gwf_model* model, int64_t n) {
     switch (model->id) {
         case GWF_TAYLORF2: rec = std::max(sizeof(TF2Rec<4>), sizeof(TF2Rec<6>)); break;
         case GWF_IMRPHENOMD: rec = sizeof(PhenomDRec<4>); break;
+        case GWF_IMRPHENOMD_NRTIDALV2: rec = std::max(sizeof(NRTidalRec<4>), sizeof(NRTidalRec<6>)); break;
         default: rec = 0;
     }
     return rec * (size_t)n;
@@ -432,6 +433,9 @@ int gwf_fisher(const gwf_model* model, const gwf_detector* dets, int32_t ndet, c
             return run_fisher<kTaylorF2, 4>(model, dets, ndet, psds, npsd, ev, n, opts, fisher_packed, snr2, workspace, workspace_bytes, st);
         case GWF_IMRPHENOMD:
             return run_fisher<kPhenomD, 4>(model, dets, ndet, psds, npsd, ev, n, opts, fisher_packed, snr2, workspace, workspace_bytes, st);
+        case GWF_IMRPHENOMD_NRTIDALV2:
+            if (!ev.p[11] || !ev.p[12]) return fail(GWF_ERR_ARG, "tidal model needs Lambda1, Lambda2");
+            return run_fisher<kNRTidalv2, 6>(model, dets, ndet, psds, npsd, ev, n, opts, fisher_packed, snr2, workspace, workspace_bytes, st);
         default:
             return fail(GWF_ERR_UNSUPPORTED, "model not built yet");
     }
@@ -451,6 +455,9 @@ int gwf_snr(const gwf_model* model, const gwf_detector* dets, int32_t ndet, cons
             return run_snr<kTaylorF2>(model, dets, ndet, psds, npsd, ev, n, opts, snr2_arm, workspace, workspace_bytes, st);
         case GWF_IMRPHENOMD:
             return run_snr<kPhenomD>(model, dets, ndet, psds, npsd, ev, n, opts, snr2_arm, workspace, workspace_bytes, st);
+        case GWF_IMRPHENOMD_NRTIDALV2:
+            if (!ev.p[11] || !ev.p[12]) return fail(GWF_ERR_ARG, "tidal model needs Lambda1, Lambda2");
+            return run_snr<kNRTidalv2>(model, dets, ndet, psds, npsd, ev, n, opts, snr2_arm, workspace, workspace_bytes, st);
         default:
             return fail(GWF_ERR_UNSUPPORTED, "model not built yet");
     }

@@ -348,9 +348,10 @@ GWF_HD void phenomd_phase(const PhenomDRec<NT>& r, int g, const XPow& p, bool ap
     for (int j = 0; j < NT; ++j) phi_d[j] = d[j] + dx * r.lam[j] + r.pc[g][1 + j];
 }
 
-// amplitude A and d ln A at x
+// amplitude shape function ampIMR(x) (the three-region where of waveforms.py:1250) and its TOTAL tangents
+// dv[j] = sum_k dc_kj b_k + lam_j x d/dx.  Returns false beyond the cut (ampIMR identically 0).
 template <int NT>
-GWF_HD void phenomd_amp(const PhenomDRec<NT>& r, const XPow& p, bool apply_cut, double& A, double* lnA_d) {
+GWF_HD bool phenomd_amp_core(const PhenomDRec<NT>& r, const XPow& p, bool apply_cut, double& v_out, double* dv) {
     const double x = p.x;
     double v = 0., dx = 0., d[NT];
 #pragma unroll
@@ -368,25 +369,40 @@ GWF_HD void phenomd_amp(const PhenomDRec<NT>& r, const XPow& p, bool apply_cut, 
     } else if (!apply_cut || x < kMfCut) {
         // exp(-(x-fr) g) * P / ((x-fr)^2 + w^2);  amrd = {fr, g, w, P}
         const double u = x - r.amrd[0][0], g = r.amrd[1][0], w = r.amrd[2][0], P = r.amrd[3][0];
-        const double iden = 1.0 / (u * u + w * w);
+        const double iden = 1.0 / (u * u + w * w), iP = 1.0 / P;
         v = exp(-u * g) * P * iden;
         // d ln v = -(du) g - u dg + dP/P - (2 u du + 2 w dw)/den, with du_j = x lam_j - dfr_j
         const double ku = -g - 2. * u * iden;
         dx = v * ku * x;
 #pragma unroll
         for (int j = 0; j < NT; ++j)
-            d[j] = v * (-ku * r.amrd[0][1 + j] - u * r.amrd[1][1 + j] + r.amrd[3][1 + j] / P - 2. * w * iden * r.amrd[2][1 + j]);
+            d[j] = v * (-ku * r.amrd[0][1 + j] - u * r.amrd[1][1 + j] + r.amrd[3][1 + j] * iP - 2. * w * iden * r.amrd[2][1 + j]);
     } else {
+        v_out = 0.;
+#pragma unroll
+        for (int j = 0; j < NT; ++j) dv[j] = 0.;
+        return false;
+    }
+    v_out = v;
+#pragma unroll
+    for (int j = 0; j < NT; ++j) dv[j] = fma(dx, r.lam[j], d[j]);
+    return true;
+}
+
+// amplitude A = C x^(-7/6) ampIMR(x) and d ln A at x
+template <int NT>
+GWF_HD void phenomd_amp(const PhenomDRec<NT>& r, const XPow& p, bool apply_cut, double& A, double* lnA_d) {
+    double v, dv[NT];
+    if (!phenomd_amp_core(r, p, apply_cut, v, dv)) {
         A = 0.;
 #pragma unroll
         for (int j = 0; j < NT; ++j) lnA_d[j] = 0.;
         return;
     }
-    // A = C x^(-7/6) v = C76 f^(-7/6) v
     A = r.C76 * p.fm76 * v;
     const double iv = 1.0 / v;
 #pragma unroll
-    for (int j = 0; j < NT; ++j) lnA_d[j] = r.lnC_d[j] + (dx * iv - 7. / 6.) * r.lam[j] + d[j] * iv;
+    for (int j = 0; j < NT; ++j) lnA_d[j] = fma(dv[j], iv, fma(-7. / 6., r.lam[j], r.lnC_d[j]));
 }
 
 }  // namespace gwf

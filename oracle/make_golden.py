@@ -129,10 +129,48 @@ def fx_variants():
         save('var_' + tag, cfg, ev, run_network(cfg, ev))
 
 
+def masked_last_sample(cfg, ev):
+    """Reference outputs with the LAST grid sample of every arm forced to zero, computed from the reference's own
+    GWAmplitudes / derivative arrays (signal.py:425, 1094-1098) and its trapezoid rule.  Used for IMRPhenomD_NRTidalv2, whose
+    last sample sits on the end of the Planck taper and is 0 or 1 by last-bit rounding."""
+    wf, sig, net, utils, glob = reference.load()
+    sigs = synthetic.build_network(sig.GWSignal, _model(wf, cfg['model']), cfg['network'], useEarthMotion=cfg['rot'], fmin=cfg['fmin'], psd_root=REF_PSDS)
+    snr2 = 0.
+    F = 0.
+    for s in sigs.values():
+        e = _copy(ev)
+        utils.check_evparams(e)
+        fcut = s.wf_model.fcut(**e)
+        fg = np.geomspace(np.full(fcut.shape, s.fmin), fcut, num=1000)
+        Sn = np.interp(fg, s.strainFreq, s.noiseCurve, left=1., right=1.)
+        rots = [0.] if s.detector_shape == 'L' else [0., 60.]
+        amps = [s.GWAmplitudes(e, fg, rot=r) for r in rots]
+        if s.detector_shape == 'T':
+            amps.append((-(amps[0][0] + amps[1][0]), -(amps[0][1] + amps[1][1])))
+        for Ap, Ac in amps:
+            y = (Ap * Ap + Ac * Ac) / Sn
+            y[-1] = 0.
+            snr2 = snr2 + 4. * np.trapezoid(y, fg, axis=0)
+        Fs, Ds = s.FisherMatr(_copy(ev), return_derivatives=True)
+        # FisherMatr's own grid (fcut evaluated on the dict as FisherMatr sees it, signal.py:884)
+        for D in Ds:
+            D = np.array(D)
+            D[:, :, -1] = 0.
+            nP = D.shape[0]
+            Fa = np.zeros((nP, nP, D.shape[1]))
+            for a in range(nP):
+                for b in range(a, nP):
+                    Fa[a, b] = Fa[b, a] = 4. * np.trapezoid((np.conj(D[a]) * D[b]).real.T / Sn, fg, axis=0)
+            F = F + Fa
+    return {'snr_masked': np.sqrt(snr2), 'fisher_masked': F}
+
+
 def fx_c3():
     cfg = dict(model=dict(cls='IMRPhenomD_NRTidalv2'), network='ET+2CE', rot=True, fmin=2.)
     ev = take(synthetic.bns_catalog(10000, synthetic.SEEDS['C3'], tidal=True), 32)
-    save('c3_nrtidal_et2ce', cfg, ev, run_network(cfg, ev))
+    out = run_network(cfg, ev)
+    out.update(masked_last_sample(cfg, ev))
+    save('c3_nrtidal_et2ce', cfg, ev, out)
 
 
 def fx_c4():

@@ -505,8 +505,13 @@ def _f_merger(eta, k2T):
     return (0.3586 / np.sqrt(q)) * (num / den) / (2. * PI)
 
 
-def planck_taper(x, y):
-    """waveforms.py:1702-1722 incl. the custom JVP: zero tangent w.r.t. x, hand-written rule w.r.t. y."""
+def planck_taper(x, y, end_zero=False):
+    """waveforms.py:1702-1722 incl. the custom JVP: zero tangent w.r.t. x, hand-written rule w.r.t. y.
+
+    ``end_zero``: the documented carve-out of SURVEY.md App. A-3 -- the reference's last grid sample sits exactly on the
+    end of the taper (x = 1.2 y) where ``where(x > yp, 0, ...)`` returns 0 or 1 depending on last-bit rounding; with
+    ``end_zero`` the taper is 0 for x >= 1.2 y (1 - 1e-12), which is what the CUDA engine implements.
+    """
     from ..dual import Dual
     xv = x.v if isinstance(x, Dual) else x
     yv = y.v if isinstance(y, Dual) else y
@@ -515,11 +520,15 @@ def planck_taper(x, y):
     with np.errstate(all='ignore'):
         e = np.exp((yp - yv) / (xv - yv) + (yp - yv) / (xv - yp))
         val = np.nan_to_num(np.where(xv < yv, 1., np.where(xv > yp, 0., 1. - 1. / (e + 1.))))
+        if end_zero:
+            val = np.where(xv >= yp * (1. - 1e-12), 0., val)
         if not isinstance(y, Dual):
             return val
         dy = np.where(xv < yv, 0., np.where(xv > yp, 0., e * ((-1. + a) / (xv - yv) + (-1. + a) / (xv - yp) + (-yv + yp) / ((xv - yv) ** 2)
                                                                + 1.2 * (-yv + yp) / ((xv - yp) ** 2)) / ((e + 1.) ** 2)))
         dy = np.nan_to_num(dy)
+        if end_zero:
+            dy = np.where(xv >= yp * (1. - 1e-12), 0., dy)
     # the outer nan_to_num of the reference (waveforms.py:1722) also acts on the tangent
     return Dual(val, np.nan_to_num(dy[..., None] * y.d))
 
@@ -527,6 +536,10 @@ def planck_taper(x, y):
 class IMRPhenomD_NRTidalv2(IMRPhenomD):
     is_tidal = True
     objType = 'BNS'
+
+    def __init__(self, fRef=None, apply_fcut=True, taper_end_zero=False, **kw):
+        self.taper_end_zero = taper_end_zero
+        super().__init__(fRef=fRef, apply_fcut=apply_fcut, **kw)
 
     def _lams(self, ev, like):
         if 'Lambda1' in ev:
@@ -577,7 +590,7 @@ class IMRPhenomD_NRTidalv2(IMRPhenomD):
         xt = (PI * x) ** (2. / 3.)
         poly = (1.0 + 4.157407407407407 * xt + 2519.111111111111 * (xt ** 2.89)) / (1. + 13477.8073677 * (xt ** 4))
         amp_tidal = -9.0 * k2T * (xt ** 3.25) * poly
-        taper = planck_taper(x, _f_merger(eta, k2T))
+        taper = planck_taper(x, _f_merger(eta, k2T), self.taper_end_zero)
         return overall * (core.amp0 * (x ** (-7. / 6.)) * core.amplitude(x, True) + 2 * np.sqrt(PI / 5.) * amp_tidal) * taper
 
     def fcut(self, **ev):

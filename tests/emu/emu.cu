@@ -140,6 +140,7 @@ int emu_fisher(const gwf_model* model, const gwf_detector* dets, int ndet, const
         switch (model->id) {
             case GWF_TAYLORF2: return emu_run_snr<kTaylorF2>(model, dets, ndet, pd, npsd, ev, n, opts, fisher);
             case GWF_IMRPHENOMD: return emu_run_snr<kPhenomD>(model, dets, ndet, pd, npsd, ev, n, opts, fisher);
+            case GWF_IMRPHENOMD_NRTIDALV2: return emu_run_snr<kNRTidalv2>(model, dets, ndet, pd, npsd, ev, n, opts, fisher);
         }
         return -2;
     }
@@ -148,6 +149,7 @@ int emu_fisher(const gwf_model* model, const gwf_detector* dets, int ndet, const
             if (model->flags & GWF_MODEL_TIDAL) return emu_run<kTaylorF2, 6>(model, dets, ndet, pd, npsd, ev, n, opts, fisher, snr2);
             return emu_run<kTaylorF2, 4>(model, dets, ndet, pd, npsd, ev, n, opts, fisher, snr2);
         case GWF_IMRPHENOMD: return emu_run<kPhenomD, 4>(model, dets, ndet, pd, npsd, ev, n, opts, fisher, snr2);
+        case GWF_IMRPHENOMD_NRTIDALV2: return emu_run<kNRTidalv2, 6>(model, dets, ndet, pd, npsd, ev, n, opts, fisher, snr2);
     }
     return -2;
 }

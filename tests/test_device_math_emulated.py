@@ -44,3 +44,17 @@ def test_emulated_device_math_matches_reference(name):
     assert snr_err(np.sqrt(arms.sum(axis=0)), out['snr'][:n]) < SNR_RTOL
     # tighter than the gate: what the formulation actually achieves
     assert fisher_err(F, out['fisher'][..., :n]) < 5e-9
+
+
+def test_emulated_nrtidal_matches_masked_reference():
+    """IMRPhenomD_NRTidalv2 (13 parameters, custom-JVP taper): against the reference with its rounding-fragile last grid
+    sample forced to zero, and within the size of that artefact against the raw reference."""
+    import emu_driver as E
+    cfg, ev, out = load_golden('c3_nrtidal_et2ce')
+    model, dets, psds = _emu_inputs(cfg)
+    packed, _ = E.run(model._descriptor(ev), dets, psds, ev)
+    F = E.unpack(packed, 13)[0]
+    arms, _ = E.run(model._descriptor(ev), dets, psds, ev, snr_mode=True)
+    snr = np.sqrt(arms.sum(axis=0))
+    assert snr_err(snr, out['snr_masked']) < SNR_RTOL and fisher_err(F, out['fisher_masked']) < FISHER_TOL
+    assert snr_err(snr, out['snr']) < 1e-5 and fisher_err(F, out['fisher']) < 5e-3

@@ -5,6 +5,7 @@
 #include "model_phenomd.cuh"
 #include "model_tf2.cuh"
 #include "model_nrtidal.cuh"
+#include "model_phenomhm.cuh"
 
 namespace gwf {
 
@@ -194,7 +195,7 @@ GWF_HD void scratch_set(EventScratch& s, const NetworkDev& net, const EvGeom& ge
 // ------------------------------------------------------------------ one frequency point of one grid group
 // acc: packed lower-triangular Fisher (NP(NP+1)/2), snr2: sum of 4 w |h|^2 / Sn over the arms of the pass
 template <int MODEL, int NT>
-GWF_HD void fisher_point(const typename ModelTraits<MODEL, NT>::Rec& rec, const ModelCfg& cfg, const EvGeom& geom, const NetworkDev& net,
+GWF_HD void amp_phase_point(const typename ModelTraits<MODEL, NT>::Rec& rec, const ModelCfg& cfg, const EvGeom& geom, const NetworkDev& net,
                          const EventScratch& sc, int g, bool group_rot, const FreqPoint& fp, double* __restrict__ acc, double& snr2) {
     const double f = fp.f, l2f = fp.lnf * 1.4426950408889634073599246810018921;   // log2 f
     PointWf<NT> w;
@@ -221,7 +222,7 @@ GWF_HD void fisher_point(const typename ModelTraits<MODEL, NT>::Rec& rec, const 
 
 // value-only point for the SNR kernel: per-arm SNR^2 contributions (signal.py:725-767)
 template <int MODEL>
-GWF_HD void snr_point(const typename ModelTraits<MODEL, 4>::Rec& rec, const ModelCfg& cfg, const EvGeom& geom, const NetworkDev& net,
+GWF_HD void amp_phase_snr_point(const typename ModelTraits<MODEL, 4>::Rec& rec, const ModelCfg& cfg, const EvGeom& geom, const NetworkDev& net,
                       const EventScratch& sc, int g, bool group_rot, const FreqPoint& fp, double* __restrict__ snr2_arm) {
     const double f = fp.f, l2f = fp.lnf * 1.4426950408889634073599246810018921;   // log2 f
     PointWf<4> w;
@@ -246,5 +247,182 @@ GWF_HD void snr_point(const typename ModelTraits<MODEL, 4>::Rec& rec, const Mode
         }
     }
 }
+
+// ------------------------------------------------------------------ IMRPhenomHM point functions
+// per-event extras of a model (harmonic weights for HM; nothing for the (2,2)-only models)
+struct NoExtra {
+    GWF_HD void set(const EventIn&) {}
+};
+struct HMExtra {
+    HMWeights w;
+    GWF_HD void set(const EventIn& e) { w.set(e.iota); }
+};
+
+template <int NT>
+GWF_HD void hm_point(const HMRec<NT>& rec, const ModelCfg& cfg, const EvGeom& geom, const NetworkDev& net, const EventScratch& sc,
+                     const HMExtra& ex, int g, bool group_rot, const FreqPoint& fp, double* __restrict__ acc, double& snr2) {
+    typedef Dual<NT> D;
+    constexpr int NP = NT + 7;
+    const double f = fp.f, l2f = fp.lnf * 1.4426950408889634073599246810018921;
+    const bool cut = !(cfg.flags & kFlagNoFcut);
+    D zre[kHMModes], zim[kHMModes];
+    phenomhm_modes<D, NT>(rec, g, f, cut, zre, zim);
+    // hp = sum z_m Wp_m ; hc = i sum z_m Wc_m ; and their iota derivatives (waveforms.py:2613-2614)
+    D hpr(0.0), hpi(0.0), hcr(0.0), hci(0.0);
+    double hpr_i = 0., hpi_i = 0., hcr_i = 0., hci_i = 0.;
+#pragma unroll
+    for (int m = 0; m < kHMModes; ++m) {
+        hpr = hpr + zre[m] * ex.w.wp[m];
+        hpi = hpi + zim[m] * ex.w.wp[m];
+        hcr = hcr - zim[m] * ex.w.wc[m];
+        hci = hci + zre[m] * ex.w.wc[m];
+        hpr_i = fma(zre[m].v, ex.w.dwp[m], hpr_i);
+        hpi_i = fma(zim[m].v, ex.w.dwp[m], hpi_i);
+        hcr_i = fma(-zim[m].v, ex.w.dwc[m], hcr_i);
+        hci_i = fma(zre[m].v, ex.w.dwc[m], hci_i);
+    }
+    if (hpr.v == 0.0 && hpi.v == 0.0 && hcr.v == 0.0 && hci.v == 0.0) return;
+    PointWf<NT> w;
+    w.f = f;
+#pragma unroll
+    for (int j = 0; j < NT; ++j) w.phi_d[j] = 0.;
+    w.dtn[0] = w.dtn[1] = 0.;
+    double sBr = 0., cBr = 1.;
+    if (group_rot) {
+        double tau, dtau[2];
+        const double x13 = cbrt(rec.s.v * f), lpx3 = log(kPi * rec.s.v * f) * (1. / 3.);
+        tau_eval(rec.tau, 0.68278406325529568146702083315816 / x13, lpx3, rec.lam, tau, dtau);
+        w.dtn[0] = -dtau[0] * kInvDay;
+        w.dtn[1] = -dtau[1] * kInvDay;
+        sincos(2.0 * kPi * fma(-tau, kInvDay, geom.tcoal), &sBr, &cBr);
+    }
+    const double w4 = 4.0 * fp.w;
+    for (int di = 0; di < net.ndet; ++di) {
+        const DetDev& d = net.det[di];
+        if (d.group != g || d.arm_begin == d.arm_end) continue;
+        const double Sn = psd_lookup(net.psd[d.psd], f, l2f);
+        DetPoint dp;
+        if (d.use_rot) det_point(sc.ed[di], cBr, sBr, dp);
+        else dp = sc.fixed[di];
+        DetRows<NT> dr;
+        dr.set(w, dp, d.use_rot != 0, d.no_motion != 0);
+        const double wgt = w4 / Sn;
+        for (int ai = d.arm_begin; ai < d.arm_end; ++ai) {
+            const ArmDev& a = net.arm[ai];
+            const double av = a.S2 * dp.aS + a.C2 * dp.aC, bv = a.C2 * dp.bC + a.S2 * dp.bS;
+            const double ag = a.S2 * dp.aS_g + a.C2 * dp.aC_g, bg = a.C2 * dp.bC_g + a.S2 * dp.bS_g;
+            const double ad = a.S2 * dp.aS_d + a.C2 * dp.aC_d, bd = a.C2 * dp.bC_d + a.S2 * dp.bS_d;
+            const double Fp = av * geom.c2psi + bv * geom.s2psi, Fc = bv * geom.c2psi - av * geom.s2psi;
+            const double Fpg = ag * geom.c2psi + bg * geom.s2psi, Fcg = bg * geom.c2psi - ag * geom.s2psi;
+            const double Fpd = ad * geom.c2psi + bd * geom.s2psi, Fcd = bd * geom.c2psi - ad * geom.s2psi;
+            const double Hr = hpr.v * Fp + hcr.v * Fc, Hi = hpi.v * Fp + hci.v * Fc;           // signal.py:586-607
+            const double Hgr = hpr.v * Fpg + hcr.v * Fcg, Hgi = hpi.v * Fpg + hci.v * Fcg;
+            const double Hdr = hpr.v * Fpd + hcr.v * Fcd, Hdi = hpi.v * Fpd + hci.v * Fcd;
+            double ra[NP], rb[NP];
+#pragma unroll
+            for (int j = 0; j < NT; ++j) {
+                const int row = j < 2 ? j : 7 + j;
+                double re = hpr.d[j] * Fp + hcr.d[j] * Fc - Hi * dr.psi_x[j], im = hpi.d[j] * Fp + hci.d[j] * Fc + Hr * dr.psi_x[j];
+                if (j < 2) {
+                    re = fma(Hgr, dr.ang_x[j], re);
+                    im = fma(Hgi, dr.ang_x[j], im);
+                }
+                ra[row] = re;
+                rb[row] = im;
+            }
+            ra[2] = -Hr * geom.inv_dL;                                   rb[2] = -Hi * geom.inv_dL;
+            ra[3] = fma(Hgr, dr.ang_t, -Hdr) - Hi * dr.ph_t;             rb[3] = fma(Hgi, dr.ang_t, -Hdi) + Hr * dr.ph_t;
+            ra[4] = fma(Hgr, dr.ang_p, -Hi * dr.ph_p);                   rb[4] = fma(Hgi, dr.ang_p, Hr * dr.ph_p);
+            ra[5] = hpr_i * Fp + hcr_i * Fc;                             rb[5] = hpi_i * Fp + hci_i * Fc;     // iota: harmonics only
+            ra[6] = 2.0 * (hpr.v * Fc - hcr.v * Fp);                     rb[6] = 2.0 * (hpi.v * Fc - hci.v * Fp);   // psi: Fp' = 2 Fc, Fc' = -2 Fp
+            ra[7] = fma(Hgr, dr.ang_c, -Hi * dr.ph_c);                   rb[7] = fma(Hgi, dr.ang_c, Hr * dr.ph_c);
+            ra[8] = Hi;                                                  rb[8] = -Hr;
+            const double wg = wgt * a.weight;
+            snr2 = fma(wg, Hr * Hr + Hi * Hi, snr2);
+#pragma unroll
+            for (int i = 0; i < NP; ++i) {
+                const double wa = wg * ra[i], wb = wg * rb[i];
+#pragma unroll
+                for (int j = 0; j <= i; ++j) acc[tri(i, j)] = fma(wa, ra[j], fma(wb, rb[j], acc[tri(i, j)]));
+            }
+        }
+    }
+}
+
+// HM SNR as the reference defines it: Ap = |hp| Fp, Ac = |hc| Fc (the +/x cross term is dropped, signal.py:457-460, 727)
+GWF_HD void hm_snr_point(const HMRec<4>& rec, const ModelCfg& cfg, const EvGeom& geom, const NetworkDev& net, const EventScratch& sc,
+                         const HMExtra& ex, int g, bool group_rot, const FreqPoint& fp, double* __restrict__ snr2_arm) {
+    const double f = fp.f, l2f = fp.lnf * 1.4426950408889634073599246810018921;
+    const bool cut = !(cfg.flags & kFlagNoFcut);
+    double zre[kHMModes], zim[kHMModes];
+    phenomhm_modes<double, 4>(rec, g, f, cut, zre, zim);
+    double hpr = 0., hpi = 0., hcr = 0., hci = 0.;
+#pragma unroll
+    for (int m = 0; m < kHMModes; ++m) {
+        hpr = fma(zre[m], ex.w.wp[m], hpr);
+        hpi = fma(zim[m], ex.w.wp[m], hpi);
+        hcr = fma(-zim[m], ex.w.wc[m], hcr);
+        hci = fma(zre[m], ex.w.wc[m], hci);
+    }
+    const double hp2 = hpr * hpr + hpi * hpi, hc2 = hcr * hcr + hci * hci;
+    if (hp2 == 0.0 && hc2 == 0.0) return;
+    double sBr = 0., cBr = 1.;
+    if (group_rot) {
+        double tau, dtau[2];
+        const double x13 = cbrt(rec.s.v * f), lpx3 = log(kPi * rec.s.v * f) * (1. / 3.);
+        tau_eval(rec.tau, 0.68278406325529568146702083315816 / x13, lpx3, rec.lam, tau, dtau);
+        sincos(2.0 * kPi * fma(-tau, kInvDay, geom.tcoal), &sBr, &cBr);
+    }
+    const double w4 = 4.0 * fp.w;
+    for (int di = 0; di < net.ndet; ++di) {
+        const DetDev& d = net.det[di];
+        if (d.group != g) continue;
+        const double Sn = psd_lookup(net.psd[d.psd], f, l2f);
+        DetPoint dp;
+        if (d.use_rot) det_point(sc.ed[di], cBr, sBr, dp);
+        else dp = sc.fixed[di];
+        const double wgt = w4 / Sn;
+        for (int ai = d.arm_begin; ai < d.arm_end; ++ai) {
+            double Fp, Fc;
+            arm_pattern(dp, net.arm[ai], geom, Fp, Fc);
+            snr2_arm[net.arm[ai].out] = fma(wgt * net.arm[ai].weight, hp2 * Fp * Fp + hc2 * Fc * Fc, snr2_arm[net.arm[ai].out]);
+        }
+    }
+}
+
+template <int NT> struct ModelTraits<kPhenomHM, NT> {
+    typedef HMRec<NT> Rec;
+    typedef HMExtra Extra;
+    static GWF_HD void prologue(Rec& r, const EventIn& e, const ModelCfg& cfg, int opt_flags, const QnmTables&, const double* fmin_g, int ng) {
+        const Intrinsic<NT> p = seed_intrinsic<NT>(e, opt_flags, false);
+        phenomhm_prologue(r, p, e.dL, fmin_g, ng, cfg);
+    }
+};
+
+// uniform entry points used by the kernels and the emulation harness
+template <int MODEL, int NT> struct PointFns {
+    typedef NoExtra Extra;
+    typedef typename ModelTraits<MODEL, NT>::Rec Rec;
+    static GWF_HD void fisher(const Rec& rec, const ModelCfg& cfg, const EvGeom& geom, const NetworkDev& net, const EventScratch& sc, const Extra&, int g,
+                              bool rot, const FreqPoint& fp, double* __restrict__ acc, double& snr2) {
+        amp_phase_point<MODEL, NT>(rec, cfg, geom, net, sc, g, rot, fp, acc, snr2);
+    }
+    static GWF_HD void snr(const Rec& rec, const ModelCfg& cfg, const EvGeom& geom, const NetworkDev& net, const EventScratch& sc, const Extra&, int g,
+                           bool rot, const FreqPoint& fp, double* __restrict__ s2) {
+        amp_phase_snr_point<MODEL>(rec, cfg, geom, net, sc, g, rot, fp, s2);
+    }
+};
+template <int NT> struct PointFns<kPhenomHM, NT> {
+    typedef HMExtra Extra;
+    typedef HMRec<NT> Rec;
+    static GWF_HD void fisher(const Rec& rec, const ModelCfg& cfg, const EvGeom& geom, const NetworkDev& net, const EventScratch& sc, const Extra& ex, int g,
+                              bool rot, const FreqPoint& fp, double* __restrict__ acc, double& snr2) {
+        hm_point<NT>(rec, cfg, geom, net, sc, ex, g, rot, fp, acc, snr2);
+    }
+    static GWF_HD void snr(const Rec& rec, const ModelCfg& cfg, const EvGeom& geom, const NetworkDev& net, const EventScratch& sc, const Extra& ex, int g,
+                           bool rot, const FreqPoint& fp, double* __restrict__ s2) {
+        hm_snr_point(rec, cfg, geom, net, sc, ex, g, rot, fp, s2);
+    }
+};
 
 }  // namespace gwf

@@ -107,13 +107,15 @@ template <int L> struct Fold {
 };
 
 // per-warp shared memory: the event's coefficient record followed by the detector scratch
-template <class Rec> struct WarpSmem {
+template <class Rec, class Extra> struct WarpSmem {
     Rec rec;
     EventScratch sc;
+    Extra ex;
 };
 
-template <class Rec>
-__device__ __forceinline__ void stage_event(WarpSmem<Rec>* mine, const Rec* recs, long long e, const NetworkDev& net, const EvGeom& geom, int lane) {
+template <class Rec, class Extra>
+__device__ __forceinline__ void stage_event(WarpSmem<Rec, Extra>* mine, const Rec* recs, long long e, const NetworkDev& net, const EvGeom& geom,
+                                            const EventIn& in, int lane) {
     constexpr int kRecDoubles = (int)(sizeof(Rec) / sizeof(double));
     const double* src = reinterpret_cast<const double*>(recs + e);
     double* dst = reinterpret_cast<double*>(&mine->rec);
@@ -121,6 +123,7 @@ __device__ __forceinline__ void stage_event(WarpSmem<Rec>* mine, const Rec* recs
     // coefficient record: coalesced 8-byte loads, later read by broadcast
     for (int i = lane; i < kRecDoubles; i += 32) dst[i] = __ldg(src + i);
     if (lane < net.ndet) scratch_set(mine->sc, net, geom, lane);
+    if (lane == 31) mine->ex.set(in);
     __syncwarp();
 }
 
@@ -129,16 +132,19 @@ __global__ void __launch_bounds__(kFisherThreads, 1)
 fisher_kernel(const typename ModelTraits<MODEL, NT>::Rec* __restrict__ recs, EventsDev ev, long long n, int res, int lin, ModelCfg cfg,
               const __grid_constant__ NetworkDev net, double* __restrict__ out, double* __restrict__ snr2_out) {
     typedef typename ModelTraits<MODEL, NT>::Rec Rec;
+    typedef PointFns<MODEL, NT> PF;
+    typedef WarpSmem<Rec, typename PF::Extra> WS;
     constexpr int NP = NT + 7, NPACK = NP * (NP + 1) / 2;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    WarpSmem<Rec>* mine = reinterpret_cast<WarpSmem<Rec>*>(smem_raw) + wid;
+    WS* mine = reinterpret_cast<WS*>(smem_raw) + wid;
     const Rec& rec = mine->rec;
     const long long nwarps = (long long)gridDim.x * kWarpsPerCta;
     for (long long e = (long long)blockIdx.x * kWarpsPerCta + wid; e < n; e += nwarps) {
         EvGeom geom;
-        geom.set(load_event(ev, e));
-        stage_event(mine, recs, e, net, geom, lane);
+        const EventIn in = load_event(ev, e);
+        geom.set(in);
+        stage_event(mine, recs, e, net, geom, in, lane);
         double acc[NPACK + 1];                 // packed Fisher, then the SNR^2 accumulator
 #pragma unroll
         for (int p = 0; p <= NPACK; ++p) acc[p] = 0.0;
@@ -152,7 +158,7 @@ fisher_kernel(const typename ModelTraits<MODEL, NT>::Rec* __restrict__ recs, Eve
             if (lane < res) grid.start(lane, fp);
             for (int k = lane; k < res; k += 32) {
                 if (k != lane) grid.advance(k, fp);
-                fisher_point<MODEL, NT>(rec, cfg, geom, net, mine->sc, g, rot, fp, acc, acc[NPACK]);
+                PF::fisher(rec, cfg, geom, net, mine->sc, mine->ex, g, rot, fp, acc, acc[NPACK]);
             }
         }
         typedef Fold<NPACK + 1> F;
@@ -173,15 +179,18 @@ __global__ void __launch_bounds__(kFisherThreads, 2)
 snr_kernel(const typename ModelTraits<MODEL, 4>::Rec* __restrict__ recs, EventsDev ev, long long n, int res, int lin, ModelCfg cfg,
            const __grid_constant__ NetworkDev net, int narm_out, double* __restrict__ snr2_arm) {
     typedef typename ModelTraits<MODEL, 4>::Rec Rec;
+    typedef PointFns<MODEL, 4> PF;
+    typedef WarpSmem<Rec, typename PF::Extra> WS;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    WarpSmem<Rec>* mine = reinterpret_cast<WarpSmem<Rec>*>(smem_raw) + wid;
+    WS* mine = reinterpret_cast<WS*>(smem_raw) + wid;
     const Rec& rec = mine->rec;
     const long long nwarps = (long long)gridDim.x * kWarpsPerCta;
     for (long long e = (long long)blockIdx.x * kWarpsPerCta + wid; e < n; e += nwarps) {
         EvGeom geom;
-        geom.set(load_event(ev, e));
-        stage_event(mine, recs, e, net, geom, lane);
+        const EventIn in = load_event(ev, e);
+        geom.set(in);
+        stage_event(mine, recs, e, net, geom, in, lane);
         double s2[kMaxArms];
 #pragma unroll
         for (int a = 0; a < kMaxArms; ++a) s2[a] = 0.0;
@@ -195,7 +204,7 @@ snr_kernel(const typename ModelTraits<MODEL, 4>::Rec* __restrict__ recs, EventsD
             if (lane < res) grid.start(lane, fp);
             for (int k = lane; k < res; k += 32) {
                 if (k != lane) grid.advance(k, fp);
-                snr_point<MODEL>(rec, cfg, geom, net, mine->sc, g, rot, fp, s2);
+                PF::snr(rec, cfg, geom, net, mine->sc, mine->ex, g, rot, fp, s2);
             }
         }
         for (int a = 0; a < narm_out; ++a) {
@@ -269,7 +278,7 @@ static int run_fisher(const gwf_model* model, const gwf_detector* dets, int ndet
     int dev = 0, sms = 0;
     GWF_CUDA(cudaGetDevice(&dev));
     GWF_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    const size_t shmem = sizeof(WarpSmem<Rec>) * kWarpsPerCta;
+    const size_t shmem = sizeof(WarpSmem<Rec, typename PointFns<MODEL, NT>::Extra>) * kWarpsPerCta;
     auto kern = fisher_kernel<MODEL, NT>;
     GWF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem));
     int per_sm = 1;
@@ -314,7 +323,7 @@ static int run_snr(const gwf_model* model, const gwf_detector* dets, int ndet, c
     int dev = 0, sms = 0;
     GWF_CUDA(cudaGetDevice(&dev));
     GWF_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    const size_t shmem = sizeof(WarpSmem<Rec>) * kWarpsPerCta;
+    const size_t shmem = sizeof(WarpSmem<Rec, typename PointFns<MODEL, 4>::Extra>) * kWarpsPerCta;
     auto kern = snr_kernel<MODEL>;
     GWF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem));
     int per_sm = 1;
@@ -356,6 +365,7 @@ size_t gwf_workspace_bytes(const gwf_model* model, int64_t n) {
         case GWF_TAYLORF2: rec = std::max(sizeof(TF2Rec<4>), sizeof(TF2Rec<6>)); break;
         case GWF_IMRPHENOMD: rec = sizeof(PhenomDRec<4>); break;
         case GWF_IMRPHENOMD_NRTIDALV2: rec = std::max(sizeof(NRTidalRec<4>), sizeof(NRTidalRec<6>)); break;
+        case GWF_IMRPHENOMHM: rec = sizeof(HMRec<4>); break;
         default: rec = 0;
     }
     return rec * (size_t)n;
@@ -436,6 +446,8 @@ int gwf_fisher(const gwf_model* model, const gwf_detector* dets, int32_t ndet, c
         case GWF_IMRPHENOMD_NRTIDALV2:
             if (!ev.p[11] || !ev.p[12]) return fail(GWF_ERR_ARG, "tidal model needs Lambda1, Lambda2");
             return run_fisher<kNRTidalv2, 6>(model, dets, ndet, psds, npsd, ev, n, opts, fisher_packed, snr2, workspace, workspace_bytes, st);
+        case GWF_IMRPHENOMHM:
+            return run_fisher<kPhenomHM, 4>(model, dets, ndet, psds, npsd, ev, n, opts, fisher_packed, snr2, workspace, workspace_bytes, st);
         default:
             return fail(GWF_ERR_UNSUPPORTED, "model not built yet");
     }
@@ -458,6 +470,8 @@ int gwf_snr(const gwf_model* model, const gwf_detector* dets, int32_t ndet, cons
         case GWF_IMRPHENOMD_NRTIDALV2:
             if (!ev.p[11] || !ev.p[12]) return fail(GWF_ERR_ARG, "tidal model needs Lambda1, Lambda2");
             return run_snr<kNRTidalv2>(model, dets, ndet, psds, npsd, ev, n, opts, snr2_arm, workspace, workspace_bytes, st);
+        case GWF_IMRPHENOMHM:
+            return run_snr<kPhenomHM>(model, dets, ndet, psds, npsd, ev, n, opts, snr2_arm, workspace, workspace_bytes, st);
         default:
             return fail(GWF_ERR_UNSUPPORTED, "model not built yet");
     }

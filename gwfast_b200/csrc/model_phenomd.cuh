@@ -147,14 +147,19 @@ struct PhenomDCore {
         return ((-2. * fdamp * u * fit[GAM3] * fit[GAM1]) / den - (fit[GAM2] * fit[GAM1])) / (dexp(u * fit[GAM2] / fd3) * den);
     }
 
+    // ringdown/damping frequencies from the QNM tables (IMRPhenomD, NRTidalv2; waveforms.py:1034-1035)
     GWF_HD void build(const D& eta_, const D& chi1, const D& chi2, const D& qm1, const D& qm2, const QnmTables& q) {
+        const D aeff = final_spin(eta_, chi1, chi2), erad = radiated_energy(eta_, chi1, chi2);
+        build_rd(eta_, chi1, chi2, qm1, qm2, qnm_interp(q, q.fring, aeff) / (1.0 - erad), qnm_interp(q, q.fdamp, aeff) / (1.0 - erad));
+    }
+    // ... or supplied by the caller (IMRPhenomHM uses polynomial fits, waveforms.py:2336-2345)
+    GWF_HD void build_rd(const D& eta_, const D& chi1, const D& chi2, const D& qm1, const D& qm2, const D& fring_, const D& fdamp_) {
         eta = eta_;
+        fring = fring_;
+        fdamp = fdamp_;
         const D e2 = eta * eta, sq = seta_of(eta);
         const D xs = 0.5 * (chi1 + chi2), xa = 0.5 * (chi1 - chi2);
         const D xi = -1.0 + (xs * (1.0 - eta * 76.0 / 113.0) + sq * xa);
-        const D aeff = final_spin(eta, chi1, chi2), erad = radiated_energy(eta, chi1, chi2);
-        fring = qnm_interp(q, q.fring, aeff) / (1.0 - erad);
-        fdamp = qnm_interp(q, q.fdamp, aeff) / (1.0 - erad);
         for (int k = 0; k < kNumFits; ++k) fit[k] = phenomd_fit(k, eta, e2, xi);
         pn = pn_phase_coeffs(eta, chi1, chi2, qm1, qm2, false);
         pn.c6 = pn.c6 - pn.ss6;                     // waveforms.py:1077

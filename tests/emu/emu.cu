@@ -42,6 +42,8 @@ static int emu_run(const gwf_model* model, const gwf_detector* dets, int ndet, c
             geom.set(in);
             EventScratch sc;
             for (int di = 0; di < net.ndet; ++di) scratch_set(sc, net, geom, di);
+            typename PointFns<MODEL, NT>::Extra ex;
+            ex.set(in);
             double acc[NPACK];
             for (int p = 0; p < NPACK; ++p) acc[p] = 0.;
             double s2 = 0.;
@@ -56,7 +58,7 @@ static int emu_run(const gwf_model* model, const gwf_detector* dets, int ndet, c
                     grid.start(lane, fp);
                     for (int k = lane; k < opts->res; k += 32) {
                         if (k != lane) grid.advance(k, fp);
-                        fisher_point<MODEL, NT>(rec, cfg, geom, net, sc, g, net.group_rot[g] != 0, fp, acc, s2);
+                        PointFns<MODEL, NT>::fisher(rec, cfg, geom, net, sc, ex, g, net.group_rot[g] != 0, fp, acc, s2);
                     }
                 }
             }
@@ -86,6 +88,8 @@ static int emu_run_snr(const gwf_model* model, const gwf_detector* dets, int nde
         geom.set(in);
         EventScratch sc;
         for (int di = 0; di < net.ndet; ++di) scratch_set(sc, net, geom, di);
+        typename PointFns<MODEL, 4>::Extra ex;
+        ex.set(in);
         double s2[kMaxArms] = {0};
         for (int g = 0; g < net.ngroups; ++g) {
             double fcut = rec.fcut_hz;
@@ -97,7 +101,7 @@ static int emu_run_snr(const gwf_model* model, const gwf_detector* dets, int nde
                 grid.start(lane, fp);
                 for (int k = lane; k < opts->res; k += 32) {
                     if (k != lane) grid.advance(k, fp);
-                    snr_point<MODEL>(rec, cfg, geom, net, sc, g, net.group_rot[g] != 0, fp, s2);
+                    PointFns<MODEL, 4>::snr(rec, cfg, geom, net, sc, ex, g, net.group_rot[g] != 0, fp, s2);
                 }
             }
         }
@@ -141,6 +145,7 @@ int emu_fisher(const gwf_model* model, const gwf_detector* dets, int ndet, const
             case GWF_TAYLORF2: return emu_run_snr<kTaylorF2>(model, dets, ndet, pd, npsd, ev, n, opts, fisher);
             case GWF_IMRPHENOMD: return emu_run_snr<kPhenomD>(model, dets, ndet, pd, npsd, ev, n, opts, fisher);
             case GWF_IMRPHENOMD_NRTIDALV2: return emu_run_snr<kNRTidalv2>(model, dets, ndet, pd, npsd, ev, n, opts, fisher);
+            case GWF_IMRPHENOMHM: return emu_run_snr<kPhenomHM>(model, dets, ndet, pd, npsd, ev, n, opts, fisher);
         }
         return -2;
     }
@@ -150,6 +155,7 @@ int emu_fisher(const gwf_model* model, const gwf_detector* dets, int ndet, const
             return emu_run<kTaylorF2, 4>(model, dets, ndet, pd, npsd, ev, n, opts, fisher, snr2);
         case GWF_IMRPHENOMD: return emu_run<kPhenomD, 4>(model, dets, ndet, pd, npsd, ev, n, opts, fisher, snr2);
         case GWF_IMRPHENOMD_NRTIDALV2: return emu_run<kNRTidalv2, 6>(model, dets, ndet, pd, npsd, ev, n, opts, fisher, snr2);
+        case GWF_IMRPHENOMHM: return emu_run<kPhenomHM, 4>(model, dets, ndet, pd, npsd, ev, n, opts, fisher, snr2);
     }
     return -2;
 }

@@ -162,7 +162,7 @@ def run_engine(args):
     dets = [s._detector_struct(i) for i, s in enumerate(sigs.values())]
     handles = [s._psd_handle() for s in sigs.values()]
     darr, parr = _engine._call_arrays(dets, handles)
-    dev_ev, host_ev, evs, _ = _engine._upload(st, ev, n, K.EVENT_KEYS)
+    dev_ev, host_ev, evs, _ = _engine._upload(st, signal._engine_events(wf, ev), n, K.EVENT_KEYS)
     nP, npack, narms = 11, 66, 5
     ws = _engine._workspace(st, lib.gwf_workspace_bytes(C.byref(model), n))
     packed = torch.empty((n, npack), dtype=torch.float64, device=dev)
@@ -238,7 +238,7 @@ def run_engine(args):
             dist.all_gather_into_tensor(g.view(-1), torch.from_numpy(F_).to(dev).view(-1))
         torch.cuda.synchronize()
         t_e2e += time.perf_counter() - t
-        h2d = 2 * 11 * n * 8
+        h2d = 2 * 13 * n * 8
         d2h = (F_.size + n + narms * n) * 8
     sampler.stop_flag = True
     time.sleep(0.15)

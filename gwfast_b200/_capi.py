@@ -13,9 +13,10 @@ GWF_TAYLORF2, GWF_IMRPHENOMD, GWF_IMRPHENOMD_NRTIDALV2, GWF_IMRPHENOMHM = 0, 1, 
 GWF_MODEL_TIDAL, GWF_MODEL_3P5PN_SPINHO, GWF_MODEL_PHIREF_VLSO, GWF_MODEL_QUADMON_TID = 1, 2, 4, 8
 GWF_MODEL_KERR_ISCO, GWF_MODEL_NO_FCUT, GWF_MODEL_HAS_FREF, GWF_MODEL_LAMBDA_GIVEN = 16, 32, 64, 128
 GWF_OPT_M1M2, GWF_OPT_CHIS_CHIA, GWF_OPT_LIN_GRID, GWF_OPT_REUSE_WORKSPACE = 1, 2, 4, 8
-GWF_NPARAM_IN = 13
+GWF_NPARAM_IN = 15
 # order of gwf_events.p[]
-EVENT_KEYS = ('Mc', 'eta', 'dL', 'theta', 'phi', 'iota', 'psi', 'tcoal', 'Phicoal', 'chi1z', 'chi2z', 'Lambda1', 'Lambda2')
+EVENT_KEYS = ('Mc', 'eta', 'dL', 'theta', 'phi', 'iota', 'psi', 'tcoal', 'Phicoal', 'chi1z', 'chi2z', 'Lambda1', 'Lambda2',
+              '_fcut', '_Mtot_sec')
 
 
 class gwf_model(C.Structure):
@@ -76,7 +77,7 @@ def load():
     lib.gwf_fisher.argtypes = common + [vp, vp, vp, C.c_size_t, vp]
     lib.gwf_snr.argtypes = common + [vp, vp, C.c_size_t, vp]
     lib.gwf_unpack_fisher.argtypes = [vp, i64, i32, vp, vp]
-    lib.gwf_waveform.argtypes = [P(gwf_model), P(gwf_events), i64, vp, i32, i32, vp, vp, vp, vp, vp, C.c_size_t, vp]
+    lib.gwf_waveform.argtypes = [P(gwf_model), P(gwf_events), i64, vp, i32, i32, vp, vp, vp, vp, vp, vp, C.c_size_t, vp]
     lib.gwf_fp64_peak.argtypes = [dbl, P(dbl), vp]
     _lib = lib
     return lib

@@ -68,14 +68,19 @@ template <int N> GWF_HD Dual<N> operator*(const Dual<N>& a, double b) {
 }
 template <int N> GWF_HD Dual<N> operator*(double b, const Dual<N>& a) { return a * b; }
 template <int N> GWF_HD Dual<N> operator/(const Dual<N>& a, const Dual<N>& b) {
-    Dual<N> r; const double inv = 1.0 / b.v; r.v = a.v * inv;
+    Dual<N> r; const double inv = 1.0 / b.v; r.v = a.v / b.v;       // value by true division: bit-identical to the scalar path
 #pragma unroll
     for (int i = 0; i < N; ++i) r.d[i] = (a.d[i] - r.v * b.d[i]) * inv;
     return r;
 }
-template <int N> GWF_HD Dual<N> operator/(const Dual<N>& a, double b) { return a * (1.0 / b); }
+template <int N> GWF_HD Dual<N> operator/(const Dual<N>& a, double b) {
+    Dual<N> r; const double inv = 1.0 / b; r.v = a.v / b;
+#pragma unroll
+    for (int i = 0; i < N; ++i) r.d[i] = a.d[i] * inv;
+    return r;
+}
 template <int N> GWF_HD Dual<N> operator/(double a, const Dual<N>& b) {
-    Dual<N> r; const double inv = 1.0 / b.v; r.v = a * inv; const double s = -r.v * inv;
+    Dual<N> r; const double inv = 1.0 / b.v; r.v = a / b.v; const double s = -r.v * inv;
 #pragma unroll
     for (int i = 0; i < N; ++i) r.d[i] = s * b.d[i];
     return r;

@@ -16,7 +16,7 @@ template <int NT> struct ModelTraits<kTaylorF2, NT> {
     typedef TF2Rec<NT> Rec;
     static GWF_HD void prologue(Rec& r, const EventIn& e, const ModelCfg& cfg, int opt_flags, const QnmTables&, const double*, int) {
         const Intrinsic<NT> p = seed_intrinsic<NT>(e, opt_flags, (cfg.flags & kFlagTidal) != 0);
-        tf2_prologue(r, p, e.dL, cfg);
+        tf2_prologue(r, p, e.dL, cfg, e.fcut_host);
     }
     // waveform at f: amplitude, d ln A, d Phi and (if need_tau) d t_noloc
     static GWF_HD void eval(const Rec& r, const ModelCfg&, int, const FreqPoint& fp, bool need_tau, PointWf<NT>& w) {
@@ -43,7 +43,7 @@ template <int NT> struct ModelTraits<kPhenomD, NT> {
     typedef PhenomDRec<NT> Rec;
     static GWF_HD void prologue(Rec& r, const EventIn& e, const ModelCfg& cfg, int opt_flags, const QnmTables& q, const double* fmin_g, int ng) {
         const Intrinsic<NT> p = seed_intrinsic<NT>(e, opt_flags, false);
-        phenomd_prologue(r, p, e.dL, q, fmin_g, ng, cfg);
+        phenomd_prologue(r, p, e.dL, q, fmin_g, ng, cfg, e.s_host, e.fcut_host);
     }
     static GWF_HD void eval(const Rec& r, const ModelCfg& cfg, int g, const FreqPoint& fp, bool need_tau, PointWf<NT>& w) {
         XPow p;
@@ -70,7 +70,7 @@ template <int NT> struct ModelTraits<kNRTidalv2, NT> {
     static GWF_HD void prologue(Rec& r, const EventIn& e, const ModelCfg& cfg, int opt_flags, const QnmTables& q, const double* fmin_g, int ng) {
         // NT = 6: Fisher parametrisation (Lambda re-mapped through LambdaTilde/deltaLambda); NT = 4: SNR path, dict values as they are
         const Intrinsic<NT> p = seed_intrinsic<NT>(e, opt_flags, NT >= 6);
-        nrtidal_prologue(r, p, e.dL, q, fmin_g, ng, cfg, NT < 6 || (cfg.flags & kFlagLambdaGiven) != 0);
+        nrtidal_prologue(r, p, e.dL, q, fmin_g, ng, cfg, NT < 6 || (cfg.flags & kFlagLambdaGiven) != 0, e.s_host, e.fcut_host);
     }
     static GWF_HD void eval(const Rec& r, const ModelCfg& cfg, int g, const FreqPoint& fp, bool need_tau, PointWf<NT>& w) {
         const PhenomDRec<NT>& d = r.d;
@@ -395,7 +395,7 @@ template <int NT> struct ModelTraits<kPhenomHM, NT> {
     typedef HMExtra Extra;
     static GWF_HD void prologue(Rec& r, const EventIn& e, const ModelCfg& cfg, int opt_flags, const QnmTables&, const double* fmin_g, int ng) {
         const Intrinsic<NT> p = seed_intrinsic<NT>(e, opt_flags, false);
-        phenomhm_prologue(r, p, e.dL, fmin_g, ng, cfg);
+        phenomhm_prologue(r, p, e.dL, fmin_g, ng, cfg, e.s_host, e.fcut_host);
     }
 };
 
@@ -422,6 +422,75 @@ template <int NT> struct PointFns<kPhenomHM, NT> {
     static GWF_HD void snr(const Rec& rec, const ModelCfg& cfg, const EvGeom& geom, const NetworkDev& net, const EventScratch& sc, const Extra& ex, int g,
                            bool rot, const FreqPoint& fp, double* __restrict__ s2) {
         hm_snr_point(rec, cfg, geom, net, sc, ex, g, rot, fp, s2);
+    }
+};
+
+// ------------------------------------------------------------------ stand-alone waveform values (WaveFormModel.Phi/Ampl/tau_star/hphc)
+// out: phi[nm], amp[nm] (nm = 1, or 6 for IMRPhenomHM), tau, and for HM hp = (re, im), hc = (re, im)
+struct WaveformOut {
+    double phi[kHMModes], amp[kHMModes], tau, hp[2], hc[2];
+};
+template <int MODEL> struct WaveformFns;
+template <> struct WaveformFns<kTaylorF2> {
+    static constexpr int kModes = 1;
+    static GWF_HD void eval(const TF2Rec<4>& r, const ModelCfg&, const HMWeights&, const FreqPoint& fp, WaveformOut& o) {
+        VPow p;
+        p.set(r.sp, fp);
+        double pd[4], dtau[2];
+        tf2_phase(r, p, o.phi[0], pd);
+        o.amp[0] = r.C * fp.fm76;
+        tau_eval(r.tau, p.vm1, p.lpx3, r.lam, o.tau, dtau);
+    }
+};
+template <> struct WaveformFns<kPhenomD> {
+    static constexpr int kModes = 1;
+    static GWF_HD void eval(const PhenomDRec<4>& r, const ModelCfg& cfg, const HMWeights&, const FreqPoint& fp, WaveformOut& o) {
+        XPow p;
+        p.set(r.s, r.sp, fp);
+        const bool cut = !(cfg.flags & kFlagNoFcut);
+        double pd[4], ad[4], dtau[2];
+        phenomd_phase(r, 0, p, cut, o.phi[0], pd);
+        phenomd_amp(r, p, cut, o.amp[0], ad);
+        tau_eval(r.tau, p.xm13 * 0.68278406325529568146702083315816, p.lpx3, r.lam, o.tau, dtau);
+    }
+};
+template <> struct WaveformFns<kNRTidalv2> {
+    static constexpr int kModes = 1;
+    static GWF_HD void eval(const NRTidalRec<4>& r, const ModelCfg& cfg, const HMWeights&, const FreqPoint& fp, WaveformOut& o) {
+        const PhenomDRec<4>& d = r.d;
+        XPow p;
+        p.set(d.s, d.sp, fp);
+        const bool cut = !(cfg.flags & kFlagNoFcut);
+        const double p13 = 1.4645918875615232630201425272637904 * p.x13;
+        double pd[4], dv[4], dtau[2], v, T, Ty, Q, xQp, R, xRp;
+        phenomd_phase(d, 0, p, cut, o.phi[0], pd);
+        if (!cut || p.x < kMfCut) {
+            nrt_phase_shape(p13, R, xRp);
+            o.phi[0] += r.kph[0] * R;
+        }
+        phenomd_amp_core(d, p, true, v, dv);
+        nrt_taper(p.x, r.ym[0], T, Ty);
+        nrt_amp_shape(p13, p.lpx3, Q, xQp);
+        o.amp[0] = d.C * fma(r.sm76 * fp.fm76, v, r.kam[0] * Q) * T;
+        tau_eval(d.tau, p.xm13 * 0.68278406325529568146702083315816, p.lpx3, d.lam, o.tau, dtau);
+    }
+};
+template <> struct WaveformFns<kPhenomHM> {
+    static constexpr int kModes = kHMModes;
+    static GWF_HD void eval(const HMRec<4>& r, const ModelCfg& cfg, const HMWeights& w, const FreqPoint& fp, WaveformOut& o) {
+        const bool cut = !(cfg.flags & kFlagNoFcut);
+        phenomhm_amp_phase<double, 4>(r, 0, fp.f, cut, o.amp, o.phi);
+        o.hp[0] = o.hp[1] = o.hc[0] = o.hc[1] = 0.;
+        for (int m = 0; m < kHMModes; ++m) {
+            double sn, cs;
+            sincos(o.phi[m], &sn, &cs);
+            const double zr = o.amp[m] * cs, zi = -o.amp[m] * sn;
+            o.hp[0] = fma(zr, w.wp[m], o.hp[0]); o.hp[1] = fma(zi, w.wp[m], o.hp[1]);
+            o.hc[0] = fma(-zi, w.wc[m], o.hc[0]); o.hc[1] = fma(zr, w.wc[m], o.hc[1]);
+        }
+        double dtau[2];
+        const double x13 = cbrt(r.s.v * fp.f), lpx3 = log(kPi * r.s.v * fp.f) * (1. / 3.);
+        tau_eval(r.tau, 0.68278406325529568146702083315816 / x13, lpx3, r.lam, o.tau, dtau);
     }
 };
 

@@ -38,8 +38,13 @@ __device__ __forceinline__ EventIn load_event(const EventsDev& ev, long long e) 
     in.chi1z = ev.p[9][e]; in.chi2z = ev.p[10][e];
     in.Lambda1 = ev.p[11] ? ev.p[11][e] : 0.0;
     in.Lambda2 = ev.p[12] ? ev.p[12][e] : 0.0;
+    in.fcut_host = ev.p[13] ? ev.p[13][e] : 0.0;
+    in.s_host = ev.p[14] ? ev.p[14][e] : 0.0;
     return in;
 }
+
+constexpr int kFisherThreads = 256;
+constexpr int kWarpsPerCta = kFisherThreads / 32;
 
 struct GroupInfo {
     int n;
@@ -49,16 +54,75 @@ struct GroupInfo {
 // ------------------------------------------------------------------------------------------- K1
 template <int MODEL, int NT>
 __global__ void __launch_bounds__(128) prologue_kernel(EventsDev ev, long long n, ModelCfg cfg, int opt_flags, QnmTables q, GroupInfo gi,
-                                                      typename ModelTraits<MODEL, NT>::Rec* __restrict__ recs) {
+                                                      typename ModelTraits<MODEL, NT>::Rec* __restrict__ recs,
+                                                      const double* __restrict__ fmin_per_event = nullptr) {
     const long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (e >= n) return;
     const EventIn in = load_event(ev, e);
+    if (fmin_per_event) gi.fmin[0] = fmin_per_event[e];     // stand-alone waveform calls: fRef = min of the user's grid
     ModelTraits<MODEL, NT>::prologue(recs[e], in, cfg, opt_flags, q, gi.fmin, gi.n);
 }
 
+// per-event minimum of a user grid f[res][n] (or the shared f[res])
+__global__ void grid_min_kernel(const double* __restrict__ f, int res, long long n, int f2d, double* __restrict__ fmin) {
+    const long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    double m = f2d ? f[e] : f[0];
+    for (int k = 1; k < res; ++k) {
+        const double v = f2d ? f[(long long)k * n + e] : f[k];
+        m = v < m ? v : m;
+    }
+    fmin[e] = m;
+}
+
+template <class Rec> struct WaveBlk {
+    Rec rec;
+    HMWeights w;
+};
+
+// WaveFormModel.Phi / Ampl / tau_star / hphc on a user grid: one warp per event, lanes over the grid samples
+template <int MODEL>
+__global__ void __launch_bounds__(kFisherThreads)
+waveform_kernel(const typename ModelTraits<MODEL, 4>::Rec* __restrict__ recs, EventsDev ev, long long n, const double* __restrict__ f, int res, int f2d,
+                ModelCfg cfg, double* __restrict__ phi, double* __restrict__ ampl, double* __restrict__ tau, double* __restrict__ hphc,
+                double* __restrict__ fcut) {
+    typedef typename ModelTraits<MODEL, 4>::Rec Rec;
+    typedef WaveformFns<MODEL> WF;
+    constexpr int kRecDoubles = (int)(sizeof(Rec) / sizeof(double));
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    typedef WaveBlk<Rec> Blk;
+    Blk* mine = reinterpret_cast<Blk*>(smem_raw) + wid;
+    const long long nwarps = (long long)gridDim.x * kWarpsPerCta;
+    for (long long e = (long long)blockIdx.x * kWarpsPerCta + wid; e < n; e += nwarps) {
+        const double* src = reinterpret_cast<const double*>(recs + e);
+        double* dst = reinterpret_cast<double*>(&mine->rec);
+        __syncwarp();
+        for (int i = lane; i < kRecDoubles; i += 32) dst[i] = __ldg(src + i);
+        if (lane == 0) mine->w.set(ev.p[5][e]);
+        __syncwarp();
+        if (lane == 0 && fcut) fcut[e] = mine->rec.fcut_hz;
+        const long long plane = (long long)res * n;
+        for (int k = lane; k < res; k += 32) {
+            FreqPoint fp;
+            fp.from_f(f2d ? f[(long long)k * n + e] : f[k]);
+            fp.w = 0.;
+            WaveformOut o;
+            WF::eval(mine->rec, cfg, mine->w, fp, o);
+            const long long at = (long long)k * n + e;
+            for (int m = 0; m < WF::kModes; ++m) {
+                if (phi) phi[m * plane + at] = o.phi[m];
+                if (ampl) ampl[m * plane + at] = o.amp[m];
+            }
+            if (tau) tau[at] = o.tau;
+            if (hphc && MODEL == kPhenomHM) {
+                hphc[at] = o.hp[0]; hphc[plane + at] = o.hp[1]; hphc[2 * plane + at] = o.hc[0]; hphc[3 * plane + at] = o.hc[1];
+            }
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------- K2
-constexpr int kFisherThreads = 256;
-constexpr int kWarpsPerCta = kFisherThreads / 32;
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
@@ -337,6 +401,41 @@ static int run_snr(const gwf_model* model, const gwf_detector* dets, int ndet, c
     return GWF_OK;
 }
 
+template <int MODEL>
+static int run_waveform(const gwf_model* model, const EventsDev& ev, long long n, const double* f, int res, int f2d, double* phi, double* ampl,
+                        double* tau, double* hphc, double* fcut, void* ws, size_t ws_bytes, cudaStream_t st) {
+    typedef typename ModelTraits<MODEL, 4>::Rec Rec;
+    const size_t rec_bytes = (sizeof(Rec) * (size_t)n + 15) & ~(size_t)15;
+    if (ws_bytes < rec_bytes + sizeof(double) * (size_t)n) return fail(GWF_ERR_WORKSPACE, "workspace too small");
+    Rec* recs = reinterpret_cast<Rec*>(ws);
+    double* fmin_ev = reinterpret_cast<double*>(reinterpret_cast<char*>(ws) + rec_bytes);
+    ModelCfg cfg = {model->id, model->flags, model->fcutPar, model->fRef};
+    GroupInfo gi;
+    gi.n = 1;
+    for (int g = 0; g < kMaxGroups; ++g) gi.fmin[g] = 1.0;
+    const int pb = 128;
+    const unsigned pg = (unsigned)((n + pb - 1) / pb);
+    const double* fmin_arg = nullptr;
+    if (res > 0) {
+        grid_min_kernel<<<pg, pb, 0, st>>>(f, res, n, f2d, fmin_ev);
+        GWF_CUDA(cudaGetLastError());
+        fmin_arg = fmin_ev;
+    }
+    prologue_kernel<MODEL, 4><<<pg, pb, 0, st>>>(ev, n, cfg, 0, g_qnm, gi, recs, fmin_arg);
+    GWF_CUDA(cudaGetLastError());
+    int dev = 0, sms = 0;
+    GWF_CUDA(cudaGetDevice(&dev));
+    GWF_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const size_t shmem = sizeof(WaveBlk<Rec>) * kWarpsPerCta;
+    auto kern = waveform_kernel<MODEL>;
+    GWF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem));
+    const long long want = (n + kWarpsPerCta - 1) / kWarpsPerCta;
+    const unsigned grid = (unsigned)std::min<long long>(want, (long long)sms * 4);
+    kern<<<grid, kFisherThreads, shmem, st>>>(recs, ev, n, f, res, f2d, cfg, phi, ampl, tau, hphc, fcut);
+    GWF_CUDA(cudaGetLastError());
+    return GWF_OK;
+}
+
 }  // namespace gwf
 
 using namespace gwf;
@@ -368,7 +467,7 @@ size_t gwf_workspace_bytes(const gwf_model* model, int64_t n) {
         case GWF_IMRPHENOMHM: rec = sizeof(HMRec<4>); break;
         default: rec = 0;
     }
-    return rec * (size_t)n;
+    return ((rec * (size_t)n + 15) & ~(size_t)15) + sizeof(double) * (size_t)n;
 }
 
 int gwf_psd_create(const double* f, const double* S, int32_t n, gwf_psd** out) {
@@ -518,9 +617,27 @@ int gwf_fp64_peak(double ms, double* tflops_out, void* stream) {
     return GWF_OK;
 }
 
-int gwf_waveform(const gwf_model*, const gwf_events*, int64_t, const double*, int32_t, int32_t, double*, double*, double*, double*, void*, size_t,
-                 void*) {
-    return fail(GWF_ERR_UNSUPPORTED, "gwf_waveform: not built yet");
+int gwf_waveform(const gwf_model* model, const gwf_events* events, int64_t n, const double* f, int32_t res, int32_t f_is_2d, double* phi_out,
+                 double* ampl_out, double* tau_out, double* hphc_out, double* fcut_out, void* workspace, size_t workspace_bytes, void* stream) {
+    if (!model || !events) return fail(GWF_ERR_ARG, "null argument");
+    if (n < 0 || res < 0 || (res > 0 && !f)) return fail(GWF_ERR_ARG, "gwf_waveform: bad grid");
+    for (int i = 0; i < 11; ++i)
+        if (!events->p[i] && n > 0) return fail(GWF_ERR_ARG, "missing event parameter array");
+    if ((model->id == GWF_IMRPHENOMD || model->id == GWF_IMRPHENOMD_NRTIDALV2) && !g_qnm.a) return fail(GWF_ERR_ARG, "QNM tables not set (gwf_set_qnm_tables)");
+    if (hphc_out && model->id != GWF_IMRPHENOMHM) return fail(GWF_ERR_UNSUPPORTED, "hphc is only defined for IMRPhenomHM");
+    if (n == 0) return GWF_OK;
+    EventsDev ev;
+    for (int i = 0; i < GWF_NPARAM_IN; ++i) ev.p[i] = events->p[i];
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    switch (model->id) {
+        case GWF_TAYLORF2: return run_waveform<kTaylorF2>(model, ev, n, f, res, f_is_2d, phi_out, ampl_out, tau_out, hphc_out, fcut_out, workspace, workspace_bytes, st);
+        case GWF_IMRPHENOMD: return run_waveform<kPhenomD>(model, ev, n, f, res, f_is_2d, phi_out, ampl_out, tau_out, hphc_out, fcut_out, workspace, workspace_bytes, st);
+        case GWF_IMRPHENOMD_NRTIDALV2:
+            if (!ev.p[11] || !ev.p[12]) return fail(GWF_ERR_ARG, "tidal model needs Lambda1, Lambda2");
+            return run_waveform<kNRTidalv2>(model, ev, n, f, res, f_is_2d, phi_out, ampl_out, tau_out, hphc_out, fcut_out, workspace, workspace_bytes, st);
+        case GWF_IMRPHENOMHM: return run_waveform<kPhenomHM>(model, ev, n, f, res, f_is_2d, phi_out, ampl_out, tau_out, hphc_out, fcut_out, workspace, workspace_bytes, st);
+        default: return fail(GWF_ERR_ARG, "unknown model");
+    }
 }
 
 }  // extern "C"

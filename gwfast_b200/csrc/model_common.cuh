@@ -38,6 +38,7 @@ struct ModelCfg {
 // plain per-event inputs as the events dict carries them
 struct EventIn {
     double Mc, eta, dL, theta, phi, iota, psi, tcoal, Phicoal, chi1z, chi2z, Lambda1, Lambda2;
+    double fcut_host, s_host;   // optional host-computed wf_model.fcut and M*GMsun_over_c3 (0 = compute on the device)
 };
 
 // intrinsic parameters seeded for differentiation.  Slots: 0,1 = (Mc,eta) or (m1,m2); 2,3 = (chi1z,chi2z) or

@@ -37,7 +37,7 @@ template <class T> GWF_HD T nrt_fmerger(const T& eta, const T& k2T) {           
 
 template <int NT>
 GWF_HD void nrtidal_prologue(NRTidalRec<NT>& r, const Intrinsic<NT>& p, double dL, const QnmTables& q, const double* fmin_g, int ngroups,
-                             const ModelCfg& cfg, bool lambda_for_fcut) {
+                             const ModelCfg& cfg, bool lambda_for_fcut, double s_host = 0.0, double fcut_host = 0.0) {
     typedef Dual<NT> D;
     const D qm1 = quad_mon(p.L1), qm2 = quad_mon(p.L2);            // waveforms.py:1394-1395
     PhenomDCore<NT> c;
@@ -45,7 +45,7 @@ GWF_HD void nrtidal_prologue(NRTidalRec<NT>& r, const Intrinsic<NT>& p, double d
     const D M = p.Mc / dpow(p.eta, 3. / 5.);
     ModelCfg cfg_cut = cfg;
     cfg_cut.flags &= ~kFlagNoFcut;                                 // the amplitude always applies the cut (waveforms.py:1673)
-    phenomd_fill(r.d, c, M, D(dL), fmin_g, ngroups, cfg);
+    phenomd_fill(r.d, c, M, D(dL), fmin_g, ngroups, cfg, s_host, 0.0);
     const D sq = seta_of(p.eta);
     const D m1 = 0.5 * (1.0 + sq), m2 = 0.5 * (1.0 - sq);
     const D k2T = nrt_kappa2T(p.eta, p.L1, p.L2);
@@ -58,7 +58,7 @@ GWF_HD void nrtidal_prologue(NRTidalRec<NT>& r, const Intrinsic<NT>& p, double d
     r.sm76 = sm13 * sm13 * sm13 * sqrt(sm13);
     // fcut uses whatever Lambda the events dict carried when fcut() ran (0 if absent: waveforms.py:1809-1812, SURVEY A-20)
     const double k2T_cut = lambda_for_fcut ? k2T.v : 0.0;
-    r.fcut_hz = 1.2 * nrt_fmerger(p.eta.v, k2T_cut) / r.d.s;
+    r.fcut_hz = fcut_host > 0.0 ? fcut_host : 1.2 * nrt_fmerger(p.eta.v, k2T_cut) / r.d.s;
     r.d.fcut_hz = r.fcut_hz;
     // 3.5PN spin-squared / spin-cubed terms, waveforms.py:1564-1568: (SS+SSS) * 3/(128 eta) * (pi x)^(2/3)
     const D c12 = p.chi1 * p.chi1, c22 = p.chi2 * p.chi2, m1s = m1 * m1, m2s = m2 * m2;

@@ -207,14 +207,15 @@ struct PhenomDCore {
 // fill the record from the core; xref[g] = dimensionless reference frequency of grid group g
 template <int NT>
 GWF_HD void phenomd_fill(PhenomDRec<NT>& r, const PhenomDCore<NT>& c, const Dual<NT>& M, const Dual<NT>& dL, const double* fmin_g, int ngroups,
-                         const ModelCfg& cfg) {
+                         const ModelCfg& cfg, double s_host = 0.0, double fcut_host = 0.0) {
     typedef Dual<NT> D;
-    const D s = M * kGMsunC3;
+    D s = M * kGMsunC3;
+    if (s_host > 0.0) s.v = s_host;       // the host's M*GMsun_over_c3: x = s f then rounds like the reference's fgrid
     r.s = s.v;
     r.sp.set(s.v);
 #pragma unroll
     for (int j = 0; j < NT; ++j) r.lam[j] = s.d[j] / s.v;
-    r.fcut_hz = kMfCut / s.v;                                 // waveforms.py:1333
+    r.fcut_hz = fcut_host > 0.0 ? fcut_host : kMfCut / s.v;   // waveforms.py:1333
     r.x_mrd = c.fMRDJoin.v;
     r.x_peak = c.fpeak_amp.v;
     // waveforms.py:1248, 1204, 1254
@@ -275,12 +276,12 @@ GWF_HD void phenomd_fill(PhenomDRec<NT>& r, const PhenomDCore<NT>& c, const Dual
 
 template <int NT>
 GWF_HD void phenomd_prologue(PhenomDRec<NT>& r, const Intrinsic<NT>& p, double dL, const QnmTables& q, const double* fmin_g, int ngroups,
-                             const ModelCfg& cfg) {
+                             const ModelCfg& cfg, double s_host = 0.0, double fcut_host = 0.0) {
     typedef Dual<NT> D;
     PhenomDCore<NT> c;
     c.build(p.eta, p.chi1, p.chi2, D(1.0), D(1.0), q);
     const D M = p.Mc / dpow(p.eta, 3. / 5.);
-    phenomd_fill(r, c, M, D(dL), fmin_g, ngroups, cfg);
+    phenomd_fill(r, c, M, D(dL), fmin_g, ngroups, cfg, s_host, fcut_host);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -240,16 +240,18 @@ struct HMWeights {
 
 // ------------------------------------------------------------------------------------------------ prologue
 template <int NT>
-GWF_HD void phenomhm_prologue(HMRec<NT>& r, const Intrinsic<NT>& p, double dL, const double* fmin_g, int ngroups, const ModelCfg& cfg) {
+GWF_HD void phenomhm_prologue(HMRec<NT>& r, const Intrinsic<NT>& p, double dL, const double* fmin_g, int ngroups, const ModelCfg& cfg,
+                              double s_host = 0.0, double fcut_host = 0.0) {
     typedef Dual<NT> D;
     const bool apply_cut = !(cfg.flags & kFlagNoFcut);
     const D eta = p.eta;
     const D M = p.Mc / dpow(eta, 3. / 5.);
-    const D s = M * kGMsunC3;
+    D s = M * kGMsunC3;
+    if (s_host > 0.0) s.v = s_host;       // the host's M*GMsun_over_c3: x = s f then rounds like the reference's fgrid
     r.s = s;
 #pragma unroll
     for (int j = 0; j < NT; ++j) r.lam[j] = s.d[j] / s.v;
-    r.fcut_hz = kMfCut / s.v;                                  // waveforms.py:2737-2749
+    r.fcut_hz = fcut_host > 0.0 ? fcut_host : kMfCut / s.v;    // waveforms.py:2737-2749
     r.eta = eta;
     r.seta = seta_of(eta);
     r.chis = 0.5 * (p.chi1 + p.chi2);
@@ -335,9 +337,10 @@ GWF_HD void phenomhm_prologue(HMRec<NT>& r, const Intrinsic<NT>& p, double dL, c
 }
 
 // ------------------------------------------------------------------------------------------------ per frequency
-// mode strains z_m = A_m exp(-i Phi_m) for the six modes; T = Dual<NT> (tangents w.r.t. the intrinsic slots) or double
+// amplitude A_lm and phase Phi_lm of the six modes (IMRPhenomHM.Ampl / .Phi, waveforms.py:1874-2254, as vectorised in hphc);
+// T = Dual<NT> (tangents w.r.t. the intrinsic slots) or double
 template <class T, int NT>
-GWF_HD void phenomhm_modes(const HMRec<NT>& r, int g, double f, bool apply_cut, T* zre, T* zim) {
+GWF_HD void phenomhm_amp_phase(const HMRec<NT>& r, int g, double f, bool apply_cut, T* amp, T* phase) {
     typedef Ld<T> L;
     const T x = L::get(r.s) * f;
     const double xv = val(x);
@@ -364,17 +367,28 @@ GWF_HD void phenomhm_modes(const HMRec<NT>& r, int g, double f, bool apply_cut, 
             const T ym76 = 1.0 / (y * dsqrt(y13));
             A = L::get(r.Camp) * ym76 * shape * (h1 * hS / h2);
         }
+        amp[m] = A;
         // phase, waveforms.py:2600-2607
         T ph;
         const T c1 = L::get(o.c1), c2 = L::get(o.c2), at_c = L::get(o.at_c), at_a = L::get(o.at_a), at_w = L::get(o.at_w);
         if (xv < o.fi_phi.v) ph = hm_complete_phase<T, NT>(r, x * ai, c1, c2, at_c, at_a, at_w, apply_cut) * (1.0 / ai);
         else if (xv < o.fr.v) ph = L::get(o.kB) + hm_complete_phase<T, NT>(r, x * L::get(o.am_phi) + L::get(o.bm_phi), c1, c2, at_c, at_a, at_w, apply_cut) / L::get(o.am_phi);
         else ph = L::get(o.kC) + hm_complete_phase<T, NT>(r, x * L::get(o.rho), c1, c2, at_c, at_a, at_w, apply_cut) / L::get(o.rho);
-        ph = ph - lin - mm * L::get(r.phi0[g]) + hm_shift((int)mm);
+        phase[m] = ph - lin - mm * L::get(r.phi0[g]) + hm_shift((int)mm);
+    }
+}
+
+// mode strains z_m = A_m exp(-i Phi_m)
+template <class T, int NT>
+GWF_HD void phenomhm_modes(const HMRec<NT>& r, int g, double f, bool apply_cut, T* zre, T* zim) {
+    T amp[kHMModes], ph[kHMModes];
+    phenomhm_amp_phase<T, NT>(r, g, f, apply_cut, amp, ph);
+#pragma unroll 1
+    for (int m = 0; m < kHMModes; ++m) {
         T sn, cs;
-        dsincos(ph, sn, cs);
-        zre[m] = A * cs;
-        zim[m] = -(A * sn);
+        dsincos(ph[m], sn, cs);
+        zre[m] = amp[m] * cs;
+        zim[m] = -(amp[m] * sn);
     }
 }
 

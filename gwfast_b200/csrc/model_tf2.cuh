@@ -53,7 +53,7 @@ GWF_HD double tf2_fcut_kerr(double Mc, double eta, double chi1, double chi2) {
 }
 
 template <int NT>
-GWF_HD void tf2_prologue(TF2Rec<NT>& r, const Intrinsic<NT>& p, double dL, const ModelCfg& cfg) {
+GWF_HD void tf2_prologue(TF2Rec<NT>& r, const Intrinsic<NT>& p, double dL, const ModelCfg& cfg, double fcut_host = 0.0) {
     typedef Dual<NT> D;
     const bool tidal = cfg.flags & kFlagTidal;
     const D M = p.Mc / dpow(p.eta, 3. / 5.);
@@ -62,7 +62,8 @@ GWF_HD void tf2_prologue(TF2Rec<NT>& r, const Intrinsic<NT>& p, double dL, const
     r.sp.set(s.v);
 #pragma unroll
     for (int j = 0; j < NT; ++j) r.lam[j] = s.d[j] / s.v;
-    r.fcut_hz = (cfg.flags & kFlagKerrISCO) ? tf2_fcut_kerr(p.Mc.v, p.eta.v, p.chi1.v, p.chi2.v) : cfg.fcutPar / M.v;   // waveforms.py:918-953
+    r.fcut_hz = fcut_host > 0.0 ? fcut_host
+                                : ((cfg.flags & kFlagKerrISCO) ? tf2_fcut_kerr(p.Mc.v, p.eta.v, p.chi1.v, p.chi2.v) : cfg.fcutPar / M.v);   // waveforms.py:918-953
     // amplitude, waveforms.py:875
     const D Cc = sqrt(5. / 24.) * pow(kPi, -2. / 3.) * kClightGpc / dL * dpow(kGMsunC3 * p.Mc, 5. / 6.);
     r.C = Cc.v;

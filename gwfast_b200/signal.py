@@ -7,6 +7,7 @@ duty-cycle masks drawn from numpy's global RNG, ``return_all`` shapes.
 import numpy as onp
 
 from . import gwfastUtils as utils
+from . import gwfastGlobals as glob
 from . import _capi as K
 from . import _engine
 
@@ -27,12 +28,25 @@ def _num_events(evParams):
     return len(onp.atleast_1d(evParams['Mc']))
 
 
-def _engine_events(wf_model, evParams, lambdas=None):
-    """the arrays the engine consumes (never mutates the caller's dict)."""
+def _engine_events(wf_model, evParams, lambdas=None, use_m1m2=False):
+    """the arrays the engine consumes (never mutates the caller's dict).
+
+    Besides the dict entries this passes two per-event scalars computed HERE with the reference's own numpy expressions:
+    ``wf_model.fcut(**evParams)`` (signal.py:715, 884) and ``M*GMsun_over_c3`` (waveforms.py:1026).  With them the last
+    grid sample lands on ``Mf = fcutPar`` with the reference's rounding, which decides whether it is inside the waveform
+    cut -- a 1e-9 effect on the IMRPhenomHM SNR (the (2,2) mode switches off while the higher modes are still on).
+    """
     ev = {k: evParams[k] for k in K.EVENT_KEYS[:11]}
     if wf_model.is_tidal:
         L1, L2 = lambdas if lambdas is not None else (evParams['Lambda1'], evParams['Lambda2'])
         ev['Lambda1'], ev['Lambda2'] = L1, L2
+    if not (wf_model._model_id == K.GWF_TAYLORF2 and wf_model.which_ISCO == 'Kerr'):
+        ev['_fcut'] = wf_model.fcut(**evParams)
+    if wf_model._model_id != K.GWF_TAYLORF2:
+        Mc, eta = evParams['Mc'], evParams['eta']
+        if use_m1m2:
+            Mc, eta = utils.Mceta_from_m1m2(*utils.m1m2_from_Mceta(Mc, eta))      # GWstrain's round trip, signal.py:522-524
+        ev['_Mtot_sec'] = (Mc / (eta ** (3. / 5.))) * glob.GMsun_over_c3
     return ev
 
 
@@ -71,7 +85,7 @@ def hot_fisher(signals, evParams, lambdas, res, spacing, use_m1m2, use_chi1chi2,
     for s in signals:
         dets.append(s._detector_struct(len(handles)))
         handles.append(s._psd_handle())
-    F, snr2, io = _engine.fisher(wf._descriptor(evParams), dets, handles, _engine_events(wf, evParams, lambdas), n, res, flags, per_arm)
+    F, snr2, io = _engine.fisher(wf._descriptor(evParams), dets, handles, _engine_events(wf, evParams, lambdas, use_m1m2), n, res, flags, per_arm)
     return F, snr2, io
 
 

@@ -69,8 +69,12 @@ void gwf_psd_destroy(gwf_psd* psd);
 int gwf_set_qnm_tables(const double* a_host, const double* fring_host, const double* fdamp_host, int32_t n);
 
 /* the events dict as device SoA; order of p[]:
- * Mc eta dL theta phi iota psi tcoal Phicoal chi1z chi2z Lambda1 Lambda2 (p[11], p[12] may be NULL for BBH) */
-#define GWF_NPARAM_IN 13
+ * Mc eta dL theta phi iota psi tcoal Phicoal chi1z chi2z Lambda1 Lambda2 fcut Mtot_sec
+ * p[11], p[12] may be NULL for BBH.  p[13] (wf_model.fcut(**events) in Hz, signal.py:715/884) and p[14]
+ * (M*GMsun_over_c3 in seconds, waveforms.py:1026) are optional: when the host passes the values it computed with the
+ * reference's own expressions, the last grid sample lands on Mf = fcutPar with the reference's rounding, which decides
+ * whether that sample is inside the waveform cut (waveforms.py:1145-1147); when NULL both are computed on the device. */
+#define GWF_NPARAM_IN 15
 typedef struct {
     const double* p[GWF_NPARAM_IN];
 } gwf_events;
@@ -118,10 +122,14 @@ int gwf_snr(const gwf_model* model, const gwf_detector* dets, int32_t ndet, cons
 /* packed lower triangle [n][nP(nP+1)/2] -> the reference's (nP, nP, N) layout, event axis fastest (signal.py:924) */
 int gwf_unpack_fisher(const double* packed, int64_t n, int32_t nP, double* full, void* stream);
 
-/* Replaces WaveFormModel.Phi / Ampl / tau_star / fcut evaluated on a user grid (waveforms.py:149-199).
- *   f: [res][n] if f_is_2d else [res]; outputs [res][n] (any may be NULL); fcut_out: [n] */
+/* Replaces WaveFormModel.Phi / Ampl / tau_star / fcut (and IMRPhenomHM.hphc) evaluated on a user grid (waveforms.py:149-199,
+ * 2256-2616), with the dict entries handed straight to the waveform (no Fisher re-parametrisation).
+ *   f:        [res][n] if f_is_2d else [res] (shared by all events); the PhenomD-family reference frequency is min_k f (waveforms.py:1139)
+ *   phi_out:  [nm][res][n], ampl_out: [nm][res][n] with nm = 1, or 6 for IMRPhenomHM in the order 21, 22, 32, 33, 43, 44 (waveforms.py:2075)
+ *   tau_out:  [res][n];  hphc_out: [4][res][n] = Re hp, Im hp, Re hc, Im hc (IMRPhenomHM only);  fcut_out: [n]
+ * Any output may be NULL; res may be 0 (f NULL) if only fcut_out is wanted. */
 int gwf_waveform(const gwf_model* model, const gwf_events* events, int64_t n, const double* f, int32_t res, int32_t f_is_2d,
-                 double* phi_out, double* ampl_out, double* tau_out, double* fcut_out,
+                 double* phi_out, double* ampl_out, double* tau_out, double* hphc_out, double* fcut_out,
                  void* workspace, size_t workspace_bytes, void* stream);
 
 /* Diagnostics (no reference counterpart): sustained FP64 FMA throughput of the current device in TFLOP/s, measured with a

@@ -203,7 +203,35 @@ def fx_gw170817():
     save('gw170817', dict(model=dict(cls='IMRPhenomD_NRTidalv2'), detectors=list(files), rot=False, fmin=10.), ev, out, extra)
 
 
-ALL = {'init': fx_init, 'c1': fx_c1, 'c1b': fx_c1b, 'c2': fx_c2, 'var': fx_variants, 'c3': fx_c3, 'c4': fx_c4, 'gw170817': fx_gw170817}
+def fx_wfvalues():
+    """WaveFormModel.Phi / Ampl / tau_star / fcut (+ IMRPhenomHM.hphc) of the reference on a per-event grid."""
+    wf, sig, net, utils, glob = reference.load()
+    out = {}
+    evs = {}
+    for cls, cat in (('TaylorF2_RestrictedPN', synthetic.bbh_catalog(5, 31)), ('IMRPhenomD', synthetic.bbh_catalog(5, 32)),
+                     ('IMRPhenomD_NRTidalv2', synthetic.bns_catalog(5, 33, tidal=True)), ('IMRPhenomHM', synthetic.bbh_catalog(5, 34))):
+        m = getattr(wf, cls)()
+        fg = np.geomspace(np.full(5, 5.), 0.97 * m.fcut(**cat), 160)
+        out[cls + '__f'] = fg
+        out[cls + '__fcut'] = m.fcut(**cat)
+        out[cls + '__tau'] = m.tau_star(fg, **cat)
+        P, A = m.Phi(fg, **cat), m.Ampl(fg, **cat)
+        if cls == 'IMRPhenomHM':
+            for k in P:
+                out[cls + '__phi' + k], out[cls + '__ampl' + k] = P[k], A[k]
+            hp, hc = m.hphc(fg, **cat)
+            out[cls + '__hp'], out[cls + '__hc'] = hp, hc
+        else:
+            out[cls + '__phi'], out[cls + '__ampl'] = P, A
+        # 1-D grid with scalar parameters (first event)
+        one = {k: v[0] for k, v in cat.items()}
+        out[cls + '__phi1d'] = np.asarray(m.Phi(fg[:, 0], **one)['22'] if cls == 'IMRPhenomHM' else m.Phi(fg[:, 0], **one))
+        for k, v in cat.items():
+            evs[cls + '__' + k] = v
+    save('wf_values', dict(note='per-model events stored as ev__<cls>__<key>'), evs, out)
+
+
+ALL = {'init': fx_init, 'c1': fx_c1, 'c1b': fx_c1b, 'c2': fx_c2, 'var': fx_variants, 'c3': fx_c3, 'c4': fx_c4, 'gw170817': fx_gw170817, 'wf': fx_wfvalues}
 
 if __name__ == '__main__':
     warnings.filterwarnings('ignore')

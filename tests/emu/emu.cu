@@ -36,6 +36,7 @@ static int emu_run(const gwf_model* model, const gwf_detector* dets, int ndet, c
             in.Mc = ev[0][e]; in.eta = ev[1][e]; in.dL = ev[2][e]; in.theta = ev[3][e]; in.phi = ev[4][e]; in.iota = ev[5][e];
             in.psi = ev[6][e]; in.tcoal = ev[7][e]; in.Phicoal = ev[8][e]; in.chi1z = ev[9][e]; in.chi2z = ev[10][e];
             in.Lambda1 = ev[11] ? ev[11][e] : 0.; in.Lambda2 = ev[12] ? ev[12][e] : 0.;
+            in.fcut_host = ev[13] ? ev[13][e] : 0.; in.s_host = ev[14] ? ev[14][e] : 0.;
             Rec rec;
             ModelTraits<MODEL, NT>::prologue(rec, in, cfg, opts->flags, g_q, net.group_fmin, net.ngroups);
             EvGeom geom;
@@ -82,6 +83,7 @@ static int emu_run_snr(const gwf_model* model, const gwf_detector* dets, int nde
         in.Mc = ev[0][e]; in.eta = ev[1][e]; in.dL = ev[2][e]; in.theta = ev[3][e]; in.phi = ev[4][e]; in.iota = ev[5][e];
         in.psi = ev[6][e]; in.tcoal = ev[7][e]; in.Phicoal = ev[8][e]; in.chi1z = ev[9][e]; in.chi2z = ev[10][e];
         in.Lambda1 = ev[11] ? ev[11][e] : 0.; in.Lambda2 = ev[12] ? ev[12][e] : 0.;
+            in.fcut_host = ev[13] ? ev[13][e] : 0.; in.s_host = ev[14] ? ev[14][e] : 0.;
         Rec rec;
         ModelTraits<MODEL, 4>::prologue(rec, in, cfg, 0, g_q, net.group_fmin, net.ngroups);
         EvGeom geom;
@@ -110,7 +112,70 @@ static int emu_run_snr(const gwf_model* model, const gwf_detector* dets, int nde
     return 0;
 }
 
+template <int MODEL>
+static int emu_run_waveform(const gwf_model* model, const double* const* ev, long long n, const double* f, int res, int f2d, double* phi, double* ampl,
+                            double* tau, double* hphc, double* fcut) {
+    typedef typename ModelTraits<MODEL, 4>::Rec Rec;
+    typedef WaveformFns<MODEL> WF;
+    ModelCfg cfg = {model->id, model->flags, model->fcutPar, model->fRef};
+    const long long plane = (long long)res * n;
+    for (long long e = 0; e < n; ++e) {
+        EventIn in;
+        in.Mc = ev[0][e]; in.eta = ev[1][e]; in.dL = ev[2][e]; in.theta = ev[3][e]; in.phi = ev[4][e]; in.iota = ev[5][e];
+        in.psi = ev[6][e]; in.tcoal = ev[7][e]; in.Phicoal = ev[8][e]; in.chi1z = ev[9][e]; in.chi2z = ev[10][e];
+        in.Lambda1 = ev[11] ? ev[11][e] : 0.; in.Lambda2 = ev[12] ? ev[12][e] : 0.;
+            in.fcut_host = ev[13] ? ev[13][e] : 0.; in.s_host = ev[14] ? ev[14][e] : 0.;
+        double fm = 1.0;
+        if (res > 0) {
+            fm = f2d ? f[e] : f[0];
+            for (int k = 1; k < res; ++k) fm = std::min(fm, f2d ? f[(long long)k * n + e] : f[k]);
+        }
+        double fmin_g[kMaxGroups] = {fm, fm, fm, fm};
+        Rec rec;
+        ModelTraits<MODEL, 4>::prologue(rec, in, cfg, 0, g_q, fmin_g, 1);
+        HMWeights w;
+        w.set(in.iota);
+        if (fcut) fcut[e] = rec.fcut_hz;
+        for (int k = 0; k < res; ++k) {
+            FreqPoint fp;
+            fp.from_f(f2d ? f[(long long)k * n + e] : f[k]);
+            fp.w = 0.;
+            WaveformOut o;
+            WF::eval(rec, cfg, w, fp, o);
+            const long long at = (long long)k * n + e;
+            for (int m = 0; m < WF::kModes; ++m) {
+                if (phi) phi[m * plane + at] = o.phi[m];
+                if (ampl) ampl[m * plane + at] = o.amp[m];
+            }
+            if (tau) tau[at] = o.tau;
+            if (hphc && MODEL == kPhenomHM) { hphc[at] = o.hp[0]; hphc[plane + at] = o.hp[1]; hphc[2 * plane + at] = o.hc[0]; hphc[3 * plane + at] = o.hc[1]; }
+        }
+    }
+    return 0;
+}
+
 extern "C" {
+
+int emu_psd_lookup(const double* psd_f, const double* psd_S, int n, const double* f, int nf, double* out) {
+    EmuPsd P;
+    int rc = build_psd_tables(psd_f, psd_S, n, P.tab, P.bucket, P.dev);
+    if (rc) return rc;
+    P.dev.tab = P.tab.data();
+    P.dev.bucket = P.bucket.data();
+    for (int i = 0; i < nf; ++i) out[i] = psd_lookup(P.dev, f[i], std::log(f[i]) * 1.4426950408889634073599246810018921);
+    return 0;
+}
+
+int emu_waveform(const gwf_model* model, const double* const* ev, long long n, const double* f, int res, int f2d, double* phi, double* ampl, double* tau,
+                 double* hphc, double* fcut) {
+    switch (model->id) {
+        case GWF_TAYLORF2: return emu_run_waveform<kTaylorF2>(model, ev, n, f, res, f2d, phi, ampl, tau, hphc, fcut);
+        case GWF_IMRPHENOMD: return emu_run_waveform<kPhenomD>(model, ev, n, f, res, f2d, phi, ampl, tau, hphc, fcut);
+        case GWF_IMRPHENOMD_NRTIDALV2: return emu_run_waveform<kNRTidalv2>(model, ev, n, f, res, f2d, phi, ampl, tau, hphc, fcut);
+        case GWF_IMRPHENOMHM: return emu_run_waveform<kPhenomHM>(model, ev, n, f, res, f2d, phi, ampl, tau, hphc, fcut);
+    }
+    return -2;
+}
 
 int gwf_num_arms(const gwf_detector* dets, int32_t ndet) {
     int n = 0;

@@ -39,7 +39,7 @@ def run(model, dets, psds, ev, res=1000, flags=0, per_arm=False, snr_mode=False)
     n = len(ev['Mc'])
     dp = C.POINTER(C.c_double)
     arrs = [np.ascontiguousarray(ev[k], dtype=float) if k in ev else None for k in K.EVENT_KEYS]
-    evp = (dp * 13)(*[a.ctypes.data_as(dp) if a is not None else None for a in arrs])
+    evp = (dp * K.GWF_NPARAM_IN)(*[a.ctypes.data_as(dp) if a is not None else None for a in arrs])
     pf = [np.ascontiguousarray(p[0], dtype=float) for p in psds]
     pS = [np.ascontiguousarray(p[1], dtype=float) for p in psds]
     pfp = (dp * len(psds))(*[a.ctypes.data_as(dp) for a in pf])
@@ -72,3 +72,27 @@ def unpack(packed, nP):
         for j in range(i + 1):
             F[..., i, j, :] = F[..., j, i, :] = packed[..., i * (i + 1) // 2 + j]
     return F
+
+
+def waveform(model, ev, f, want=('phi', 'ampl', 'tau')):
+    """CPU emulation of gwf_waveform: f (res,) or (res, n); returns dict of arrays [nm, res, n] / [res, n] / hphc complex."""
+    L = lib()
+    n = len(ev['Mc'])
+    dp = C.POINTER(C.c_double)
+    arrs = [np.ascontiguousarray(ev[k], dtype=float) if k in ev else None for k in K.EVENT_KEYS]
+    evp = (dp * K.GWF_NPARAM_IN)(*[a.ctypes.data_as(dp) if a is not None else None for a in arrs])
+    f = np.ascontiguousarray(f, dtype=float)
+    res = f.shape[0]
+    nm = 6 if model.id == 3 else 1
+    out = {k: np.zeros((nm, res, n)) for k in ('phi', 'ampl') if k in want}
+    if 'tau' in want:
+        out['tau'] = np.zeros((res, n))
+    if 'hphc' in want:
+        out['hphc'] = np.zeros((4, res, n))
+    out['fcut'] = np.zeros(n)
+    ptr = lambda k: out[k].ctypes.data_as(dp) if k in out else None
+    rc = L.emu_waveform(C.byref(model), evp, C.c_longlong(n), f.ctypes.data_as(dp), res, int(f.ndim == 2), ptr('phi'), ptr('ampl'), ptr('tau'),
+                        ptr('hphc'), ptr('fcut'))
+    if rc != 0:
+        raise RuntimeError('emu_waveform failed %d' % rc)
+    return out

@@ -37,10 +37,11 @@ def test_emulated_device_math_matches_reference(name):
     flags = (K.GWF_OPT_M1M2 if fkw.get('use_m1m2') else 0) | (0 if fkw.get('use_chi1chi2', True) else K.GWF_OPT_CHIS_CHIA) | \
             (K.GWF_OPT_LIN_GRID if fkw.get('spacing') == 'lin' else 0)
     res = cfg.get('res', 1000)
-    packed, s2 = E.run(model._descriptor(sub), dets, psds, sub, res=res, flags=flags)
+    from gwfast_b200 import signal
+    packed, s2 = E.run(model._descriptor(sub), dets, psds, signal._engine_events(model, sub, None, bool(fkw.get('use_m1m2'))), res=res, flags=flags)
     F = E.unpack(packed, model.nParams)[0]
     assert fisher_err(F, out['fisher'][..., :n]) < FISHER_TOL
-    arms, _ = E.run(model._descriptor(sub), dets, psds, sub, res=res, snr_mode=True)
+    arms, _ = E.run(model._descriptor(sub), dets, psds, signal._engine_events(model, sub), res=res, snr_mode=True)
     assert snr_err(np.sqrt(arms.sum(axis=0)), out['snr'][:n]) < SNR_RTOL
     # tighter than the gate: what the formulation actually achieves
     assert fisher_err(F, out['fisher'][..., :n]) < 5e-9
@@ -52,6 +53,8 @@ def test_emulated_nrtidal_matches_masked_reference():
     import emu_driver as E
     cfg, ev, out = load_golden('c3_nrtidal_et2ce')
     model, dets, psds = _emu_inputs(cfg)
+    from gwfast_b200 import signal
+    ev = signal._engine_events(model, ev)
     packed, _ = E.run(model._descriptor(ev), dets, psds, ev)
     F = E.unpack(packed, 13)[0]
     arms, _ = E.run(model._descriptor(ev), dets, psds, ev, snr_mode=True)
@@ -67,6 +70,8 @@ def test_emulated_phenomhm_matches_reference(name):
     import emu_driver as E
     cfg, ev, out = load_golden(name)
     model, dets, psds = _emu_inputs(cfg)
+    from gwfast_b200 import signal
+    ev = signal._engine_events(model, ev)
     packed, _ = E.run(model._descriptor(ev), dets, psds, ev)
     F = E.unpack(packed, 11)[0]
     arms, _ = E.run(model._descriptor(ev), dets, psds, ev, snr_mode=True)
@@ -75,3 +80,38 @@ def test_emulated_phenomhm_matches_reference(name):
     # the HM SNR is NOT (h|h)^(1/2): F[dL,dL] dL^2 / SNR^2 deviates from 1 at the 1e-3 level by design
     r = F[2, 2] * ev['dL'] ** 2 / out['snr'] ** 2
     assert np.all(np.abs(r - 1) < 0.05) and np.any(np.abs(r - 1) > 1e-6)
+
+
+def test_emulated_waveform_values_match_reference(has_reference):
+    """WaveFormModel.Phi / Ampl / tau_star (+ IMRPhenomHM.hphc) on a user grid against the reference's own methods (container only).
+    The very last sample (Mf == fcutPar up to rounding) is excluded: the reference itself returns 0 or the MRD value there
+    depending on the last bit of M*GMsun_over_c3*f."""
+    if not has_reference:
+        pytest.skip('reference tree not mounted')
+    import warnings
+    warnings.filterwarnings('ignore')
+    import emu_driver as E
+    from oracle import reference
+    from gwfast_b200 import waveforms as W, synthetic
+    wf, sig, net, utils, glob = reference.load()
+    for cls, cat in (('TaylorF2_RestrictedPN', synthetic.bbh_catalog(6, 3)), ('IMRPhenomD', synthetic.bbh_catalog(6, 3)),
+                     ('IMRPhenomD_NRTidalv2', synthetic.bns_catalog(6, 3, tidal=True)), ('IMRPhenomHM', synthetic.bbh_catalog(6, 3))):
+        rm, m = getattr(wf, cls)(), getattr(W, cls)()
+        fg = np.geomspace(np.full(6, 5.), 0.97 * rm.fcut(**cat), 200)
+        ev = dict(cat)
+        if cls != 'TaylorF2_RestrictedPN':
+            ev['_Mtot_sec'] = (cat['Mc'] / (cat['eta'] ** (3. / 5.))) * glob.GMsun_over_c3
+        out = E.waveform(m._descriptor(cat), ev, fg, want=('phi', 'ampl', 'tau') + (('hphc',) if cls == 'IMRPhenomHM' else ()))
+        P, A, T = rm.Phi(fg, **cat), rm.Ampl(fg, **cat), rm.tau_star(fg, **cat)
+        assert np.max(np.abs(out['tau'] / T - 1)) < 1e-9
+        assert np.max(np.abs(out['fcut'] / rm.fcut(**cat) - 1)) < 1e-14
+        if cls == 'IMRPhenomHM':
+            for i, k in enumerate(('21', '22', '32', '33', '43', '44')):
+                assert np.max(np.abs(out['phi'][i] - P[k])) < 1e-8, k
+                assert np.max(np.abs(out['ampl'][i] - A[k]) / np.max(np.abs(A[k]), axis=0)) < 1e-11, k
+            hp, hc = rm.hphc(fg, **cat)
+            assert np.max(np.abs(out['hphc'][0] + 1j * out['hphc'][1] - hp) / np.max(np.abs(hp), axis=0)) < 1e-10
+            assert np.max(np.abs(out['hphc'][2] + 1j * out['hphc'][3] - hc) / np.max(np.abs(hc), axis=0)) < 1e-10
+        else:
+            assert np.max(np.abs(out['phi'][0] - P)) < 1e-8, cls
+            assert np.max(np.abs(out['ampl'][0] - A) / np.max(np.abs(A), axis=0)) < 1e-11, cls

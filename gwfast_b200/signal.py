@@ -40,9 +40,9 @@ def _engine_events(wf_model, evParams, lambdas=None, use_m1m2=False):
     if wf_model.is_tidal:
         L1, L2 = lambdas if lambdas is not None else (evParams['Lambda1'], evParams['Lambda2'])
         ev['Lambda1'], ev['Lambda2'] = L1, L2
-    if not (wf_model._model_id == K.GWF_TAYLORF2 and wf_model.which_ISCO == 'Kerr'):
+    if wf_model.is_HigherModes:
+        # only IMRPhenomHM needs it at the 1e-9 level (3e-12 for IMRPhenomD); two numpy pow() per event on the host
         ev['_fcut'] = wf_model.fcut(**evParams)
-    if wf_model._model_id != K.GWF_TAYLORF2:
         Mc, eta = evParams['Mc'], evParams['eta']
         if use_m1m2:
             Mc, eta = utils.Mceta_from_m1m2(*utils.m1m2_from_Mceta(Mc, eta))      # GWstrain's round trip, signal.py:522-524

@@ -196,8 +196,16 @@ GWF_HD void scratch_set(EventScratch& s, const NetworkDev& net, const EvGeom& ge
 // acc: packed lower-triangular Fisher (NP(NP+1)/2), snr2: sum of 4 w |h|^2 / Sn over the arms of the pass
 template <int MODEL, int NT>
 GWF_HD void amp_phase_point(const typename ModelTraits<MODEL, NT>::Rec& rec, const ModelCfg& cfg, const EvGeom& geom, const NetworkDev& net,
-                         const EventScratch& sc, int g, bool group_rot, const FreqPoint& fp, double* __restrict__ acc, double& snr2) {
+                         const EventScratch& sc, int g, bool group_rot, const FreqPoint& fp, double* __restrict__ acc) {
     const double f = fp.f, l2f = fp.lnf * 1.4426950408889634073599246810018921;   // log2 f
+    // PSD rows of the first detectors are requested before the waveform is evaluated: the dependent loads
+    // (bucket -> row) then overlap with the waveform arithmetic instead of stalling the detector loop
+    constexpr int kPre = 4;
+    double sn_pre[kPre];
+#pragma unroll
+    for (int di = 0; di < kPre; ++di)
+        sn_pre[di] = (di < net.ndet && net.det[di].group == g && net.det[di].arm_begin != net.det[di].arm_end)
+                         ? psd_lookup(net.psd[net.det[di].psd], f, l2f) : 1.0;
     PointWf<NT> w;
     ModelTraits<MODEL, NT>::eval(rec, cfg, g, fp, group_rot, w);
     w.f = f;
@@ -209,14 +217,14 @@ GWF_HD void amp_phase_point(const typename ModelTraits<MODEL, NT>::Rec& rec, con
     for (int di = 0; di < net.ndet; ++di) {
         const DetDev& d = net.det[di];
         if (d.group != g || d.arm_begin == d.arm_end) continue;
-        const double Sn = psd_lookup(net.psd[d.psd], f, l2f);
+        const double Sn = di == 0 ? sn_pre[0] : (di == 1 ? sn_pre[1] : (di == 2 ? sn_pre[2] : (di == 3 ? sn_pre[3] : psd_lookup(net.psd[d.psd], f, l2f))));
         DetPoint dp;
         if (d.use_rot) det_point(sc.ed[di], cBr, sBr, dp);
         else dp = sc.fixed[di];
         DetRows<NT> dr;
         dr.set(w, dp, d.use_rot != 0, d.no_motion != 0);
         const double wgt = wA2 / Sn;
-        for (int ai = d.arm_begin; ai < d.arm_end; ++ai) arm_rows_accumulate<NT>(w, dp, dr, net.arm[ai], geom, wgt, acc, snr2);
+        for (int ai = d.arm_begin; ai < d.arm_end; ++ai) arm_rows_accumulate<NT>(w, dp, dr, net.arm[ai], geom, wgt, acc);
     }
 }
 
@@ -260,9 +268,10 @@ struct HMExtra {
 
 template <int NT>
 GWF_HD void hm_point(const HMRec<NT>& rec, const ModelCfg& cfg, const EvGeom& geom, const NetworkDev& net, const EventScratch& sc,
-                     const HMExtra& ex, int g, bool group_rot, const FreqPoint& fp, double* __restrict__ acc, double& snr2) {
+                     const HMExtra& ex, int g, bool group_rot, const FreqPoint& fp, double* __restrict__ acc) {
     typedef Dual<NT> D;
     constexpr int NP = NT + 7;
+    double& snr2 = acc[NP * (NP + 1) / 2];
     const double f = fp.f, l2f = fp.lnf * 1.4426950408889634073599246810018921;
     const bool cut = !(cfg.flags & kFlagNoFcut);
     D zre[kHMModes], zim[kHMModes];
@@ -399,14 +408,18 @@ template <int NT> struct ModelTraits<kPhenomHM, NT> {
     }
 };
 
-// uniform entry points used by the kernels and the emulation harness
+// uniform entry points used by the kernels and the emulation harness.  kAcc = number of per-lane accumulators; after the
+// reduction entry(p) rebuilds packed Fisher element p (row-major lower triangle) and snr2() the SNR^2 of the pass.
 template <int MODEL, int NT> struct PointFns {
     typedef NoExtra Extra;
     typedef typename ModelTraits<MODEL, NT>::Rec Rec;
+    static constexpr int kAcc = Compact<NT>::kAcc;
     static GWF_HD void fisher(const Rec& rec, const ModelCfg& cfg, const EvGeom& geom, const NetworkDev& net, const EventScratch& sc, const Extra&, int g,
-                              bool rot, const FreqPoint& fp, double* __restrict__ acc, double& snr2) {
-        amp_phase_point<MODEL, NT>(rec, cfg, geom, net, sc, g, rot, fp, acc, snr2);
+                              bool rot, const FreqPoint& fp, double* __restrict__ acc) {
+        amp_phase_point<MODEL, NT>(rec, cfg, geom, net, sc, g, rot, fp, acc);
     }
+    static GWF_HD double entry(int i, int j, const double* __restrict__ red, const EvGeom& geom) { return compact_entry<NT>(i, j, red, geom); }
+    static GWF_HD double snr2(const double* __restrict__ red, const EvGeom& geom) { return compact_snr2<NT>(red, geom); }
     static GWF_HD void snr(const Rec& rec, const ModelCfg& cfg, const EvGeom& geom, const NetworkDev& net, const EventScratch& sc, const Extra&, int g,
                            bool rot, const FreqPoint& fp, double* __restrict__ s2) {
         amp_phase_snr_point<MODEL>(rec, cfg, geom, net, sc, g, rot, fp, s2);
@@ -415,10 +428,13 @@ template <int MODEL, int NT> struct PointFns {
 template <int NT> struct PointFns<kPhenomHM, NT> {
     typedef HMExtra Extra;
     typedef HMRec<NT> Rec;
+    static constexpr int kAcc = (NT + 7) * (NT + 8) / 2 + 1;
     static GWF_HD void fisher(const Rec& rec, const ModelCfg& cfg, const EvGeom& geom, const NetworkDev& net, const EventScratch& sc, const Extra& ex, int g,
-                              bool rot, const FreqPoint& fp, double* __restrict__ acc, double& snr2) {
-        hm_point<NT>(rec, cfg, geom, net, sc, ex, g, rot, fp, acc, snr2);
+                              bool rot, const FreqPoint& fp, double* __restrict__ acc) {
+        hm_point<NT>(rec, cfg, geom, net, sc, ex, g, rot, fp, acc);
     }
+    static GWF_HD double entry(int i, int j, const double* __restrict__ red, const EvGeom&) { return red[tri(i, j)]; }
+    static GWF_HD double snr2(const double* __restrict__ red, const EvGeom&) { return red[(NT + 7) * (NT + 8) / 2]; }
     static GWF_HD void snr(const Rec& rec, const ModelCfg& cfg, const EvGeom& geom, const NetworkDev& net, const EventScratch& sc, const Extra& ex, int g,
                            bool rot, const FreqPoint& fp, double* __restrict__ s2) {
         hm_snr_point(rec, cfg, geom, net, sc, ex, g, rot, fp, s2);

@@ -43,7 +43,13 @@ __device__ __forceinline__ EventIn load_event(const EventsDev& ev, long long e) 
     return in;
 }
 
-constexpr int kFisherThreads = 256;
+#ifndef GWF_FISHER_THREADS
+#define GWF_FISHER_THREADS 256
+#endif
+#ifndef GWF_FISHER_MINBLOCKS
+#define GWF_FISHER_MINBLOCKS 1
+#endif
+constexpr int kFisherThreads = GWF_FISHER_THREADS;
 constexpr int kWarpsPerCta = kFisherThreads / 32;
 
 struct GroupInfo {
@@ -174,6 +180,7 @@ template <int L> struct Fold {
 template <class Rec, class Extra> struct WarpSmem {
     Rec rec;
     EventScratch sc;
+    EvGeom geom;       // per-event sky/orientation constants: read by broadcast instead of living in 30 registers
     Extra ex;
 };
 
@@ -188,11 +195,12 @@ __device__ __forceinline__ void stage_event(WarpSmem<Rec, Extra>* mine, const Re
     for (int i = lane; i < kRecDoubles; i += 32) dst[i] = __ldg(src + i);
     if (lane < net.ndet) scratch_set(mine->sc, net, geom, lane);
     if (lane == 31) mine->ex.set(in);
+    if (lane == 30) mine->geom = geom;
     __syncwarp();
 }
 
 template <int MODEL, int NT>
-__global__ void __launch_bounds__(kFisherThreads, 1)
+__global__ void __launch_bounds__(kFisherThreads, GWF_FISHER_MINBLOCKS)
 fisher_kernel(const typename ModelTraits<MODEL, NT>::Rec* __restrict__ recs, EventsDev ev, long long n, int res, int lin, ModelCfg cfg,
               const __grid_constant__ NetworkDev net, double* __restrict__ out, double* __restrict__ snr2_out) {
     typedef typename ModelTraits<MODEL, NT>::Rec Rec;
@@ -205,13 +213,16 @@ fisher_kernel(const typename ModelTraits<MODEL, NT>::Rec* __restrict__ recs, Eve
     const Rec& rec = mine->rec;
     const long long nwarps = (long long)gridDim.x * kWarpsPerCta;
     for (long long e = (long long)blockIdx.x * kWarpsPerCta + wid; e < n; e += nwarps) {
-        EvGeom geom;
-        const EventIn in = load_event(ev, e);
-        geom.set(in);
-        stage_event(mine, recs, e, net, geom, in, lane);
-        double acc[NPACK + 1];                 // packed Fisher, then the SNR^2 accumulator
+        {
+            EvGeom g0;
+            const EventIn in = load_event(ev, e);
+            g0.set(in);
+            stage_event(mine, recs, e, net, g0, in, lane);
+        }
+        const EvGeom& geom = mine->geom;
+        double acc[PF::kAcc];
 #pragma unroll
-        for (int p = 0; p <= NPACK; ++p) acc[p] = 0.0;
+        for (int p = 0; p < PF::kAcc; ++p) acc[p] = 0.0;
         for (int g = 0; g < net.ngroups; ++g) {
             double fcut = rec.fcut_hz;
             if (net.group_fmax[g] > 0.0 && fcut > net.group_fmax[g]) fcut = net.group_fmax[g];   // signal.py:717-718
@@ -222,18 +233,29 @@ fisher_kernel(const typename ModelTraits<MODEL, NT>::Rec* __restrict__ recs, Eve
             if (lane < res) grid.start(lane, fp);
             for (int k = lane; k < res; k += 32) {
                 if (k != lane) grid.advance(k, fp);
-                PF::fisher(rec, cfg, geom, net, mine->sc, mine->ex, g, rot, fp, acc, acc[NPACK]);
+                PF::fisher(rec, cfg, geom, net, mine->sc, mine->ex, g, rot, fp, acc);
             }
         }
-        typedef Fold<NPACK + 1> F;
+        // warp reduction by recursive halving; the reduced accumulators land in shared memory (the record is no longer
+        // needed), from where every lane rebuilds its share of the packed Fisher matrix: coalesced stores
+        typedef Fold<PF::kAcc> F;
+        static_assert(sizeof(Rec) >= sizeof(double) * PF::kAcc, "record too small to hold the reduced accumulators");
         F::run(acc, lane);
-        double* o = out + e * NPACK;
+        double* red = reinterpret_cast<double*>(&mine->rec);
+        __syncwarp();
 #pragma unroll
         for (int i = 0; i < F::kOut; ++i) {
             const int idx = F::index(lane, i);
-            if (idx >= 0 && idx < NPACK) o[idx] = acc[i];
-            else if (idx == NPACK && snr2_out) snr2_out[e] = acc[i];
+            if (idx >= 0) red[idx] = acc[i];
         }
+        __syncwarp();
+        double* o = out + e * NPACK;
+        for (int p = lane; p < NPACK; p += 32) {
+            int i = 0;
+            while (tri(i + 1, 0) <= p) ++i;                   // row of packed index p
+            o[p] = PF::entry(i, p - tri(i, 0), red, geom);
+        }
+        if (lane == 0 && snr2_out) snr2_out[e] = PF::snr2(red, geom);
     }
 }
 

@@ -45,9 +45,9 @@ static int emu_run(const gwf_model* model, const gwf_detector* dets, int ndet, c
             for (int di = 0; di < net.ndet; ++di) scratch_set(sc, net, geom, di);
             typename PointFns<MODEL, NT>::Extra ex;
             ex.set(in);
-            double acc[NPACK];
-            for (int p = 0; p < NPACK; ++p) acc[p] = 0.;
-            double s2 = 0.;
+            typedef PointFns<MODEL, NT> PF;
+            double acc[PF::kAcc];
+            for (int p = 0; p < PF::kAcc; ++p) acc[p] = 0.;
             for (int g = 0; g < net.ngroups; ++g) {
                 double fcut = rec.fcut_hz;
                 if (net.group_fmax[g] > 0.0 && fcut > net.group_fmax[g]) fcut = net.group_fmax[g];
@@ -59,12 +59,14 @@ static int emu_run(const gwf_model* model, const gwf_detector* dets, int ndet, c
                     grid.start(lane, fp);
                     for (int k = lane; k < opts->res; k += 32) {
                         if (k != lane) grid.advance(k, fp);
-                        PointFns<MODEL, NT>::fisher(rec, cfg, geom, net, sc, ex, g, net.group_rot[g] != 0, fp, acc, s2);
+                        PF::fisher(rec, cfg, geom, net, sc, ex, g, net.group_rot[g] != 0, fp, acc);
                     }
                 }
             }
-            std::memcpy(fisher + ((size_t)pass * n + e) * NPACK, acc, sizeof(acc));
-            if (snr2) snr2[(size_t)pass * n + e] = s2;
+            double* o = fisher + ((size_t)pass * n + e) * NPACK;
+            for (int i = 0; i < NP; ++i)
+                for (int j = 0; j <= i; ++j) o[tri(i, j)] = PF::entry(i, j, acc, geom);
+            if (snr2) snr2[(size_t)pass * n + e] = PF::snr2(acc, geom);
         }
     }
     return 0;

@@ -14,6 +14,16 @@ template <int MODEL, int NT> struct ModelTraits;
 
 template <int NT> struct ModelTraits<kTaylorF2, NT> {
     typedef TF2Rec<NT> Rec;
+    static GWF_HD void eval_amp(const Rec& r, const ModelCfg&, const FreqPoint& fp, bool need_tau, double& A, double& tau) {
+        A = r.C * fp.fm76;
+        tau = 0.;
+        if (need_tau) {
+            VPow p;
+            p.set(r.sp, fp);
+            double dtau[2];
+            tau_eval(r.tau, p.vm1, p.lpx3, r.lam, tau, dtau);
+        }
+    }
     static GWF_HD void prologue(Rec& r, const EventIn& e, const ModelCfg& cfg, int opt_flags, const QnmTables&, const double*, int) {
         const Intrinsic<NT> p = seed_intrinsic<NT>(e, opt_flags, (cfg.flags & kFlagTidal) != 0);
         tf2_prologue(r, p, e.dL, cfg, e.fcut_host);
@@ -41,6 +51,17 @@ template <int NT> struct ModelTraits<kTaylorF2, NT> {
 
 template <int NT> struct ModelTraits<kPhenomD, NT> {
     typedef PhenomDRec<NT> Rec;
+    // amplitude (and tau) only: the SNR needs neither the phase nor any tangent
+    static GWF_HD void eval_amp(const Rec& r, const ModelCfg& cfg, const FreqPoint& fp, bool need_tau, double& A, double& tau) {
+        XPow p;
+        p.set(r.s, r.sp, fp);
+        A = r.C76 * fp.fm76 * phenomd_amp_value(r, p, !(cfg.flags & kFlagNoFcut));
+        tau = 0.;
+        if (need_tau) {
+            double dtau[2];
+            tau_eval(r.tau, p.xm13 * 0.68278406325529568146702083315816, p.lpx3, r.lam, tau, dtau);
+        }
+    }
     static GWF_HD void prologue(Rec& r, const EventIn& e, const ModelCfg& cfg, int opt_flags, const QnmTables& q, const double* fmin_g, int ng) {
         const Intrinsic<NT> p = seed_intrinsic<NT>(e, opt_flags, false);
         phenomd_prologue(r, p, e.dL, q, fmin_g, ng, cfg, e.s_host, e.fcut_host);
@@ -67,6 +88,23 @@ template <int NT> struct ModelTraits<kPhenomD, NT> {
 
 template <int NT> struct ModelTraits<kNRTidalv2, NT> {
     typedef NRTidalRec<NT> Rec;
+    static GWF_HD void eval_amp(const Rec& r, const ModelCfg&, const FreqPoint& fp, bool need_tau, double& A, double& tau) {
+        const PhenomDRec<NT>& d = r.d;
+        XPow p;
+        p.set(d.s, d.sp, fp);
+        double T, Ty;
+        nrt_taper(p.x, r.ym[0], T, Ty);
+        A = 0.;
+        tau = 0.;
+        if (T == 0.0) return;
+        double Q, xQp;
+        nrt_amp_shape(1.4645918875615232630201425272637904 * p.x13, p.lpx3, Q, xQp);
+        A = d.C * fma(r.sm76 * fp.fm76, phenomd_amp_value(d, p, true), r.kam[0] * Q) * T;
+        if (need_tau) {
+            double dtau[2];
+            tau_eval(d.tau, p.xm13 * 0.68278406325529568146702083315816, p.lpx3, d.lam, tau, dtau);
+        }
+    }
     static GWF_HD void prologue(Rec& r, const EventIn& e, const ModelCfg& cfg, int opt_flags, const QnmTables& q, const double* fmin_g, int ng) {
         // NT = 6: Fisher parametrisation (Lambda re-mapped through LambdaTilde/deltaLambda); NT = 4: SNR path, dict values as they are
         const Intrinsic<NT> p = seed_intrinsic<NT>(e, opt_flags, NT >= 6);
@@ -233,12 +271,13 @@ template <int MODEL>
 GWF_HD void amp_phase_snr_point(const typename ModelTraits<MODEL, 4>::Rec& rec, const ModelCfg& cfg, const EvGeom& geom, const NetworkDev& net,
                       const EventScratch& sc, int g, bool group_rot, const FreqPoint& fp, double* __restrict__ snr2_arm) {
     const double f = fp.f, l2f = fp.lnf * 1.4426950408889634073599246810018921;   // log2 f
-    PointWf<4> w;
-    ModelTraits<MODEL, 4>::eval(rec, cfg, g, fp, group_rot, w);
-    if (w.A == 0.0) return;
-    const double wA2 = 4.0 * fp.w * w.A * w.A;
+    double A, tau;
+    ModelTraits<MODEL, 4>::eval_amp(rec, cfg, fp, group_rot, A, tau);
+    (void)g;
+    if (A == 0.0) return;
+    const double wA2 = 4.0 * fp.w * A * A;
     double sBr = 0., cBr = 1.;
-    if (group_rot) sincos(2.0 * kPi * fma(-w.tau, kInvDay, geom.tcoal), &sBr, &cBr);
+    if (group_rot) sincos(2.0 * kPi * fma(-tau, kInvDay, geom.tcoal), &sBr, &cBr);
     for (int di = 0; di < net.ndet; ++di) {
         const DetDev& d = net.det[di];
         if (d.group != g) continue;

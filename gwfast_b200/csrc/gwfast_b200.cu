@@ -273,10 +273,13 @@ snr_kernel(const typename ModelTraits<MODEL, 4>::Rec* __restrict__ recs, EventsD
     const Rec& rec = mine->rec;
     const long long nwarps = (long long)gridDim.x * kWarpsPerCta;
     for (long long e = (long long)blockIdx.x * kWarpsPerCta + wid; e < n; e += nwarps) {
-        EvGeom geom;
-        const EventIn in = load_event(ev, e);
-        geom.set(in);
-        stage_event(mine, recs, e, net, geom, in, lane);
+        {
+            EvGeom g0;
+            const EventIn in = load_event(ev, e);
+            g0.set(in);
+            stage_event(mine, recs, e, net, g0, in, lane);
+        }
+        const EvGeom& geom = mine->geom;
         double s2[kMaxArms];
 #pragma unroll
         for (int a = 0; a < kMaxArms; ++a) s2[a] = 0.0;

@@ -395,6 +395,26 @@ GWF_HD bool phenomd_amp_core(const PhenomDRec<NT>& r, const XPow& p, bool apply_
     return true;
 }
 
+// value-only ampIMR(x) (SNR path: no tangents needed)
+template <int NT>
+GWF_HD double phenomd_amp_value(const PhenomDRec<NT>& r, const XPow& p, bool apply_cut) {
+    const double x = p.x;
+    if (x < kAmpJoinIns) {
+        const double x2 = x * x;
+        return r.ains[0][0] + r.ains[1][0] * p.x23 + r.ains[2][0] * x + r.ains[3][0] * (x * p.x13) + r.ains[4][0] * (x * p.x23) + r.ains[5][0] * x2 +
+               r.ains[6][0] * (x2 * p.x13) + r.ains[7][0] * (x2 * p.x23) + r.ains[8][0] * (x2 * x);
+    }
+    if (x < r.x_peak) {
+        const double u = x - kAmpJoinIns;
+        return r.aint[0][0] + u * (r.aint[1][0] + u * (r.aint[2][0] + u * (r.aint[3][0] + u * r.aint[4][0])));
+    }
+    if (!apply_cut || x < kMfCut) {
+        const double u = x - r.amrd[0][0], w = r.amrd[2][0];
+        return exp(-u * r.amrd[1][0]) * r.amrd[3][0] / (u * u + w * w);
+    }
+    return 0.0;
+}
+
 // amplitude A = C x^(-7/6) ampIMR(x) and d ln A at x
 template <int NT>
 GWF_HD void phenomd_amp(const PhenomDRec<NT>& r, const XPow& p, bool apply_cut, double& A, double* lnA_d) {

@@ -21,6 +21,12 @@ struct PsdDev {
     int n, nb;
     double lo, inv;       // bucket coordinate = (log2 f - lo) * inv
     double f_first, f_last;
+    // log-uniform node spacing (every PSD file shipped with gwfast): row index ~ (log2 f - u_lo) * u_inv, no bucket load
+    int uni;
+    double u_lo, u_inv;
+    // window [c_j0, c_j0 + c_n) of the rows cached in the CTA's dynamic shared memory at byte offset c_off (kernels that
+    // call psd_cache_fill; planned per launch by plan_psd_cache, -1 = not cached): F[c_n + 1], S[c_n], slope[c_n]
+    int c_off, c_j0, c_n;
 };
 
 struct DetDev {
@@ -60,8 +66,23 @@ struct NetworkDev {
 #else
 #define GWF_LDG(ptr) (*(ptr))
 #endif
+#ifdef __CUDA_ARCH__
+extern __shared__ __align__(16) unsigned char gwf_dyn_smem[];
+#endif
 GWF_HD double psd_lookup(const PsdDev& p, double f, double l2f) {
     if (!(f >= p.f_first) || f > p.f_last) return 1.0;
+#ifdef __CUDA_ARCH__
+    if (p.c_off >= 0) {
+        // shared-memory window: two dependent ~25-cycle loads instead of two dependent L1/L2 round trips
+        const double* F = reinterpret_cast<const double*>(gwf_dyn_smem + p.c_off);
+        const int last = p.c_n - 1;
+        int j = (int)((l2f - p.u_lo) * p.u_inv) - p.c_j0;
+        j = j < 0 ? 0 : (j > last ? last : j);
+        while (j > 0 && f < F[j]) --j;                      // rounding of the index guess (rare)
+        while (j < last && f >= F[j + 1]) ++j;
+        return fma(F[2 * p.c_n + 1 + j], f - F[j], F[p.c_n + 1 + j]);
+    }
+#endif
     int b = (int)((l2f - p.lo) * p.inv);
     b = b < 0 ? 0 : (b > p.nb - 1 ? p.nb - 1 : b);
     int j = GWF_LDG(p.bucket + b);
@@ -254,20 +275,19 @@ GWF_HD double compact_snr2(const double* __restrict__ acc, const EvGeom& g) {
     return g.K * g.K * acc[Compact<NT>::kUU] + g.ci * g.ci * acc[Compact<NT>::kVV];     // 4 sum w |h|^2 / Sn, signal.py:727
 }
 
-// general rows of d h / d p (divided by A e^{i Psi}) for one arm and the compact weighted Gram
+// general rows of d h / d p (divided by A e^{i Psi}) for one arm: ra + i rb for the NG general parameters, and the
+// pattern functions Fp, Fc that generate the four fixed-combination rows (see Compact)
 template <int NT>
-GWF_HD void arm_rows_accumulate(const PointWf<NT>& w, const DetPoint& p, const DetRows<NT>& dr, const ArmDev& a, const EvGeom& g, double wgt,
-                                double* __restrict__ acc) {
-    typedef Compact<NT> C;
-    constexpr int NG = C::NG;
+GWF_HD void arm_rows(const PointWf<NT>& w, const DetPoint& p, const DetRows<NT>& dr, const ArmDev& a, const EvGeom& g,
+                     double* __restrict__ ra, double* __restrict__ rb, double& Fp, double& Fc) {
     const double av = a.S2 * p.aS + a.C2 * p.aC, bv = a.C2 * p.bC + a.S2 * p.bS;
     const double ag = a.S2 * p.aS_g + a.C2 * p.aC_g, bg = a.C2 * p.bC_g + a.S2 * p.bS_g;
     const double ad = a.S2 * p.aS_d + a.C2 * p.aC_d, bd = a.C2 * p.bC_d + a.S2 * p.bS_d;
-    const double Fp = av * g.c2psi + bv * g.s2psi, Fc = bv * g.c2psi - av * g.s2psi;
+    Fp = av * g.c2psi + bv * g.s2psi;
+    Fc = bv * g.c2psi - av * g.s2psi;
     const double Gr = Fp * g.K, Gi = Fc * g.ci;                                       // signal.py:463-464
     const double Ggr = (ag * g.c2psi + bg * g.s2psi) * g.K, Ggi = (bg * g.c2psi - ag * g.s2psi) * g.ci;
     const double Gdr = (ad * g.c2psi + bd * g.s2psi) * g.K, Gdi = (bd * g.c2psi - ad * g.s2psi) * g.ci;
-    double ra[NG], rb[NG];
     // intrinsic rows (the AD rows of the reference, signal.py:1153-1189): general indices 0, 1, 5, 6 [, 7, 8]
 #pragma unroll
     for (int j = 0; j < NT; ++j) {
@@ -286,8 +306,14 @@ GWF_HD void arm_rows_accumulate(const PointWf<NT>& w, const DetPoint& p, const D
     rb[3] = fma(Ggi, dr.ang_p, Gr * dr.ph_p);
     ra[4] = fma(Ggr, dr.ang_c, -Gi * dr.ph_c);                // tcoal, signal.py:1525-1565
     rb[4] = fma(Ggi, dr.ang_c, Gr * dr.ph_c);
-    // 4 Re int conj(d_a h) d_b h / Sn df, signal.py:922-931
-    const double wg = wgt * a.weight;
+}
+
+// compact weighted Gram of one arm-sample: 4 Re int conj(d_a h) d_b h / Sn df, signal.py:922-931
+template <int NT>
+GWF_HD void gram_accumulate(double wg, double Fp, double Fc, const double* __restrict__ ra, const double* __restrict__ rb,
+                            double* __restrict__ acc) {
+    typedef Compact<NT> C;
+    constexpr int NG = C::NG;
     const double wu = wg * Fp, wv = wg * Fc;
     acc[C::kUU] = fma(wu, Fp, acc[C::kUU]);
     acc[C::kVV] = fma(wv, Fc, acc[C::kVV]);
@@ -303,6 +329,14 @@ GWF_HD void arm_rows_accumulate(const PointWf<NT>& w, const DetPoint& p, const D
 #pragma unroll
         for (int j = 0; j <= i; ++j) acc[tri(i, j)] = fma(wa, ra[j], fma(wb, rb[j], acc[tri(i, j)]));
     }
+}
+
+template <int NT>
+GWF_HD void arm_rows_accumulate(const PointWf<NT>& w, const DetPoint& p, const DetRows<NT>& dr, const ArmDev& a, const EvGeom& g, double wgt,
+                                double* __restrict__ acc) {
+    double ra[Compact<NT>::NG], rb[Compact<NT>::NG], Fp, Fc;
+    arm_rows<NT>(w, p, dr, a, g, ra, rb, Fp, Fc);
+    gram_accumulate<NT>(wgt * a.weight, Fp, Fc, ra, rb, acc);
 }
 
 }  // namespace gwf

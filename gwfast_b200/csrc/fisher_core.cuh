@@ -267,6 +267,14 @@ GWF_HD void amp_phase_point(const typename ModelTraits<MODEL, NT>::Rec& rec, con
 }
 
 // value-only point for the SNR kernel: per-arm SNR^2 contributions (signal.py:725-767)
+// Per-arm SNR^2 accumulators: on the device they live in shared memory as [arm][lane] (a dynamically indexed register
+// array would be demoted to local memory); the host emulation keeps a plain array.
+#ifdef __CUDA_ARCH__
+#define GWF_SNR_SLOT(a) ((a) * 32)
+#else
+#define GWF_SNR_SLOT(a) (a)
+#endif
+
 template <int MODEL>
 GWF_HD void amp_phase_snr_point(const typename ModelTraits<MODEL, 4>::Rec& rec, const ModelCfg& cfg, const EvGeom& geom, const NetworkDev& net,
                       const EventScratch& sc, int g, bool group_rot, const FreqPoint& fp, double* __restrict__ snr2_arm) {
@@ -290,7 +298,8 @@ GWF_HD void amp_phase_snr_point(const typename ModelTraits<MODEL, 4>::Rec& rec, 
             double Fp, Fc;
             arm_pattern(dp, net.arm[ai], geom, Fp, Fc);
             const double Gr = Fp * geom.K, Gi = Fc * geom.ci;
-            snr2_arm[net.arm[ai].out] = fma(wgt * net.arm[ai].weight, Gr * Gr + Gi * Gi, snr2_arm[net.arm[ai].out]);
+            double& slot = snr2_arm[GWF_SNR_SLOT(net.arm[ai].out)];
+            slot = fma(wgt * net.arm[ai].weight, Gr * Gr + Gi * Gi, slot);
         }
     }
 }
@@ -433,7 +442,8 @@ GWF_HD void hm_snr_point(const HMRec<4>& rec, const ModelCfg& cfg, const EvGeom&
         for (int ai = d.arm_begin; ai < d.arm_end; ++ai) {
             double Fp, Fc;
             arm_pattern(dp, net.arm[ai], geom, Fp, Fc);
-            snr2_arm[net.arm[ai].out] = fma(wgt * net.arm[ai].weight, hp2 * Fp * Fp + hc2 * Fc * Fc, snr2_arm[net.arm[ai].out]);
+            double& slot = snr2_arm[GWF_SNR_SLOT(net.arm[ai].out)];
+            slot = fma(wgt * net.arm[ai].weight, hp2 * Fp * Fp + hc2 * Fc * Fc, slot);
         }
     }
 }

@@ -10,6 +10,7 @@
 // The derivative strain never exists in memory (the reference materialises (nP,N,res) complex128 per arm,
 // gwfast/signal.py:917-922).
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -51,6 +52,7 @@ __device__ __forceinline__ EventIn load_event(const EventsDev& ev, long long e) 
 #endif
 constexpr int kFisherThreads = GWF_FISHER_THREADS;
 constexpr int kWarpsPerCta = kFisherThreads / 32;
+constexpr int kSnrThreads = 512, kSnrWarps = kSnrThreads / 32;     // SNR kernel: 16 warps, one CTA per SM
 
 struct GroupInfo {
     int n;
@@ -176,6 +178,67 @@ template <int L> struct Fold {
     }
 };
 
+// ---- PSD windows in shared memory -------------------------------------------------------------------------------
+// The three PSD tables of a network are ~240 KB of rows + bucket index: together with the spill slots they do not
+// fit L1, and a lookup was two dependent L1/L2 round trips per detector and sample (19 % of the Fisher kernel's stall
+// samples in profiles/r01).  Log-uniform tables need no bucket index, and the rows above the lowest grid frequency fit
+// the CTA's shared memory as (f, S, slope) = 24 B per row.
+constexpr size_t kSmemLimit = 227 * 1024;
+// host: choose the windows (byte offsets from the dynamic-smem base, behind `base` bytes of staging blocks); returns the
+// dynamic shared memory size of the launch.  Tables that are not log-uniform or do not fit stay on the global path.
+static size_t plan_psd_cache(NetworkDev& net, size_t base, size_t limit) {
+    size_t off = (base + 15) & ~(size_t)15;
+    for (int i = 0; i < net.npsd; ++i) net.psd[i].c_off = -1;
+    for (int i = 0; i < net.npsd; ++i) {
+        PsdDev& p = net.psd[i];
+        double fq = 0.0;
+        bool used = false;
+        for (int d = 0; d < net.ndet; ++d)
+            if (net.det[d].psd == i && net.det[d].arm_begin != net.det[d].arm_end) {
+                const double f0 = net.group_fmin[net.det[d].group];
+                fq = used ? std::min(fq, f0) : f0;
+                used = true;
+            }
+        if (!used || !p.uni || !(fq > 0.0)) continue;
+        bool shared = false;
+        for (int k = 0; k < i && !shared; ++k)
+            if (net.psd[k].tab == p.tab && net.psd[k].c_off >= 0 && net.psd[k].c_j0 <= (int)std::floor((std::log2(fq) - p.u_lo) * p.u_inv) - 2) {
+                p.c_off = net.psd[k].c_off; p.c_j0 = net.psd[k].c_j0; p.c_n = net.psd[k].c_n;
+                shared = true;
+            }
+        if (shared) continue;
+        int j0 = (int)std::floor((std::log2(fq) - p.u_lo) * p.u_inv) - 2;
+        j0 = std::max(0, std::min(j0, p.n - 2));
+        const int cn = (p.n - 1) - j0;
+        const size_t bytes = ((size_t)(3 * cn + 1) * sizeof(double) + 15) & ~(size_t)15;
+        if (off + bytes > limit) continue;
+        p.c_off = (int)off; p.c_j0 = j0; p.c_n = cn;
+        off += bytes;
+    }
+    return off;
+}
+// device: all threads of the CTA copy the windows; ends with a CTA barrier
+__device__ __forceinline__ void psd_cache_fill(const NetworkDev& net, unsigned char* smem) {
+    for (int i = 0; i < net.npsd; ++i) {
+        const PsdDev& p = net.psd[i];
+        if (p.c_off < 0) continue;
+        bool dup = false;
+        for (int k = 0; k < i; ++k) dup = dup || net.psd[k].c_off == p.c_off;
+        if (dup) continue;
+        double* F = reinterpret_cast<double*>(smem + p.c_off);
+        const int cn = p.c_n;
+        const double2* rows = reinterpret_cast<const double2*>(p.tab + p.c_j0);
+        for (int j = threadIdx.x; j < cn; j += blockDim.x) {
+            const double2 a = __ldg(rows + 2 * j), b = __ldg(rows + 2 * j + 1);      // (f_j, S_j), (slope_j, f_{j+1})
+            F[j] = a.x;
+            F[cn + 1 + j] = a.y;
+            F[2 * cn + 1 + j] = b.x;
+            if (j == cn - 1) F[cn] = b.y;
+        }
+    }
+    __syncthreads();
+}
+
 // per-warp shared memory: the event's coefficient record followed by the detector scratch
 template <class Rec, class Extra> struct WarpSmem {
     Rec rec;
@@ -211,6 +274,7 @@ fisher_kernel(const typename ModelTraits<MODEL, NT>::Rec* __restrict__ recs, Eve
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     WS* mine = reinterpret_cast<WS*>(smem_raw) + wid;
     const Rec& rec = mine->rec;
+    psd_cache_fill(net, smem_raw);
     const long long nwarps = (long long)gridDim.x * kWarpsPerCta;
     for (long long e = (long long)blockIdx.x * kWarpsPerCta + wid; e < n; e += nwarps) {
         {
@@ -261,7 +325,7 @@ fisher_kernel(const typename ModelTraits<MODEL, NT>::Rec* __restrict__ recs, Eve
 
 // SNR: per-arm integrals, value-only
 template <int MODEL>
-__global__ void __launch_bounds__(kFisherThreads, 2)
+__global__ void __launch_bounds__(kSnrThreads, 1)
 snr_kernel(const typename ModelTraits<MODEL, 4>::Rec* __restrict__ recs, EventsDev ev, long long n, int res, int lin, ModelCfg cfg,
            const __grid_constant__ NetworkDev net, int narm_out, double* __restrict__ snr2_arm) {
     typedef typename ModelTraits<MODEL, 4>::Rec Rec;
@@ -270,9 +334,12 @@ snr_kernel(const typename ModelTraits<MODEL, 4>::Rec* __restrict__ recs, EventsD
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     WS* mine = reinterpret_cast<WS*>(smem_raw) + wid;
+    // per-lane, per-arm accumulators: [warp][arm][lane] behind the per-warp staging blocks
+    double* s2 = reinterpret_cast<double*>(reinterpret_cast<WS*>(smem_raw) + kSnrWarps) + (wid * narm_out) * 32 + lane;
     const Rec& rec = mine->rec;
-    const long long nwarps = (long long)gridDim.x * kWarpsPerCta;
-    for (long long e = (long long)blockIdx.x * kWarpsPerCta + wid; e < n; e += nwarps) {
+    psd_cache_fill(net, smem_raw);
+    const long long nwarps = (long long)gridDim.x * kSnrWarps;
+    for (long long e = (long long)blockIdx.x * kSnrWarps + wid; e < n; e += nwarps) {
         {
             EvGeom g0;
             const EventIn in = load_event(ev, e);
@@ -280,9 +347,7 @@ snr_kernel(const typename ModelTraits<MODEL, 4>::Rec* __restrict__ recs, EventsD
             stage_event(mine, recs, e, net, g0, in, lane);
         }
         const EvGeom& geom = mine->geom;
-        double s2[kMaxArms];
-#pragma unroll
-        for (int a = 0; a < kMaxArms; ++a) s2[a] = 0.0;
+        for (int a = 0; a < narm_out; ++a) s2[a * 32] = 0.0;
         for (int g = 0; g < net.ngroups; ++g) {
             double fcut = rec.fcut_hz;
             if (net.group_fmax[g] > 0.0 && fcut > net.group_fmax[g]) fcut = net.group_fmax[g];
@@ -297,7 +362,7 @@ snr_kernel(const typename ModelTraits<MODEL, 4>::Rec* __restrict__ recs, EventsD
             }
         }
         for (int a = 0; a < narm_out; ++a) {
-            const double v = warp_sum(s2[a]);
+            const double v = warp_sum(s2[a * 32]);
             if (lane == 0) snr2_arm[(long long)a * n + e] = v;
         }
     }
@@ -367,7 +432,9 @@ static int run_fisher(const gwf_model* model, const gwf_detector* dets, int ndet
     int dev = 0, sms = 0;
     GWF_CUDA(cudaGetDevice(&dev));
     GWF_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    const size_t shmem = sizeof(WarpSmem<Rec, typename PointFns<MODEL, NT>::Extra>) * kWarpsPerCta;
+    // dynamic shared memory: per-warp staging blocks, then the PSD windows (as many tables as fit in 227 KB)
+    const size_t ws_bytes_smem = sizeof(WarpSmem<Rec, typename PointFns<MODEL, NT>::Extra>) * kWarpsPerCta;
+    const size_t shmem = plan_psd_cache(net, ws_bytes_smem, kSmemLimit);
     auto kern = fisher_kernel<MODEL, NT>;
     GWF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem));
     int per_sm = 1;
@@ -381,6 +448,7 @@ static int run_fisher(const gwf_model* model, const gwf_detector* dets, int ndet
         if (opts->per_arm) {
             rc = build_network(dets, ndet, pd, npsd, pass, false, net);
             if (rc) return rc;
+            plan_psd_cache(net, ws_bytes_smem, kSmemLimit);
         }
         kern<<<grid, kFisherThreads, shmem, st>>>(recs, ev, n, opts->res, lin, cfg, net, fisher + (size_t)pass * n * NPACK,
                                                   snr2 ? snr2 + (size_t)pass * n : nullptr);
@@ -412,16 +480,14 @@ static int run_snr(const gwf_model* model, const gwf_detector* dets, int ndet, c
     int dev = 0, sms = 0;
     GWF_CUDA(cudaGetDevice(&dev));
     GWF_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    const size_t shmem = sizeof(WarpSmem<Rec, typename PointFns<MODEL, 4>::Extra>) * kWarpsPerCta;
+    const size_t base = (sizeof(WarpSmem<Rec, typename PointFns<MODEL, 4>::Extra>) + sizeof(double) * net.narms * 32) * kSnrWarps;
+    const size_t shmem = plan_psd_cache(net, base, kSmemLimit);
     auto kern = snr_kernel<MODEL>;
     GWF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem));
-    int per_sm = 1;
-    GWF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kFisherThreads, shmem));
-    if (per_sm < 1) per_sm = 1;
-    const long long want = (n + kWarpsPerCta - 1) / kWarpsPerCta;
-    const unsigned grid = (unsigned)std::min<long long>(want, (long long)sms * per_sm);
+    const long long want = (n + kSnrWarps - 1) / kSnrWarps;
+    const unsigned grid = (unsigned)std::min<long long>(want, (long long)sms);
     const int lin = (opts->flags & GWF_OPT_LIN_GRID) ? 1 : 0;
-    kern<<<grid, kFisherThreads, shmem, st>>>(recs, ev, n, opts->res, lin, cfg, net, net.narms, snr2_arm);
+    kern<<<grid, kSnrThreads, shmem, st>>>(recs, ev, n, opts->res, lin, cfg, net, net.narms, snr2_arm);
     GWF_CUDA(cudaGetLastError());
     return GWF_OK;
 }

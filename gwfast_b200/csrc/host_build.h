@@ -47,6 +47,15 @@ static int build_psd_tables(const double* f, const double* S, int n, std::vector
     dev.inv = inv;
     dev.f_first = f[0];
     dev.f_last = f[n - 1];
+    // log-uniform nodes: the row index follows from log2 f directly (within +-1, fixed up by the lookup)
+    const double dl = (hi - lo) / (n - 1);
+    double dev_max = 0.0;
+    for (int i = 0; i < n; ++i) dev_max = std::max(dev_max, std::fabs(std::log2(f[i]) - (lo + i * dl)));
+    dev.uni = dev_max < 0.25 * dl ? 1 : 0;
+    dev.u_lo = lo;
+    dev.u_inv = 1.0 / dl;
+    dev.c_off = -1;
+    dev.c_j0 = dev.c_n = 0;
     return GWF_OK;
 }
 

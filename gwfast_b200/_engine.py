@@ -95,6 +95,11 @@ def _call_arrays(dets, psd_handles):
     return darr, parr
 
 
+# extra gwf_opts.flags OR-ed into every launch (tests set GWF_OPT_GENERIC_LOOP / GWF_OPT_ONE_WARP_PER_EVENT to compare the
+# kernel variants; production leaves it 0 and the launcher picks the fastest applicable form)
+KERNEL_FLAGS = 0
+
+
 def fisher(model, dets, psd_handles, ev, n, res, flags, per_arm, want_snr2=True, keep_on_device=False):
     """Run gwf_fisher (+ gwf_unpack_fisher) on the current device.
 
@@ -115,7 +120,7 @@ def fisher(model, dets, psd_handles, ev, n, res, flags, per_arm, want_snr2=True,
     sp = C.c_void_p(stream.cuda_stream)
     full = torch.empty((npass, nP, nP, n), dtype=torch.float64, device=st.device)
     snr2 = torch.empty((npass, n), dtype=torch.float64, device=st.device)
-    opts = K.gwf_opts(int(res), int(flags), int(bool(per_arm)), 0)
+    opts = K.gwf_opts(int(res), int(flags) | KERNEL_FLAGS, int(bool(per_arm)), 0)
     h2d = 0
     keep = []
     for lo in range(0, n, CHUNK_EVENTS):
@@ -164,7 +169,7 @@ def snr(model, dets, psd_handles, ev, n, res, flags=0, keep_on_device=False):
     stream = torch.cuda.current_stream(st.device)
     sp = C.c_void_p(stream.cuda_stream)
     out = torch.empty((narms, n), dtype=torch.float64, device=st.device)
-    opts = K.gwf_opts(int(res), int(flags), 0, 0)
+    opts = K.gwf_opts(int(res), int(flags) | KERNEL_FLAGS, 0, 0)
     h2d = 0
     keep = []
     for lo in range(0, n, CHUNK_EVENTS):

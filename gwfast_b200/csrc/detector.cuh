@@ -24,8 +24,8 @@ struct PsdDev {
     // log-uniform node spacing (every PSD file shipped with gwfast): row index ~ (log2 f - u_lo) * u_inv, no bucket load
     int uni;
     double u_lo, u_inv;
-    // window [c_j0, c_j0 + c_n) of the rows cached in the CTA's dynamic shared memory at byte offset c_off (kernels that
-    // call psd_cache_fill; planned per launch by plan_psd_cache, -1 = not cached): F[c_n + 1], S[c_n], slope[c_n]
+    // window [c_j0, c_j0 + c_n) of the table rows cached in the CTA's dynamic shared memory at byte offset c_off (kernels
+    // that call psd_cache_fill; planned per launch by plan_psd_cache, -1 = not cached); same 32-byte rows as `tab`
     int c_off, c_j0, c_n;
 };
 
@@ -47,6 +47,7 @@ struct ArmDev {
     int pad;
 };
 
+constexpr int kMaxFastDet = 4;
 struct NetworkDev {
     int ndet, narms, ngroups, npsd;
     int group_rot[kMaxGroups];      // any detector of the group uses the Earth rotation
@@ -55,6 +56,13 @@ struct NetworkDev {
     DetDev det[kMaxDet];
     ArmDev arm[kMaxArms];
     PsdDev psd[kMaxPsd];
+    // "fast" form of a single-group network with at most kMaxFastDet active detectors whose PSD windows all sit in shared
+    // memory: the active detectors compacted to fdet[0..fnd) with their PSD descriptor copied next to them, so that a
+    // fully unrolled detector loop reads every field as a kernel-parameter operand at a compile-time offset (no indexed
+    // constant loads, no group / empty-detector / cache-miss branches).  fast = 0: not available (generic loop).
+    int fast, fnd;
+    DetDev fdet[kMaxFastDet];
+    PsdDev fpsd[kMaxFastDet];
 };
 
 // np.interp(f, strainFreq, noiseCurve, left=1., right=1.)  (signal.py:723, 901).  The table row j is
@@ -73,14 +81,15 @@ GWF_HD double psd_lookup(const PsdDev& p, double f, double l2f) {
     if (!(f >= p.f_first) || f > p.f_last) return 1.0;
 #ifdef __CUDA_ARCH__
     if (p.c_off >= 0) {
-        // shared-memory window: two dependent ~25-cycle loads instead of two dependent L1/L2 round trips
-        const double* F = reinterpret_cast<const double*>(gwf_dyn_smem + p.c_off);
+        // shared-memory window: the whole row (f_j, S_j, slope_j, f_{j+1}) arrives with two 16-byte loads
+        const double2* R = reinterpret_cast<const double2*>(gwf_dyn_smem + p.c_off);
         const int last = p.c_n - 1;
         int j = (int)((l2f - p.u_lo) * p.u_inv) - p.c_j0;
         j = j < 0 ? 0 : (j > last ? last : j);
-        while (j > 0 && f < F[j]) --j;                      // rounding of the index guess (rare)
-        while (j < last && f >= F[j + 1]) ++j;
-        return fma(F[2 * p.c_n + 1 + j], f - F[j], F[p.c_n + 1 + j]);
+        double2 fs = R[2 * j], sn = R[2 * j + 1];
+        while (j > 0 && f < fs.x) { --j; fs = R[2 * j]; sn = R[2 * j + 1]; }        // rounding of the index guess (rare)
+        while (j < last && f >= sn.y) { ++j; fs = R[2 * j]; sn = R[2 * j + 1]; }
+        return fma(sn.x, f - fs.x, fs.y);
     }
 #endif
     int b = (int)((l2f - p.lo) * p.inv);
@@ -99,6 +108,39 @@ GWF_HD double psd_lookup(const PsdDev& p, double f, double l2f) {
         fs = GWF_LDG(row); sn = GWF_LDG(row + 1);
     }
     return fma(sn.x, f - fs.x, fs.y);
+}
+
+#ifdef __CUDA_ARCH__
+// the same interpolation for a table known to be log-uniform and resident in shared memory (NetworkDev::fpsd): no
+// cache-miss path, the out-of-range case is a select, and the index fix-up is one rarely taken branch
+__device__ __forceinline__ double psd_lookup_fast(const PsdDev& p, double f, double l2f) {
+    const double2* R = reinterpret_cast<const double2*>(gwf_dyn_smem + p.c_off);
+    const int last = p.c_n - 1;
+    int j = (int)((l2f - p.u_lo) * p.u_inv) - p.c_j0;
+    j = max(0, min(j, last));
+    double2 fs = R[2 * j], sn = R[2 * j + 1];
+    if ((j > 0 && f < fs.x) || (j < last && f >= sn.y)) {
+        while (j > 0 && f < fs.x) { --j; fs = R[2 * j]; sn = R[2 * j + 1]; }
+        while (j < last && f >= sn.y) { ++j; fs = R[2 * j]; sn = R[2 * j + 1]; }
+    }
+    const double v = fma(sn.x, f - fs.x, fs.y);
+    return (f >= p.f_first && f <= p.f_last) ? v : 1.0;
+}
+#endif
+
+// reciprocal for the per-sample weights: MUFU seed + two Newton steps (error < 1 ulp; no denormal/special-case branch
+// of the IEEE division -- the arguments here are PSD values and amplitude denominators, always normal and positive)
+GWF_HD double rcp_fast(double x) {
+#ifdef __CUDA_ARCH__
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.0);
+    return fma(r, e, r);          // seed 2^-23 -> 2^-46 -> rounding level
+#else
+    return 1.0 / x;
+#endif
 }
 
 // per-event sky / orientation constants

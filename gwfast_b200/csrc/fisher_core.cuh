@@ -230,6 +230,14 @@ GWF_HD void scratch_set(EventScratch& s, const NetworkDev& net, const EvGeom& ge
     else if (!d.use_rot) det_point(s.ed[di], geom.cT, geom.sT, s.fixed[di]);   // t = tcoal, signal.py:452
 }
 
+// compact detector `i` of a network in fast form
+GWF_HD void scratch_set_fast(EventScratch& s, const NetworkDev& net, const EvGeom& geom, int i) {
+    const DetDev& d = net.fdet[i];
+    s.ed[i].set(d, geom);
+    if (d.no_motion) det_point(s.ed[i], 1.0, 0.0, s.fixed[i]);
+    else if (!d.use_rot) det_point(s.ed[i], geom.cT, geom.sT, s.fixed[i]);
+}
+
 // ------------------------------------------------------------------ one frequency point of one grid group
 // acc: packed lower-triangular Fisher (NP(NP+1)/2), snr2: sum of 4 w |h|^2 / Sn over the arms of the pass
 template <int MODEL, int NT>
@@ -265,6 +273,42 @@ GWF_HD void amp_phase_point(const typename ModelTraits<MODEL, NT>::Rec& rec, con
         for (int ai = d.arm_begin; ai < d.arm_end; ++ai) arm_rows_accumulate<NT>(w, dp, dr, net.arm[ai], geom, wgt, acc);
     }
 }
+
+#ifdef __CUDA_ARCH__
+// The same point for a network in "fast" form (NetworkDev::fast): fully unrolled detector loop over net.fdet[i] / net.fpsd[i]
+// with compile-time i, ROT = every active detector follows the Earth rotation (else none does).  sc.ed / sc.fixed are
+// indexed by the compact detector index.
+template <int MODEL, int NT, bool ROT>
+__device__ __forceinline__ void amp_phase_point_fast(const typename ModelTraits<MODEL, NT>::Rec& rec, const ModelCfg& cfg, const EvGeom& geom,
+                                                     const NetworkDev& net, const EventScratch& sc, const FreqPoint& fp, double* __restrict__ acc) {
+    const double f = fp.f, l2f = fp.lnf * 1.4426950408889634073599246810018921;   // log2 f
+    // the PSD row of detector i + 1 is requested before detector i is processed (and the first one before the waveform):
+    // the dependent shared-memory loads overlap with arithmetic, and only two PSD values are ever live
+    double sn_next = psd_lookup_fast(net.fpsd[0], f, l2f);
+    PointWf<NT> w;
+    ModelTraits<MODEL, NT>::eval(rec, cfg, 0, fp, ROT, w);
+    w.f = f;
+    if (w.A == 0.0) return;
+    const double wA2 = 4.0 * fp.w * w.A * w.A;
+    double sBr = 0., cBr = 1.;
+    if (ROT) sincos(2.0 * kPi * fma(-w.tau, kInvDay, geom.tcoal), &sBr, &cBr);
+#pragma unroll
+    for (int i = 0; i < kMaxFastDet; ++i) {
+        if (i < net.fnd) {
+            const DetDev& d = net.fdet[i];
+            const double sn_i = sn_next;
+            if (i + 1 < kMaxFastDet && i + 1 < net.fnd) sn_next = psd_lookup_fast(net.fpsd[i + 1 < kMaxFastDet ? i + 1 : 0], f, l2f);
+            DetPoint dp;
+            if (ROT) det_point(sc.ed[i], cBr, sBr, dp);
+            else dp = sc.fixed[i];
+            DetRows<NT> dr;
+            dr.set(w, dp, ROT, d.no_motion != 0);
+            const double wgt = wA2 * rcp_fast(sn_i);
+            for (int ai = d.arm_begin; ai < d.arm_end; ++ai) arm_rows_accumulate<NT>(w, dp, dr, net.arm[ai], geom, wgt, acc);
+        }
+    }
+}
+#endif
 
 // value-only point for the SNR kernel: per-arm SNR^2 contributions (signal.py:725-767)
 // Per-arm SNR^2 accumulators: on the device they live in shared memory as [arm][lane] (a dynamically indexed register
@@ -467,6 +511,14 @@ template <int MODEL, int NT> struct PointFns {
                               bool rot, const FreqPoint& fp, double* __restrict__ acc) {
         amp_phase_point<MODEL, NT>(rec, cfg, geom, net, sc, g, rot, fp, acc);
     }
+    static constexpr bool kHasFast = true;
+#ifdef __CUDA_ARCH__
+    template <bool ROT>
+    static __device__ __forceinline__ void fisher_fast(const Rec& rec, const ModelCfg& cfg, const EvGeom& geom, const NetworkDev& net, const EventScratch& sc,
+                                                       const Extra&, const FreqPoint& fp, double* __restrict__ acc) {
+        amp_phase_point_fast<MODEL, NT, ROT>(rec, cfg, geom, net, sc, fp, acc);
+    }
+#endif
     static GWF_HD double entry(int i, int j, const double* __restrict__ red, const EvGeom& geom) { return compact_entry<NT>(i, j, red, geom); }
     static GWF_HD double snr2(const double* __restrict__ red, const EvGeom& geom) { return compact_snr2<NT>(red, geom); }
     static GWF_HD void snr(const Rec& rec, const ModelCfg& cfg, const EvGeom& geom, const NetworkDev& net, const EventScratch& sc, const Extra&, int g,
@@ -482,6 +534,14 @@ template <int NT> struct PointFns<kPhenomHM, NT> {
                               bool rot, const FreqPoint& fp, double* __restrict__ acc) {
         hm_point<NT>(rec, cfg, geom, net, sc, ex, g, rot, fp, acc);
     }
+    static constexpr bool kHasFast = false;
+#ifdef __CUDA_ARCH__
+    template <bool ROT>
+    static __device__ __forceinline__ void fisher_fast(const Rec& rec, const ModelCfg& cfg, const EvGeom& geom, const NetworkDev& net, const EventScratch& sc,
+                                                       const Extra& ex, const FreqPoint& fp, double* __restrict__ acc) {
+        hm_point<NT>(rec, cfg, geom, net, sc, ex, 0, ROT, fp, acc);
+    }
+#endif
     static GWF_HD double entry(int i, int j, const double* __restrict__ red, const EvGeom&) { return red[tri(i, j)]; }
     static GWF_HD double snr2(const double* __restrict__ red, const EvGeom&) { return red[(NT + 7) * (NT + 8) / 2]; }
     static GWF_HD void snr(const Rec& rec, const ModelCfg& cfg, const EvGeom& geom, const NetworkDev& net, const EventScratch& sc, const Extra& ex, int g,

@@ -182,7 +182,7 @@ template <int L> struct Fold {
 // The three PSD tables of a network are ~240 KB of rows + bucket index: together with the spill slots they do not
 // fit L1, and a lookup was two dependent L1/L2 round trips per detector and sample (19 % of the Fisher kernel's stall
 // samples in profiles/r01).  Log-uniform tables need no bucket index, and the rows above the lowest grid frequency fit
-// the CTA's shared memory as (f, S, slope) = 24 B per row.
+// the CTA's shared memory as the table's own 32-byte rows (f_j, S_j, slope_j, f_{j+1}): one index, two 16-byte loads.
 constexpr size_t kSmemLimit = 227 * 1024;
 // host: choose the windows (byte offsets from the dynamic-smem base, behind `base` bytes of staging blocks); returns the
 // dynamic shared memory size of the launch.  Tables that are not log-uniform or do not fit stay on the global path.
@@ -210,13 +210,36 @@ static size_t plan_psd_cache(NetworkDev& net, size_t base, size_t limit) {
         int j0 = (int)std::floor((std::log2(fq) - p.u_lo) * p.u_inv) - 2;
         j0 = std::max(0, std::min(j0, p.n - 2));
         const int cn = (p.n - 1) - j0;
-        const size_t bytes = ((size_t)(3 * cn + 1) * sizeof(double) + 15) & ~(size_t)15;
+        const size_t bytes = (size_t)cn * sizeof(double4);
         if (off + bytes > limit) continue;
         p.c_off = (int)off; p.c_j0 = j0; p.c_n = cn;
         off += bytes;
     }
     return off;
 }
+// host: fast form of the network (see NetworkDev::fast) -- call after plan_psd_cache.  Returns 0 (generic loop), 1 (fast,
+// no detector follows the Earth rotation) or 2 (fast, every active detector does).
+static int plan_fast(NetworkDev& net) {
+    net.fast = 0;
+    net.fnd = 0;
+    if (net.ngroups != 1) return 0;
+    int nrot = 0;
+    for (int d = 0; d < net.ndet; ++d) {
+        const DetDev& D = net.det[d];
+        if (D.arm_begin == D.arm_end) continue;
+        if (net.fnd == kMaxFastDet) return 0;
+        const PsdDev& P = net.psd[D.psd];
+        if (P.c_off < 0) return 0;
+        net.fdet[net.fnd] = D;
+        net.fpsd[net.fnd] = P;
+        nrot += D.use_rot ? 1 : 0;
+        ++net.fnd;
+    }
+    if (net.fnd == 0 || (nrot != 0 && nrot != net.fnd)) { net.fnd = 0; return 0; }
+    net.fast = nrot ? 2 : 1;
+    return net.fast;
+}
+
 // device: all threads of the CTA copy the windows; ends with a CTA barrier
 __device__ __forceinline__ void psd_cache_fill(const NetworkDev& net, unsigned char* smem) {
     for (int i = 0; i < net.npsd; ++i) {
@@ -225,16 +248,9 @@ __device__ __forceinline__ void psd_cache_fill(const NetworkDev& net, unsigned c
         bool dup = false;
         for (int k = 0; k < i; ++k) dup = dup || net.psd[k].c_off == p.c_off;
         if (dup) continue;
-        double* F = reinterpret_cast<double*>(smem + p.c_off);
-        const int cn = p.c_n;
+        double2* dst = reinterpret_cast<double2*>(smem + p.c_off);
         const double2* rows = reinterpret_cast<const double2*>(p.tab + p.c_j0);
-        for (int j = threadIdx.x; j < cn; j += blockDim.x) {
-            const double2 a = __ldg(rows + 2 * j), b = __ldg(rows + 2 * j + 1);      // (f_j, S_j), (slope_j, f_{j+1})
-            F[j] = a.x;
-            F[cn + 1 + j] = a.y;
-            F[2 * cn + 1 + j] = b.x;
-            if (j == cn - 1) F[cn] = b.y;
-        }
+        for (int j = threadIdx.x; j < 2 * p.c_n; j += blockDim.x) dst[j] = __ldg(rows + j);
     }
     __syncthreads();
 }
@@ -245,9 +261,10 @@ template <class Rec, class Extra> struct WarpSmem {
     EventScratch sc;
     EvGeom geom;       // per-event sky/orientation constants: read by broadcast instead of living in 30 registers
     Extra ex;
+    double gridc[8];   // geometric-grid walk constants of the current group: r, r13, rm13, rm76, dln, hw_in, hw_hi, fcut
 };
 
-template <class Rec, class Extra>
+template <bool FAST, class Rec, class Extra>
 __device__ __forceinline__ void stage_event(WarpSmem<Rec, Extra>* mine, const Rec* recs, long long e, const NetworkDev& net, const EvGeom& geom,
                                             const EventIn& in, int lane) {
     constexpr int kRecDoubles = (int)(sizeof(Rec) / sizeof(double));
@@ -256,16 +273,22 @@ __device__ __forceinline__ void stage_event(WarpSmem<Rec, Extra>* mine, const Re
     __syncwarp();
     // coefficient record: coalesced 8-byte loads, later read by broadcast
     for (int i = lane; i < kRecDoubles; i += 32) dst[i] = __ldg(src + i);
-    if (lane < net.ndet) scratch_set(mine->sc, net, geom, lane);
+    if (FAST) {
+        if (lane < net.fnd) scratch_set_fast(mine->sc, net, geom, lane);
+    } else if (lane < net.ndet) scratch_set(mine->sc, net, geom, lane);
     if (lane == 31) mine->ex.set(in);
     if (lane == 30) mine->geom = geom;
     __syncwarp();
 }
 
-template <int MODEL, int NT>
+template <int MODEL, int NT, int FAST>
+#ifdef GWF_FISHER_MAXNREG
+__global__ void __maxnreg__(GWF_FISHER_MAXNREG)
+#else
 __global__ void __launch_bounds__(kFisherThreads, GWF_FISHER_MINBLOCKS)
+#endif
 fisher_kernel(const typename ModelTraits<MODEL, NT>::Rec* __restrict__ recs, EventsDev ev, long long n, int res, int lin, ModelCfg cfg,
-              const __grid_constant__ NetworkDev net, double* __restrict__ out, double* __restrict__ snr2_out) {
+              const __grid_constant__ NetworkDev net, double* __restrict__ out, double* __restrict__ snr2_out, int pair) {
     typedef typename ModelTraits<MODEL, NT>::Rec Rec;
     typedef PointFns<MODEL, NT> PF;
     typedef WarpSmem<Rec, typename PF::Extra> WS;
@@ -275,13 +298,17 @@ fisher_kernel(const typename ModelTraits<MODEL, NT>::Rec* __restrict__ recs, Eve
     WS* mine = reinterpret_cast<WS*>(smem_raw) + wid;
     const Rec& rec = mine->rec;
     psd_cache_fill(net, smem_raw);
-    const long long nwarps = (long long)gridDim.x * kWarpsPerCta;
-    for (long long e = (long long)blockIdx.x * kWarpsPerCta + wid; e < n; e += nwarps) {
+    // pair mode (small catalogs): warps w and w + kWarpsPerCta/2 share an event, each taking every other block of 32
+    // samples, so the work unit is half an event and the last round of the persistent loop wastes half as much
+    constexpr int kHalfWarps = kWarpsPerCta / 2;
+    const int half = pair ? wid / kHalfWarps : 0, slot = pair ? wid % kHalfWarps : wid;
+    const int per_cta = pair ? kHalfWarps : kWarpsPerCta, stride = pair ? 64 : 32, k0 = lane + 32 * half;
+    for (long long e = (long long)blockIdx.x * per_cta + slot; e < n; e += (long long)gridDim.x * per_cta) {
         {
             EvGeom g0;
             const EventIn in = load_event(ev, e);
             g0.set(in);
-            stage_event(mine, recs, e, net, g0, in, lane);
+            stage_event<FAST != 0>(mine, recs, e, net, g0, in, lane);
         }
         const EvGeom& geom = mine->geom;
         double acc[PF::kAcc];
@@ -291,13 +318,32 @@ fisher_kernel(const typename ModelTraits<MODEL, NT>::Rec* __restrict__ recs, Eve
             double fcut = rec.fcut_hz;
             if (net.group_fmax[g] > 0.0 && fcut > net.group_fmax[g]) fcut = net.group_fmax[g];   // signal.py:717-718
             Grid grid;
-            grid.set(net.group_fmin[g], fcut, res, lin != 0, 32);
+            grid.set(net.group_fmin[g], fcut, res, lin != 0, stride);
             const bool rot = net.group_rot[g] != 0;
+            // the walk constants are warp-uniform: kept in shared memory and re-read (volatile) every step instead of
+            // occupying 16 registers next to the Gram accumulators
+            __syncwarp();
+            if (lane == 0) {
+                mine->gridc[0] = grid.r; mine->gridc[1] = grid.r13; mine->gridc[2] = grid.rm13; mine->gridc[3] = grid.rm76;
+                mine->gridc[4] = grid.dln; mine->gridc[5] = grid.hw_in; mine->gridc[6] = grid.hw_hi; mine->gridc[7] = fcut;
+            }
+            __syncwarp();
+            const volatile double* gc = mine->gridc;
             FreqPoint fp;
-            if (lane < res) grid.start(lane, fp);
-            for (int k = lane; k < res; k += 32) {
-                if (k != lane) grid.advance(k, fp);
-                PF::fisher(rec, cfg, geom, net, mine->sc, mine->ex, g, rot, fp, acc);
+            if (k0 < res) grid.start(k0, fp);
+            for (int k = k0; k < res; k += stride) {
+                if (k != k0) {
+                    if (lin) grid.advance(k, fp);
+                    else {
+                        const bool last = k == res - 1;
+                        fp.f = last ? gc[7] : fp.f * gc[0];
+                        fp.f13 *= gc[1]; fp.fm13 *= gc[2]; fp.fm76 *= gc[3]; fp.lnf += gc[4];
+                        fp.w = fp.f * (last ? gc[6] : gc[5]);
+                    }
+                }
+                if (FAST == 2) PF::template fisher_fast<true>(rec, cfg, geom, net, mine->sc, mine->ex, fp, acc);
+                else if (FAST == 1) PF::template fisher_fast<false>(rec, cfg, geom, net, mine->sc, mine->ex, fp, acc);
+                else PF::fisher(rec, cfg, geom, net, mine->sc, mine->ex, g, rot, fp, acc);
             }
         }
         // warp reduction by recursive halving; the reduced accumulators land in shared memory (the record is no longer
@@ -313,13 +359,26 @@ fisher_kernel(const typename ModelTraits<MODEL, NT>::Rec* __restrict__ recs, Eve
             if (idx >= 0) red[idx] = acc[i];
         }
         __syncwarp();
-        double* o = out + e * NPACK;
-        for (int p = lane; p < NPACK; p += 32) {
-            int i = 0;
-            while (tri(i + 1, 0) <= p) ++i;                   // row of packed index p
-            o[p] = PF::entry(i, p - tri(i, 0), red, geom);
+        if (pair) {
+            // named barrier of the two warps of the pair: the partner's partial sums are complete
+            asm volatile("bar.sync %0, 64;" ::"r"(1 + slot) : "memory");
+            if (half == 0) {
+                const double* other = reinterpret_cast<const double*>(&(mine + kHalfWarps)->rec);
+                for (int p = lane; p < PF::kAcc; p += 32) red[p] += other[p];
+                __syncwarp();
+            }
         }
-        if (lane == 0 && snr2_out) snr2_out[e] = PF::snr2(red, geom);
+        if (half == 0) {
+            double* o = out + e * NPACK;
+            for (int p = lane; p < NPACK; p += 32) {
+                int i = 0;
+                while (tri(i + 1, 0) <= p) ++i;                   // row of packed index p
+                o[p] = PF::entry(i, p - tri(i, 0), red, geom);
+            }
+            if (lane == 0 && snr2_out) snr2_out[e] = PF::snr2(red, geom);
+        }
+        // the partner may only overwrite its staging block once its sums have been read
+        if (pair) asm volatile("bar.sync %0, 64;" ::"r"(1 + slot) : "memory");
     }
 }
 
@@ -344,7 +403,7 @@ snr_kernel(const typename ModelTraits<MODEL, 4>::Rec* __restrict__ recs, EventsD
             EvGeom g0;
             const EventIn in = load_event(ev, e);
             g0.set(in);
-            stage_event(mine, recs, e, net, g0, in, lane);
+            stage_event<false>(mine, recs, e, net, g0, in, lane);
         }
         const EvGeom& geom = mine->geom;
         for (int a = 0; a < narm_out; ++a) s2[a * 32] = 0.0;
@@ -435,13 +494,20 @@ static int run_fisher(const gwf_model* model, const gwf_detector* dets, int ndet
     // dynamic shared memory: per-warp staging blocks, then the PSD windows (as many tables as fit in 227 KB)
     const size_t ws_bytes_smem = sizeof(WarpSmem<Rec, typename PointFns<MODEL, NT>::Extra>) * kWarpsPerCta;
     const size_t shmem = plan_psd_cache(net, ws_bytes_smem, kSmemLimit);
-    auto kern = fisher_kernel<MODEL, NT>;
-    GWF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem));
-    int per_sm = 1;
-    GWF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kFisherThreads, shmem));
-    if (per_sm < 1) per_sm = 1;
-    const long long want = (n + kWarpsPerCta - 1) / kWarpsPerCta;
-    const unsigned grid = (unsigned)std::min<long long>(want, (long long)sms * per_sm);
+    constexpr bool kHasFast = PointFns<MODEL, NT>::kHasFast;
+    typedef void (*Kern)(const Rec*, EventsDev, long long, int, int, ModelCfg, const NetworkDev, double*, double*, int);
+    const Kern kerns[3] = {fisher_kernel<MODEL, NT, 0>, kHasFast ? fisher_kernel<MODEL, NT, 1> : fisher_kernel<MODEL, NT, 0>,
+                           kHasFast ? fisher_kernel<MODEL, NT, 2> : fisher_kernel<MODEL, NT, 0>};
+    for (int k = 0; k < 3; ++k) GWF_CUDA(cudaFuncSetAttribute(kerns[k], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem));
+    const bool allow_fast = kHasFast && !(opts->flags & GWF_OPT_GENERIC_LOOP);
+    int fast = allow_fast ? plan_fast(net) : 0;
+    // one event per warp, or per pair of warps when that shortens the persistent loop's longest chain of work units
+    const long long W = (long long)sms * kWarpsPerCta;
+    const long long rounds1 = (n + W - 1) / W, rounds2 = (n + W / 2 - 1) / (W / 2);
+    const int pair = (!(opts->flags & GWF_OPT_ONE_WARP_PER_EVENT) && (double)rounds2 * 0.5 * 1.01 < (double)rounds1) ? 1 : 0;
+    const int per_cta = pair ? kWarpsPerCta / 2 : kWarpsPerCta;
+    const long long want = (n + per_cta - 1) / per_cta;
+    const unsigned grid = (unsigned)std::min<long long>(want, (long long)sms);
     const int lin = (opts->flags & GWF_OPT_LIN_GRID) ? 1 : 0;
     const int npass = opts->per_arm ? gwf_num_arms(dets, ndet) : 1;
     for (int pass = 0; pass < npass; ++pass) {
@@ -449,9 +515,10 @@ static int run_fisher(const gwf_model* model, const gwf_detector* dets, int ndet
             rc = build_network(dets, ndet, pd, npsd, pass, false, net);
             if (rc) return rc;
             plan_psd_cache(net, ws_bytes_smem, kSmemLimit);
+            fast = allow_fast ? plan_fast(net) : 0;
         }
-        kern<<<grid, kFisherThreads, shmem, st>>>(recs, ev, n, opts->res, lin, cfg, net, fisher + (size_t)pass * n * NPACK,
-                                                  snr2 ? snr2 + (size_t)pass * n : nullptr);
+        kerns[fast]<<<grid, kFisherThreads, shmem, st>>>(recs, ev, n, opts->res, lin, cfg, net, fisher + (size_t)pass * n * NPACK,
+                                                  snr2 ? snr2 + (size_t)pass * n : nullptr, pair);
         GWF_CUDA(cudaGetLastError());
     }
     return GWF_OK;

@@ -85,6 +85,10 @@ typedef struct {
 #define GWF_OPT_LIN_GRID 4   /* spacing='lin'      */
 #define GWF_OPT_REUSE_WORKSPACE 8 /* the workspace still holds the coefficient records of the previous gwf_fisher call on the
                                      same events/model/options: skip the prologue kernel (used to time the main kernel alone) */
+#define GWF_OPT_GENERIC_LOOP 16   /* run the general detector loop even when the network qualifies for the unrolled single-group
+                                     form with all PSD windows in shared memory (tests compare the two kernels) */
+#define GWF_OPT_ONE_WARP_PER_EVENT 32 /* never split an event over two warps (the launcher does that when it shortens the
+                                     persistent loop of a small catalog; tests compare the two mappings) */
 typedef struct {
     int32_t res;    /* frequency samples per event (res=1000) */
     int32_t flags;  /* GWF_OPT_* */

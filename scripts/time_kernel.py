@@ -18,9 +18,11 @@ sp = C.c_void_p(torch.cuda.current_stream().cuda_stream)
 def call(flags):
     o = K.gwf_opts(res, flags, 0, 0)
     K.check(lib.gwf_fisher(C.byref(model), darr, len(dets), parr, len(handles), C.byref(evs), n, C.byref(o), C.c_void_p(packed.data_ptr()), C.c_void_p(snr2.data_ptr()), C.c_void_p(ws.data_ptr()), ws.numel(), sp), 'f')
-for _ in range(3): call(0)
-ts = []
-for _ in range(10):
-    torch.cuda.synchronize(); e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(); call(K.GWF_OPT_REUSE_WORKSPACE); e1.record(); torch.cuda.synchronize(); ts.append(e0.elapsed_time(e1))
-print('%s: fisher_kernel %.3f ms (min %.3f)  checksum %.6e' % (os.environ.get('GWFAST_B200_LIB', 'default'), np.median(ts), min(ts), float(packed.sum())))
+for extra, tag in ((0, 'fast+pair'), (16, 'generic+pair'), (32, 'fast, 1 warp/event'), (48, 'generic, 1 warp/event')):
+    for _ in range(3): call(extra)
+    ref = packed.clone()
+    ts = []
+    for _ in range(10):
+        torch.cuda.synchronize(); e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); call(extra | K.GWF_OPT_REUSE_WORKSPACE); e1.record(); torch.cuda.synchronize(); ts.append(e0.elapsed_time(e1))
+    print('%s [%s]: fisher_kernel %.3f ms (min %.3f)  checksum %.10e' % (os.environ.get('GWFAST_B200_LIB', 'default'), tag, np.median(ts), min(ts), float(packed.sum())))

@@ -103,15 +103,34 @@ def run_reference(args):
 
 # ----------------------------------------------------------------------------------------------- GPU arm
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe).  Read in-process through NVML
+    (the same counters `nvidia-smi --query-gpu=clocks.sm,clocks.max.sm,clocks_event_reasons.*` prints): an nvidia-smi child
+    polling every 100 ms stalls the CUDA driver for milliseconds at a time, which the host-timed e2e region then pays for.
+    Falls back to the nvidia-smi loop if NVML cannot be loaded."""
     Q = 'clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+    BITS = (('hw_slowdown', 0x8), ('hw_thermal_slowdown', 0x40), ('sw_thermal_slowdown', 0x20), ('sw_power_cap', 0x4))
 
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.rows, self.stop_flag = index, [], False
 
-    def run(self):
+    def _run_nvml(self):
+        import pynvml as N
+        N.nvmlInit()
+        # LOCAL_RANK indexes the visible devices; NVML enumerates all of them
+        vis = os.environ.get('CUDA_VISIBLE_DEVICES')
+        idx = int(vis.split(',')[self.index]) if vis and all(t.strip().isdigit() for t in vis.split(',')) else self.index
+        h = N.nvmlDeviceGetHandleByIndex(idx)
+        mx = N.nvmlDeviceGetMaxClockInfo(h, N.NVML_CLOCK_SM)
+        reasons = getattr(N, 'nvmlDeviceGetCurrentClocksEventReasons', None) or N.nvmlDeviceGetCurrentClocksThrottleReasons
+        while not self.stop_flag:
+            sm = N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM)
+            mask = int(reasons(h))
+            self.rows.append([str(sm), str(mx), ''] + ['Active' if mask & bit else 'Not Active' for _, bit in self.BITS])
+            time.sleep(0.02)
+
+    def _run_smi(self):
         try:
             p = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q, '--format=csv,noheader,nounits', '-lms', '100'],
                                  stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -124,10 +143,16 @@ class ClockSampler(threading.Thread):
             self.rows.append([x.strip() for x in ln.split(',')])
         p.terminate()
 
+    def run(self):
+        try:
+            self._run_nvml()
+        except Exception:
+            self._run_smi()
+
     def summary(self):
         sm = [float(r[0]) for r in self.rows if r and r[0].replace('.', '').isdigit()]
         mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace('.', '').isdigit()]
-        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        names = [n for n, _ in self.BITS]
         reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i] == 'Active' for r in self.rows)]
         return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None, reasons=reasons, samples=len(sm))
 

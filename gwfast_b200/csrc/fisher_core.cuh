@@ -348,6 +348,41 @@ GWF_HD void amp_phase_snr_point(const typename ModelTraits<MODEL, 4>::Rec& rec, 
     }
 }
 
+#ifdef __CUDA_ARCH__
+// value-only point for a network in fast form (see amp_phase_point_fast)
+template <int MODEL, bool ROT>
+__device__ __forceinline__ void amp_phase_snr_point_fast(const typename ModelTraits<MODEL, 4>::Rec& rec, const ModelCfg& cfg, const EvGeom& geom,
+                                                         const NetworkDev& net, const EventScratch& sc, const FreqPoint& fp, double* __restrict__ snr2_arm) {
+    const double f = fp.f, l2f = fp.lnf * 1.4426950408889634073599246810018921;   // log2 f
+    double sn[kMaxFastDet];
+#pragma unroll
+    for (int i = 0; i < kMaxFastDet; ++i) sn[i] = i < net.fnd ? psd_lookup_fast(net.fpsd[i], f, l2f) : 1.0;
+    double A, tau;
+    ModelTraits<MODEL, 4>::eval_amp(rec, cfg, fp, ROT, A, tau);
+    if (A == 0.0) return;
+    const double wA2 = 4.0 * fp.w * A * A;
+    double sBr = 0., cBr = 1.;
+    if (ROT) sincos(2.0 * kPi * fma(-tau, kInvDay, geom.tcoal), &sBr, &cBr);
+#pragma unroll
+    for (int i = 0; i < kMaxFastDet; ++i) {
+        if (i < net.fnd) {
+            const DetDev& d = net.fdet[i];
+            DetPoint dp;
+            if (ROT) det_point(sc.ed[i], cBr, sBr, dp);
+            else dp = sc.fixed[i];
+            const double wgt = wA2 * rcp_fast(sn[i]);
+            for (int ai = d.arm_begin; ai < d.arm_end; ++ai) {
+                double Fp, Fc;
+                arm_pattern(dp, net.arm[ai], geom, Fp, Fc);
+                const double Gr = Fp * geom.K, Gi = Fc * geom.ci;
+                double& slot = snr2_arm[GWF_SNR_SLOT(net.arm[ai].out)];
+                slot = fma(wgt * net.arm[ai].weight, Gr * Gr + Gi * Gi, slot);
+            }
+        }
+    }
+}
+#endif
+
 // ------------------------------------------------------------------ IMRPhenomHM point functions
 // per-event extras of a model (harmonic weights for HM; nothing for the (2,2)-only models)
 struct NoExtra {
@@ -518,6 +553,11 @@ template <int MODEL, int NT> struct PointFns {
                                                        const Extra&, const FreqPoint& fp, double* __restrict__ acc) {
         amp_phase_point_fast<MODEL, NT, ROT>(rec, cfg, geom, net, sc, fp, acc);
     }
+    template <bool ROT>
+    static __device__ __forceinline__ void snr_fast(const Rec& rec, const ModelCfg& cfg, const EvGeom& geom, const NetworkDev& net, const EventScratch& sc,
+                                                    const Extra&, const FreqPoint& fp, double* __restrict__ s2) {
+        amp_phase_snr_point_fast<MODEL, ROT>(rec, cfg, geom, net, sc, fp, s2);
+    }
 #endif
     static GWF_HD double entry(int i, int j, const double* __restrict__ red, const EvGeom& geom) { return compact_entry<NT>(i, j, red, geom); }
     static GWF_HD double snr2(const double* __restrict__ red, const EvGeom& geom) { return compact_snr2<NT>(red, geom); }
@@ -540,6 +580,11 @@ template <int NT> struct PointFns<kPhenomHM, NT> {
     static __device__ __forceinline__ void fisher_fast(const Rec& rec, const ModelCfg& cfg, const EvGeom& geom, const NetworkDev& net, const EventScratch& sc,
                                                        const Extra& ex, const FreqPoint& fp, double* __restrict__ acc) {
         hm_point<NT>(rec, cfg, geom, net, sc, ex, 0, ROT, fp, acc);
+    }
+    template <bool ROT>
+    static __device__ __forceinline__ void snr_fast(const Rec& rec, const ModelCfg& cfg, const EvGeom& geom, const NetworkDev& net, const EventScratch& sc,
+                                                    const Extra& ex, const FreqPoint& fp, double* __restrict__ s2) {
+        hm_snr_point(rec, cfg, geom, net, sc, ex, 0, ROT, fp, s2);
     }
 #endif
     static GWF_HD double entry(int i, int j, const double* __restrict__ red, const EvGeom&) { return red[tri(i, j)]; }

@@ -382,8 +382,10 @@ fisher_kernel(const typename ModelTraits<MODEL, NT>::Rec* __restrict__ recs, Eve
     }
 }
 
-// SNR: per-arm integrals, value-only
-template <int MODEL>
+// SNR: per-arm integrals, value-only.  Four warps share an event (warp `sub` takes every fourth block of 32 samples), so a
+// CTA of 16 warps stages only four coefficient records and the PSD windows still fit next to them in shared memory.
+constexpr int kSnrSplit = 4, kSnrGroups = kSnrWarps / kSnrSplit;
+template <int MODEL, int FAST>
 __global__ void __launch_bounds__(kSnrThreads, 1)
 snr_kernel(const typename ModelTraits<MODEL, 4>::Rec* __restrict__ recs, EventsDev ev, long long n, int res, int lin, ModelCfg cfg,
            const __grid_constant__ NetworkDev net, int narm_out, double* __restrict__ snr2_arm) {
@@ -392,38 +394,65 @@ snr_kernel(const typename ModelTraits<MODEL, 4>::Rec* __restrict__ recs, EventsD
     typedef WarpSmem<Rec, typename PF::Extra> WS;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    WS* mine = reinterpret_cast<WS*>(smem_raw) + wid;
-    // per-lane, per-arm accumulators: [warp][arm][lane] behind the per-warp staging blocks
-    double* s2 = reinterpret_cast<double*>(reinterpret_cast<WS*>(smem_raw) + kSnrWarps) + (wid * narm_out) * 32 + lane;
+    const int slot = wid % kSnrGroups, sub = wid / kSnrGroups, gt = sub * 32 + lane;      // gt: thread index inside the group
+    WS* mine = reinterpret_cast<WS*>(smem_raw) + slot;
+    // per-lane, per-arm accumulators [warp][arm][lane], then the per-warp totals [group][sub][arm]
+    double* s2_base = reinterpret_cast<double*>(reinterpret_cast<WS*>(smem_raw) + kSnrGroups);
+    double* s2 = s2_base + (wid * narm_out) * 32 + lane;
+    double* comb = s2_base + kSnrWarps * narm_out * 32 + slot * kSnrSplit * narm_out;
     const Rec& rec = mine->rec;
     psd_cache_fill(net, smem_raw);
-    const long long nwarps = (long long)gridDim.x * kSnrWarps;
-    for (long long e = (long long)blockIdx.x * kSnrWarps + wid; e < n; e += nwarps) {
+    constexpr int kRecDoubles = (int)(sizeof(Rec) / sizeof(double));
+    constexpr int stride = 32 * kSnrSplit;
+    const int k0 = gt;
+    for (long long e = (long long)blockIdx.x * kSnrGroups + slot; e < n; e += (long long)gridDim.x * kSnrGroups) {
         {
-            EvGeom g0;
-            const EventIn in = load_event(ev, e);
-            g0.set(in);
-            stage_event<false>(mine, recs, e, net, g0, in, lane);
+            // the 128 threads of the group stage the event: coefficient record (coalesced), detector scratch, geometry
+            const double* src = reinterpret_cast<const double*>(recs + e);
+            double* dst = reinterpret_cast<double*>(&mine->rec);
+            for (int i = gt; i < kRecDoubles; i += stride) dst[i] = __ldg(src + i);
+            if (sub == 0) {
+                EvGeom g0;
+                const EventIn in = load_event(ev, e);
+                g0.set(in);
+                if (FAST) {
+                    if (lane < net.fnd) scratch_set_fast(mine->sc, net, g0, lane);
+                } else if (lane < net.ndet) scratch_set(mine->sc, net, g0, lane);
+                if (lane == 31) mine->ex.set(in);
+                if (lane == 30) mine->geom = g0;
+            }
         }
+        asm volatile("bar.sync %0, %1;" ::"r"(1 + slot), "r"(stride) : "memory");
         const EvGeom& geom = mine->geom;
         for (int a = 0; a < narm_out; ++a) s2[a * 32] = 0.0;
         for (int g = 0; g < net.ngroups; ++g) {
             double fcut = rec.fcut_hz;
             if (net.group_fmax[g] > 0.0 && fcut > net.group_fmax[g]) fcut = net.group_fmax[g];
             Grid grid;
-            grid.set(net.group_fmin[g], fcut, res, lin != 0, 32);
+            grid.set(net.group_fmin[g], fcut, res, lin != 0, stride);
             const bool rot = net.group_rot[g] != 0;
             FreqPoint fp;
-            if (lane < res) grid.start(lane, fp);
-            for (int k = lane; k < res; k += 32) {
-                if (k != lane) grid.advance(k, fp);
-                PF::snr(rec, cfg, geom, net, mine->sc, mine->ex, g, rot, fp, s2);
+            if (k0 < res) grid.start(k0, fp);
+            for (int k = k0; k < res; k += stride) {
+                if (k != k0) grid.advance(k, fp);
+                if (FAST == 2) PF::template snr_fast<true>(rec, cfg, geom, net, mine->sc, mine->ex, fp, s2);
+                else if (FAST == 1) PF::template snr_fast<false>(rec, cfg, geom, net, mine->sc, mine->ex, fp, s2);
+                else PF::snr(rec, cfg, geom, net, mine->sc, mine->ex, g, rot, fp, s2);
             }
         }
         for (int a = 0; a < narm_out; ++a) {
             const double v = warp_sum(s2[a * 32]);
-            if (lane == 0) snr2_arm[(long long)a * n + e] = v;
+            if (lane == 0) comb[sub * narm_out + a] = v;
         }
+        // all warps of the group are done with the record and have left their totals
+        asm volatile("bar.sync %0, %1;" ::"r"(1 + slot), "r"(stride) : "memory");
+        if (sub == 0)
+            for (int a = lane; a < narm_out; a += 32) {
+                double v = 0.0;
+                for (int w = 0; w < kSnrSplit; ++w) v += comb[w * narm_out + a];
+                snr2_arm[(long long)a * n + e] = v;
+            }
+        // comb is next written after the following event's staging barrier, which warp 0 only reaches after this read
     }
 }
 
@@ -494,17 +523,21 @@ static int run_fisher(const gwf_model* model, const gwf_detector* dets, int ndet
     // dynamic shared memory: per-warp staging blocks, then the PSD windows (as many tables as fit in 227 KB)
     const size_t ws_bytes_smem = sizeof(WarpSmem<Rec, typename PointFns<MODEL, NT>::Extra>) * kWarpsPerCta;
     const size_t shmem = plan_psd_cache(net, ws_bytes_smem, kSmemLimit);
-    constexpr bool kHasFast = PointFns<MODEL, NT>::kHasFast;
+    // the unrolled form pays off where the waveform leaves registers for it (measured: IMRPhenomD 1.55 -> 1.31 ms, NRTidalv2
+    // 3.73 -> 3.21 ms per 1e4 events; TaylorF2's version spills and is 7-20 % slower than the general loop)
+    constexpr bool kHasFast = PointFns<MODEL, NT>::kHasFast && MODEL != kTaylorF2;
     typedef void (*Kern)(const Rec*, EventsDev, long long, int, int, ModelCfg, const NetworkDev, double*, double*, int);
     const Kern kerns[3] = {fisher_kernel<MODEL, NT, 0>, kHasFast ? fisher_kernel<MODEL, NT, 1> : fisher_kernel<MODEL, NT, 0>,
                            kHasFast ? fisher_kernel<MODEL, NT, 2> : fisher_kernel<MODEL, NT, 0>};
     for (int k = 0; k < 3; ++k) GWF_CUDA(cudaFuncSetAttribute(kerns[k], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem));
     const bool allow_fast = kHasFast && !(opts->flags & GWF_OPT_GENERIC_LOOP);
     int fast = allow_fast ? plan_fast(net) : 0;
-    // one event per warp, or per pair of warps when that shortens the persistent loop's longest chain of work units
-    const long long W = (long long)sms * kWarpsPerCta;
-    const long long rounds1 = (n + W - 1) / W, rounds2 = (n + W / 2 - 1) / (W / 2);
-    const int pair = (!(opts->flags & GWF_OPT_ONE_WARP_PER_EVENT) && (double)rounds2 * 0.5 * 1.01 < (double)rounds1) ? 1 : 0;
+    // One event per pair of warps (each warp takes every other block of 32 samples): the work unit of the persistent loop is
+    // half an event, which shortens its last round (1e4 events on 1184 warps: 8.45 -> 9 rounds of whole events, 16.9 -> 17 of
+    // halves; measured 1.36 -> 1.31 ms).  The mapping is fixed per model -- never chosen from n -- so that an event's result
+    // does not depend on the size of the batch it is computed in.  TaylorF2 events are too cheap for the repeated staging
+    // (measured 4 % slower), so they keep one warp per event.
+    const int pair = (MODEL != kTaylorF2 && !(opts->flags & GWF_OPT_ONE_WARP_PER_EVENT)) ? 1 : 0;
     const int per_cta = pair ? kWarpsPerCta / 2 : kWarpsPerCta;
     const long long want = (n + per_cta - 1) / per_cta;
     const unsigned grid = (unsigned)std::min<long long>(want, (long long)sms);
@@ -547,11 +580,14 @@ static int run_snr(const gwf_model* model, const gwf_detector* dets, int ndet, c
     int dev = 0, sms = 0;
     GWF_CUDA(cudaGetDevice(&dev));
     GWF_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    const size_t base = (sizeof(WarpSmem<Rec, typename PointFns<MODEL, 4>::Extra>) + sizeof(double) * net.narms * 32) * kSnrWarps;
+    const size_t base = sizeof(WarpSmem<Rec, typename PointFns<MODEL, 4>::Extra>) * kSnrGroups + sizeof(double) * net.narms * (32 * kSnrWarps + kSnrWarps);
     const size_t shmem = plan_psd_cache(net, base, kSmemLimit);
-    auto kern = snr_kernel<MODEL>;
-    GWF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem));
-    const long long want = (n + kSnrWarps - 1) / kSnrWarps;
+    constexpr bool kHasFast = PointFns<MODEL, 4>::kHasFast;
+    typedef void (*Kern)(const Rec*, EventsDev, long long, int, int, ModelCfg, const NetworkDev, int, double*);
+    const Kern kerns[3] = {snr_kernel<MODEL, 0>, kHasFast ? snr_kernel<MODEL, 1> : snr_kernel<MODEL, 0>, kHasFast ? snr_kernel<MODEL, 2> : snr_kernel<MODEL, 0>};
+    for (int k = 0; k < 3; ++k) GWF_CUDA(cudaFuncSetAttribute(kerns[k], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem));
+    const Kern kern = kerns[(kHasFast && !(opts->flags & GWF_OPT_GENERIC_LOOP)) ? plan_fast(net) : 0];
+    const long long want = (n + kSnrGroups - 1) / kSnrGroups;
     const unsigned grid = (unsigned)std::min<long long>(want, (long long)sms);
     const int lin = (opts->flags & GWF_OPT_LIN_GRID) ? 1 : 0;
     kern<<<grid, kSnrThreads, shmem, st>>>(recs, ev, n, opts->res, lin, cfg, net, net.narms, snr2_arm);

@@ -115,7 +115,9 @@ GWF_HD void nrt_taper(double x, double y, double& T, double& Ty) {
     const double e = exp(ex);
     const double ie1 = 1.0 / (e + 1.0);
     T = 1.0 - ie1;
-    Ty = e * ((a - 1.) / u + (a - 1.) / v + w / (u * u) + 1.2 * w / (v * v)) * ie1 * ie1;
+    // e/(e+1)^2 = T/(e+1): no overflow of e*(...) or underflow of 1/(e+1)^2 for e up to exp(700) (the reference's inf/inf
+    // there is turned into 0 by its nan_to_num, waveforms.py:1717; the true value is < 1e-290)
+    Ty = ((a - 1.) / u + (a - 1.) / v + w / (u * u) + 1.2 * w / (v * v)) * T * ie1;
 }
 
 }  // namespace gwf

@@ -7,7 +7,7 @@ import numpy as np
 from gwfast_b200 import _capi as K
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_SO = os.path.join(_HERE, 'emu', 'libgwfast_emu.so')
+_SO = os.environ.get("GWF_EMU_SO", os.path.join(_HERE, "emu", "libgwfast_emu.so"))
 _lib = None
 
 

@@ -63,6 +63,24 @@ def test_emulated_nrtidal_matches_masked_reference():
     assert snr_err(snr, out['snr']) < 1e-5 and fisher_err(F, out['fisher']) < 5e-3
 
 
+def test_emulated_nrtidal_taper_tangent_does_not_overflow():
+    """Event 5487 of the C3 catalog has a grid sample 5e-6 (in Mf) above f_merger: exp(...) ~ 1e300 in the Planck taper tangent
+    (waveforms.py:1714); the reference's inf/inf -> nan_to_num -> 0 must come out as a finite ~0 here, not inf*0 = NaN."""
+    import emu_driver as E
+    from conftest import make_network, copy_events
+    from gwfast_b200 import synthetic, signal
+    cfg = dict(model=dict(cls='IMRPhenomD_NRTidalv2'), network='ET+2CE', rot=True, fmin=2.)
+    ev = synthetic.bns_catalog(10000, synthetic.SEEDS['C3'], tidal=True)
+    sub = {k: v[[5487]] for k, v in ev.items()}
+    model, dets, psds = _emu_inputs(cfg)
+    e2 = signal._engine_events(model, sub)
+    packed, _ = E.run(model._descriptor(e2), dets, psds, e2)
+    F = E.unpack(packed, 13)[0]
+    assert np.all(np.isfinite(F))
+    port = make_network('port', dict(cfg, model=dict(cls='IMRPhenomD_NRTidalv2', kw=dict(taper_end_zero=True))))
+    assert fisher_err(F, port.FisherMatr(copy_events(sub))) < FISHER_TOL
+
+
 @pytest.mark.parametrize('name', ['c4_phenomhm_lvk', 'c4b_phenomhm_et'])
 def test_emulated_phenomhm_matches_reference(name):
     """IMRPhenomHM: six modes, complex mode sum, iota differentiated through the spin-weighted harmonics; the SNR keeps the

@@ -56,6 +56,9 @@ constexpr int kPInt = 5;    // 1, x, x^-3, log x, x^2/3 (the last only for NRTid
 constexpr int kPMrd = 5;    // 1, x, 1/x, x^3/4, x^2/3 (idem)
 constexpr int kAIns = 9;    // 1, x^2/3, x, x^4/3, x^5/3, x^2, x^7/3, x^8/3, x^3
 constexpr int kAInt = 5;    // (x - 0.014)^k, k=0..4
+// rows of the expanded tables are padded to an even number of doubles and 16-byte aligned: the per-frequency evaluation
+// reads a row (value + NT tangents) with 16-byte shared-memory loads
+template <int NT> struct RowLen { static constexpr int v = (NT + 2) & ~1; };
 template <int NT>
 struct PhenomDRec {
     double s;                 // x = s f      (s = M GMsun/c^3)
@@ -66,12 +69,12 @@ struct PhenomDRec {
     double C, lnC_d[NT];      // overall amplitude factor 2 sqrt(5/64pi) M^2 GMsun_c2_Gpc GMsun_c3/dL * amp0, and d ln C
     double C76;               // C * s^(-7/6): A = C76 f^(-7/6) ampIMR(x)
     double pc[kMaxGroups][1 + NT];   // per grid group: t0*xRef - phiRef  (xRef = s*fmin unless fRef given)
-    double pins[kPIns][1 + NT];
-    double pint[kPInt][1 + NT];
-    double pmrd[kPMrd][1 + NT];
+    alignas(16) double pins[kPIns][RowLen<NT>::v];
+    alignas(16) double pint[kPInt][RowLen<NT>::v];
+    alignas(16) double pmrd[kPMrd][RowLen<NT>::v];
     double atn[3][1 + NT];    // MRD arctan term: alpha4/eta, alpha5*fring, fdamp
-    double ains[kAIns][1 + NT];
-    double aint[kAInt][1 + NT];
+    alignas(16) double ains[kAIns][RowLen<NT>::v];
+    alignas(16) double aint[kAInt][RowLen<NT>::v];
     double amrd[4][1 + NT];   // fring, gamma2/(fdamp gamma3), fdamp*gamma3, fdamp*gamma3*gamma1
     TauRec tau;
 };
@@ -287,13 +290,21 @@ GWF_HD void phenomd_prologue(PhenomDRec<NT>& r, const Intrinsic<NT>& p, double d
 // ------------------------------------------------------------------------------------------------
 // per-frequency evaluation
 template <int K, int NT>
-GWF_HD void expand(const double (*c)[1 + NT], const double* b, const double* bx, double& v, double* d, double& dx) {
+GWF_HD void expand(const double (*c)[RowLen<NT>::v], const double* b, const double* bx, double& v, double* d, double& dx) {
 #pragma unroll
     for (int k = 0; k < K; ++k) {
-        v = fma(c[k][0], b[k], v);
-        dx = fma(c[k][0], bx[k], dx);
+        double row[RowLen<NT>::v];
+        const double2* src = reinterpret_cast<const double2*>(c[k]);
 #pragma unroll
-        for (int j = 0; j < NT; ++j) d[j] = fma(c[k][1 + j], b[k], d[j]);
+        for (int q = 0; q < RowLen<NT>::v / 2; ++q) {
+            const double2 t = src[q];
+            row[2 * q] = t.x;
+            row[2 * q + 1] = t.y;
+        }
+        v = fma(row[0], b[k], v);
+        dx = fma(row[0], bx[k], dx);
+#pragma unroll
+        for (int j = 0; j < NT; ++j) d[j] = fma(row[1 + j], b[k], d[j]);
     }
 }
 

@@ -119,10 +119,18 @@ __host__ __device__ inline void dd_jacobi(dd* a, dd* v, int n) {
     }
 }
 
+// inversion methods (invMethodIn of CovMatr, fisherTools.py:33-49)
+enum CovMethod {
+    kCovCholesky = 0,   // 'cho' (also serves 'inv' and 'lu': the same inverse), eigen route if not positive definite
+    kCovEigen = 1,      // 'svd': V diag(1/lambda) V^T
+    kCovEigenTrunc = 2, // 'svd' with truncate=True: singular values below thresh * max are raised to thresh * max (fisherTools.py:137-142)
+    kCovEigenReg = 3,   // 'svd_reg': singular values <= thresh (absolute) are excluded (fisherTools.py:164-175)
+};
+
 // One event of CovMatr.  F, C: element (i, j) at [(i * nP + j) * stride]; scratch: 3 * nP * nP dd.
 // Returns the status; *inv_err = max |C F - 1| (compute_inversion_error, evaluated in double like the reference).
-__host__ __device__ inline int cov_one(const double* __restrict__ F, long long stride, int nP, double* __restrict__ C, double* __restrict__ inv_err,
-                                       dd* __restrict__ A, dd* __restrict__ L, dd* __restrict__ V) {
+__host__ __device__ inline int cov_one(const double* __restrict__ F, long long stride, int nP, int method, double thresh, double* __restrict__ C,
+                                       double* __restrict__ inv_err, dd* __restrict__ A, dd* __restrict__ L, dd* __restrict__ V) {
     const int n = nP;
     bool all_nan = true;
     for (int i = 0; i < n * n; ++i) all_nan = all_nan && isnan(F[(long long)i * stride]);
@@ -139,7 +147,7 @@ __host__ __device__ inline int cov_one(const double* __restrict__ F, long long s
     for (int i = 0; i < n; ++i)
         for (int j = 0; j < n; ++j) A[i * n + j] = ws[i] * dd_make(F[(long long)(i * n + j) * stride]) * ws[j];
     // Cholesky A = L L^T
-    bool pd = true;
+    bool pd = method == kCovCholesky;
     for (int j = 0; j < n && pd; ++j) {
         dd d = A[j * n + j];
         for (int k = 0; k < j; ++k) d = d - L[j * n + k] * L[j * n + k];
@@ -174,10 +182,20 @@ __host__ __device__ inline int cov_one(const double* __restrict__ F, long long s
         // symmetric eigen route: inverse = V diag(1/lambda) V^T
         for (int i = 0; i < n * n; ++i) L[i] = A[i];
         dd_jacobi(L, V, n);
+        double smax = 0.0;
+        for (int k = 0; k < n; ++k) smax = fmax(smax, fabs(L[k * n + k].hi));
+        dd inv[kCovMaxP];
+        for (int k = 0; k < n; ++k) {
+            const dd lam = L[k * n + k];
+            const double sv = fabs(lam.hi);
+            if (method == kCovEigenTrunc && !(sv > thresh * smax)) inv[k] = dd_make((lam.hi < 0.0 ? -1.0 : 1.0) / (thresh * smax));
+            else if (method == kCovEigenReg && !(sv > thresh)) inv[k] = dd_make(0.0);
+            else inv[k] = dd_make(1.0) / lam;
+        }
         for (int i = 0; i < n; ++i)
             for (int j = 0; j <= i; ++j) {
                 dd s = dd_make(0.0);
-                for (int k = 0; k < n; ++k) s = s + V[i * n + k] * V[j * n + k] / L[k * n + k];
+                for (int k = 0; k < n; ++k) s = s + V[i * n + k] * V[j * n + k] * inv[k];
                 A[i * n + j] = A[j * n + i] = s;
             }
         if (!zero_diag) status = kCovOkEigen;
@@ -190,12 +208,14 @@ __host__ __device__ inline int cov_one(const double* __restrict__ F, long long s
             C[(long long)(i * n + j) * stride] = c.hi;
             finite = finite && isfinite(c.hi);
         }
+    // inversion error of the float64 covariance just written; the products are accumulated in double-double (the reference
+    // evaluates Cov @ Fisher in float128, fisherTools.py:56-57, 185), so what is measured is the rounding of Cov, not of the check
     double err = 0.0;
     for (int i = 0; i < n; ++i)
         for (int j = 0; j < n; ++j) {
-            double s = 0.0;
-            for (int k = 0; k < n; ++k) s += C[(long long)(i * n + k) * stride] * F[(long long)(k * n + j) * stride];
-            const double e = fabs(s - (i == j ? 1.0 : 0.0));
+            dd s = dd_make(i == j ? -1.0 : 0.0);
+            for (int k = 0; k < n; ++k) s = s + two_prod(C[(long long)(i * n + k) * stride], F[(long long)(k * n + j) * stride]);
+            const double e = fabs(s.hi);
             err = (e > err || isnan(e)) ? e : err;
         }
     *inv_err = err;
@@ -239,13 +259,13 @@ __host__ __device__ inline void eig_one(const double* __restrict__ F, long long 
 }
 
 #ifdef __CUDACC__
-__global__ void __launch_bounds__(64) covariance_kernel(const double* __restrict__ F, long long n, int nP, double* __restrict__ C, double* __restrict__ inv_err,
-                                                        int* __restrict__ status) {
+__global__ void __launch_bounds__(64) covariance_kernel(const double* __restrict__ F, long long n, int nP, int method, double thresh, double* __restrict__ C,
+                                                        double* __restrict__ inv_err, int* __restrict__ status) {
     const long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (e >= n) return;
     dd A[kCovMaxP * kCovMaxP], L[kCovMaxP * kCovMaxP], V[kCovMaxP * kCovMaxP];
     double err;
-    const int st = cov_one(F + e, n, nP, C + e, &err, A, L, V);
+    const int st = cov_one(F + e, n, nP, method, thresh, C + e, &err, A, L, V);
     inv_err[e] = err;
     if (status) status[e] = st;
 }
@@ -257,6 +277,21 @@ __global__ void __launch_bounds__(64) eigen_kernel(const double* __restrict__ F,
     double c;
     eig_one(F + e, n, nP, evals + e, evecs ? evecs + e : nullptr, &c, A, V);
     cond[e] = c;
+}
+// max |C F - 1| per event (compute_inversion_error, fisherTools.py:199-211)
+__global__ void __launch_bounds__(128) inversion_error_kernel(const double* __restrict__ F, const double* __restrict__ Cv, long long n, int nP,
+                                                              double* __restrict__ err) {
+    const long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    double m = 0.0;
+    for (int i = 0; i < nP; ++i)
+        for (int j = 0; j < nP; ++j) {
+            dd s = dd_make(i == j ? -1.0 : 0.0);
+            for (int k = 0; k < nP; ++k) s = s + two_prod(Cv[(long long)(i * nP + k) * n + e], F[(long long)(k * nP + j) * n + e]);
+            const double d = fabs(s.hi);
+            m = (d > m || isnan(d)) ? d : m;
+        }
+    err[e] = m;
 }
 #endif
 

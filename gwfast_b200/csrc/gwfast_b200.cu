@@ -20,6 +20,7 @@
 #include "../../include/gwfast_b200.h"
 #include "fisher_core.cuh"
 #include "host_build.h"
+#include "covariance.cuh"
 
 namespace gwf {
 
@@ -832,6 +833,39 @@ int gwf_waveform(const gwf_model* model, const gwf_events* events, int64_t n, co
         case GWF_IMRPHENOMHM: return run_waveform<kPhenomHM>(model, ev, n, f, res, f_is_2d, phi_out, ampl_out, tau_out, hphc_out, fcut_out, workspace, workspace_bytes, st);
         default: return fail(GWF_ERR_ARG, "unknown model");
     }
+}
+
+int gwf_covariance(const double* fisher, int64_t n, int32_t nP, int32_t method, double thresh, double* cov, double* inv_err, int32_t* status,
+                   void* stream) {
+    if (!fisher || !cov || !inv_err) return fail(GWF_ERR_ARG, "gwf_covariance: null argument");
+    if (nP < 1 || nP > kCovMaxP) return fail(GWF_ERR_ARG, "gwf_covariance: nP must be in [1, 16]");
+    if (method < 0 || method > 3) return fail(GWF_ERR_ARG, "gwf_covariance: unknown method");
+    if (n < 0) return fail(GWF_ERR_ARG, "negative event count");
+    if (n == 0) return GWF_OK;
+    const int tb = 64;
+    covariance_kernel<<<(unsigned)((n + tb - 1) / tb), tb, 0, reinterpret_cast<cudaStream_t>(stream)>>>(fisher, n, nP, method, thresh, cov, inv_err, status);
+    GWF_CUDA(cudaGetLastError());
+    return GWF_OK;
+}
+
+int gwf_eigen(const double* fisher, int64_t n, int32_t nP, double* evals, double* evecs, double* cond, void* stream) {
+    if (!fisher || !evals || !cond) return fail(GWF_ERR_ARG, "gwf_eigen: null argument");
+    if (nP < 1 || nP > kCovMaxP) return fail(GWF_ERR_ARG, "gwf_eigen: nP must be in [1, 16]");
+    if (n < 0) return fail(GWF_ERR_ARG, "negative event count");
+    if (n == 0) return GWF_OK;
+    const int tb = 64;
+    eigen_kernel<<<(unsigned)((n + tb - 1) / tb), tb, 0, reinterpret_cast<cudaStream_t>(stream)>>>(fisher, n, nP, evals, evecs, cond);
+    GWF_CUDA(cudaGetLastError());
+    return GWF_OK;
+}
+
+int gwf_inversion_error(const double* fisher, const double* cov, int64_t n, int32_t nP, double* err, void* stream) {
+    if (!fisher || !cov || !err || nP < 1) return fail(GWF_ERR_ARG, "gwf_inversion_error: bad arguments");
+    if (n == 0) return GWF_OK;
+    const int tb = 128;
+    inversion_error_kernel<<<(unsigned)((n + tb - 1) / tb), tb, 0, reinterpret_cast<cudaStream_t>(stream)>>>(fisher, cov, n, nP, err);
+    GWF_CUDA(cudaGetLastError());
+    return GWF_OK;
 }
 
 }  // extern "C"

@@ -136,6 +136,24 @@ int gwf_waveform(const gwf_model* model, const gwf_events* events, int64_t n, co
                  double* phi_out, double* ampl_out, double* tau_out, double* hphc_out, double* fcut_out,
                  void* workspace, size_t workspace_bytes, void* stream);
 
+/* Replaces fisherTools.CovMatr (gwfast/fisherTools.py:32-196): per event, normalise by the diagonal (ws F ws), invert, symmetrise,
+ * undo the normalisation; double-double arithmetic on the device instead of the reference's per-event mpmath loop.
+ *   fisher, cov: device (nP, nP, N) arrays, event axis fastest (the layout FisherMatr returns);  inv_err: [N] = max|cov F - 1|
+ *   method: 0 Cholesky ('cho'; also 'inv'/'lu'), falling back to the symmetric eigen-decomposition when the matrix is not positive
+ *           definite (the reference's alt_method='svd'); 1 eigen ('svd'); 2 eigen with singular values below thresh*max raised to it
+ *           (truncate=True, svals_thresh); 3 eigen with singular values <= thresh excluded ('svd_reg')
+ *   status: [N] or NULL: 0 Cholesky, 1 eigen route, 2 all-NaN input (NaN output, fisherTools.py:64-67), 3 non-finite result,
+ *           4 zero on the diagonal (normalisation skipped, fisherTools.py:97-99) */
+int gwf_covariance(const double* fisher, int64_t n, int32_t nP, int32_t method, double thresh, double* cov, double* inv_err, int32_t* status,
+                   void* stream);
+
+/* Replaces fisherTools.CheckFisher (fisherTools.py:216-279): eigenvalues ascending [nP][N], eigenvectors [nP][nP][N] (component i of
+ * vector k at (i, k); may be NULL), condition number max|lambda|/min|lambda| [N]. */
+int gwf_eigen(const double* fisher, int64_t n, int32_t nP, double* evals, double* evecs, double* cond, void* stream);
+
+/* Replaces fisherTools.compute_inversion_error (fisherTools.py:199-211): err[N] = max |cov F - 1|. */
+int gwf_inversion_error(const double* fisher, const double* cov, int64_t n, int32_t nP, double* err, void* stream);
+
 /* Diagnostics (no reference counterpart): sustained FP64 FMA throughput of the current device in TFLOP/s, measured with a
  * register-resident DFMA chain kernel over ~`ms` milliseconds; used by bench.py as the measured FP64 roofline denominator.
  * Synchronises the stream. */

@@ -8,6 +8,7 @@
 #include <cstring>
 #include "../../gwfast_b200/csrc/fisher_core.cuh"
 #include "../../gwfast_b200/csrc/host_build.h"
+#include "../../gwfast_b200/csrc/covariance.cuh"
 
 using namespace gwf;
 
@@ -157,6 +158,18 @@ static int emu_run_waveform(const gwf_model* model, const double* const* ev, lon
 }
 
 extern "C" {
+
+// fisherTools row: the double-double covariance / eigen routines of csrc/covariance.cuh driven on the host
+int emu_covariance(const double* F, long long n, int nP, int method, double thresh, double* cov, double* inv_err, int* status) {
+    std::vector<dd> A(kCovMaxP * kCovMaxP), L(kCovMaxP * kCovMaxP), V(kCovMaxP * kCovMaxP);
+    for (long long e = 0; e < n; ++e) status[e] = cov_one(F + e, n, nP, method, thresh, cov + e, inv_err + e, A.data(), L.data(), V.data());
+    return 0;
+}
+int emu_eigen(const double* F, long long n, int nP, double* evals, double* evecs, double* cond) {
+    std::vector<dd> A(kCovMaxP * kCovMaxP), V(kCovMaxP * kCovMaxP);
+    for (long long e = 0; e < n; ++e) eig_one(F + e, n, nP, evals + e, evecs ? evecs + e : nullptr, cond + e, A.data(), V.data());
+    return 0;
+}
 
 int emu_psd_lookup(const double* psd_f, const double* psd_S, int n, const double* f, int nf, double* out) {
     EmuPsd P;

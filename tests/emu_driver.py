@@ -96,3 +96,26 @@ def waveform(model, ev, f, want=('phi', 'ampl', 'tau')):
     if rc != 0:
         raise RuntimeError('emu_waveform failed %d' % rc)
     return out
+
+
+def covariance(F, method=0, thresh=1e-15):
+    """csrc/covariance.cuh:cov_one on the host: F (nP,nP,N) -> (cov, inv_err, status)."""
+    L = lib()
+    F = np.ascontiguousarray(F, dtype=float)
+    nP, _, n = F.shape
+    cov, err, st = np.zeros_like(F), np.zeros(n), np.zeros(n, dtype=np.int32)
+    dp = C.POINTER(C.c_double)
+    L.emu_covariance(F.ctypes.data_as(dp), C.c_longlong(n), nP, method, C.c_double(thresh), cov.ctypes.data_as(dp), err.ctypes.data_as(dp),
+                     st.ctypes.data_as(C.POINTER(C.c_int)))
+    return cov, err, st
+
+
+def eigen(F):
+    """csrc/covariance.cuh:eig_one on the host: F (nP,nP,N) -> (evals (nP,N), evecs (nP,nP,N), cond (N,))."""
+    L = lib()
+    F = np.ascontiguousarray(F, dtype=float)
+    nP, _, n = F.shape
+    ev, vec, cond = np.zeros((nP, n)), np.zeros_like(F), np.zeros(n)
+    dp = C.POINTER(C.c_double)
+    L.emu_eigen(F.ctypes.data_as(dp), C.c_longlong(n), nP, ev.ctypes.data_as(dp), vec.ctypes.data_as(dp), cond.ctypes.data_as(dp))
+    return ev, vec, cond

@@ -100,11 +100,12 @@ def _call_arrays(dets, psd_handles):
 KERNEL_FLAGS = 0
 
 
-def fisher(model, dets, psd_handles, ev, n, res, flags, per_arm, want_snr2=True, keep_on_device=False):
+def fisher(model, dets, psd_handles, ev, n, res, flags, per_arm, want_snr2=True, keep_on_device=False, want_snr_derivs=False):
     """Run gwf_fisher (+ gwf_unpack_fisher) on the current device.
 
     Returns ``(F, snr2, io)`` with ``F`` of shape ``(npass, nP, nP, n)`` and ``snr2`` ``(npass, n)`` as numpy arrays
-    (or device tensors if ``keep_on_device``); ``io`` = (h2d_bytes, d2h_bytes).
+    (or device tensors if ``keep_on_device``); ``io`` = (h2d_bytes, d2h_bytes).  With ``want_snr_derivs`` the second element
+    is the pair ``(snr2, snr_derivs)`` with ``snr_derivs`` of shape ``(npass, n, nP)`` (gwf_fisher_ex).
     """
     global launch_count
     st = state()
@@ -120,6 +121,7 @@ def fisher(model, dets, psd_handles, ev, n, res, flags, per_arm, want_snr2=True,
     sp = C.c_void_p(stream.cuda_stream)
     full = torch.empty((npass, nP, nP, n), dtype=torch.float64, device=st.device)
     snr2 = torch.empty((npass, n), dtype=torch.float64, device=st.device)
+    sder = torch.empty((npass, n, nP), dtype=torch.float64, device=st.device) if want_snr_derivs else None
     opts = K.gwf_opts(int(res), int(flags) | KERNEL_FLAGS, int(bool(per_arm)), 0)
     h2d = 0
     keep = []
@@ -131,9 +133,12 @@ def fisher(model, dets, psd_handles, ev, n, res, flags, per_arm, want_snr2=True,
         ws = _workspace(st, lib.gwf_workspace_bytes(C.byref(model), m))
         packed = torch.empty((npass, m, npack), dtype=torch.float64, device=st.device)
         s2 = torch.empty((npass, m), dtype=torch.float64, device=st.device)
-        K.check(lib.gwf_fisher(C.byref(model), darr, len(dets), parr, len(psd_handles), C.byref(evs), m, C.byref(opts),
-                               C.c_void_p(packed.data_ptr()), C.c_void_p(s2.data_ptr()), C.c_void_p(ws.data_ptr()), ws.numel(), sp),
-                'gwf_fisher')
+        sd = torch.empty((npass, m, nP), dtype=torch.float64, device=st.device) if want_snr_derivs else None
+        K.check(lib.gwf_fisher_ex(C.byref(model), darr, len(dets), parr, len(psd_handles), C.byref(evs), m, C.byref(opts),
+                                  C.c_void_p(packed.data_ptr()), C.c_void_p(s2.data_ptr()), C.c_void_p(sd.data_ptr()) if want_snr_derivs else None,
+                                  C.c_void_p(ws.data_ptr()), ws.numel(), sp), 'gwf_fisher')
+        if want_snr_derivs:
+            sder[:, lo:lo + m] = sd
         launch_count += 1 + npass
         if m == n:
             for p in range(npass):
@@ -149,13 +154,44 @@ def fisher(model, dets, psd_handles, ev, n, res, flags, per_arm, want_snr2=True,
             snr2[:, lo:lo + m] = s2
         keep.append((dev_ev, host_ev, packed))
     if keep_on_device:
-        return full, snr2, (h2d, 0)
+        return full, ((snr2, sder) if want_snr_derivs else snr2), (h2d, 0)
+    if want_snr_derivs:
+        stream.synchronize()
+        return full.cpu().numpy(), (snr2.cpu().numpy(), sder.cpu().numpy()), (h2d, (full.numel() + snr2.numel() + sder.numel()) * 8)
     out_f = torch.empty(full.shape, dtype=torch.float64, pin_memory=True)
     out_s = torch.empty(snr2.shape, dtype=torch.float64, pin_memory=True)
     out_f.copy_(full, non_blocking=True)
     out_s.copy_(snr2, non_blocking=True)
     stream.synchronize()
     return out_f.numpy(), out_s.numpy(), (h2d, (out_f.numel() + out_s.numel()) * 8)
+
+
+def strain_derivs(model, dets, psd_handles, ev, n, res, flags):
+    """Run gwf_strain_derivs: complex128 array (n_arms, nP, n, res)."""
+    global launch_count
+    st = state()
+    torch = st.torch
+    lib = st.lib
+    nP = lib.gwf_num_params(C.byref(model))
+    darr, parr = _call_arrays(dets, psd_handles)
+    narms = lib.gwf_num_arms(darr, len(dets))
+    stream = torch.cuda.current_stream(st.device)
+    sp = C.c_void_p(stream.cuda_stream)
+    out = np.empty((narms, nP, n, int(res)), dtype=np.complex128)
+    opts = K.gwf_opts(int(res), int(flags) | KERNEL_FLAGS, 1, 0)
+    # chunks of events sized to ~256 MB of output per launch group
+    chunk = max(1, min(n, int(2 ** 28 // (narms * nP * int(res) * 16)) or 1))
+    for lo in range(0, n, chunk):
+        m = min(chunk, n - lo)
+        sub = ev if (lo == 0 and m == n) else {k: np.asarray(v)[lo:lo + m] for k, v in ev.items() if k in K.EVENT_KEYS}
+        dev_ev, host_ev, evs, _ = _upload(st, sub, m, K.EVENT_KEYS)
+        ws = _workspace(st, lib.gwf_workspace_bytes(C.byref(model), m))
+        d = torch.empty((narms, nP, m, int(res), 2), dtype=torch.float64, device=st.device)
+        K.check(lib.gwf_strain_derivs(C.byref(model), darr, len(dets), parr, len(psd_handles), C.byref(evs), m, C.byref(opts),
+                                      C.c_void_p(d.data_ptr()), C.c_void_p(ws.data_ptr()), ws.numel(), sp), 'gwf_strain_derivs')
+        launch_count += 1 + narms
+        out[:, :, lo:lo + m, :] = torch.view_as_complex(d).cpu().numpy()
+    return out
 
 
 def snr(model, dets, psd_handles, ev, n, res, flags=0, keep_on_device=False):

@@ -239,6 +239,7 @@ struct PointWf {
     double phi_d[NT];
     double dtn[2];       // d t_noloc / d slot (days) = -dtau/86400 when the Earth rotates, else 0
     double tau;          // time to coalescence [s] (only when requested)
+    double phi;          // waveform phase Phi(f) (only read by the derivative write-out kernel)
 };
 
 // packed lower-triangular index
@@ -315,6 +316,20 @@ GWF_HD double compact_entry(int i, int j, const double* __restrict__ acc, const 
 template <int NT>
 GWF_HD double compact_snr2(const double* __restrict__ acc, const EvGeom& g) {
     return g.K * g.K * acc[Compact<NT>::kUU] + g.ci * g.ci * acc[Compact<NT>::kVV];     // 4 sum w |h|^2 / Sn, signal.py:727
+}
+
+// (h | d_row h) = 4 Re int conj(d_row h) h / Sn df from the same accumulators (return_SNR_derivatives, signal.py:938-945):
+// h = A e^{i Psi} (K u + i c v), so a general row contributes K P + c Q and the fixed-combination rows only UU, VV, UV
+template <int NT>
+GWF_HD double compact_snr_deriv(int row, const double* __restrict__ acc, const EvGeom& g) {
+    typedef Compact<NT> C;
+    const int gx = C::g_of(row);
+    if (gx >= 0) return g.K * acc[C::kGG + 4 * gx] + g.ci * acc[C::kGG + 4 * gx + 1];
+    const double al[4] = {-g.K * g.inv_dL, -g.ci * g.si, -2.0 * g.ci, -g.K};
+    const double be[4] = {-g.ci * g.inv_dL, -g.si, 2.0 * g.K, g.ci};
+    const int sidx = -gx - 1;
+    if (sidx < 2) return al[sidx] * g.K * acc[C::kUU] + be[sidx] * g.ci * acc[C::kVV];     // rows (alpha u, beta v)
+    return (be[sidx] * g.K + al[sidx] * g.ci) * acc[C::kUV];                               // rows (beta v, alpha u)
 }
 
 // general rows of d h / d p (divided by A e^{i Psi}) for one arm: ra + i rb for the NG general parameters, and the

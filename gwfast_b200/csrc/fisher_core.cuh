@@ -32,8 +32,7 @@ template <int NT> struct ModelTraits<kTaylorF2, NT> {
     static GWF_HD void eval(const Rec& r, const ModelCfg&, int, const FreqPoint& fp, bool need_tau, PointWf<NT>& w) {
         VPow p;
         p.set(r.sp, fp);
-        double phi;
-        tf2_phase(r, p, phi, w.phi_d);
+        tf2_phase(r, p, w.phi, w.phi_d);
         w.A = r.C * fp.fm76;
 #pragma unroll
         for (int j = 0; j < NT; ++j) w.lnA_d[j] = r.lnC_d[j];
@@ -70,8 +69,7 @@ template <int NT> struct ModelTraits<kPhenomD, NT> {
         XPow p;
         p.set(r.s, r.sp, fp);
         const bool cut = !(cfg.flags & kFlagNoFcut);
-        double phi;
-        phenomd_phase(r, g, p, cut, phi, w.phi_d);
+        phenomd_phase(r, g, p, cut, w.phi, w.phi_d);
         phenomd_amp(r, p, cut, w.A, w.lnA_d);
         w.dtn[0] = w.dtn[1] = 0.;
         w.tau = 0.;
@@ -116,6 +114,7 @@ template <int NT> struct ModelTraits<kNRTidalv2, NT> {
         p.set(d.s, d.sp, fp);
         w.dtn[0] = w.dtn[1] = 0.;
         w.tau = 0.;
+        w.phi = 0.;
         const double cp = 1.4645918875615232630201425272637904;      // pi^(1/3)
         const double p13 = cp * p.x13;
         // amplitude: C [x^(-7/6) ampIMR + kam Q] T, waveforms.py:1724
@@ -142,11 +141,11 @@ template <int NT> struct ModelTraits<kNRTidalv2, NT> {
         (void)inside;
         // phase: PhenomD regions (+ SS/SSS folded into the x^(2/3) slots) + Pade tidal term, all inside the cut (waveforms.py:1570)
         const bool cut = !(cfg.flags & kFlagNoFcut);
-        double phi;
-        phenomd_phase(d, g, p, cut, phi, w.phi_d);
+        phenomd_phase(d, g, p, cut, w.phi, w.phi_d);
         if (!cut || p.x < kMfCut) {
             double R, xRp;
             nrt_phase_shape(p13, R, xRp);
+            w.phi += r.kph[0] * R;
 #pragma unroll
             for (int j = 0; j < NT; ++j) w.phi_d[j] += r.kph[1 + j] * R + r.kph[0] * xRp * d.lam[j];
         }
@@ -393,7 +392,8 @@ struct HMExtra {
     GWF_HD void set(const EventIn& e) { w.set(e.iota); }
 };
 
-template <int NT>
+// SD: also accumulate (h | d_i h) behind the SNR^2 slot (return_SNR_derivatives)
+template <int NT, bool SD = false>
 GWF_HD void hm_point(const HMRec<NT>& rec, const ModelCfg& cfg, const EvGeom& geom, const NetworkDev& net, const EventScratch& sc,
                      const HMExtra& ex, int g, bool group_rot, const FreqPoint& fp, double* __restrict__ acc) {
     typedef Dual<NT> D;
@@ -475,6 +475,11 @@ GWF_HD void hm_point(const HMRec<NT>& rec, const ModelCfg& cfg, const EvGeom& ge
             ra[8] = Hi;                                                  rb[8] = -Hr;
             const double wg = wgt * a.weight;
             snr2 = fma(wg, Hr * Hr + Hi * Hi, snr2);
+            if (SD) {
+                const double wr = wg * Hr, wi = wg * Hi;
+#pragma unroll
+                for (int i = 0; i < NP; ++i) acc[NP * (NP + 1) / 2 + 1 + i] = fma(wr, ra[i], fma(wi, rb[i], acc[NP * (NP + 1) / 2 + 1 + i]));
+            }
 #pragma unroll
             for (int i = 0; i < NP; ++i) {
                 const double wa = wg * ra[i], wb = wg * rb[i];
@@ -561,25 +566,28 @@ template <int MODEL, int NT> struct PointFns {
 #endif
     static GWF_HD double entry(int i, int j, const double* __restrict__ red, const EvGeom& geom) { return compact_entry<NT>(i, j, red, geom); }
     static GWF_HD double snr2(const double* __restrict__ red, const EvGeom& geom) { return compact_snr2<NT>(red, geom); }
+    static GWF_HD double snr_deriv(int row, const double* __restrict__ red, const EvGeom& geom) { return compact_snr_deriv<NT>(row, red, geom); }
     static GWF_HD void snr(const Rec& rec, const ModelCfg& cfg, const EvGeom& geom, const NetworkDev& net, const EventScratch& sc, const Extra&, int g,
                            bool rot, const FreqPoint& fp, double* __restrict__ s2) {
         amp_phase_snr_point<MODEL>(rec, cfg, geom, net, sc, g, rot, fp, s2);
     }
 };
-template <int NT> struct PointFns<kPhenomHM, NT> {
+// IMRPhenomHM: SD = true adds the (h | d_i h) accumulators (the (2,2)-only models get them from the compact Gram for free)
+template <int NT, bool SD = false> struct PointFnsHM {
     typedef HMExtra Extra;
     typedef HMRec<NT> Rec;
-    static constexpr int kAcc = (NT + 7) * (NT + 8) / 2 + 1;
+    static constexpr int kAcc = (NT + 7) * (NT + 8) / 2 + 1 + (SD ? NT + 7 : 0);
     static GWF_HD void fisher(const Rec& rec, const ModelCfg& cfg, const EvGeom& geom, const NetworkDev& net, const EventScratch& sc, const Extra& ex, int g,
                               bool rot, const FreqPoint& fp, double* __restrict__ acc) {
-        hm_point<NT>(rec, cfg, geom, net, sc, ex, g, rot, fp, acc);
+        hm_point<NT, SD>(rec, cfg, geom, net, sc, ex, g, rot, fp, acc);
     }
+    static GWF_HD double snr_deriv(int row, const double* __restrict__ red, const EvGeom&) { return SD ? red[(NT + 7) * (NT + 8) / 2 + 1 + row] : 0.0; }
     static constexpr bool kHasFast = false;
 #ifdef __CUDA_ARCH__
     template <bool ROT>
     static __device__ __forceinline__ void fisher_fast(const Rec& rec, const ModelCfg& cfg, const EvGeom& geom, const NetworkDev& net, const EventScratch& sc,
                                                        const Extra& ex, const FreqPoint& fp, double* __restrict__ acc) {
-        hm_point<NT>(rec, cfg, geom, net, sc, ex, 0, ROT, fp, acc);
+        hm_point<NT, SD>(rec, cfg, geom, net, sc, ex, 0, ROT, fp, acc);
     }
     template <bool ROT>
     static __device__ __forceinline__ void snr_fast(const Rec& rec, const ModelCfg& cfg, const EvGeom& geom, const NetworkDev& net, const EventScratch& sc,
@@ -594,6 +602,11 @@ template <int NT> struct PointFns<kPhenomHM, NT> {
         hm_snr_point(rec, cfg, geom, net, sc, ex, g, rot, fp, s2);
     }
 };
+
+template <int NT> struct PointFns<kPhenomHM, NT> : PointFnsHM<NT, false> {};
+// selects the accumulator set of a launch: SD only changes IMRPhenomHM
+template <int MODEL, int NT, bool SD> struct PointFnsSel { typedef PointFns<MODEL, NT> type; };
+template <int NT> struct PointFnsSel<kPhenomHM, NT, true> { typedef PointFnsHM<NT, true> type; };
 
 // ------------------------------------------------------------------ stand-alone waveform values (WaveFormModel.Phi/Ampl/tau_star/hphc)
 // out: phi[nm], amp[nm] (nm = 1, or 6 for IMRPhenomHM), tau, and for HM hp = (re, im), hc = (re, im)

@@ -282,16 +282,16 @@ __device__ __forceinline__ void stage_event(WarpSmem<Rec, Extra>* mine, const Re
     __syncwarp();
 }
 
-template <int MODEL, int NT, int FAST>
+template <int MODEL, int NT, int FAST, bool SD>
 #ifdef GWF_FISHER_MAXNREG
 __global__ void __maxnreg__(GWF_FISHER_MAXNREG)
 #else
 __global__ void __launch_bounds__(kFisherThreads, GWF_FISHER_MINBLOCKS)
 #endif
 fisher_kernel(const typename ModelTraits<MODEL, NT>::Rec* __restrict__ recs, EventsDev ev, long long n, int res, int lin, ModelCfg cfg,
-              const __grid_constant__ NetworkDev net, double* __restrict__ out, double* __restrict__ snr2_out, int pair) {
+              const __grid_constant__ NetworkDev net, double* __restrict__ out, double* __restrict__ snr2_out, double* __restrict__ sd_out, int pair) {
     typedef typename ModelTraits<MODEL, NT>::Rec Rec;
-    typedef PointFns<MODEL, NT> PF;
+    typedef typename PointFnsSel<MODEL, NT, SD>::type PF;
     typedef WarpSmem<Rec, typename PF::Extra> WS;
     constexpr int NP = NT + 7, NPACK = NP * (NP + 1) / 2;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -377,9 +377,93 @@ fisher_kernel(const typename ModelTraits<MODEL, NT>::Rec* __restrict__ recs, Eve
                 o[p] = PF::entry(i, p - tri(i, 0), red, geom);
             }
             if (lane == 0 && snr2_out) snr2_out[e] = PF::snr2(red, geom);
+            if (sd_out && lane < NP) sd_out[e * NP + lane] = PF::snr_deriv(lane, red, geom);     // (h | d_i h), signal.py:938-945
         }
         // the partner may only overwrite its staging block once its sums have been read
         if (pair) asm volatile("bar.sync %0, 64;" ::"r"(1 + slot) : "memory");
+    }
+}
+
+// return_derivatives (signal.py:917-945): the derivative strain d h / d p_i of ONE arm (a per-arm pass network) written out as
+// complex128 [nP][n][res] -- the array the Fisher kernel deliberately never materialises.  Same rows as arm_rows / Compact, times
+// A e^{i Psi} with Psi = 2 pi f tcoal 86400 - Phicoal - Phi(f) + 2 pi f Delta t (signal.py:484, 580, 641); HBM-write bound.
+template <int MODEL, int NT>
+__global__ void __launch_bounds__(kFisherThreads)
+derivs_kernel(const typename ModelTraits<MODEL, NT>::Rec* __restrict__ recs, EventsDev ev, long long n, int res, int lin, ModelCfg cfg,
+              const __grid_constant__ NetworkDev net, double2* __restrict__ out) {
+    typedef typename ModelTraits<MODEL, NT>::Rec Rec;
+    typedef PointFns<MODEL, NT> PF;
+    typedef WarpSmem<Rec, typename PF::Extra> WS;
+    typedef Compact<NT> CP;
+    constexpr int NP = NT + 7;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    WS* mine = reinterpret_cast<WS*>(smem_raw) + wid;
+    const Rec& rec = mine->rec;
+    const long long nwarps = (long long)gridDim.x * kWarpsPerCta;
+    for (long long e = (long long)blockIdx.x * kWarpsPerCta + wid; e < n; e += nwarps) {
+        double phicoal;
+        {
+            EvGeom g0;
+            const EventIn in = load_event(ev, e);
+            phicoal = in.Phicoal;
+            g0.set(in);
+            stage_event<false>(mine, recs, e, net, g0, in, lane);
+        }
+        const EvGeom& geom = mine->geom;
+        // the one detector / arm of this pass
+        int di = 0;
+        while (di < net.ndet - 1 && net.det[di].arm_begin == net.det[di].arm_end) ++di;
+        const DetDev& d = net.det[di];
+        const ArmDev& arm = net.arm[d.arm_begin];
+        const int g = d.group;
+        double fcut = rec.fcut_hz;
+        if (net.group_fmax[g] > 0.0 && fcut > net.group_fmax[g]) fcut = net.group_fmax[g];
+        Grid grid;
+        grid.set(net.group_fmin[g], fcut, res, lin != 0, 32);
+        const bool rot = d.use_rot != 0;
+        for (int k = lane; k < res; k += 32) {
+            FreqPoint fp;
+            grid.start(k, fp);
+            PointWf<NT> w;
+            ModelTraits<MODEL, NT>::eval(rec, cfg, g, fp, rot, w);
+            w.f = fp.f;
+            double2 row[NP];
+#pragma unroll
+            for (int i = 0; i < NP; ++i) row[i] = make_double2(0.0, 0.0);
+            if (w.A != 0.0) {
+                double sBr = 0., cBr = 1.;
+                if (rot) sincos(2.0 * kPi * fma(-w.tau, kInvDay, geom.tcoal), &sBr, &cBr);
+                DetPoint dp;
+                if (rot) det_point(mine->sc.ed[di], cBr, sBr, dp);
+                else dp = mine->sc.fixed[di];
+                DetRows<NT> dr;
+                dr.set(w, dp, rot, d.no_motion != 0);
+                double ra[CP::NG], rb[CP::NG], u, v;
+                arm_rows<NT>(w, dp, dr, arm, geom, ra, rb, u, v);
+                const double W2 = 2.0 * kPi * fp.f;
+                const double Psi = (W2 * (geom.tcoal * 3600. * 24.) - phicoal - w.phi) + W2 * dp.dt;
+                double sP, cP;
+                sincos(Psi, &sP, &cP);
+                const double zr = w.A * cP, zi = w.A * sP;
+                const double al[4] = {-geom.K * geom.inv_dL, -geom.ci * geom.si, -2.0 * geom.ci, -geom.K};
+                const double be[4] = {-geom.ci * geom.inv_dL, -geom.si, 2.0 * geom.K, geom.ci};
+#pragma unroll
+                for (int i = 0; i < NP; ++i) {
+                    const int gx = CP::g_of(i);
+                    double a, b;
+                    if (gx >= 0) { a = ra[gx]; b = rb[gx]; }
+                    else {
+                        const int sidx = -gx - 1;
+                        if (sidx < 2) { a = al[sidx] * u; b = be[sidx] * v; }
+                        else { a = be[sidx] * v; b = al[sidx] * u; }
+                    }
+                    row[i] = make_double2(a * zr - b * zi, a * zi + b * zr);
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < NP; ++i) out[((long long)i * n + e) * res + k] = row[i];
+        }
     }
 }
 
@@ -498,7 +582,7 @@ static int collect_psds(const gwf_psd* const* psds, int npsd, PsdDev* out) {
 
 template <int MODEL, int NT>
 static int run_fisher(const gwf_model* model, const gwf_detector* dets, int ndet, const gwf_psd* const* psds, int npsd, const EventsDev& ev,
-                      long long n, const gwf_opts* opts, double* fisher, double* snr2, void* ws, size_t ws_bytes, cudaStream_t st) {
+                      long long n, const gwf_opts* opts, double* fisher, double* snr2, double* snr_derivs, void* ws, size_t ws_bytes, cudaStream_t st) {
     typedef typename ModelTraits<MODEL, NT>::Rec Rec;
     constexpr int NP = NT + 7, NPACK = NP * (NP + 1) / 2;
     if (ws_bytes < sizeof(Rec) * (size_t)n) return fail(GWF_ERR_WORKSPACE, "workspace too small");
@@ -527,9 +611,12 @@ static int run_fisher(const gwf_model* model, const gwf_detector* dets, int ndet
     // the unrolled form pays off where the waveform leaves registers for it (measured: IMRPhenomD 1.55 -> 1.31 ms, NRTidalv2
     // 3.73 -> 3.21 ms per 1e4 events; TaylorF2's version spills and is 7-20 % slower than the general loop)
     constexpr bool kHasFast = PointFns<MODEL, NT>::kHasFast && MODEL != kTaylorF2;
-    typedef void (*Kern)(const Rec*, EventsDev, long long, int, int, ModelCfg, const NetworkDev, double*, double*, int);
-    const Kern kerns[3] = {fisher_kernel<MODEL, NT, 0>, kHasFast ? fisher_kernel<MODEL, NT, 1> : fisher_kernel<MODEL, NT, 0>,
-                           kHasFast ? fisher_kernel<MODEL, NT, 2> : fisher_kernel<MODEL, NT, 0>};
+    typedef void (*Kern)(const Rec*, EventsDev, long long, int, int, ModelCfg, const NetworkDev, double*, double*, double*, int);
+    // IMRPhenomHM needs extra accumulators for the SNR derivatives (its own instantiation); the other models rebuild them
+    // from the compact Gram whenever the output pointer is given
+    constexpr bool kSdKernel = MODEL == kPhenomHM;
+    const Kern k0 = (kSdKernel && snr_derivs) ? fisher_kernel<MODEL, NT, 0, kSdKernel> : fisher_kernel<MODEL, NT, 0, false>;
+    const Kern kerns[3] = {k0, kHasFast ? fisher_kernel<MODEL, NT, 1, false> : k0, kHasFast ? fisher_kernel<MODEL, NT, 2, false> : k0};
     for (int k = 0; k < 3; ++k) GWF_CUDA(cudaFuncSetAttribute(kerns[k], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem));
     const bool allow_fast = kHasFast && !(opts->flags & GWF_OPT_GENERIC_LOOP);
     int fast = allow_fast ? plan_fast(net) : 0;
@@ -552,7 +639,49 @@ static int run_fisher(const gwf_model* model, const gwf_detector* dets, int ndet
             fast = allow_fast ? plan_fast(net) : 0;
         }
         kerns[fast]<<<grid, kFisherThreads, shmem, st>>>(recs, ev, n, opts->res, lin, cfg, net, fisher + (size_t)pass * n * NPACK,
-                                                  snr2 ? snr2 + (size_t)pass * n : nullptr, pair);
+                                                  snr2 ? snr2 + (size_t)pass * n : nullptr,
+                                                  snr_derivs ? snr_derivs + (size_t)pass * n * NP : nullptr, pair);
+        GWF_CUDA(cudaGetLastError());
+    }
+    return GWF_OK;
+}
+
+template <int MODEL, int NT>
+static int run_derivs(const gwf_model* model, const gwf_detector* dets, int ndet, const gwf_psd* const* psds, int npsd, const EventsDev& ev,
+                      long long n, const gwf_opts* opts, double* derivs, void* ws, size_t ws_bytes, cudaStream_t st) {
+    typedef typename ModelTraits<MODEL, NT>::Rec Rec;
+    constexpr int NP = NT + 7;
+    if (ws_bytes < sizeof(Rec) * (size_t)n) return fail(GWF_ERR_WORKSPACE, "workspace too small");
+    Rec* recs = reinterpret_cast<Rec*>(ws);
+    ModelCfg cfg = {model->id, model->flags, model->fcutPar, model->fRef};
+    NetworkDev net;
+    PsdDev pd[kMaxPsd];
+    int rc = collect_psds(psds, npsd, pd);
+    if (rc) return rc;
+    rc = build_network(dets, ndet, pd, npsd, -1, false, net);
+    if (rc) return rc;
+    GroupInfo gi;
+    gi.n = net.ngroups;
+    for (int g = 0; g < kMaxGroups; ++g) gi.fmin[g] = net.group_fmin[g];
+    const int pb = 128;
+    prologue_kernel<MODEL, NT><<<(unsigned)((n + pb - 1) / pb), pb, 0, st>>>(ev, n, cfg, opts->flags, g_qnm, gi, recs);
+    GWF_CUDA(cudaGetLastError());
+    int dev = 0, sms = 0;
+    GWF_CUDA(cudaGetDevice(&dev));
+    GWF_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const size_t shmem = sizeof(WarpSmem<Rec, typename PointFns<MODEL, NT>::Extra>) * kWarpsPerCta;
+    auto kern = derivs_kernel<MODEL, NT>;
+    GWF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem));
+    const long long want = (n + kWarpsPerCta - 1) / kWarpsPerCta;
+    const unsigned grid = (unsigned)std::min<long long>(want, (long long)sms * 2);
+    const int lin = (opts->flags & GWF_OPT_LIN_GRID) ? 1 : 0;
+    const int npass = gwf_num_arms(dets, ndet);
+    for (int pass = 0; pass < npass; ++pass) {
+        rc = build_network(dets, ndet, pd, npsd, pass, false, net);
+        if (rc) return rc;
+        for (int i = 0; i < net.npsd; ++i) net.psd[i].c_off = -1;
+        kern<<<grid, kFisherThreads, shmem, st>>>(recs, ev, n, opts->res, lin, cfg, net,
+                                                  reinterpret_cast<double2*>(derivs) + (size_t)pass * NP * n * opts->res);
         GWF_CUDA(cudaGetLastError());
     }
     return GWF_OK;
@@ -719,8 +848,9 @@ static int check_common(const gwf_model* model, const gwf_detector* dets, const 
     return GWF_OK;
 }
 
-int gwf_fisher(const gwf_model* model, const gwf_detector* dets, int32_t ndet, const gwf_psd* const* psds, int32_t npsd, const gwf_events* events,
-               int64_t n, const gwf_opts* opts, double* fisher_packed, double* snr2, void* workspace, size_t workspace_bytes, void* stream) {
+int gwf_fisher_ex(const gwf_model* model, const gwf_detector* dets, int32_t ndet, const gwf_psd* const* psds, int32_t npsd, const gwf_events* events,
+                  int64_t n, const gwf_opts* opts, double* fisher_packed, double* snr2, double* snr_derivs, void* workspace, size_t workspace_bytes,
+                  void* stream) {
     int rc = check_common(model, dets, psds, events, n, opts);
     if (rc) return rc;
     if (!fisher_packed) return fail(GWF_ERR_ARG, "null output");
@@ -732,18 +862,49 @@ int gwf_fisher(const gwf_model* model, const gwf_detector* dets, int32_t ndet, c
         case GWF_TAYLORF2:
             if (model->flags & GWF_MODEL_TIDAL) {
                 if (!ev.p[11] || !ev.p[12]) return fail(GWF_ERR_ARG, "tidal model needs Lambda1, Lambda2");
-                return run_fisher<kTaylorF2, 6>(model, dets, ndet, psds, npsd, ev, n, opts, fisher_packed, snr2, workspace, workspace_bytes, st);
+                return run_fisher<kTaylorF2, 6>(model, dets, ndet, psds, npsd, ev, n, opts, fisher_packed, snr2, snr_derivs, workspace, workspace_bytes, st);
             }
-            return run_fisher<kTaylorF2, 4>(model, dets, ndet, psds, npsd, ev, n, opts, fisher_packed, snr2, workspace, workspace_bytes, st);
+            return run_fisher<kTaylorF2, 4>(model, dets, ndet, psds, npsd, ev, n, opts, fisher_packed, snr2, snr_derivs, workspace, workspace_bytes, st);
         case GWF_IMRPHENOMD:
-            return run_fisher<kPhenomD, 4>(model, dets, ndet, psds, npsd, ev, n, opts, fisher_packed, snr2, workspace, workspace_bytes, st);
+            return run_fisher<kPhenomD, 4>(model, dets, ndet, psds, npsd, ev, n, opts, fisher_packed, snr2, snr_derivs, workspace, workspace_bytes, st);
         case GWF_IMRPHENOMD_NRTIDALV2:
             if (!ev.p[11] || !ev.p[12]) return fail(GWF_ERR_ARG, "tidal model needs Lambda1, Lambda2");
-            return run_fisher<kNRTidalv2, 6>(model, dets, ndet, psds, npsd, ev, n, opts, fisher_packed, snr2, workspace, workspace_bytes, st);
+            return run_fisher<kNRTidalv2, 6>(model, dets, ndet, psds, npsd, ev, n, opts, fisher_packed, snr2, snr_derivs, workspace, workspace_bytes, st);
         case GWF_IMRPHENOMHM:
-            return run_fisher<kPhenomHM, 4>(model, dets, ndet, psds, npsd, ev, n, opts, fisher_packed, snr2, workspace, workspace_bytes, st);
+            return run_fisher<kPhenomHM, 4>(model, dets, ndet, psds, npsd, ev, n, opts, fisher_packed, snr2, snr_derivs, workspace, workspace_bytes, st);
         default:
             return fail(GWF_ERR_UNSUPPORTED, "model not built yet");
+    }
+}
+
+int gwf_fisher(const gwf_model* model, const gwf_detector* dets, int32_t ndet, const gwf_psd* const* psds, int32_t npsd, const gwf_events* events,
+               int64_t n, const gwf_opts* opts, double* fisher_packed, double* snr2, void* workspace, size_t workspace_bytes, void* stream) {
+    return gwf_fisher_ex(model, dets, ndet, psds, npsd, events, n, opts, fisher_packed, snr2, nullptr, workspace, workspace_bytes, stream);
+}
+
+int gwf_strain_derivs(const gwf_model* model, const gwf_detector* dets, int32_t ndet, const gwf_psd* const* psds, int32_t npsd, const gwf_events* events,
+                      int64_t n, const gwf_opts* opts, double* derivs, void* workspace, size_t workspace_bytes, void* stream) {
+    int rc = check_common(model, dets, psds, events, n, opts);
+    if (rc) return rc;
+    if (!derivs) return fail(GWF_ERR_ARG, "null output");
+    if (n == 0) return GWF_OK;
+    EventsDev ev;
+    for (int i = 0; i < GWF_NPARAM_IN; ++i) ev.p[i] = events->p[i];
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    switch (model->id) {
+        case GWF_TAYLORF2:
+            if (model->flags & GWF_MODEL_TIDAL) {
+                if (!ev.p[11] || !ev.p[12]) return fail(GWF_ERR_ARG, "tidal model needs Lambda1, Lambda2");
+                return run_derivs<kTaylorF2, 6>(model, dets, ndet, psds, npsd, ev, n, opts, derivs, workspace, workspace_bytes, st);
+            }
+            return run_derivs<kTaylorF2, 4>(model, dets, ndet, psds, npsd, ev, n, opts, derivs, workspace, workspace_bytes, st);
+        case GWF_IMRPHENOMD:
+            return run_derivs<kPhenomD, 4>(model, dets, ndet, psds, npsd, ev, n, opts, derivs, workspace, workspace_bytes, st);
+        case GWF_IMRPHENOMD_NRTIDALV2:
+            if (!ev.p[11] || !ev.p[12]) return fail(GWF_ERR_ARG, "tidal model needs Lambda1, Lambda2");
+            return run_derivs<kNRTidalv2, 6>(model, dets, ndet, psds, npsd, ev, n, opts, derivs, workspace, workspace_bytes, st);
+        default:
+            return fail(GWF_ERR_UNSUPPORTED, "gwf_strain_derivs: not built for this model (IMRPhenomHM: use the Fisher / SNR-derivative outputs)");
     }
 }
 

@@ -73,10 +73,32 @@ class DetNet(object):
     def FisherMatr(self, evParams, return_all=False, return_derivatives=False, return_SNR_derivatives=False, **kwargs):
         """Total Fisher matrix, shape (nParams, nParams, N); with ``return_all`` a dict per detector/arm plus 'net'."""
         utils.check_evparams(evParams)
-        if return_derivatives or return_SNR_derivatives:
-            raise NotImplementedError('return_derivatives / return_SNR_derivatives are not built yet')
         names = list(self.signals.keys())
         sigs = [self.signals[d] for d in names]
+        if return_derivatives or return_SNR_derivatives:
+            # network.py:124-152: per-detector calls, every arm separately; 'net' of the SNR derivatives = sum over arms / network SNR
+            SNRs_net = kwargs.pop('SNRs', None)
+            allF, allDer = {}, {}
+            for d, s in zip(names, sigs):
+                if self.verbose:
+                    print('Computing Fisher for %s...' % d)
+                F_, D_ = s.FisherMatr(evParams, return_all=True, return_derivatives=return_derivatives,
+                                      return_SNR_derivatives=return_SNR_derivatives, **kwargs)
+                if s.detector_shape == 'T':
+                    for i in range(3):
+                        allF[d + '_%s' % i] = F_[i]
+                        allDer[d + '_%s' % i] = D_[i]
+                else:
+                    allF[d] = F_[0]
+                    allDer[d] = D_[0]
+            if return_SNR_derivatives and not return_derivatives:
+                if SNRs_net is None:
+                    SNRs_net = self.SNR(evParams, return_all=False)
+                allDer['net'] = onp.array([allDer[k] for k in allDer.keys()]).sum(axis=0) / SNRs_net
+            if self.verbose:
+                print('Done.')
+            allF['net'] = onp.array([allF[k] for k in allF.keys()]).sum(axis=0)
+            return allF, allDer
         if not self._fusable():
             allF = {}
             for d, s in zip(names, sigs):

@@ -28,7 +28,7 @@ def _num_events(evParams):
     return len(onp.atleast_1d(evParams['Mc']))
 
 
-def _engine_events(wf_model, evParams, lambdas=None, use_m1m2=False):
+def _engine_events(wf_model, evParams, lambdas=None, use_m1m2=False, exact_cut=False):
     """the arrays the engine consumes (never mutates the caller's dict).
 
     Besides the dict entries this passes two per-event scalars computed HERE with the reference's own numpy expressions:
@@ -40,8 +40,9 @@ def _engine_events(wf_model, evParams, lambdas=None, use_m1m2=False):
     if wf_model.is_tidal:
         L1, L2 = lambdas if lambdas is not None else (evParams['Lambda1'], evParams['Lambda2'])
         ev['Lambda1'], ev['Lambda2'] = L1, L2
-    if wf_model.is_HigherModes:
-        # only IMRPhenomHM needs it at the 1e-9 level (3e-12 for IMRPhenomD); two numpy pow() per event on the host
+    if wf_model.is_HigherModes or (exact_cut and not wf_model.is_tidal and type(wf_model).__name__ != 'TaylorF2_RestrictedPN'):
+        # only IMRPhenomHM needs it at the 1e-9 level (3e-12 for IMRPhenomD); two numpy pow() per event on the host.
+        # exact_cut: the strain-derivative output exposes the last sample itself, so IMRPhenomD asks for it there too
         ev['_fcut'] = wf_model.fcut(**evParams)
         Mc, eta = evParams['Mc'], evParams['eta']
         if use_m1m2:
@@ -68,7 +69,32 @@ def hot_snr(signals, evParams, res):
     return out, slices, io
 
 
-def hot_fisher(signals, evParams, lambdas, res, spacing, use_m1m2, use_chi1chi2, per_arm):
+def _fisher_flags(spacing, use_m1m2, use_chi1chi2):
+    flags = 0
+    if use_m1m2:
+        flags |= K.GWF_OPT_M1M2
+    if not use_chi1chi2:
+        flags |= K.GWF_OPT_CHIS_CHIA
+    if spacing == 'lin':
+        flags |= K.GWF_OPT_LIN_GRID
+    elif spacing != 'geom':
+        raise ValueError("spacing has to be 'geom' or 'lin'")
+    return flags
+
+
+def hot_strain_derivs(signals, evParams, lambdas, res, spacing, use_m1m2, use_chi1chi2):
+    """d h / d p_i per arm, complex128 (n_arms, nP, N, res) (return_derivatives, signal.py:917-945)."""
+    wf = signals[0].wf_model
+    n = _num_events(evParams)
+    dets, handles = [], []
+    for s in signals:
+        dets.append(s._detector_struct(len(handles)))
+        handles.append(s._psd_handle())
+    return _engine.strain_derivs(wf._descriptor(evParams), dets, handles, _engine_events(wf, evParams, lambdas, use_m1m2, exact_cut=True), n, res,
+                                 _fisher_flags(spacing, use_m1m2, use_chi1chi2))
+
+
+def hot_fisher(signals, evParams, lambdas, res, spacing, use_m1m2, use_chi1chi2, per_arm, want_snr_derivs=False):
     """Fisher matrices for a list of GWSignal sharing one waveform model: ONE prologue + one launch per block."""
     wf = signals[0].wf_model
     n = _num_events(evParams)
@@ -85,7 +111,8 @@ def hot_fisher(signals, evParams, lambdas, res, spacing, use_m1m2, use_chi1chi2,
     for s in signals:
         dets.append(s._detector_struct(len(handles)))
         handles.append(s._psd_handle())
-    F, snr2, io = _engine.fisher(wf._descriptor(evParams), dets, handles, _engine_events(wf, evParams, lambdas, use_m1m2), n, res, flags, per_arm)
+    F, snr2, io = _engine.fisher(wf._descriptor(evParams), dets, handles, _engine_events(wf, evParams, lambdas, use_m1m2), n, res, flags, per_arm,
+                                 want_snr_derivs=want_snr_derivs)
     return F, snr2, io
 
 
@@ -202,8 +229,8 @@ class GWSignal(object):
         if computeDerivFinDiff:
             raise NotImplementedError('finite-difference derivatives (numdifftools) are only used by the LAL/TEOBResumS wrappers of the reference; '
                                       'this engine always differentiates exactly')
-        if return_derivatives or return_SNR_derivatives:
-            raise NotImplementedError('return_derivatives / return_SNR_derivatives are not built yet (the derivative strain never leaves the GPU registers)')
+        if return_derivatives and self.wf_model.is_HigherModes:
+            raise NotImplementedError('return_derivatives is not built for IMRPhenomHM (return_SNR_derivatives is)')
         if res is None and df is not None:
             fcut = self.wf_model.fcut(**evParams)
             if self.fmax is not None:
@@ -224,6 +251,20 @@ class GWSignal(object):
             onp.random.seed(self.seedUse)
         lambdas, res = self._prepare_fisher(evParams, res, df, computeDerivFinDiff, return_derivatives, return_SNR_derivatives)
         n = _num_events(evParams)
+        if return_derivatives or return_SNR_derivatives:
+            # the reference returns (allFishers, allDerivs) or (allFishers, allSNRDerivs), one entry per arm (signal.py:1091-1098)
+            F, (_, sd), _ = hot_fisher([self], evParams, lambdas, res, spacing, use_m1m2, use_chi1chi2, True, want_snr_derivs=True)
+            D = hot_strain_derivs([self], evParams, lambdas, res, spacing, use_m1m2, use_chi1chi2) if return_derivatives else None
+            masks = onp.array(self._duty_masks(n)) if self.DutyFactor is not None else None
+            if masks is not None:
+                F = F * masks[:, None, None, :]
+                sd = sd * masks[:, :, None]
+                if D is not None:
+                    D = D * masks[:, None, :, None]
+            allF = [F[i] for i in range(F.shape[0])]
+            if return_derivatives:
+                return allF, [D[i] for i in range(D.shape[0])]
+            return allF, [onp.ascontiguousarray(sd[i].T) for i in range(sd.shape[0])]
         per_arm = return_all or (self.DutyFactor is not None)
         F, _, _ = hot_fisher([self], evParams, lambdas, res, spacing, use_m1m2, use_chi1chi2, per_arm)
         if self.DutyFactor is not None:

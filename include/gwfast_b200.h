@@ -117,6 +117,23 @@ int gwf_fisher(const gwf_model* model, const gwf_detector* dets, int32_t ndet, c
                const gwf_events* events, int64_t n, const gwf_opts* opts, double* fisher_packed, double* snr2,
                void* workspace, size_t workspace_bytes, void* stream);
 
+/* gwf_fisher with the return_SNR_derivatives output of GWSignal.FisherMatr (signal.py:938-945, network.py:124-152):
+ *   snr_derivs: NULL, or [n] (per_arm=0) / [n_arms][n] blocks of nP doubles: 4 Re int conj(d_i h) h / Sn df of the arms in the block,
+ *               rows in ParNums order (the tcoal row per second like the Fisher).  The reference returns this per arm
+ *               (per_arm=1) and divides the sum over arms by the network SNR on the host (network.py:143). */
+int gwf_fisher_ex(const gwf_model* model, const gwf_detector* dets, int32_t ndet, const gwf_psd* const* psds, int32_t npsd,
+                  const gwf_events* events, int64_t n, const gwf_opts* opts, double* fisher_packed, double* snr2, double* snr_derivs,
+                  void* workspace, size_t workspace_bytes, void* stream);
+
+/* The return_derivatives output of GWSignal.FisherMatr (signal.py:917-945, network.py:124-141): the derivative strain itself,
+ *   derivs: complex128 (re, im) [n_arms][nP][n][res], one block per arm (triangle arms 0, 60 deg, -(1+2)), rows in ParNums order, the
+ *           tcoal row per second (signal.py:920); samples beyond the waveform cut are 0.  TaylorF2, IMRPhenomD, IMRPhenomD_NRTidalv2.
+ * This is the array gwf_fisher never writes (nP * res * 16 B per event and arm); use it only when the strain derivatives themselves
+ * are wanted. */
+int gwf_strain_derivs(const gwf_model* model, const gwf_detector* dets, int32_t ndet, const gwf_psd* const* psds, int32_t npsd,
+                      const gwf_events* events, int64_t n, const gwf_opts* opts, double* derivs,
+                      void* workspace, size_t workspace_bytes, void* stream);
+
 /* Replaces DetNet.SNR / GWSignal.SNRInteg (network.py:53-81, signal.py:658-777).
  *   snr2_arm: [n_arms][n], the per-arm integrals 4 int (Ap^2+Ac^2)/Sn df (SNR_arm = sqrt of it) */
 int gwf_snr(const gwf_model* model, const gwf_detector* dets, int32_t ndet, const gwf_psd* const* psds, int32_t npsd,

@@ -17,3 +17,13 @@ round = _np.round
 complex128 = _np.complex128
 float64 = _np.float64
 ndarray = _np.ndarray
+
+
+def fabs(x, *a, **k):
+    """numpy.fabs, tolerant of complex input with zero imaginary part.  GWSignal.FisherMatr(return_SNR_derivatives=True) calls
+    GWstrain with the parameters cast to complex128 (gwfast/signal.py:815-816, 1017); IMRPhenomD's np.fabs (waveforms.py:1134, 1193)
+    then raises TypeError in numpy and in JAX alike -- a defect of the reference on that path.  The golden SNR derivatives
+    are generated with this one call made lenient (the imaginary parts are identically zero)."""
+    if _np.iscomplexobj(x):
+        x = _np.real(x)
+    return _np.fabs(x, *a, **k)

@@ -21,9 +21,9 @@ struct EmuPsd {
 static QnmTables g_q = {nullptr, nullptr, nullptr, 0};
 static std::vector<double> g_qbuf;
 
-template <int MODEL, int NT>
+template <int MODEL, int NT, bool SD = false>
 static int emu_run(const gwf_model* model, const gwf_detector* dets, int ndet, const PsdDev* pd, int npsd, const double* const* ev, long long n,
-                   const gwf_opts* opts, double* fisher, double* snr2) {
+                   const gwf_opts* opts, double* fisher, double* snr2, double* sd = nullptr) {
     typedef typename ModelTraits<MODEL, NT>::Rec Rec;
     constexpr int NP = NT + 7, NPACK = NP * (NP + 1) / 2;
     ModelCfg cfg = {model->id, model->flags, model->fcutPar, model->fRef};
@@ -46,7 +46,7 @@ static int emu_run(const gwf_model* model, const gwf_detector* dets, int ndet, c
             for (int di = 0; di < net.ndet; ++di) scratch_set(sc, net, geom, di);
             typename PointFns<MODEL, NT>::Extra ex;
             ex.set(in);
-            typedef PointFns<MODEL, NT> PF;
+            typedef typename PointFnsSel<MODEL, NT, SD>::type PF;
             double acc[PF::kAcc];
             for (int p = 0; p < PF::kAcc; ++p) acc[p] = 0.;
             for (int g = 0; g < net.ngroups; ++g) {
@@ -68,6 +68,8 @@ static int emu_run(const gwf_model* model, const gwf_detector* dets, int ndet, c
             for (int i = 0; i < NP; ++i)
                 for (int j = 0; j <= i; ++j) o[tri(i, j)] = PF::entry(i, j, acc, geom);
             if (snr2) snr2[(size_t)pass * n + e] = PF::snr2(acc, geom);
+            if (sd)
+                for (int i = 0; i < NP; ++i) sd[((size_t)pass * n + e) * NP + i] = PF::snr_deriv(i, acc, geom);
         }
     }
     return 0;
@@ -236,6 +238,29 @@ int emu_fisher(const gwf_model* model, const gwf_detector* dets, int ndet, const
         case GWF_IMRPHENOMD: return emu_run<kPhenomD, 4>(model, dets, ndet, pd, npsd, ev, n, opts, fisher, snr2);
         case GWF_IMRPHENOMD_NRTIDALV2: return emu_run<kNRTidalv2, 6>(model, dets, ndet, pd, npsd, ev, n, opts, fisher, snr2);
         case GWF_IMRPHENOMHM: return emu_run<kPhenomHM, 4>(model, dets, ndet, pd, npsd, ev, n, opts, fisher, snr2);
+    }
+    return -2;
+}
+
+// Fisher + (h | d_i h) (gwf_fisher_ex)
+int emu_fisher_sd(const gwf_model* model, const gwf_detector* dets, int ndet, const double* const* psd_f, const double* const* psd_S, const int* psd_n,
+                  int npsd, const double* const* ev, long long n, const gwf_opts* opts, double* fisher, double* snr2, double* sd) {
+    std::vector<EmuPsd> P(npsd);
+    PsdDev pd[kMaxPsd];
+    for (int i = 0; i < npsd; ++i) {
+        int rc = build_psd_tables(psd_f[i], psd_S[i], psd_n[i], P[i].tab, P[i].bucket, P[i].dev);
+        if (rc) return rc;
+        P[i].dev.tab = P[i].tab.data();
+        P[i].dev.bucket = P[i].bucket.data();
+        pd[i] = P[i].dev;
+    }
+    switch (model->id) {
+        case GWF_TAYLORF2:
+            if (model->flags & GWF_MODEL_TIDAL) return emu_run<kTaylorF2, 6>(model, dets, ndet, pd, npsd, ev, n, opts, fisher, snr2, sd);
+            return emu_run<kTaylorF2, 4>(model, dets, ndet, pd, npsd, ev, n, opts, fisher, snr2, sd);
+        case GWF_IMRPHENOMD: return emu_run<kPhenomD, 4>(model, dets, ndet, pd, npsd, ev, n, opts, fisher, snr2, sd);
+        case GWF_IMRPHENOMD_NRTIDALV2: return emu_run<kNRTidalv2, 6>(model, dets, ndet, pd, npsd, ev, n, opts, fisher, snr2, sd);
+        case GWF_IMRPHENOMHM: return emu_run<kPhenomHM, 4, true>(model, dets, ndet, pd, npsd, ev, n, opts, fisher, snr2, sd);
     }
     return -2;
 }

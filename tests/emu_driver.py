@@ -33,8 +33,9 @@ def lib():
     return _lib
 
 
-def run(model, dets, psds, ev, res=1000, flags=0, per_arm=False, snr_mode=False):
-    """model: gwf_model; dets: list of gwf_detector; psds: list of (f, S); ev: dict of arrays. Returns (packed, snr2)."""
+def run(model, dets, psds, ev, res=1000, flags=0, per_arm=False, snr_mode=False, snr_derivs=False):
+    """model: gwf_model; dets: list of gwf_detector; psds: list of (f, S); ev: dict of arrays. Returns (packed, snr2)
+    (or (packed, snr2, sd[npass, n, nP]) with snr_derivs)."""
     L = lib()
     n = len(ev['Mc'])
     dp = C.POINTER(C.c_double)
@@ -57,6 +58,13 @@ def run(model, dets, psds, ev, res=1000, flags=0, per_arm=False, snr_mode=False)
         npass = narms if per_arm else 1
         out = np.zeros((npass, n, npack))
         s2 = np.zeros((npass, n))
+    if snr_derivs:
+        sd = np.zeros((npass, n, nP))
+        rc = L.emu_fisher_sd(C.byref(model), darr, len(dets), pfp, pSp, pn, len(psds), evp, C.c_longlong(n), C.byref(opts),
+                             out.ctypes.data_as(dp), s2.ctypes.data_as(dp), sd.ctypes.data_as(dp))
+        if rc != 0:
+            raise RuntimeError('emu failed %d: %s' % (rc, L.emu_last_error().decode()))
+        return out, s2, sd
     rc = L.emu_fisher(C.byref(model), darr, len(dets), pfp, pSp, pn, len(psds), evp, C.c_longlong(n), C.byref(opts),
                       out.ctypes.data_as(dp), s2.ctypes.data_as(dp) if s2 is not None else None, int(snr_mode))
     if rc != 0:

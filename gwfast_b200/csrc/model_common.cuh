@@ -19,6 +19,7 @@ enum ModelFlags {
     kFlagNoFcut = 32,        // apply_fcut=False
     kFlagHasFRef = 64,       // PhenomD-family fRef given by the user
     kFlagLambdaGiven = 128,  // the events carried Lambda1/Lambda2 when fcut() was evaluated
+    kFlagNewtonian = 256,    // NewtInspiral (waveforms.py:205-260): leading-order phase, numerical tau_star of the base class
 };
 
 // Fisher parametrisation flags (gwf_opts.flags)
@@ -153,6 +154,17 @@ GWF_HD void tau_eval(const TauRec& r, double vm1, double lpx3, const double* lam
     tau = v;
     dtau[0] = fma(dx, lam[0], d0);
     dtau[1] = fma(dx, lam[1], d1);
+}
+// WaveFormModel.tau_star, the base-class default used by NewtInspiral (waveforms.py:176-186):
+// 2.18567 (1.21/Mc)^(5/3) (100/f)^(8/3), written on the v^-8 basis slot: tau = t0 (pi s f)^(-8/3)
+template <int NT>
+GWF_HD void tau_fill_newtonian(TauRec& r, const Dual<NT>& Ms, const Dual<NT>& Mc) {
+    const Dual<NT> t0 = 2.18567 * dpow(1.21 / Mc, 5. / 3.) * pow(100., 8. / 3.) * dpow(kPi * Ms, 8. / 3.);
+#pragma unroll
+    for (int k = 0; k < kTau; ++k) r.t[k] = r.td[0][k] = r.td[1][k] = 0.0;
+    r.t[0] = t0.v;
+    r.td[0][0] = t0.d[0];
+    r.td[1][0] = t0.d[1];
 }
 template <int NT>
 GWF_HD void tau_fill(TauRec& r, const Dual<NT>& Ms, const Dual<NT>& eta) {

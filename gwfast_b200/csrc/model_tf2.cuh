@@ -77,6 +77,14 @@ GWF_HD void tf2_prologue(TF2Rec<NT>& r, const Intrinsic<NT>& p, double dL, const
     D c5 = c.c5;
     double phiR = kPi;
     if (cfg.flags & kFlagPhirefVlso) { c5 = c.c5 * (1. - 3. * log(1. / sqrt(6.))); phiR = 0.; }
+    if (cfg.flags & kFlagNewtonian) {
+        // NewtInspiral.Phi = 3/4 (8 pi GMsun/c^3 Mc f)^(-5/3) - pi/4 = 3/(128 eta) v^-5 - pi/4 (waveforms.py:226-227)
+        for (int k = 0; k < kTF2; ++k) put_tf2(r.ph[k], D(0.0));
+        put_tf2(r.ph[0], 0.75 * dpow(8.0 * kGMsunC3 * p.Mc, -5. / 3.) * dpow(s, 5. / 3.));     // times v^-5 = (pi s f)^(-5/3)
+        put_tf2(r.ph[4], D(-kPi * 0.25));
+        tau_fill_newtonian(r.tau, s, p.Mc);
+        return;
+    }
     put_tf2(r.ph[0], n);
     put_tf2(r.ph[1], n * c.c2);
     put_tf2(r.ph[2], n * c.c3);

@@ -90,8 +90,10 @@ def hot_strain_derivs(signals, evParams, lambdas, res, spacing, use_m1m2, use_ch
     for s in signals:
         dets.append(s._detector_struct(len(handles)))
         handles.append(s._psd_handle())
-    return _engine.strain_derivs(wf._descriptor(evParams), dets, handles, _engine_events(wf, evParams, lambdas, use_m1m2, exact_cut=True), n, res,
-                                 _fisher_flags(spacing, use_m1m2, use_chi1chi2))
+    D = _engine.strain_derivs(wf._descriptor(evParams), dets, handles, _engine_events(wf, evParams, lambdas, use_m1m2, exact_cut=True), n, res,
+                              _fisher_flags(spacing, use_m1m2, use_chi1chi2))
+    rows = getattr(wf, '_engine_rows', None)
+    return D if rows is None else onp.ascontiguousarray(D[:, rows])
 
 
 def hot_fisher(signals, evParams, lambdas, res, spacing, use_m1m2, use_chi1chi2, per_arm, want_snr_derivs=False):
@@ -113,6 +115,12 @@ def hot_fisher(signals, evParams, lambdas, res, spacing, use_m1m2, use_chi1chi2,
         handles.append(s._psd_handle())
     F, snr2, io = _engine.fisher(wf._descriptor(evParams), dets, handles, _engine_events(wf, evParams, lambdas, use_m1m2), n, res, flags, per_arm,
                                  want_snr_derivs=want_snr_derivs)
+    rows = getattr(wf, '_engine_rows', None)
+    if rows is not None:
+        # NewtInspiral: the engine's eta / spin rows are identically zero and are not part of the model's 8 parameters
+        F = onp.ascontiguousarray(F[:, rows][:, :, rows])
+        if want_snr_derivs:
+            snr2 = (snr2[0], onp.ascontiguousarray(snr2[1][:, :, rows]))
     return F, snr2, io
 
 

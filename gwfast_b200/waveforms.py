@@ -19,9 +19,9 @@ class WaveFormModel(ABC):
 
     def __init__(self, objType, fcutPar, is_newtonian=False, is_tidal=False, is_HigherModes=False, is_chi1chi2=True,
                  is_Precessing=False, is_LAL=False, is_prec_ang=False, is_eccentric=False, is_holomorphic=False, apply_fcut=True):
-        if is_newtonian or is_Precessing or is_LAL or is_eccentric:
+        if is_Precessing or is_LAL or is_eccentric:
             raise NotImplementedError('gwfast_b200 builds the non-precessing, quasi-circular native models only '
-                                      '(TaylorF2_RestrictedPN, IMRPhenomD, IMRPhenomD_NRTidalv2, IMRPhenomHM)')
+                                      '(NewtInspiral, TaylorF2_RestrictedPN, IMRPhenomD, IMRPhenomD_NRTidalv2, IMRPhenomHM)')
         self.objType = objType
         self.fcutPar = fcutPar
         self.is_newtonian = is_newtonian
@@ -38,6 +38,16 @@ class WaveFormModel(ABC):
         if is_tidal:
             # the Fisher is computed for LambdaTilde and deltaLambda although the waveforms take Lambda1, Lambda2
             names += ['LambdaTilde', 'deltaLambda']
+        # rows of the engine's 11/13-parameter layout that this model's Fisher keeps (all of them except for NewtInspiral)
+        self._engine_rows = None
+        if is_newtonian:
+            if is_chi1chi2:
+                # the reference renames ParNums['chiS'] -> 'chi1z' after replacing the dict by the 8-parameter one and fails
+                # (waveforms.py:96, 130-131): NewtInspiral has to be built with is_chi1chi2=False there, and so here
+                raise KeyError('chiS')
+            # mass ratio and spins do not enter: 8 parameters (waveforms.py:94-96)
+            self._engine_rows = [0, 2, 3, 4, 5, 6, 7, 8]
+            names = ['Mc', 'dL', 'theta', 'phi', 'iota', 'psi', 'tcoal', 'Phicoal']
         self.ParNums = {k: i for i, k in enumerate(names)}
         self.nParams = len(names)
 
@@ -76,6 +86,22 @@ class WaveFormModel(ABC):
     @abstractmethod
     def fcut(self, **kwargs):
         pass
+
+
+class NewtInspiral(WaveFormModel):
+    """Leading-order inspiral, waveforms.py:205-260.  Runs on the TaylorF2 kernels with every PN coefficient but the first
+    switched off (GWF_MODEL_NEWTONIAN) and the base class's numerical ``tau_star``; 8 Fisher parameters."""
+    _model_id = K.GWF_TAYLORF2
+
+    def __init__(self, **kwargs):
+        super().__init__('BBH', 1. / (6. * np.pi * np.sqrt(6.) * glob.GMsun_over_c3), is_newtonian=True, is_holomorphic=True, **kwargs)
+
+    def _flags(self):
+        return K.GWF_MODEL_NEWTONIAN
+
+    def fcut(self, **kwargs):
+        """WaveFormModel.fcut, waveforms.py:188-199."""
+        return self.fcutPar / (kwargs['Mc'] / (kwargs['eta'] ** (3. / 5.)))
 
 
 class TaylorF2_RestrictedPN(WaveFormModel):

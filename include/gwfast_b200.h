@@ -42,6 +42,9 @@ typedef enum { GWF_TAYLORF2 = 0, GWF_IMRPHENOMD = 1, GWF_IMRPHENOMD_NRTIDALV2 = 
 #define GWF_MODEL_NO_FCUT 32       /* WaveFormModel(apply_fcut=False)                 waveforms.py:1142-1153 */
 #define GWF_MODEL_HAS_FREF 64      /* IMRPhenomD(fRef=...)                            waveforms.py:1139-1141 */
 #define GWF_MODEL_LAMBDA_GIVEN 128 /* events carried Lambda1/Lambda2 when fcut() ran  signal.py:884 (SURVEY A-20) */
+#define GWF_MODEL_NEWTONIAN 256    /* NewtInspiral (with id GWF_TAYLORF2): leading-order phase, base-class tau_star; the engine
+                                      still returns the 11-parameter layout, whose eta/chi rows the 8-parameter NewtInspiral
+                                      contract drops on the host (waveforms.py:94-96, 205-260; signal.py:1143-1151) */
 
 typedef struct {
     int32_t id;      /* gwf_model_id */

@@ -129,6 +129,69 @@ def fx_variants():
         save('var_' + tag, cfg, ev, run_network(cfg, ev))
 
 
+def newt_reference(cfg, ev, use_m1m2=False):
+    """NewtInspiral through the reference's own functions.  SNR: DetNet.SNR unmodified.  Fisher: the reference's FisherMatr cannot
+    run for this model without numdifftools -- `derivargs = (1)` is an int and `derivargs[:-2]` raises (signal.py:1147, 1166) --
+    so the derivative strain is taken from the reference's UNMODIFIED GWstrain (signal.py:486-655) differentiated w.r.t. its 8
+    parameters with the oracle's forward-mode duals (what computeAnalyticalDeriv=False intends, signal.py:1150), and contracted with
+    the reference's trapezoid rule (signal.py:917-931), tcoal row per second (:920)."""
+    wf, sig, net, utils, glob = reference.load()
+    import jax          # the oracle shim (oracle/refshim), on sys.path after reference.load()
+    # GWSignal.__init__ runs a warm-up FisherMatr (signal.py:198), which raises for NewtInspiral for the reason above: the detectors
+    # are constructed with TaylorF2 and the model is swapped afterwards; every method used below is the reference's own
+    sigs = synthetic.build_network(sig.GWSignal, wf.TaylorF2_RestrictedPN(), cfg['network'], useEarthMotion=cfg['rot'], fmin=cfg['fmin'], psd_root=REF_PSDS)
+    for s in sigs.values():
+        s.wf_model = _model(wf, cfg['model'])
+    N = net.DetNet(sigs, verbose=False)
+    out = {'snr': N.SNR(_copy(ev)), 'fisher': 0.}
+    sa = N.SNR(_copy(ev), return_all=True)
+    for k in sa:
+        out['snr__' + k] = sa[k]
+    n = len(ev['Mc'])
+    z = np.zeros(n)
+    for name, s in sigs.items():
+        e = _copy(ev)
+        fcut = s.wf_model.fcut(**e)
+        fg = np.geomspace(np.full(fcut.shape, s.fmin), fcut, num=1000)
+        Sn = np.interp(fg, s.strainFreq, s.noiseCurve, left=1., right=1.)
+        m0, m1 = (utils.m1m2_from_Mceta(e['Mc'], e['eta']) if use_m1m2 else (e['Mc'], e['eta']))
+        rots = [0.] if s.detector_shape == 'L' else [0., 60.]
+        Ds = []
+        for r in rots:
+            f = lambda fgr, Mc, eta, dL, theta, phi, iota, psi, tcoal, Phicoal: s.GWstrain(
+                fgr, Mc, eta, dL, theta, phi, iota, psi, tcoal, Phicoal, e['chi1z'], e['chi2z'], z, z, z, z, z, z, z, rot=r,
+                is_m1m2=use_m1m2, is_chi1chi2=True)
+            J = jax.vmap(jax.jacrev(f, argnums=(1, 3, 4, 5, 6, 7, 8, 9)))(fg.T, m0, m1, e['dL'], e['theta'], e['phi'], e['iota'], e['psi'], e['tcoal'], e['Phicoal'])
+            D = np.array([np.asarray(j) for j in J])          # (8, N, res)
+            D[6] /= 86400.
+            Ds.append(D)
+        if s.detector_shape == 'T':
+            Ds.append(-(Ds[0] + Ds[1]))
+        for i, D in enumerate(Ds):
+            Fa = np.zeros((8, 8, n))
+            for a in range(8):
+                for b in range(a, 8):
+                    Fa[a, b] = Fa[b, a] = 4. * np.trapezoid((np.conj(D[a]) * D[b]).real.T / Sn, fg, axis=0)
+            out['fisher__' + (name if s.detector_shape == 'L' else '%s_%d' % (name, i))] = Fa
+            out['fisher'] = out['fisher'] + Fa
+    return out
+
+
+def fx_newt():
+    """NewtInspiral (8 parameters): triangle with Earth rotation, and the LVK network with (m1, m2) as mass parameters."""
+    ev = take(synthetic.bbh_catalog(10000, synthetic.SEEDS['C2']), 16)
+    cfg = dict(model=dict(cls='NewtInspiral', kw=dict(is_chi1chi2=False)), network='ET', rot=True, fmin=2.)
+    out = newt_reference(cfg, ev)
+    # stand-alone methods of the reference class (these do work): Phi, Ampl, tau_star, fcut on a per-event grid
+    wf = reference.load()[0]
+    m = wf.NewtInspiral(is_chi1chi2=False)
+    fg = np.geomspace(np.full(16, 5.), 0.97 * m.fcut(**ev), 120)
+    out.update(wf_f=fg, wf_fcut=m.fcut(**ev), wf_tau=m.tau_star(fg, **ev), wf_phi=m.Phi(fg, **ev), wf_ampl=m.Ampl(fg, **ev))
+    save('newt_et', cfg, ev, out)
+    cfg = dict(model=dict(cls='NewtInspiral', kw=dict(is_chi1chi2=False)), network='LVK-O4', rot=False, fmin=10., fisher_kw=dict(use_m1m2=True))
+    save('newt_lvk_m1m2', cfg, ev, newt_reference(cfg, ev, use_m1m2=True))
+
+
 def masked_last_sample(cfg, ev):
     """Reference outputs with the LAST grid sample of every arm forced to zero, computed from the reference's own
     GWAmplitudes / derivative arrays (signal.py:425, 1094-1098) and its trapezoid rule.  Used for IMRPhenomD_NRTidalv2, whose
@@ -231,7 +294,7 @@ def fx_wfvalues():
     save('wf_values', dict(note='per-model events stored as ev__<cls>__<key>'), evs, out)
 
 
-ALL = {'init': fx_init, 'c1': fx_c1, 'c1b': fx_c1b, 'c2': fx_c2, 'var': fx_variants, 'c3': fx_c3, 'c4': fx_c4, 'gw170817': fx_gw170817, 'wf': fx_wfvalues}
+ALL = {'init': fx_init, 'c1': fx_c1, 'c1b': fx_c1b, 'c2': fx_c2, 'var': fx_variants, 'c3': fx_c3, 'c4': fx_c4, 'gw170817': fx_gw170817, 'wf': fx_wfvalues, 'newt': fx_newt}
 
 if __name__ == '__main__':
     warnings.filterwarnings('ignore')

@@ -63,6 +63,27 @@ def test_emulated_nrtidal_matches_masked_reference():
     assert snr_err(snr, out['snr']) < 1e-5 and fisher_err(F, out['fisher']) < 5e-3
 
 
+@pytest.mark.parametrize('name', ['newt_et', 'newt_lvk_m1m2'])
+def test_emulated_newtinspiral_matches_reference(name):
+    """NewtInspiral = the TaylorF2 point functions with GWF_MODEL_NEWTONIAN; the engine's 11-parameter layout reduced to the model's 8."""
+    import emu_driver as E
+    from gwfast_b200 import signal, _capi as K
+    cfg, ev, out = load_golden(name)
+    model, dets, psds = _emu_inputs(cfg)
+    flags = K.GWF_OPT_M1M2 if cfg.get('fisher_kw', {}).get('use_m1m2') else 0
+    e2 = signal._engine_events(model, ev, None, bool(flags))
+    packed, _ = E.run(model._descriptor(ev), dets, psds, e2, flags=flags)
+    rows = model._engine_rows
+    F = E.unpack(packed, 11)[0][rows][:, rows]
+    assert fisher_err(F, out['fisher']) < FISHER_TOL
+    # the dropped eta / spin rows vanish up to the rounding of M = Mc/eta^(3/5) cancelling against Mc (1e-14 of the Mc row)
+    # (with use_m1m2 slot 1 is m2, which does enter through Mc; the reference differentiates w.r.t. m1 only, signal.py:1147)
+    dropped = [9, 10] if flags else [1, 9, 10]
+    assert np.max(np.abs(E.unpack(packed, 11)[0][dropped])) < 1e-10 * np.max(np.abs(F))
+    arms, _ = E.run(model._descriptor(ev), dets, psds, signal._engine_events(model, ev), snr_mode=True)
+    assert snr_err(np.sqrt(arms.sum(axis=0)), out['snr']) < SNR_RTOL
+
+
 def test_emulated_nrtidal_taper_tangent_does_not_overflow():
     """Event 5487 of the C3 catalog has a grid sample 5e-6 (in Mf) above f_merger: exp(...) ~ 1e300 in the Planck taper tangent
     (waveforms.py:1714); the reference's inf/inf -> nan_to_num -> 0 must come out as a finite ~0 here, not inf*0 = NaN."""

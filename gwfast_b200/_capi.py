@@ -11,12 +11,12 @@ LIB_PATH = os.environ.get('GWFAST_B200_LIB', os.path.join(_HERE, 'lib', 'libgwfa
 
 GWF_TAYLORF2, GWF_IMRPHENOMD, GWF_IMRPHENOMD_NRTIDALV2, GWF_IMRPHENOMHM = 0, 1, 2, 3
 GWF_MODEL_TIDAL, GWF_MODEL_3P5PN_SPINHO, GWF_MODEL_PHIREF_VLSO, GWF_MODEL_QUADMON_TID = 1, 2, 4, 8
-GWF_MODEL_KERR_ISCO, GWF_MODEL_NO_FCUT, GWF_MODEL_HAS_FREF, GWF_MODEL_LAMBDA_GIVEN, GWF_MODEL_NEWTONIAN = 16, 32, 64, 128, 256
+GWF_MODEL_KERR_ISCO, GWF_MODEL_NO_FCUT, GWF_MODEL_HAS_FREF, GWF_MODEL_LAMBDA_GIVEN, GWF_MODEL_NEWTONIAN, GWF_MODEL_ECCENTRIC = 16, 32, 64, 128, 256, 512
 GWF_OPT_M1M2, GWF_OPT_CHIS_CHIA, GWF_OPT_LIN_GRID, GWF_OPT_REUSE_WORKSPACE, GWF_OPT_GENERIC_LOOP, GWF_OPT_ONE_WARP_PER_EVENT = 1, 2, 4, 8, 16, 32
-GWF_NPARAM_IN = 15
+GWF_NPARAM_IN = 16
 # order of gwf_events.p[]
 EVENT_KEYS = ('Mc', 'eta', 'dL', 'theta', 'phi', 'iota', 'psi', 'tcoal', 'Phicoal', 'chi1z', 'chi2z', 'Lambda1', 'Lambda2',
-              '_fcut', '_Mtot_sec')
+              '_fcut', '_Mtot_sec', 'ecc')
 
 
 class gwf_model(C.Structure):

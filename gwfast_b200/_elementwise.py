@@ -30,6 +30,8 @@ def evaluate(model, f, what, ev):
     if model.is_tidal and 'Lambda1' not in events:
         events['Lambda1'] = np.zeros(n)                                    # waveforms.py:1397-1399
         events['Lambda2'] = np.zeros(n)
+    if getattr(model, 'is_eccentric', False):
+        events['ecc'] = np.broadcast_to(np.atleast_1d(np.real(np.asarray(ev['ecc']))).astype(np.float64), (n,))
     if model._model_id != K.GWF_TAYLORF2:
         events['_Mtot_sec'] = (events['Mc'] / (events['eta'] ** (3. / 5.))) * glob.GMsun_over_c3
     desc = model._descriptor(ev)

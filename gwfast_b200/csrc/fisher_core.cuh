@@ -24,15 +24,15 @@ template <int NT> struct ModelTraits<kTaylorF2, NT> {
             tau_eval(r.tau, p.vm1, p.lpx3, r.lam, tau, dtau);
         }
     }
-    static GWF_HD void prologue(Rec& r, const EventIn& e, const ModelCfg& cfg, int opt_flags, const QnmTables&, const double*, int) {
+    static GWF_HD void prologue(Rec& r, const EventIn& e, const ModelCfg& cfg, int opt_flags, const QnmTables&, const double* fmin_g, int ng) {
         const Intrinsic<NT> p = seed_intrinsic<NT>(e, opt_flags, (cfg.flags & kFlagTidal) != 0);
-        tf2_prologue(r, p, e.dL, cfg, e.fcut_host);
+        tf2_prologue(r, p, e.dL, cfg, e.fcut_host, fmin_g, ng);
     }
     // waveform at f: amplitude, d ln A, d Phi and (if need_tau) d t_noloc
-    static GWF_HD void eval(const Rec& r, const ModelCfg&, int, const FreqPoint& fp, bool need_tau, PointWf<NT>& w) {
+    static GWF_HD void eval(const Rec& r, const ModelCfg&, int g, const FreqPoint& fp, bool need_tau, PointWf<NT>& w) {
         VPow p;
         p.set(r.sp, fp);
-        tf2_phase(r, p, w.phi, w.phi_d);
+        tf2_phase(r, p, w.phi, w.phi_d, g);
         w.A = r.C * fp.fm76;
 #pragma unroll
         for (int j = 0; j < NT; ++j) w.lnA_d[j] = r.lnC_d[j];

@@ -42,6 +42,7 @@ __device__ __forceinline__ EventIn load_event(const EventsDev& ev, long long e) 
     in.Lambda2 = ev.p[12] ? ev.p[12][e] : 0.0;
     in.fcut_host = ev.p[13] ? ev.p[13][e] : 0.0;
     in.s_host = ev.p[14] ? ev.p[14][e] : 0.0;
+    in.ecc = ev.p[15] ? ev.p[15][e] : 0.0;
     return in;
 }
 
@@ -785,7 +786,7 @@ size_t gwf_workspace_bytes(const gwf_model* model, int64_t n) {
     if (!model || n < 0) return 0;
     size_t rec = 0;
     switch (model->id) {
-        case GWF_TAYLORF2: rec = std::max(sizeof(TF2Rec<4>), sizeof(TF2Rec<6>)); break;
+        case GWF_TAYLORF2: rec = sizeof(TF2Rec<7>); break;
         case GWF_IMRPHENOMD: rec = sizeof(PhenomDRec<4>); break;
         case GWF_IMRPHENOMD_NRTIDALV2: rec = std::max(sizeof(NRTidalRec<4>), sizeof(NRTidalRec<6>)); break;
         case GWF_IMRPHENOMHM: rec = sizeof(HMRec<4>); break;
@@ -859,12 +860,17 @@ int gwf_fisher_ex(const gwf_model* model, const gwf_detector* dets, int32_t ndet
     for (int i = 0; i < GWF_NPARAM_IN; ++i) ev.p[i] = events->p[i];
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     switch (model->id) {
-        case GWF_TAYLORF2:
+        case GWF_TAYLORF2: {
+            const bool ecc = (model->flags & GWF_MODEL_ECCENTRIC) != 0;
+            if (ecc && !ev.p[15]) return fail(GWF_ERR_ARG, "eccentric model needs ecc");
             if (model->flags & GWF_MODEL_TIDAL) {
                 if (!ev.p[11] || !ev.p[12]) return fail(GWF_ERR_ARG, "tidal model needs Lambda1, Lambda2");
+                if (ecc) return run_fisher<kTaylorF2, 7>(model, dets, ndet, psds, npsd, ev, n, opts, fisher_packed, snr2, snr_derivs, workspace, workspace_bytes, st);
                 return run_fisher<kTaylorF2, 6>(model, dets, ndet, psds, npsd, ev, n, opts, fisher_packed, snr2, snr_derivs, workspace, workspace_bytes, st);
             }
+            if (ecc) return run_fisher<kTaylorF2, 5>(model, dets, ndet, psds, npsd, ev, n, opts, fisher_packed, snr2, snr_derivs, workspace, workspace_bytes, st);
             return run_fisher<kTaylorF2, 4>(model, dets, ndet, psds, npsd, ev, n, opts, fisher_packed, snr2, snr_derivs, workspace, workspace_bytes, st);
+        }
         case GWF_IMRPHENOMD:
             return run_fisher<kPhenomD, 4>(model, dets, ndet, psds, npsd, ev, n, opts, fisher_packed, snr2, snr_derivs, workspace, workspace_bytes, st);
         case GWF_IMRPHENOMD_NRTIDALV2:
@@ -892,12 +898,17 @@ int gwf_strain_derivs(const gwf_model* model, const gwf_detector* dets, int32_t 
     for (int i = 0; i < GWF_NPARAM_IN; ++i) ev.p[i] = events->p[i];
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     switch (model->id) {
-        case GWF_TAYLORF2:
+        case GWF_TAYLORF2: {
+            const bool ecc = (model->flags & GWF_MODEL_ECCENTRIC) != 0;
+            if (ecc && !ev.p[15]) return fail(GWF_ERR_ARG, "eccentric model needs ecc");
             if (model->flags & GWF_MODEL_TIDAL) {
                 if (!ev.p[11] || !ev.p[12]) return fail(GWF_ERR_ARG, "tidal model needs Lambda1, Lambda2");
+                if (ecc) return run_derivs<kTaylorF2, 7>(model, dets, ndet, psds, npsd, ev, n, opts, derivs, workspace, workspace_bytes, st);
                 return run_derivs<kTaylorF2, 6>(model, dets, ndet, psds, npsd, ev, n, opts, derivs, workspace, workspace_bytes, st);
             }
+            if (ecc) return run_derivs<kTaylorF2, 5>(model, dets, ndet, psds, npsd, ev, n, opts, derivs, workspace, workspace_bytes, st);
             return run_derivs<kTaylorF2, 4>(model, dets, ndet, psds, npsd, ev, n, opts, derivs, workspace, workspace_bytes, st);
+        }
         case GWF_IMRPHENOMD:
             return run_derivs<kPhenomD, 4>(model, dets, ndet, psds, npsd, ev, n, opts, derivs, workspace, workspace_bytes, st);
         case GWF_IMRPHENOMD_NRTIDALV2:

@@ -67,7 +67,7 @@ struct PsdHost {
 
 static int model_nt(const gwf_model& m) {
     switch (m.id) {
-        case GWF_TAYLORF2: return (m.flags & GWF_MODEL_TIDAL) ? 6 : 4;
+        case GWF_TAYLORF2: return ((m.flags & GWF_MODEL_TIDAL) ? 6 : 4) + ((m.flags & GWF_MODEL_ECCENTRIC) ? 1 : 0);
         case GWF_IMRPHENOMD: return 4;
         case GWF_IMRPHENOMD_NRTIDALV2: return 6;
         case GWF_IMRPHENOMHM: return 4;

@@ -19,6 +19,7 @@ enum ModelFlags {
     kFlagNoFcut = 32,        // apply_fcut=False
     kFlagHasFRef = 64,       // PhenomD-family fRef given by the user
     kFlagLambdaGiven = 128,  // the events carried Lambda1/Lambda2 when fcut() was evaluated
+    kFlagEccentric = 512,    // TaylorF2(is_eccentric=True): extra parameter ecc, reference frequency fRef_ecc in ModelCfg::fRef if kFlagHasFRef
     kFlagNewtonian = 256,    // NewtInspiral (waveforms.py:205-260): leading-order phase, numerical tau_star of the base class
 };
 
@@ -40,14 +41,15 @@ struct ModelCfg {
 struct EventIn {
     double Mc, eta, dL, theta, phi, iota, psi, tcoal, Phicoal, chi1z, chi2z, Lambda1, Lambda2;
     double fcut_host, s_host;   // optional host-computed wf_model.fcut and M*GMsun_over_c3 (0 = compute on the device)
+    double ecc;                 // orbital eccentricity e0 (eccentric TaylorF2 only)
 };
 
 // intrinsic parameters seeded for differentiation.  Slots: 0,1 = (Mc,eta) or (m1,m2); 2,3 = (chi1z,chi2z) or
-// (chiS,chiA); 4,5 = (LambdaTilde, deltaLambda) for tidal models.  The re-mapping back to what the waveform
+// (chiS,chiA); 4,5 = (LambdaTilde, deltaLambda) for tidal models; the last slot of an odd NT (5, 7) = ecc.  The re-mapping back to what the waveform
 // consumes is done in dual arithmetic exactly like GWstrain does it (signal.py:522-559).
 template <int NT>
 struct Intrinsic {
-    Dual<NT> Mc, eta, chi1, chi2, L1, L2;
+    Dual<NT> Mc, eta, chi1, chi2, L1, L2, ecc;
 };
 
 template <int NT>
@@ -74,6 +76,8 @@ GWF_HD Intrinsic<NT> seed_intrinsic(const EventIn& e, int opt_flags, bool tidal)
         p.chi1 = D::seed(e.chi1z, 2);
         p.chi2 = D::seed(e.chi2z, 3);
     }
+    // eccentric TaylorF2: e0 is differentiated in the last slot (ParNums['ecc'] = 11 or 13, waveforms.py:113-124)
+    p.ecc = (NT == 5 || NT == 7) ? D::seed(e.ecc, NT - 1) : D(e.ecc);
     if (tidal && NT >= 6) {
         // FisherMatr: (Lambda1,Lambda2,etaOr) -> (LambdaTilde, deltaLambda) (signal.py:871); GWstrain maps them
         // back with the *seeded* eta (signal.py:554), which adds an eta-dependence on the AD path.

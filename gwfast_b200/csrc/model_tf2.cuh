@@ -7,6 +7,7 @@
 namespace gwf {
 
 constexpr int kTF2 = 11;   // v^-5, v^-3, v^-2, v^-1, 1, log v, v, v log v, v^2, v^5, v^7
+constexpr int kTF2Ecc = 7; // eccentric phase: v^(-34/3) * {1, v^2, v^3, v^4, v^5, v^6, v^6 log v}
 template <int NT>
 struct TF2Rec {
     double s;
@@ -16,6 +17,8 @@ struct TF2Rec {
     double C, lnC_d[NT];          // A = C f^(-7/6)
     double ph[kTF2][1 + NT];
     TauRec tau;
+    int has_ecc, pad_;
+    double ec[kMaxGroups][kTF2Ecc][1 + NT];   // eccentric phase coefficients per grid group (v0ecc = v at the group's fmin unless fRef_ecc is given)
 };
 
 template <int NT> GWF_HD void put_tf2(double* dst, const Dual<NT>& c) {
@@ -52,9 +55,50 @@ GWF_HD double tf2_fcut_kerr(double Mc, double eta, double chi1, double chi2) {
     return om / (kPi * Mfin * kGMsunC3);
 }
 
+// eccentric phase, low-eccentricity limit to 3PN (arXiv:1605.00304; waveforms.py:814-845): coefficients of the powers of v with the
+// reference velocity v0 folded in; everything multiplied by 3/(128 eta) * (-2355/1462) e0^2 v0^(19/3)
 template <int NT>
-GWF_HD void tf2_prologue(TF2Rec<NT>& r, const Intrinsic<NT>& p, double dL, const ModelCfg& cfg, double fcut_host = 0.0) {
+GWF_HD void tf2_ecc_coeffs(double (*ec)[1 + NT], const Dual<NT>& eta, const Dual<NT>& ecc, const Dual<NT>& v0) {
     typedef Dual<NT> D;
+    const D e2 = eta * eta, e3 = e2 * eta;
+    const D v02 = v0 * v0, v03 = v02 * v0, v04 = v02 * v02, v05 = v04 * v0, v06 = v03 * v03;
+    const D twoV = 29.9076223 / 8.1976608 + 18.766963 / 2.927736 * eta, twoV0 = 2.833 / 1.008 - 19.7 / 3.6 * eta;
+    const double threeV = -28.19123 / 2.82600 * kPi, threeV0 = 37.7 / 7.2 * kPi;
+    const D fourV4 = 16.237683263 / 3.330429696 + 241.33060753 / 9.71375328 * eta + 156.2608261 / 6.9383952 * e2;
+    const D fourV2V02 = 84.7282939759 / 8.2632420864 - 7.18901219 / 3.68894736 * eta - 36.97091711 / 1.05398496 * e2;
+    const D fourV04 = -1.193251 / 3.048192 - 66.317 / 9.072 * eta + 18.155 / 1.296 * e2;
+    const D fiveV5 = -28.31492681 / 1.18395270 * kPi - 115.52066831 / 2.70617760 * kPi * eta;
+    const D fiveV3V02 = -79.86575459 / 2.84860800 * kPi + 55.5367231 / 1.0173600 * kPi * eta;
+    const D fiveV2V03 = 112.751736071 / 5.902315776 * kPi + 70.75145051 / 2.10796992 * kPi * eta;
+    const D fiveV05 = 76.4881 / 9.0720 * kPi - 94.9457 / 2.2680 * kPi * eta;
+    const D sixV6 = -436.03153867072577087 / 1.32658535116800000 + 53.6803271 / 1.9782000 * kEuler + 157.22503703 / 3.25555200 * kPi * kPi +
+                    (2991.72861614477 / 6.89135247360 - 15.075413 / 1.446912 * kPi * kPi) * eta + 345.5209264991 / 4.1019955200 * e2 +
+                    506.12671711 / 8.78999040 * e3 + 384.3505163 / 5.9346000 * log(2.) - 112.1397129 / 1.7584000 * log(3.);
+    const D sixV4V02 = 46.001356684079 / 3.357073133568 + 253.471410141755 / 5.874877983744 * eta - 169.3852244423 / 2.3313007872 * e2 -
+                       307.833827417 / 2.497822272 * e3;
+    const double sixV3V03 = -106.2809371 / 2.0347200 * kPi * kPi;
+    const D sixV2V04 = -3.56873002170973 / 2.49880440692736 - 260.399751935005 / 8.924301453312 * eta + 15.0484695827 / 3.5413894656 * e2 +
+                       340.714213265 / 3.794345856 * e3;
+    const D sixV06 = 265.31900578691 / 1.68991764480 - 33.17 / 1.26 * kEuler + 12.2833 / 1.0368 * kPi * kPi +
+                     (91.55185261 / 5.48674560 - 3.977 / 1.152 * kPi * kPi) * eta - 5.732473 / 1.306368 * e2 - 30.90307 / 1.39968 * e3 +
+                     87.419 / 1.890 * log(2.) - 260.01 / 5.60 * log(3.);
+    const double kL = 53.6803271 / 3.9564000;
+    const D pre = (3. / (128. * eta)) * (-2.355 / 1.462) * ecc * ecc * dpow(v0, 19. / 3.);
+    put_tf2(ec[0], pre * (1. + twoV0 * v02 + threeV0 * v03 + fourV04 * v04 + fiveV05 * v05 + (sixV06 - 33.17 / 2.52 * dlog(16. * v02)) * v06));
+    put_tf2(ec[1], pre * (twoV + fourV2V02 * v02 + fiveV2V03 * v03 + sixV2V04 * v04));
+    put_tf2(ec[2], pre * (threeV + fiveV3V02 * v02 + sixV3V03 * v03));
+    put_tf2(ec[3], pre * (fourV4 + sixV4V02 * v02));
+    put_tf2(ec[4], pre * fiveV5);
+    put_tf2(ec[5], pre * (sixV6 + kL * log(16.)));
+    put_tf2(ec[6], pre * (2. * kL));
+}
+
+template <int NT>
+GWF_HD void tf2_prologue(TF2Rec<NT>& r, const Intrinsic<NT>& p, double dL, const ModelCfg& cfg, double fcut_host = 0.0,
+                         const double* fmin_g = nullptr, int ngroups = 0) {
+    typedef Dual<NT> D;
+    r.has_ecc = 0;
+    r.pad_ = 0;
     const bool tidal = cfg.flags & kFlagTidal;
     const D M = p.Mc / dpow(p.eta, 3. / 5.);
     const D s = M * kGMsunC3;
@@ -104,6 +148,14 @@ GWF_HD void tf2_prologue(TF2Rec<NT>& r, const Intrinsic<NT>& p, double dL, const
         put_tf2(r.ph[10], D(0.0));
     }
     tau_fill(r.tau, s, p.eta);
+    if ((cfg.flags & kFlagEccentric) && fmin_g) {
+        r.has_ecc = 1;
+        for (int g = 0; g < ngroups; ++g) {
+            // v0ecc = min_f v (the grid's first sample) or (pi M fRef_ecc)^(1/3), waveforms.py:817-820
+            const double f0 = (cfg.flags & kFlagHasFRef) ? cfg.fRef : fmin_g[g];
+            tf2_ecc_coeffs<NT>(r.ec[g], p.eta, p.ecc, dpow(kPi * s * f0, 1. / 3.));
+        }
+    }
 }
 
 // v-powers at x
@@ -120,7 +172,7 @@ struct VPow {
 };
 
 template <int NT>
-GWF_HD void tf2_phase(const TF2Rec<NT>& r, const VPow& p, double& phi, double* phi_d) {
+GWF_HD void tf2_phase(const TF2Rec<NT>& r, const VPow& p, double& phi, double* phi_d, int g = 0) {
     const double v = p.v, v2 = v * v, vm2 = p.vm1 * p.vm1, vm3 = vm2 * p.vm1, vm5 = vm3 * vm2, v5 = v2 * v2 * v, v7 = v5 * v2, vl = v * p.lv;
     const double b[kTF2] = {vm5, vm3, vm2, p.vm1, 1., p.lv, v, vl, v2, v5, v7};
     const double bx[kTF2] = {-5. / 3. * vm5, -vm3, -2. / 3. * vm2, -1. / 3. * p.vm1, 0., 1. / 3., 1. / 3. * v, 1. / 3. * (vl + v), 2. / 3. * v2,
@@ -134,6 +186,21 @@ GWF_HD void tf2_phase(const TF2Rec<NT>& r, const VPow& p, double& phi, double* p
         dx = fma(r.ph[k][0], bx[k], dx);
 #pragma unroll
         for (int j = 0; j < NT; ++j) d[j] = fma(r.ph[k][1 + j], b[k], d[j]);
+    }
+    if (r.has_ecc) {
+        // v^(-34/3) = v^-11 v^(-1/3)
+        const double vm13 = 1.0 / cbrt(v), vm11 = vm5 * vm5 * p.vm1, e0 = vm11 * vm13, v3 = v2 * v, v4 = v2 * v2, v6 = v3 * v3;
+        const double eb[kTF2Ecc] = {e0, e0 * v2, e0 * v3, e0 * v4, e0 * v5, e0 * v6, e0 * v6 * p.lv};
+        const double q0 = -34. / 9.;
+        const double ebx[kTF2Ecc] = {q0 * eb[0], (q0 + 2. / 3.) * eb[1], (q0 + 1.) * eb[2], (q0 + 4. / 3.) * eb[3], (q0 + 5. / 3.) * eb[4],
+                                     (q0 + 2.) * eb[5], (q0 + 2.) * eb[6] + 1. / 3. * eb[5]};
+#pragma unroll
+        for (int k = 0; k < kTF2Ecc; ++k) {
+            val_ = fma(r.ec[g][k][0], eb[k], val_);
+            dx = fma(r.ec[g][k][0], ebx[k], dx);
+#pragma unroll
+            for (int j = 0; j < NT; ++j) d[j] = fma(r.ec[g][k][1 + j], eb[k], d[j]);
+        }
     }
     phi = val_;
 #pragma unroll

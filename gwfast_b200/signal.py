@@ -40,6 +40,8 @@ def _engine_events(wf_model, evParams, lambdas=None, use_m1m2=False, exact_cut=F
     if wf_model.is_tidal:
         L1, L2 = lambdas if lambdas is not None else (evParams['Lambda1'], evParams['Lambda2'])
         ev['Lambda1'], ev['Lambda2'] = L1, L2
+    if wf_model.is_eccentric:
+        ev['ecc'] = evParams['ecc']              # signal.py:877-880
     if wf_model.is_HigherModes or (exact_cut and not wf_model.is_tidal and type(wf_model).__name__ != 'TaylorF2_RestrictedPN'):
         # only IMRPhenomHM needs it at the 1e-9 level (3e-12 for IMRPhenomD); two numpy pow() per event on the host.
         # exact_cut: the strain-derivative output exposes the last sample itself, so IMRPhenomD asks for it there too

@@ -19,8 +19,8 @@ class WaveFormModel(ABC):
 
     def __init__(self, objType, fcutPar, is_newtonian=False, is_tidal=False, is_HigherModes=False, is_chi1chi2=True,
                  is_Precessing=False, is_LAL=False, is_prec_ang=False, is_eccentric=False, is_holomorphic=False, apply_fcut=True):
-        if is_Precessing or is_LAL or is_eccentric:
-            raise NotImplementedError('gwfast_b200 builds the non-precessing, quasi-circular native models only '
+        if is_Precessing or is_LAL:
+            raise NotImplementedError('gwfast_b200 builds the non-precessing native models only '
                                       '(NewtInspiral, TaylorF2_RestrictedPN, IMRPhenomD, IMRPhenomD_NRTidalv2, IMRPhenomHM)')
         self.objType = objType
         self.fcutPar = fcutPar
@@ -38,6 +38,8 @@ class WaveFormModel(ABC):
         if is_tidal:
             # the Fisher is computed for LambdaTilde and deltaLambda although the waveforms take Lambda1, Lambda2
             names += ['LambdaTilde', 'deltaLambda']
+        if is_eccentric:
+            names += ['ecc']                    # waveforms.py:113-124
         # rows of the engine's 11/13-parameter layout that this model's Fisher keeps (all of them except for NewtInspiral)
         self._engine_rows = None
         if is_newtonian:
@@ -105,7 +107,7 @@ class NewtInspiral(WaveFormModel):
 
 
 class TaylorF2_RestrictedPN(WaveFormModel):
-    """waveforms.py:697-953 (the eccentric extension, :814-845, is not built)."""
+    """waveforms.py:697-953, including the low-eccentricity extension (:814-845; parameter ``ecc``, ``fRef_ecc``)."""
     _model_id = K.GWF_TAYLORF2
 
     def __init__(self, fHigh=None, is_tidal=False, use_3p5PN_SpinHO=False, phiref_vlso=False, is_eccentric=False, fRef_ecc=None,
@@ -133,7 +135,17 @@ class TaylorF2_RestrictedPN(WaveFormModel):
             fl |= K.GWF_MODEL_QUADMON_TID
         if self.which_ISCO == 'Kerr':
             fl |= K.GWF_MODEL_KERR_ISCO
+        if self.is_eccentric:
+            fl |= K.GWF_MODEL_ECCENTRIC
         return fl
+
+    def _descriptor(self, evParams=None):
+        d = super()._descriptor(evParams)
+        if self.is_eccentric and self.fRef_ecc is not None:
+            # the eccentric reference frequency travels in gwf_model.fRef (TaylorF2 has no phase reference frequency of its own)
+            d.flags |= K.GWF_MODEL_HAS_FREF
+            d.fRef = float(self.fRef_ecc)
+        return d
 
     def fcut(self, **kwargs):
         """waveforms.py:903-953."""

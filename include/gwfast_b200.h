@@ -42,6 +42,8 @@ typedef enum { GWF_TAYLORF2 = 0, GWF_IMRPHENOMD = 1, GWF_IMRPHENOMD_NRTIDALV2 = 
 #define GWF_MODEL_NO_FCUT 32       /* WaveFormModel(apply_fcut=False)                 waveforms.py:1142-1153 */
 #define GWF_MODEL_HAS_FREF 64      /* IMRPhenomD(fRef=...)                            waveforms.py:1139-1141 */
 #define GWF_MODEL_LAMBDA_GIVEN 128 /* events carried Lambda1/Lambda2 when fcut() ran  signal.py:884 (SURVEY A-20) */
+#define GWF_MODEL_ECCENTRIC 512    /* TaylorF2_RestrictedPN(is_eccentric=True): parameter ecc appended (nP = 12, or 14 with tidal);
+                                      fRef_ecc in gwf_model.fRef when GWF_MODEL_HAS_FREF, else v0ecc = v(fmin)   waveforms.py:814-845 */
 #define GWF_MODEL_NEWTONIAN 256    /* NewtInspiral (with id GWF_TAYLORF2): leading-order phase, base-class tau_star; the engine
                                       still returns the 11-parameter layout, whose eta/chi rows the 8-parameter NewtInspiral
                                       contract drops on the host (waveforms.py:94-96, 205-260; signal.py:1143-1151) */
@@ -72,12 +74,12 @@ void gwf_psd_destroy(gwf_psd* psd);
 int gwf_set_qnm_tables(const double* a_host, const double* fring_host, const double* fdamp_host, int32_t n);
 
 /* the events dict as device SoA; order of p[]:
- * Mc eta dL theta phi iota psi tcoal Phicoal chi1z chi2z Lambda1 Lambda2 fcut Mtot_sec
- * p[11], p[12] may be NULL for BBH.  p[13] (wf_model.fcut(**events) in Hz, signal.py:715/884) and p[14]
+ * Mc eta dL theta phi iota psi tcoal Phicoal chi1z chi2z Lambda1 Lambda2 fcut Mtot_sec ecc
+ * p[11], p[12] may be NULL for BBH; p[15] (orbital eccentricity e0) is read by the eccentric TaylorF2 only.  p[13] (wf_model.fcut(**events) in Hz, signal.py:715/884) and p[14]
  * (M*GMsun_over_c3 in seconds, waveforms.py:1026) are optional: when the host passes the values it computed with the
  * reference's own expressions, the last grid sample lands on Mf = fcutPar with the reference's rounding, which decides
  * whether that sample is inside the waveform cut (waveforms.py:1145-1147); when NULL both are computed on the device. */
-#define GWF_NPARAM_IN 15
+#define GWF_NPARAM_IN 16
 typedef struct {
     const double* p[GWF_NPARAM_IN];
 } gwf_events;

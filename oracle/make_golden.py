@@ -177,6 +177,27 @@ def newt_reference(cfg, ev, use_m1m2=False):
     return out
 
 
+def fx_ecc():
+    """Eccentric TaylorF2 (SURVEY.md 8(f) #4; waveforms.py:814-845): v0ecc from the grid, from fRef_ecc, and with tidal terms (14 parameters)."""
+    rng = np.random.default_rng(77)
+    ev = take(synthetic.bns_catalog(100, synthetic.SEEDS['C1'] + 7, tidal=True), 12)
+    ev['ecc'] = rng.uniform(0.005, 0.15, 12)
+    nt = {k: v for k, v in ev.items() if not k.startswith('Lambda')}
+    wf = reference.load()[0]
+    for tag, cfg, e in (
+        ('ecc_etsl', dict(model=dict(cls='TaylorF2_RestrictedPN', kw=dict(is_eccentric=True)), network='ETSL', rot=True, fmin=2.), nt),
+        ('ecc_fref_et', dict(model=dict(cls='TaylorF2_RestrictedPN', kw=dict(is_eccentric=True, fRef_ecc=10., use_3p5PN_SpinHO=True)), network='ET', rot=True,
+                             fmin=5.), nt),
+        ('ecc_tidal_lvk', dict(model=dict(cls='TaylorF2_RestrictedPN', kw=dict(is_eccentric=True, is_tidal=True)), network='LVK-O4', rot=False, fmin=10.,
+                               fisher_kw=dict(use_m1m2=True)), ev),
+    ):
+        out = run_network(cfg, e)
+        m = _model(wf, cfg['model'])
+        fg = np.geomspace(np.full(12, 5.), 0.97 * m.fcut(**e), 100)
+        out.update(wf_f=fg, wf_phi=m.Phi(fg, **e))
+        save('tf2' + tag, cfg, e, out)
+
+
 def fx_newt():
     """NewtInspiral (8 parameters): triangle with Earth rotation, and the LVK network with (m1, m2) as mass parameters."""
     ev = take(synthetic.bbh_catalog(10000, synthetic.SEEDS['C2']), 16)
@@ -294,7 +315,7 @@ def fx_wfvalues():
     save('wf_values', dict(note='per-model events stored as ev__<cls>__<key>'), evs, out)
 
 
-ALL = {'init': fx_init, 'c1': fx_c1, 'c1b': fx_c1b, 'c2': fx_c2, 'var': fx_variants, 'c3': fx_c3, 'c4': fx_c4, 'gw170817': fx_gw170817, 'wf': fx_wfvalues, 'newt': fx_newt}
+ALL = {'init': fx_init, 'c1': fx_c1, 'c1b': fx_c1b, 'c2': fx_c2, 'var': fx_variants, 'c3': fx_c3, 'c4': fx_c4, 'gw170817': fx_gw170817, 'wf': fx_wfvalues, 'newt': fx_newt, 'ecc': fx_ecc}
 
 if __name__ == '__main__':
     warnings.filterwarnings('ignore')

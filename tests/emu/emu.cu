@@ -37,7 +37,7 @@ static int emu_run(const gwf_model* model, const gwf_detector* dets, int ndet, c
             in.Mc = ev[0][e]; in.eta = ev[1][e]; in.dL = ev[2][e]; in.theta = ev[3][e]; in.phi = ev[4][e]; in.iota = ev[5][e];
             in.psi = ev[6][e]; in.tcoal = ev[7][e]; in.Phicoal = ev[8][e]; in.chi1z = ev[9][e]; in.chi2z = ev[10][e];
             in.Lambda1 = ev[11] ? ev[11][e] : 0.; in.Lambda2 = ev[12] ? ev[12][e] : 0.;
-            in.fcut_host = ev[13] ? ev[13][e] : 0.; in.s_host = ev[14] ? ev[14][e] : 0.;
+            in.fcut_host = ev[13] ? ev[13][e] : 0.; in.s_host = ev[14] ? ev[14][e] : 0.; in.ecc = ev[15] ? ev[15][e] : 0.;
             Rec rec;
             ModelTraits<MODEL, NT>::prologue(rec, in, cfg, opts->flags, g_q, net.group_fmin, net.ngroups);
             EvGeom geom;
@@ -88,7 +88,7 @@ static int emu_run_snr(const gwf_model* model, const gwf_detector* dets, int nde
         in.Mc = ev[0][e]; in.eta = ev[1][e]; in.dL = ev[2][e]; in.theta = ev[3][e]; in.phi = ev[4][e]; in.iota = ev[5][e];
         in.psi = ev[6][e]; in.tcoal = ev[7][e]; in.Phicoal = ev[8][e]; in.chi1z = ev[9][e]; in.chi2z = ev[10][e];
         in.Lambda1 = ev[11] ? ev[11][e] : 0.; in.Lambda2 = ev[12] ? ev[12][e] : 0.;
-            in.fcut_host = ev[13] ? ev[13][e] : 0.; in.s_host = ev[14] ? ev[14][e] : 0.;
+            in.fcut_host = ev[13] ? ev[13][e] : 0.; in.s_host = ev[14] ? ev[14][e] : 0.; in.ecc = ev[15] ? ev[15][e] : 0.;
         Rec rec;
         ModelTraits<MODEL, 4>::prologue(rec, in, cfg, 0, g_q, net.group_fmin, net.ngroups);
         EvGeom geom;
@@ -129,7 +129,7 @@ static int emu_run_waveform(const gwf_model* model, const double* const* ev, lon
         in.Mc = ev[0][e]; in.eta = ev[1][e]; in.dL = ev[2][e]; in.theta = ev[3][e]; in.phi = ev[4][e]; in.iota = ev[5][e];
         in.psi = ev[6][e]; in.tcoal = ev[7][e]; in.Phicoal = ev[8][e]; in.chi1z = ev[9][e]; in.chi2z = ev[10][e];
         in.Lambda1 = ev[11] ? ev[11][e] : 0.; in.Lambda2 = ev[12] ? ev[12][e] : 0.;
-            in.fcut_host = ev[13] ? ev[13][e] : 0.; in.s_host = ev[14] ? ev[14][e] : 0.;
+            in.fcut_host = ev[13] ? ev[13][e] : 0.; in.s_host = ev[14] ? ev[14][e] : 0.; in.ecc = ev[15] ? ev[15][e] : 0.;
         double fm = 1.0;
         if (res > 0) {
             fm = f2d ? f[e] : f[0];
@@ -233,6 +233,10 @@ int emu_fisher(const gwf_model* model, const gwf_detector* dets, int ndet, const
     }
     switch (model->id) {
         case GWF_TAYLORF2:
+            if (model->flags & GWF_MODEL_ECCENTRIC) {
+                if (model->flags & GWF_MODEL_TIDAL) return emu_run<kTaylorF2, 7>(model, dets, ndet, pd, npsd, ev, n, opts, fisher, snr2);
+                return emu_run<kTaylorF2, 5>(model, dets, ndet, pd, npsd, ev, n, opts, fisher, snr2);
+            }
             if (model->flags & GWF_MODEL_TIDAL) return emu_run<kTaylorF2, 6>(model, dets, ndet, pd, npsd, ev, n, opts, fisher, snr2);
             return emu_run<kTaylorF2, 4>(model, dets, ndet, pd, npsd, ev, n, opts, fisher, snr2);
         case GWF_IMRPHENOMD: return emu_run<kPhenomD, 4>(model, dets, ndet, pd, npsd, ev, n, opts, fisher, snr2);
@@ -256,6 +260,10 @@ int emu_fisher_sd(const gwf_model* model, const gwf_detector* dets, int ndet, co
     }
     switch (model->id) {
         case GWF_TAYLORF2:
+            if (model->flags & GWF_MODEL_ECCENTRIC) {
+                if (model->flags & GWF_MODEL_TIDAL) return emu_run<kTaylorF2, 7>(model, dets, ndet, pd, npsd, ev, n, opts, fisher, snr2, sd);
+                return emu_run<kTaylorF2, 5>(model, dets, ndet, pd, npsd, ev, n, opts, fisher, snr2, sd);
+            }
             if (model->flags & GWF_MODEL_TIDAL) return emu_run<kTaylorF2, 6>(model, dets, ndet, pd, npsd, ev, n, opts, fisher, snr2, sd);
             return emu_run<kTaylorF2, 4>(model, dets, ndet, pd, npsd, ev, n, opts, fisher, snr2, sd);
         case GWF_IMRPHENOMD: return emu_run<kPhenomD, 4>(model, dets, ndet, pd, npsd, ev, n, opts, fisher, snr2, sd);

@@ -25,7 +25,7 @@ def _emu_inputs(cfg):
 
 
 @pytest.mark.parametrize('name', ['c1_tf2_bns_etsl', 'c1b_tf2tidal_et', 'c1c_tf2_options_etsl', 'c2_phenomd_et2ce', 'var_m1m2_chisa',
-                                  'var_lin_res400_fmax', 'var_fref_nocut', 'var_tf2_m1m2'])
+                                  'var_lin_res400_fmax', 'var_fref_nocut', 'var_tf2_m1m2', 'tf2ecc_etsl', 'tf2ecc_fref_et', 'tf2ecc_tidal_lvk'])
 def test_emulated_device_math_matches_reference(name):
     import emu_driver as E
     from gwfast_b200 import _capi as K

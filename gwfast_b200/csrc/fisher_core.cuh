@@ -214,6 +214,15 @@ struct Grid {
     }
 };
 
+// Per-event constants of the Fisher kernel that do not depend on the detector: sky/orientation (six sincos) and the grid of
+// every group (log10/exp10 calls).  The prologue kernel evaluates them once per event and leaves them next to the coefficient
+// records; the Fisher kernel's warps only copy them (they used to be recomputed by all 32 lanes of every warp of an event).
+struct EventAux {
+    EvGeom geom;
+    Grid grid[kMaxGroups];
+};
+static_assert(sizeof(EventAux) % sizeof(double) == 0, "EventAux is copied as doubles");
+
 // ------------------------------------------------------------------ per-event detector scratch
 // EvDet for every detector, plus the (frequency independent) DetPoint of the detectors that do not follow the
 // Earth rotation.  Lives in shared memory, one block per warp (kernels) or on the stack (emulation).

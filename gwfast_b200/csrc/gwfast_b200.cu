@@ -62,15 +62,31 @@ struct GroupInfo {
 };
 
 // ------------------------------------------------------------------------------------------- K1
+// what the Fisher launch needs to know to fill EventAux (out == nullptr: not wanted)
+struct AuxPlan {
+    EventAux* out;
+    double fmax[kMaxGroups];
+    int res, lin, stride;
+};
+
 template <int MODEL, int NT>
 __global__ void __launch_bounds__(128) prologue_kernel(EventsDev ev, long long n, ModelCfg cfg, int opt_flags, QnmTables q, GroupInfo gi,
                                                       typename ModelTraits<MODEL, NT>::Rec* __restrict__ recs,
-                                                      const double* __restrict__ fmin_per_event = nullptr) {
+                                                      const double* __restrict__ fmin_per_event = nullptr, AuxPlan aux = AuxPlan()) {
     const long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (e >= n) return;
     const EventIn in = load_event(ev, e);
     if (fmin_per_event) gi.fmin[0] = fmin_per_event[e];     // stand-alone waveform calls: fRef = min of the user's grid
     ModelTraits<MODEL, NT>::prologue(recs[e], in, cfg, opt_flags, q, gi.fmin, gi.n);
+    if (aux.out) {
+        EventAux& a = aux.out[e];
+        a.geom.set(in);
+        for (int g = 0; g < gi.n; ++g) {
+            double fcut = recs[e].fcut_hz;
+            if (aux.fmax[g] > 0.0 && fcut > aux.fmax[g]) fcut = aux.fmax[g];   // signal.py:717-718
+            a.grid[g].set(gi.fmin[g], fcut, aux.res, aux.lin != 0, aux.stride);
+        }
+    }
 }
 
 // per-event minimum of a user grid f[res][n] (or the shared f[res])
@@ -264,6 +280,7 @@ template <class Rec, class Extra> struct WarpSmem {
     EvGeom geom;       // per-event sky/orientation constants: read by broadcast instead of living in 30 registers
     Extra ex;
     double gridc[8];   // geometric-grid walk constants of the current group: r, r13, rm13, rm76, dln, hw_in, hw_hi, fcut
+    Grid grid[kMaxGroups];   // Fisher kernel: the event's grids as the prologue left them (EventAux)
 };
 
 template <bool FAST, class Rec, class Extra>
@@ -283,14 +300,39 @@ __device__ __forceinline__ void stage_event(WarpSmem<Rec, Extra>* mine, const Re
     __syncwarp();
 }
 
+// Fisher kernel: the record and the prologue's EventAux are copied (coalesced), the detector scratch is then set from the
+// staged geometry by one lane per detector
+template <bool FAST, class Rec, class Extra>
+__device__ __forceinline__ void stage_event_aux(WarpSmem<Rec, Extra>* mine, const Rec* recs, const EventAux* aux, const EventsDev& ev, long long e,
+                                                const NetworkDev& net, int lane) {
+    constexpr int kRecDoubles = (int)(sizeof(Rec) / sizeof(double));
+    constexpr int kGeomDoubles = (int)(sizeof(EvGeom) / sizeof(double)), kGridDoubles = (int)(sizeof(Grid) / sizeof(double));
+    const double* src = reinterpret_cast<const double*>(recs + e);
+    const double* asrc = reinterpret_cast<const double*>(aux + e);
+    double* dst = reinterpret_cast<double*>(&mine->rec);
+    double* gdst = reinterpret_cast<double*>(&mine->geom);
+    double* qdst = reinterpret_cast<double*>(&mine->grid[0]);
+    __syncwarp();
+    for (int i = lane; i < kRecDoubles; i += 32) dst[i] = __ldg(src + i);
+    if (lane < kGeomDoubles) gdst[lane] = __ldg(asrc + lane);
+    for (int i = lane; i < kGridDoubles * net.ngroups; i += 32) qdst[i] = __ldg(asrc + kGeomDoubles + i);
+    if (sizeof(Extra) > 1 && lane == 31) mine->ex.set(load_event(ev, e));
+    __syncwarp();
+    if (FAST) {
+        if (lane < net.fnd) scratch_set_fast(mine->sc, net, mine->geom, lane);
+    } else if (lane < net.ndet) scratch_set(mine->sc, net, mine->geom, lane);
+    __syncwarp();
+}
+
 template <int MODEL, int NT, int FAST, bool SD>
 #ifdef GWF_FISHER_MAXNREG
 __global__ void __maxnreg__(GWF_FISHER_MAXNREG)
 #else
 __global__ void __launch_bounds__(kFisherThreads, GWF_FISHER_MINBLOCKS)
 #endif
-fisher_kernel(const typename ModelTraits<MODEL, NT>::Rec* __restrict__ recs, EventsDev ev, long long n, int res, int lin, ModelCfg cfg,
-              const __grid_constant__ NetworkDev net, double* __restrict__ out, double* __restrict__ snr2_out, double* __restrict__ sd_out, int pair) {
+fisher_kernel(const typename ModelTraits<MODEL, NT>::Rec* __restrict__ recs, const EventAux* __restrict__ aux, EventsDev ev, long long n, int res, int lin,
+              ModelCfg cfg, const __grid_constant__ NetworkDev net, double* __restrict__ out, double* __restrict__ snr2_out, double* __restrict__ sd_out,
+              int pair) {
     typedef typename ModelTraits<MODEL, NT>::Rec Rec;
     typedef typename PointFnsSel<MODEL, NT, SD>::type PF;
     typedef WarpSmem<Rec, typename PF::Extra> WS;
@@ -300,52 +342,49 @@ fisher_kernel(const typename ModelTraits<MODEL, NT>::Rec* __restrict__ recs, Eve
     WS* mine = reinterpret_cast<WS*>(smem_raw) + wid;
     const Rec& rec = mine->rec;
     psd_cache_fill(net, smem_raw);
-    // pair mode (small catalogs): warps w and w + kWarpsPerCta/2 share an event, each taking every other block of 32
-    // samples, so the work unit is half an event and the last round of the persistent loop wastes half as much
+    // pair mode: warps w and w + kWarpsPerCta/2 take the two halves of an event (every other block of 32 samples each), so the
+    // work unit of the persistent loop is half an event and its last round wastes half as much.  The halves never wait for each
+    // other: each rebuilds the Fisher entries of its own partial sums (the entries are linear in the accumulators) and adds
+    // them to the zero-initialised output with one atomic per entry -- two commutative additions, so the result is
+    // deterministic.  (A named-barrier hand-over of the partial sums cost 4.3 % of the kernel in barrier stalls.)
     constexpr int kHalfWarps = kWarpsPerCta / 2;
     const int half = pair ? wid / kHalfWarps : 0, slot = pair ? wid % kHalfWarps : wid;
     const int per_cta = pair ? kHalfWarps : kWarpsPerCta, stride = pair ? 64 : 32, k0 = lane + 32 * half;
     for (long long e = (long long)blockIdx.x * per_cta + slot; e < n; e += (long long)gridDim.x * per_cta) {
-        {
-            EvGeom g0;
-            const EventIn in = load_event(ev, e);
-            g0.set(in);
-            stage_event<FAST != 0>(mine, recs, e, net, g0, in, lane);
-        }
+        stage_event_aux<FAST != 0>(mine, recs, aux, ev, e, net, lane);
         const EvGeom& geom = mine->geom;
         double acc[PF::kAcc];
 #pragma unroll
         for (int p = 0; p < PF::kAcc; ++p) acc[p] = 0.0;
         for (int g = 0; g < net.ngroups; ++g) {
-            double fcut = rec.fcut_hz;
-            if (net.group_fmax[g] > 0.0 && fcut > net.group_fmax[g]) fcut = net.group_fmax[g];   // signal.py:717-718
-            Grid grid;
-            grid.set(net.group_fmin[g], fcut, res, lin != 0, stride);
+            const Grid& grid = mine->grid[g];
             const bool rot = net.group_rot[g] != 0;
-            // the walk constants are warp-uniform: kept in shared memory and re-read (volatile) every step instead of
-            // occupying 16 registers next to the Gram accumulators
-            __syncwarp();
-            if (lane == 0) {
-                mine->gridc[0] = grid.r; mine->gridc[1] = grid.r13; mine->gridc[2] = grid.rm13; mine->gridc[3] = grid.rm76;
-                mine->gridc[4] = grid.dln; mine->gridc[5] = grid.hw_in; mine->gridc[6] = grid.hw_hi; mine->gridc[7] = fcut;
-            }
-            __syncwarp();
-            const volatile double* gc = mine->gridc;
+            // the walk constants are warp-uniform: re-read from shared memory (volatile) every step instead of occupying 16
+            // registers next to the Gram accumulators
+            const volatile Grid* gv = &mine->grid[g];
             FreqPoint fp;
             if (k0 < res) grid.start(k0, fp);
-            for (int k = k0; k < res; k += stride) {
-                if (k != k0) {
-                    if (lin) grid.advance(k, fp);
-                    else {
-                        const bool last = k == res - 1;
-                        fp.f = last ? gc[7] : fp.f * gc[0];
-                        fp.f13 *= gc[1]; fp.fm13 *= gc[2]; fp.fm76 *= gc[3]; fp.lnf += gc[4];
-                        fp.w = fp.f * (last ? gc[6] : gc[5]);
+            // kUniformLoop: warp-uniform trip count with the last block predicated (needed for a barrier inside the loop);
+            // otherwise lanes leave the loop on their own.  Same arithmetic either way; which form the compiler schedules
+            // better differs per model (measured per 1e4 events: IMRPhenomD 1.229 -> 1.208 ms, NRTidalv2 3.131 -> 3.287 ms).
+            constexpr bool kUniformLoop = MODEL == kPhenomHM || MODEL == kPhenomD;
+            for (int kb = k0 - lane; kUniformLoop ? kb < res : kb + lane < res; kb += stride) {
+                const int k = kb + lane;
+                if (!kUniformLoop || k < res) {
+                    if (k != k0) {
+                        if (lin) grid.advance(k, fp);
+                        else {
+                            const bool last = k == res - 1;
+                            fp.f = last ? gv->fcut : fp.f * gv->r;
+                            fp.f13 *= gv->r13; fp.fm13 *= gv->rm13; fp.fm76 *= gv->rm76; fp.lnf += gv->dln;
+                            fp.w = fp.f * (last ? gv->hw_hi : gv->hw_in);
+                        }
                     }
+                    if (FAST == 2) PF::template fisher_fast<true>(rec, cfg, geom, net, mine->sc, mine->ex, fp, acc);
+                    else if (FAST == 1) PF::template fisher_fast<false>(rec, cfg, geom, net, mine->sc, mine->ex, fp, acc);
+                    else PF::fisher(rec, cfg, geom, net, mine->sc, mine->ex, g, rot, fp, acc);
                 }
-                if (FAST == 2) PF::template fisher_fast<true>(rec, cfg, geom, net, mine->sc, mine->ex, fp, acc);
-                else if (FAST == 1) PF::template fisher_fast<false>(rec, cfg, geom, net, mine->sc, mine->ex, fp, acc);
-                else PF::fisher(rec, cfg, geom, net, mine->sc, mine->ex, g, rot, fp, acc);
+                if (kUniformLoop && (pair & 4)) asm volatile("bar.sync %0, 64;" ::"r"(1 + slot) : "memory");
             }
         }
         // warp reduction by recursive halving; the reduced accumulators land in shared memory (the record is no longer
@@ -361,27 +400,29 @@ fisher_kernel(const typename ModelTraits<MODEL, NT>::Rec* __restrict__ recs, Eve
             if (idx >= 0) red[idx] = acc[i];
         }
         __syncwarp();
-        if (pair) {
-            // named barrier of the two warps of the pair: the partner's partial sums are complete
-            asm volatile("bar.sync %0, 64;" ::"r"(1 + slot) : "memory");
-            if (half == 0) {
-                const double* other = reinterpret_cast<const double*>(&(mine + kHalfWarps)->rec);
-                for (int p = lane; p < PF::kAcc; p += 32) red[p] += other[p];
-                __syncwarp();
-            }
+        double* o = out + e * NPACK;
+        for (int p = lane; p < NPACK; p += 32) {
+            int i = 0;
+            while (tri(i + 1, 0) <= p) ++i;                   // row of packed index p
+            const double v = PF::entry(i, p - tri(i, 0), red, geom);
+            if (pair) atomicAdd(o + p, v);
+            else o[p] = v;
         }
-        if (half == 0) {
-            double* o = out + e * NPACK;
-            for (int p = lane; p < NPACK; p += 32) {
-                int i = 0;
-                while (tri(i + 1, 0) <= p) ++i;                   // row of packed index p
-                o[p] = PF::entry(i, p - tri(i, 0), red, geom);
-            }
-            if (lane == 0 && snr2_out) snr2_out[e] = PF::snr2(red, geom);
-            if (sd_out && lane < NP) sd_out[e * NP + lane] = PF::snr_deriv(lane, red, geom);     // (h | d_i h), signal.py:938-945
+        if (lane == 0 && snr2_out) {
+            const double v = PF::snr2(red, geom);
+            if (pair) atomicAdd(snr2_out + e, v);
+            else snr2_out[e] = v;
         }
-        // the partner may only overwrite its staging block once its sums have been read
-        if (pair) asm volatile("bar.sync %0, 64;" ::"r"(1 + slot) : "memory");
+        if (sd_out && lane < NP) {                            // (h | d_i h), signal.py:938-945
+            const double v = PF::snr_deriv(lane, red, geom);
+            if (pair) atomicAdd(sd_out + e * NP + lane, v);
+            else sd_out[e * NP + lane] = v;
+        }
+        // lock step of the two halves (no data dependence): the two warps of a pair sit on the same scheduler, and keeping them
+        // in the same stretch of code shares its instruction fetches -- the kernels are 90-300 KB of SASS (measured per 1e4
+        // events, free-running -> per event -> per block of samples: IMRPhenomD 1.251 -> 1.229 -> 1.236 ms, NRTidalv2
+        // 3.166 -> 3.131 -> 3.197 ms, IMRPhenomHM 22.1 -> 19.7 -> 17.6 ms)
+        if (pair & 2) asm volatile("bar.sync %0, 64;" ::"r"(1 + slot) : "memory");
     }
 }
 
@@ -586,8 +627,10 @@ static int run_fisher(const gwf_model* model, const gwf_detector* dets, int ndet
                       long long n, const gwf_opts* opts, double* fisher, double* snr2, double* snr_derivs, void* ws, size_t ws_bytes, cudaStream_t st) {
     typedef typename ModelTraits<MODEL, NT>::Rec Rec;
     constexpr int NP = NT + 7, NPACK = NP * (NP + 1) / 2;
-    if (ws_bytes < sizeof(Rec) * (size_t)n) return fail(GWF_ERR_WORKSPACE, "workspace too small");
+    const size_t rec_bytes = (sizeof(Rec) * (size_t)n + 15) & ~(size_t)15;
+    if (ws_bytes < rec_bytes + sizeof(EventAux) * (size_t)n) return fail(GWF_ERR_WORKSPACE, "workspace too small");
     Rec* recs = reinterpret_cast<Rec*>(ws);
+    EventAux* aux = reinterpret_cast<EventAux*>(reinterpret_cast<char*>(ws) + rec_bytes);
     ModelCfg cfg = {model->id, model->flags, model->fcutPar, model->fRef};
     NetworkDev net;
     PsdDev pd[kMaxPsd];
@@ -598,9 +641,28 @@ static int run_fisher(const gwf_model* model, const gwf_detector* dets, int ndet
     GroupInfo gi;
     gi.n = net.ngroups;
     for (int g = 0; g < kMaxGroups; ++g) gi.fmin[g] = net.group_fmin[g];
+    // One event per pair of warps (each warp takes every other block of 32 samples): the work unit of the persistent loop is
+    // half an event, which shortens its last round (1e4 events on 1184 warps: 8.45 -> 9 rounds of whole events, 16.9 -> 17 of
+    // halves; measured 1.36 -> 1.31 ms).  The mapping is fixed per model -- never chosen from n -- so that an event's result
+    // does not depend on the size of the batch it is computed in.  TaylorF2 events are too cheap for the repeated staging
+    // (measured 4 % slower), so they keep one warp per event.
+    int pair = (MODEL != kTaylorF2 && !(opts->flags & GWF_OPT_ONE_WARP_PER_EVENT)) ? 1 : 0;
+    if (pair) {
+        const char* ls = getenv("GWF_PAIR_LOCKSTEP");
+        // GWF_PAIR_LOCKSTEP (experiments): 0 = free-running halves, 1 = barrier per event, 2 = barrier per block of samples
+        const int mode = ls ? ls[0] - '0' : (MODEL == kPhenomHM ? 2 : 1);
+        if (mode >= 1) pair |= 2;
+        if (mode >= 2) pair |= 4;
+    }
+    const int lin = (opts->flags & GWF_OPT_LIN_GRID) ? 1 : 0;
     const int pb = 128;
     if (!(opts->flags & GWF_OPT_REUSE_WORKSPACE)) {
-        prologue_kernel<MODEL, NT><<<(unsigned)((n + pb - 1) / pb), pb, 0, st>>>(ev, n, cfg, opts->flags, g_qnm, gi, recs);
+        // the prologue also leaves the per-event geometry and grids (EventAux) for the Fisher kernel
+        AuxPlan ap;
+        ap.out = aux;
+        for (int g = 0; g < kMaxGroups; ++g) ap.fmax[g] = net.group_fmax[g];
+        ap.res = opts->res; ap.lin = lin; ap.stride = pair ? 64 : 32;
+        prologue_kernel<MODEL, NT><<<(unsigned)((n + pb - 1) / pb), pb, 0, st>>>(ev, n, cfg, opts->flags, g_qnm, gi, recs, nullptr, ap);
         GWF_CUDA(cudaGetLastError());
     }
     int dev = 0, sms = 0;
@@ -612,7 +674,7 @@ static int run_fisher(const gwf_model* model, const gwf_detector* dets, int ndet
     // the unrolled form pays off where the waveform leaves registers for it (measured: IMRPhenomD 1.55 -> 1.31 ms, NRTidalv2
     // 3.73 -> 3.21 ms per 1e4 events; TaylorF2's version spills and is 7-20 % slower than the general loop)
     constexpr bool kHasFast = PointFns<MODEL, NT>::kHasFast && MODEL != kTaylorF2;
-    typedef void (*Kern)(const Rec*, EventsDev, long long, int, int, ModelCfg, const NetworkDev, double*, double*, double*, int);
+    typedef void (*Kern)(const Rec*, const EventAux*, EventsDev, long long, int, int, ModelCfg, const NetworkDev, double*, double*, double*, int);
     // IMRPhenomHM needs extra accumulators for the SNR derivatives (its own instantiation); the other models rebuild them
     // from the compact Gram whenever the output pointer is given
     constexpr bool kSdKernel = MODEL == kPhenomHM;
@@ -621,16 +683,9 @@ static int run_fisher(const gwf_model* model, const gwf_detector* dets, int ndet
     for (int k = 0; k < 3; ++k) GWF_CUDA(cudaFuncSetAttribute(kerns[k], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem));
     const bool allow_fast = kHasFast && !(opts->flags & GWF_OPT_GENERIC_LOOP);
     int fast = allow_fast ? plan_fast(net) : 0;
-    // One event per pair of warps (each warp takes every other block of 32 samples): the work unit of the persistent loop is
-    // half an event, which shortens its last round (1e4 events on 1184 warps: 8.45 -> 9 rounds of whole events, 16.9 -> 17 of
-    // halves; measured 1.36 -> 1.31 ms).  The mapping is fixed per model -- never chosen from n -- so that an event's result
-    // does not depend on the size of the batch it is computed in.  TaylorF2 events are too cheap for the repeated staging
-    // (measured 4 % slower), so they keep one warp per event.
-    const int pair = (MODEL != kTaylorF2 && !(opts->flags & GWF_OPT_ONE_WARP_PER_EVENT)) ? 1 : 0;
     const int per_cta = pair ? kWarpsPerCta / 2 : kWarpsPerCta;
     const long long want = (n + per_cta - 1) / per_cta;
     const unsigned grid = (unsigned)std::min<long long>(want, (long long)sms);
-    const int lin = (opts->flags & GWF_OPT_LIN_GRID) ? 1 : 0;
     const int npass = opts->per_arm ? gwf_num_arms(dets, ndet) : 1;
     for (int pass = 0; pass < npass; ++pass) {
         if (opts->per_arm) {
@@ -639,9 +694,16 @@ static int run_fisher(const gwf_model* model, const gwf_detector* dets, int ndet
             plan_psd_cache(net, ws_bytes_smem, kSmemLimit);
             fast = allow_fast ? plan_fast(net) : 0;
         }
-        kerns[fast]<<<grid, kFisherThreads, shmem, st>>>(recs, ev, n, opts->res, lin, cfg, net, fisher + (size_t)pass * n * NPACK,
-                                                  snr2 ? snr2 + (size_t)pass * n : nullptr,
-                                                  snr_derivs ? snr_derivs + (size_t)pass * n * NP : nullptr, pair);
+        double* o_f = fisher + (size_t)pass * n * NPACK;
+        double* o_s = snr2 ? snr2 + (size_t)pass * n : nullptr;
+        double* o_d = snr_derivs ? snr_derivs + (size_t)pass * n * NP : nullptr;
+        if (pair) {
+            // the two halves of an event add their contributions
+            GWF_CUDA(cudaMemsetAsync(o_f, 0, sizeof(double) * (size_t)n * NPACK, st));
+            if (o_s) GWF_CUDA(cudaMemsetAsync(o_s, 0, sizeof(double) * (size_t)n, st));
+            if (o_d) GWF_CUDA(cudaMemsetAsync(o_d, 0, sizeof(double) * (size_t)n * NP, st));
+        }
+        kerns[fast]<<<grid, kFisherThreads, shmem, st>>>(recs, aux, ev, n, opts->res, lin, cfg, net, o_f, o_s, o_d, pair);
         GWF_CUDA(cudaGetLastError());
     }
     return GWF_OK;
@@ -792,7 +854,8 @@ size_t gwf_workspace_bytes(const gwf_model* model, int64_t n) {
         case GWF_IMRPHENOMHM: rec = sizeof(HMRec<4>); break;
         default: rec = 0;
     }
-    return ((rec * (size_t)n + 15) & ~(size_t)15) + sizeof(double) * (size_t)n;
+    // records, then the larger of the waveform path's per-event grid minimum and the Fisher path's EventAux
+    return ((rec * (size_t)n + 15) & ~(size_t)15) + std::max(sizeof(double), sizeof(EventAux)) * (size_t)n;
 }
 
 int gwf_psd_create(const double* f, const double* S, int32_t n, gwf_psd** out) {

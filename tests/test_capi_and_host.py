@@ -31,7 +31,7 @@ def test_library_exports_every_declared_symbol():
 def test_struct_layouts_and_pure_host_entry_points():
     K = _built()
     lib = K.load()
-    assert C.sizeof(K.gwf_model) == 24 and C.sizeof(K.gwf_detector) == 56 and C.sizeof(K.gwf_opts) == 16 and C.sizeof(K.gwf_events) == 15 * 8
+    assert C.sizeof(K.gwf_model) == 24 and C.sizeof(K.gwf_detector) == 56 and C.sizeof(K.gwf_opts) == 16 and C.sizeof(K.gwf_events) == 16 * 8
     for mid, flags, nP in ((0, 0, 11), (0, K.GWF_MODEL_TIDAL, 13), (1, 0, 11), (2, 0, 13), (3, 0, 11)):
         assert lib.gwf_num_params(C.byref(K.gwf_model(mid, flags, 0.2, 0.))) == nP
     dets = (K.gwf_detector * 3)(K.gwf_detector(0, 0, 0, 1, 0, 0, 0, 2., 0.), K.gwf_detector(0, 0, 0, 0, 0, 0, 0, 2., 0.), K.gwf_detector(0, 0, 0, 0, 0, 0, 0, 2., 0.))

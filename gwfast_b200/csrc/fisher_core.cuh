@@ -401,6 +401,42 @@ struct HMExtra {
     GWF_HD void set(const EventIn& e) { w.set(e.iota); }
 };
 
+// mode sums of hphc: z_m = A_m exp(-i Phi_m) is folded into h+ / hx (and their iota derivatives) as soon as it is known
+template <int NT> struct HMStrainSink {
+    typedef Dual<NT> D;
+    const HMWeights& w;
+    D hpr, hpi, hcr, hci;
+    double hpr_i, hpi_i, hcr_i, hci_i;
+    GWF_HD explicit HMStrainSink(const HMWeights& w_) : w(w_), hpr(0.0), hpi(0.0), hcr(0.0), hci(0.0), hpr_i(0.), hpi_i(0.), hcr_i(0.), hci_i(0.) {}
+    GWF_HD void operator()(int m, const D& A, const D& ph) {
+        D sn, cs;
+        dsincos(ph, sn, cs);
+        const D zre = A * cs, zim = -(A * sn);
+        hpr = hpr + zre * w.wp[m];
+        hpi = hpi + zim * w.wp[m];
+        hcr = hcr - zim * w.wc[m];
+        hci = hci + zre * w.wc[m];
+        hpr_i = fma(zre.v, w.dwp[m], hpr_i);
+        hpi_i = fma(zim.v, w.dwp[m], hpi_i);
+        hcr_i = fma(-zim.v, w.dwc[m], hcr_i);
+        hci_i = fma(zre.v, w.dwc[m], hci_i);
+    }
+};
+struct HMValueSink {
+    const HMWeights& w;
+    double hpr, hpi, hcr, hci;
+    GWF_HD explicit HMValueSink(const HMWeights& w_) : w(w_), hpr(0.), hpi(0.), hcr(0.), hci(0.) {}
+    GWF_HD void operator()(int m, double A, double ph) {
+        double sn, cs;
+        sincos(ph, &sn, &cs);
+        const double zre = A * cs, zim = -(A * sn);
+        hpr = fma(zre, w.wp[m], hpr);
+        hpi = fma(zim, w.wp[m], hpi);
+        hcr = fma(-zim, w.wc[m], hcr);
+        hci = fma(zre, w.wc[m], hci);
+    }
+};
+
 // SD: also accumulate (h | d_i h) behind the SNR^2 slot (return_SNR_derivatives)
 template <int NT, bool SD = false>
 GWF_HD void hm_point(const HMRec<NT>& rec, const ModelCfg& cfg, const EvGeom& geom, const NetworkDev& net, const EventScratch& sc,
@@ -410,22 +446,11 @@ GWF_HD void hm_point(const HMRec<NT>& rec, const ModelCfg& cfg, const EvGeom& ge
     double& snr2 = acc[NP * (NP + 1) / 2];
     const double f = fp.f, l2f = fp.lnf * 1.4426950408889634073599246810018921;
     const bool cut = !(cfg.flags & kFlagNoFcut);
-    D zre[kHMModes], zim[kHMModes];
-    phenomhm_modes<D, NT>(rec, g, f, cut, zre, zim);
-    // hp = sum z_m Wp_m ; hc = i sum z_m Wc_m ; and their iota derivatives (waveforms.py:2613-2614)
-    D hpr(0.0), hpi(0.0), hcr(0.0), hci(0.0);
-    double hpr_i = 0., hpi_i = 0., hcr_i = 0., hci_i = 0.;
-#pragma unroll
-    for (int m = 0; m < kHMModes; ++m) {
-        hpr = hpr + zre[m] * ex.w.wp[m];
-        hpi = hpi + zim[m] * ex.w.wp[m];
-        hcr = hcr - zim[m] * ex.w.wc[m];
-        hci = hci + zre[m] * ex.w.wc[m];
-        hpr_i = fma(zre[m].v, ex.w.dwp[m], hpr_i);
-        hpi_i = fma(zim[m].v, ex.w.dwp[m], hpi_i);
-        hcr_i = fma(-zim[m].v, ex.w.dwc[m], hcr_i);
-        hci_i = fma(zre[m].v, ex.w.dwc[m], hci_i);
-    }
+    // hp = sum z_m Wp_m ; hc = i sum z_m Wc_m ; and their iota derivatives (waveforms.py:2613-2614), summed mode by mode
+    HMStrainSink<NT> hs(ex.w);
+    phenomhm_foreach_mode<D, NT>(rec, g, f, cut, hs);
+    const D &hpr = hs.hpr, &hpi = hs.hpi, &hcr = hs.hcr, &hci = hs.hci;
+    const double hpr_i = hs.hpr_i, hpi_i = hs.hpi_i, hcr_i = hs.hcr_i, hci_i = hs.hci_i;
     if (hpr.v == 0.0 && hpi.v == 0.0 && hcr.v == 0.0 && hci.v == 0.0) return;
     PointWf<NT> w;
     w.f = f;
@@ -504,16 +529,9 @@ GWF_HD void hm_snr_point(const HMRec<4>& rec, const ModelCfg& cfg, const EvGeom&
                          const HMExtra& ex, int g, bool group_rot, const FreqPoint& fp, double* __restrict__ snr2_arm) {
     const double f = fp.f, l2f = fp.lnf * 1.4426950408889634073599246810018921;
     const bool cut = !(cfg.flags & kFlagNoFcut);
-    double zre[kHMModes], zim[kHMModes];
-    phenomhm_modes<double, 4>(rec, g, f, cut, zre, zim);
-    double hpr = 0., hpi = 0., hcr = 0., hci = 0.;
-#pragma unroll
-    for (int m = 0; m < kHMModes; ++m) {
-        hpr = fma(zre[m], ex.w.wp[m], hpr);
-        hpi = fma(zim[m], ex.w.wp[m], hpi);
-        hcr = fma(-zim[m], ex.w.wc[m], hcr);
-        hci = fma(zre[m], ex.w.wc[m], hci);
-    }
+    HMValueSink hs(ex.w);
+    phenomhm_foreach_mode<double, 4>(rec, g, f, cut, hs);
+    const double hpr = hs.hpr, hpi = hs.hpi, hcr = hs.hcr, hci = hs.hci;
     const double hp2 = hpr * hpr + hpi * hpi, hc2 = hcr * hcr + hci * hci;
     if (hp2 == 0.0 && hc2 == 0.0) return;
     double sBr = 0., cBr = 1.;

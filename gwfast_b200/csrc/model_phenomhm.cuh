@@ -70,6 +70,7 @@ struct HMMode {
     T fi_amp, fi_phi, fr;             // map break points (amp: 0.014/Rho, phase: 0.018/Rho, fring_lm)
     T am_amp, bm_amp, br_amp;         // amplitude map, middle and ringdown regimes (inspiral: 2/m, 0; ringdown slope 1)
     T am_phi, bm_phi, rho;            // phase map (ringdown: slope Rho, 0)
+    T inv_am_phi, inv_rho;            // reciprocals of the two map slopes (the mapped phase is divided by them)
     T c1, c2;                         // C1MRDHM, C2MRDHM
     T at_c, at_a, at_w;               // alpha4 Rho/eta, alpha5 fring, fdamp Rho Tau
     T kB, kC;                         // -PhDBconst + PhDBAterm, -PhDCconst + tmpphaseC
@@ -324,6 +325,8 @@ GWF_HD void phenomhm_prologue(HMRec<NT>& r, const Intrinsic<NT>& p, double dL, c
             o.am_phi = (Trd - Ti) / (frlm - o.fi_phi);
             o.bm_phi = Ti - o.fi_phi * o.am_phi;
         }
+        o.inv_am_phi = 1.0 / o.am_phi;
+        o.inv_rho = 1.0 / Rho;
         // continuity constants, waveforms.py:2586-2596
         auto cP = [&](const D& y) { return hm_complete_phase<D, NT>(r, y, o.c1, o.c2, o.at_c, o.at_a, o.at_w, apply_cut); };
         const D PhDBconst = cP(o.am_phi * o.fi_phi + o.bm_phi) / o.am_phi;
@@ -338,9 +341,12 @@ GWF_HD void phenomhm_prologue(HMRec<NT>& r, const Intrinsic<NT>& p, double dL, c
 
 // ------------------------------------------------------------------------------------------------ per frequency
 // amplitude A_lm and phase Phi_lm of the six modes (IMRPhenomHM.Ampl / .Phi, waveforms.py:1874-2254, as vectorised in hphc);
-// T = Dual<NT> (tangents w.r.t. the intrinsic slots) or double
-template <class T, int NT>
-GWF_HD void phenomhm_amp_phase(const HMRec<NT>& r, int g, double f, bool apply_cut, T* amp, T* phase) {
+// T = Dual<NT> (tangents w.r.t. the intrinsic slots) or double.  Every mode is handed to `sink(m, A, Phi)` as soon as it is
+// known, so that callers which only need sums over the modes keep nothing per mode (a rolled loop over per-mode arrays
+// lives in local memory).  The PhenomD phase is evaluated through ONE call site per mode -- the three frequency regimes only
+// choose its argument, offset and scale -- which keeps the kernel's code (and its instruction-cache footprint) small.
+template <class T, int NT, class Sink>
+GWF_HD void phenomhm_foreach_mode(const HMRec<NT>& r, int g, double f, bool apply_cut, Sink& sink) {
     typedef Ld<T> L;
     const T x = L::get(r.s) * f;
     const double xv = val(x);
@@ -367,29 +373,25 @@ GWF_HD void phenomhm_amp_phase(const HMRec<NT>& r, int g, double f, bool apply_c
             const T ym76 = 1.0 / (y * dsqrt(y13));
             A = L::get(r.Camp) * ym76 * shape * (h1 * hS / h2);
         }
-        amp[m] = A;
-        // phase, waveforms.py:2600-2607
-        T ph;
-        const T c1 = L::get(o.c1), c2 = L::get(o.c2), at_c = L::get(o.at_c), at_a = L::get(o.at_a), at_w = L::get(o.at_w);
-        if (xv < o.fi_phi.v) ph = hm_complete_phase<T, NT>(r, x * ai, c1, c2, at_c, at_a, at_w, apply_cut) * (1.0 / ai);
-        else if (xv < o.fr.v) ph = L::get(o.kB) + hm_complete_phase<T, NT>(r, x * L::get(o.am_phi) + L::get(o.bm_phi), c1, c2, at_c, at_a, at_w, apply_cut) / L::get(o.am_phi);
-        else ph = L::get(o.kC) + hm_complete_phase<T, NT>(r, x * L::get(o.rho), c1, c2, at_c, at_a, at_w, apply_cut) / L::get(o.rho);
-        phase[m] = ph - lin - mm * L::get(r.phi0[g]) + hm_shift((int)mm);
+        // phase, waveforms.py:2600-2607: offset + completePhase(mapped frequency) * scale
+        T yp, off, scale;
+        if (xv < o.fi_phi.v) { yp = x * ai; off = T(0.0); scale = T(1.0 / ai); }
+        else if (xv < o.fr.v) { yp = x * L::get(o.am_phi) + L::get(o.bm_phi); off = L::get(o.kB); scale = L::get(o.inv_am_phi); }
+        else { yp = x * L::get(o.rho); off = L::get(o.kC); scale = L::get(o.inv_rho); }
+        const T cph = hm_complete_phase<T, NT>(r, yp, L::get(o.c1), L::get(o.c2), L::get(o.at_c), L::get(o.at_a), L::get(o.at_w), apply_cut);
+        sink(m, A, off + cph * scale - lin - mm * L::get(r.phi0[g]) + hm_shift((int)mm));
     }
 }
 
-// mode strains z_m = A_m exp(-i Phi_m)
+template <class T> struct HMStoreSink {
+    T* amp;
+    T* phase;
+    GWF_HD void operator()(int m, const T& A, const T& ph) { amp[m] = A; phase[m] = ph; }
+};
 template <class T, int NT>
-GWF_HD void phenomhm_modes(const HMRec<NT>& r, int g, double f, bool apply_cut, T* zre, T* zim) {
-    T amp[kHMModes], ph[kHMModes];
-    phenomhm_amp_phase<T, NT>(r, g, f, apply_cut, amp, ph);
-#pragma unroll 1
-    for (int m = 0; m < kHMModes; ++m) {
-        T sn, cs;
-        dsincos(ph[m], sn, cs);
-        zre[m] = amp[m] * cs;
-        zim[m] = -(amp[m] * sn);
-    }
+GWF_HD void phenomhm_amp_phase(const HMRec<NT>& r, int g, double f, bool apply_cut, T* amp, T* phase) {
+    HMStoreSink<T> sink = {amp, phase};
+    phenomhm_foreach_mode<T, NT>(r, g, f, apply_cut, sink);
 }
 
 }  // namespace gwf

@@ -118,11 +118,14 @@ __device__ __forceinline__ double psd_lookup_fast(const PsdDev& p, double f, dou
     const int last = p.c_n - 1;
     int j = (int)((l2f - p.u_lo) * p.u_inv) - p.c_j0;
     j = max(0, min(j, last));
-    double2 fs = R[2 * j], sn = R[2 * j + 1];
-    if ((j > 0 && f < fs.x) || (j < last && f >= sn.y)) {
-        while (j > 0 && f < fs.x) { --j; fs = R[2 * j]; sn = R[2 * j + 1]; }
-        while (j < last && f >= sn.y) { ++j; fs = R[2 * j]; sn = R[2 * j + 1]; }
-    }
+    // The nodes of a "uni" table sit within a quarter of a bucket of the uniform positions (host_build.h), so the segment
+    // that holds f is j - 1, j or j + 1: the step is a pair of selects on the node frequencies of row j and the row is read
+    // again -- straight-line code the scheduler can spread over the surrounding arithmetic (the former fix-up branch waited
+    // on its shared-memory row: 8 % of the Fisher kernel's stall samples, profiles/r01f).  f == node picks the segment to
+    // its right, like np.interp.
+    const double f_lo = R[2 * j].x, f_hi = R[2 * j + 1].y;
+    j += (j < last && f >= f_hi) ? 1 : ((j > 0 && f < f_lo) ? -1 : 0);
+    const double2 fs = R[2 * j], sn = R[2 * j + 1];
     const double v = fma(sn.x, f - fs.x, fs.y);
     return (f >= p.f_first && f <= p.f_last) ? v : 1.0;
 }

@@ -194,6 +194,47 @@ def strain_derivs(model, dets, psd_handles, ev, n, res, flags):
     return out
 
 
+def overlap(model1, model2, det, psd_handle_, ev1, ev2, fcut, fmin, n, res):
+    """GWSignal.WFOverlap on one detector: gwf_strain for each waveform on the common grid, then gwf_overlap per arm.
+
+    Returns (overlap, snr2_1, snr2_2), each (n_arms, n): the per-arm integrals of signal.py:1876-1925.
+    """
+    global launch_count
+    st = state()
+    torch = st.torch
+    lib = st.lib
+    darr, parr = _call_arrays([det], [psd_handle_])
+    narms = lib.gwf_num_arms(darr, 1)
+    stream = torch.cuda.current_stream(st.device)
+    sp = C.c_void_p(stream.cuda_stream)
+    opts = K.gwf_opts(int(res), KERNEL_FLAGS, 1, 0)
+    out = np.empty((3, narms, n))
+    chunk = max(1, min(n, int(2 ** 27 // (narms * int(res) * 16)) or 1))       # ~128 MB of strain per waveform and launch group
+    for lo in range(0, n, chunk):
+        m = min(chunk, n - lo)
+        hs, keep = [], []
+        for model, ev in ((model1, ev1), (model2, ev2)):
+            sub = {k: np.asarray(v)[lo:lo + m] for k, v in ev.items() if k in K.EVENT_KEYS}
+            sub['_fcut'] = np.asarray(fcut)[lo:lo + m]
+            dev_ev, host_ev, evs, _ = _upload(st, sub, m, K.EVENT_KEYS)
+            ws = torch.empty(int(lib.gwf_workspace_bytes(C.byref(model), m)), dtype=torch.uint8, device=st.device)
+            h = torch.empty((narms, m, int(res), 2), dtype=torch.float64, device=st.device)
+            K.check(lib.gwf_strain(C.byref(model), darr, 1, parr, 1, C.byref(evs), m, C.byref(opts), C.c_void_p(h.data_ptr()),
+                                   C.c_void_p(ws.data_ptr()), ws.numel(), sp), 'gwf_strain')
+            launch_count += 1 + narms
+            hs.append(h)
+            keep.append((dev_ev, host_ev, ws, evs))
+        fc = torch.from_numpy(np.array(np.asarray(fcut, dtype=np.float64)[lo:lo + m])).to(st.device)
+        res3 = torch.empty((3, narms, m), dtype=torch.float64, device=st.device)
+        for a in range(narms):
+            K.check(lib.gwf_overlap(C.c_void_p(hs[0][a].data_ptr()), C.c_void_p(hs[1][a].data_ptr()), C.c_void_p(fc.data_ptr()), m, int(res), float(fmin),
+                                    C.c_void_p(psd_handle_), C.c_void_p(res3[0, a].data_ptr()), C.c_void_p(res3[1, a].data_ptr()),
+                                    C.c_void_p(res3[2, a].data_ptr()), sp), 'gwf_overlap')
+            launch_count += 1
+        out[:, :, lo:lo + m] = res3.cpu().numpy()
+    return out[0], out[1], out[2]
+
+
 def snr(model, dets, psd_handles, ev, n, res, flags=0, keep_on_device=False):
     """Run gwf_snr: per-arm integrals 4*int (Ap^2+Ac^2)/Sn df, shape (n_arms, n)."""
     global launch_count

@@ -509,6 +509,92 @@ derivs_kernel(const typename ModelTraits<MODEL, NT>::Rec* __restrict__ recs, Eve
     }
 }
 
+// GWSignal.GWstrain on the engine's own grid (signal.py:484-655): the strain h = A e^{i Psi} (K F+ + i cos(iota) Fx) of ONE arm
+// (a per-arm pass network) written out as complex128 [n][res]; samples beyond the waveform cut are 0.  Used by WFOverlap, whose
+// two waveforms differ in model and parameters but share the grid (the host passes the common upper frequency as fcut_host).
+template <int MODEL>
+__global__ void __launch_bounds__(kFisherThreads)
+strain_kernel(const typename ModelTraits<MODEL, 4>::Rec* __restrict__ recs, EventsDev ev, long long n, int res, int lin, ModelCfg cfg,
+              const __grid_constant__ NetworkDev net, double2* __restrict__ out) {
+    constexpr int NT = 4;
+    typedef typename ModelTraits<MODEL, NT>::Rec Rec;
+    typedef PointFns<MODEL, NT> PF;
+    typedef WarpSmem<Rec, typename PF::Extra> WS;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    WS* mine = reinterpret_cast<WS*>(smem_raw) + wid;
+    const Rec& rec = mine->rec;
+    const long long nwarps = (long long)gridDim.x * kWarpsPerCta;
+    for (long long e = (long long)blockIdx.x * kWarpsPerCta + wid; e < n; e += nwarps) {
+        double phicoal;
+        {
+            EvGeom g0;
+            const EventIn in = load_event(ev, e);
+            phicoal = in.Phicoal;
+            g0.set(in);
+            stage_event<false>(mine, recs, e, net, g0, in, lane);
+        }
+        const EvGeom& geom = mine->geom;
+        int di = 0;
+        while (di < net.ndet - 1 && net.det[di].arm_begin == net.det[di].arm_end) ++di;
+        const DetDev& d = net.det[di];
+        const ArmDev& arm = net.arm[d.arm_begin];
+        const int g = d.group;
+        double fcut = rec.fcut_hz;
+        if (net.group_fmax[g] > 0.0 && fcut > net.group_fmax[g]) fcut = net.group_fmax[g];
+        Grid grid;
+        grid.set(net.group_fmin[g], fcut, res, lin != 0, 32);
+        const bool rot = d.use_rot != 0;
+        for (int k = lane; k < res; k += 32) {
+            FreqPoint fp;
+            grid.start(k, fp);
+            PointWf<NT> w;
+            ModelTraits<MODEL, NT>::eval(rec, cfg, g, fp, rot, w);
+            double2 h = make_double2(0.0, 0.0);
+            if (w.A != 0.0) {
+                double sBr = 0., cBr = 1.;
+                if (rot) sincos(2.0 * kPi * fma(-w.tau, kInvDay, geom.tcoal), &sBr, &cBr);
+                DetPoint dp;
+                if (rot) det_point(mine->sc.ed[di], cBr, sBr, dp);
+                else dp = mine->sc.fixed[di];
+                double Fp, Fc;
+                arm_pattern(dp, arm, geom, Fp, Fc);
+                const double W2 = 2.0 * kPi * fp.f;
+                const double Psi = (W2 * (geom.tcoal * 3600. * 24.) - phicoal - w.phi) + W2 * dp.dt;      // signal.py:484, 580, 641
+                double sP, cP;
+                sincos(Psi, &sP, &cP);
+                const double ar = w.A * geom.K * Fp, ai = w.A * geom.ci * Fc;                            // Ap, Ac (signal.py:463-464)
+                h = make_double2(ar * cP - ai * sP, ar * sP + ai * cP);
+            }
+            out[e * res + k] = h;
+        }
+    }
+}
+
+// GWSignal.WFOverlap integrals (signal.py:1866-1925) for one arm: 4 int Re(h1 conj h2)/Sn df, 4 int |h1|^2/Sn df, 4 int |h2|^2/Sn df on the
+// grid geomspace(fmin, fcut[e], res); one warp per event, trapezoid weights as in the Fisher/SNR kernels.
+__global__ void __launch_bounds__(256) overlap_kernel(const double2* __restrict__ h1, const double2* __restrict__ h2, const double* __restrict__ fcut,
+                                                      long long n, int res, double fmin, PsdDev psd, double* __restrict__ ov, double* __restrict__ s1,
+                                                      double* __restrict__ s2) {
+    const int lane = threadIdx.x & 31;
+    const long long e = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+    if (e >= n) return;
+    Grid grid;
+    grid.set(fmin, fcut[e], res, false, 32);
+    double a = 0., b = 0., c = 0.;
+    for (int k = lane; k < res; k += 32) {
+        FreqPoint fp;
+        grid.start(k, fp);
+        const double wgt = 4.0 * fp.w / psd_lookup(psd, fp.f, fp.lnf * 1.4426950408889634073599246810018921);
+        const double2 x = h1[e * res + k], y = h2[e * res + k];
+        a = fma(wgt, x.x * y.x + x.y * y.y, a);
+        b = fma(wgt, x.x * x.x + x.y * x.y, b);
+        c = fma(wgt, y.x * y.x + y.y * y.y, c);
+    }
+    a = warp_sum(a); b = warp_sum(b); c = warp_sum(c);
+    if (lane == 0) { ov[e] = a; s1[e] = b; s2[e] = c; }
+}
+
 // SNR: per-arm integrals, value-only.  Four warps share an event (warp `sub` takes every fourth block of 32 samples), so a
 // CTA of 16 warps stages only four coefficient records and the PSD windows still fit next to them in shared memory.
 constexpr int kSnrSplit = 4, kSnrGroups = kSnrWarps / kSnrSplit;
@@ -745,6 +831,46 @@ static int run_derivs(const gwf_model* model, const gwf_detector* dets, int ndet
         for (int i = 0; i < net.npsd; ++i) net.psd[i].c_off = -1;
         kern<<<grid, kFisherThreads, shmem, st>>>(recs, ev, n, opts->res, lin, cfg, net,
                                                   reinterpret_cast<double2*>(derivs) + (size_t)pass * NP * n * opts->res);
+        GWF_CUDA(cudaGetLastError());
+    }
+    return GWF_OK;
+}
+
+template <int MODEL>
+static int run_strain(const gwf_model* model, const gwf_detector* dets, int ndet, const gwf_psd* const* psds, int npsd, const EventsDev& ev,
+                      long long n, const gwf_opts* opts, double* strain, void* ws, size_t ws_bytes, cudaStream_t st) {
+    typedef typename ModelTraits<MODEL, 4>::Rec Rec;
+    if (ws_bytes < sizeof(Rec) * (size_t)n) return fail(GWF_ERR_WORKSPACE, "workspace too small");
+    Rec* recs = reinterpret_cast<Rec*>(ws);
+    ModelCfg cfg = {model->id, model->flags, model->fcutPar, model->fRef};
+    NetworkDev net;
+    PsdDev pd[kMaxPsd];
+    int rc = collect_psds(psds, npsd, pd);
+    if (rc) return rc;
+    rc = build_network(dets, ndet, pd, npsd, -1, false, net);
+    if (rc) return rc;
+    GroupInfo gi;
+    gi.n = net.ngroups;
+    for (int g = 0; g < kMaxGroups; ++g) gi.fmin[g] = net.group_fmin[g];
+    const int pb = 128;
+    // GWstrain is handed the dict entries as they are (no Fisher re-parametrisation, signal.py:1871)
+    prologue_kernel<MODEL, 4><<<(unsigned)((n + pb - 1) / pb), pb, 0, st>>>(ev, n, cfg, 0, g_qnm, gi, recs);
+    GWF_CUDA(cudaGetLastError());
+    int dev = 0, sms = 0;
+    GWF_CUDA(cudaGetDevice(&dev));
+    GWF_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const size_t shmem = sizeof(WarpSmem<Rec, typename PointFns<MODEL, 4>::Extra>) * kWarpsPerCta;
+    auto kern = strain_kernel<MODEL>;
+    GWF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem));
+    const long long want = (n + kWarpsPerCta - 1) / kWarpsPerCta;
+    const unsigned grid = (unsigned)std::min<long long>(want, (long long)sms * 2);
+    const int lin = (opts->flags & GWF_OPT_LIN_GRID) ? 1 : 0;
+    const int npass = gwf_num_arms(dets, ndet);
+    for (int pass = 0; pass < npass; ++pass) {
+        rc = build_network(dets, ndet, pd, npsd, pass, false, net);
+        if (rc) return rc;
+        for (int i = 0; i < net.npsd; ++i) net.psd[i].c_off = -1;
+        kern<<<grid, kFisherThreads, shmem, st>>>(recs, ev, n, opts->res, lin, cfg, net, reinterpret_cast<double2*>(strain) + (size_t)pass * n * opts->res);
         GWF_CUDA(cudaGetLastError());
     }
     return GWF_OK;
@@ -1004,6 +1130,45 @@ int gwf_snr(const gwf_model* model, const gwf_detector* dets, int32_t ndet, cons
         default:
             return fail(GWF_ERR_UNSUPPORTED, "model not built yet");
     }
+}
+
+int gwf_strain(const gwf_model* model, const gwf_detector* dets, int32_t ndet, const gwf_psd* const* psds, int32_t npsd, const gwf_events* events,
+               int64_t n, const gwf_opts* opts, double* strain, void* workspace, size_t workspace_bytes, void* stream) {
+    int rc = check_common(model, dets, psds, events, n, opts);
+    if (rc) return rc;
+    if (!strain) return fail(GWF_ERR_ARG, "null output");
+    if (n == 0) return GWF_OK;
+    EventsDev ev;
+    for (int i = 0; i < GWF_NPARAM_IN; ++i) ev.p[i] = events->p[i];
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    switch (model->id) {
+        case GWF_TAYLORF2:
+            if ((model->flags & GWF_MODEL_ECCENTRIC) && !ev.p[15]) return fail(GWF_ERR_ARG, "eccentric model needs ecc");
+            if ((model->flags & GWF_MODEL_TIDAL) && (!ev.p[11] || !ev.p[12])) return fail(GWF_ERR_ARG, "tidal model needs Lambda1, Lambda2");
+            return run_strain<kTaylorF2>(model, dets, ndet, psds, npsd, ev, n, opts, strain, workspace, workspace_bytes, st);
+        case GWF_IMRPHENOMD:
+            return run_strain<kPhenomD>(model, dets, ndet, psds, npsd, ev, n, opts, strain, workspace, workspace_bytes, st);
+        case GWF_IMRPHENOMD_NRTIDALV2:
+            if (!ev.p[11] || !ev.p[12]) return fail(GWF_ERR_ARG, "tidal model needs Lambda1, Lambda2");
+            return run_strain<kNRTidalv2>(model, dets, ndet, psds, npsd, ev, n, opts, strain, workspace, workspace_bytes, st);
+        default:
+            return fail(GWF_ERR_UNSUPPORTED, "gwf_strain: not built for this model (IMRPhenomHM)");
+    }
+}
+
+int gwf_overlap(const double* h1, const double* h2, const double* fcut, int64_t n, int32_t res, double fmin, const gwf_psd* psd, double* overlap,
+                double* snr2_1, double* snr2_2, void* stream) {
+    if (!h1 || !h2 || !fcut || !psd || !overlap || !snr2_1 || !snr2_2) return fail(GWF_ERR_ARG, "gwf_overlap: null argument");
+    if (n < 0 || res < 2 || !(fmin > 0.0)) return fail(GWF_ERR_ARG, "gwf_overlap: bad grid");
+    if (n == 0) return GWF_OK;
+    PsdDev pd = reinterpret_cast<const PsdHost*>(psd)->dev;
+    pd.c_off = -1;
+    const int tb = 256;
+    const long long threads = (long long)n * 32;
+    overlap_kernel<<<(unsigned)((threads + tb - 1) / tb), tb, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const double2*>(h1), reinterpret_cast<const double2*>(h2), fcut, n, res, fmin, pd, overlap, snr2_1, snr2_2);
+    GWF_CUDA(cudaGetLastError());
+    return GWF_OK;
 }
 
 int gwf_unpack_fisher(const double* packed, int64_t n, int32_t nP, double* full, void* stream) {

@@ -189,3 +189,17 @@ class DetNet(object):
             allF['net'] = totF
             return allF
         return totF
+
+    def WFOverlap(self, WF1, WF2, evParams1, evParams2, res=1000, **kwargs):
+        """Overlap of two waveforms in the network, shape (N,); network.py:198-225."""
+        utils.check_evparams(evParams1)
+        utils.check_evparams(evParams2)
+        overlap_all = onp.zeros_like(evParams1['Mc'])
+        SNR1_all = onp.zeros_like(evParams1['Mc'])
+        SNR2_all = onp.zeros_like(evParams1['Mc'])
+        for d in self.signals.keys():
+            overlap_int, SNR1, SNR2 = self.signals[d].WFOverlap(WF1, WF2, evParams1, evParams2, res=res, return_separate=True)
+            overlap_all += overlap_int
+            SNR1_all += SNR1 ** 2
+            SNR2_all += SNR2 ** 2
+        return overlap_all / onp.sqrt(SNR1_all * SNR2_all)

@@ -283,3 +283,63 @@ class GWSignal(object):
         if return_all:
             return [F[i] for i in range(F.shape[0])]
         return F.sum(axis=0) if F.shape[0] > 1 else F[0]
+
+    # ------------------------------------------------------------------ overlap
+    def _prepare_overlap(self, WF, evParams):
+        """the dict bookkeeping of signal.py:1783-1849 for one of the two waveforms (mutates the dict like the reference);
+        returns the arrays the engine consumes."""
+        if WF.is_Precessing:
+            raise NotImplementedError('precessing waveforms exist in the reference only through the LAL wrapper')
+        if WF.is_HigherModes:
+            raise NotImplementedError('WFOverlap is not built for IMRPhenomHM (gwf_strain)')
+        zeros = onp.zeros_like(evParams['Mc'])
+        if 'chi1z' in evParams:
+            evParams['chi1x'], evParams['chi1y'], evParams['chi2x'], evParams['chi2y'] = zeros, zeros.copy(), zeros.copy(), zeros.copy()
+        else:
+            try:
+                if self.verbose:
+                    print('Adding chi1z, chi2z from chiS, chiA')
+                evParams['chi1z'] = evParams['chiS'] + evParams['chiA']
+                evParams['chi2z'] = evParams['chiS'] - evParams['chiA']
+            except KeyError:
+                raise ValueError('Two among chi1z, chi2z and chiS, chiA have to be provided.')
+        ev = {k: evParams[k] for k in K.EVENT_KEYS[:11]}
+        if WF.is_tidal:
+            if 'LambdaTilde' not in evParams:
+                try:
+                    evParams['LambdaTilde'], evParams['deltaLambda'] = utils.Lamt_delLam_from_Lam12(evParams['Lambda1'], evParams['Lambda2'], evParams['eta'])
+                except KeyError:
+                    raise ValueError('Two among Lambda1, Lambda2 and LambdaTilde and deltaLambda have to be provided.')
+            # GWstrain(is_chi1chi2=True) goes back to Lambda1, Lambda2 from LambdaTilde, deltaLambda (signal.py:554)
+            ev['Lambda1'], ev['Lambda2'] = utils.Lam12_from_Lamt_delLam(evParams['LambdaTilde'], evParams['deltaLambda'], evParams['eta'])
+        else:
+            evParams['LambdaTilde'], evParams['deltaLambda'] = zeros.copy(), zeros.copy()
+        if not WF.is_eccentric:
+            evParams['ecc'] = zeros.copy()
+        else:
+            ev['ecc'] = evParams['ecc']
+        return ev
+
+    def WFOverlap(self, WF1, WF2, evParams1, evParams2, res=1000, return_separate=False, **kwargs):
+        """Overlap of two waveforms in this detector, shape (N,) (or the tuple ``((h1|h2), SNR1, SNR2)`` with
+        ``return_separate``); signal.py:1759-1930.  Both strains are evaluated on the grid geomspace(fmin, max(fcut1, fcut2), res)
+        by ``gwf_strain`` and integrated by ``gwf_overlap``."""
+        utils.check_evparams(evParams1)
+        utils.check_evparams(evParams2)
+        ev1 = self._prepare_overlap(WF1, evParams1)
+        ev2 = self._prepare_overlap(WF2, evParams2)
+        fcut1 = WF1.fcut(**evParams1)
+        fcut2 = WF2.fcut(**evParams2)
+        fcutUse = onp.where(fcut1 > fcut2, fcut1, fcut2)
+        if self.fmax is not None:
+            fcutUse = onp.where(fcutUse > self.fmax, self.fmax, fcut1)      # as written in the reference, signal.py:1857-1858
+        n = _num_events(evParams1)
+        fcutUse = onp.broadcast_to(onp.asarray(fcutUse, dtype=float), (n,))
+        det = K.gwf_detector(self.det_lat_rad, self.det_long_rad, self.det_xax_rad, 0 if self.detector_shape == 'L' else 1,
+                             int(bool(self.useEarthMotion)), int(bool(self.noMotion)), 0, float(self.fmin), 0.)
+        ov, s1, s2 = _engine.overlap(WF1._descriptor(evParams1), WF2._descriptor(evParams2), det, self._psd_handle(), ev1, ev2, fcutUse,
+                                     self.fmin, n, res)
+        overlap_int, SNRh1, SNRh2 = ov.sum(axis=0), onp.sqrt(s1.sum(axis=0)), onp.sqrt(s2.sum(axis=0))
+        if return_separate:
+            return overlap_int, SNRh1, SNRh2
+        return overlap_int / (SNRh1 * SNRh2)

@@ -139,6 +139,20 @@ int gwf_strain_derivs(const gwf_model* model, const gwf_detector* dets, int32_t 
                       const gwf_events* events, int64_t n, const gwf_opts* opts, double* derivs,
                       void* workspace, size_t workspace_bytes, void* stream);
 
+/* GWSignal.GWstrain on the engine's grid (signal.py:484-655), the building block of GWSignal.WFOverlap (signal.py:1759-1930):
+ *   strain: complex128 (re, im) [n_arms][n][res], one block per arm (triangle arms 0, 60 deg, -(1+2)); the dict entries go straight to
+ *           the waveform (no Fisher re-parametrisation); the grid is geomspace(fmin, events->p[13] if given else the model's fcut, res);
+ *           samples beyond the waveform cut are 0.  TaylorF2 (all options), IMRPhenomD, IMRPhenomD_NRTidalv2. */
+int gwf_strain(const gwf_model* model, const gwf_detector* dets, int32_t ndet, const gwf_psd* const* psds, int32_t npsd,
+               const gwf_events* events, int64_t n, const gwf_opts* opts, double* strain,
+               void* workspace, size_t workspace_bytes, void* stream);
+
+/* The three integrals of GWSignal.WFOverlap for ONE arm (signal.py:1876-1925) from two gwf_strain outputs on the same grid:
+ *   h1, h2: complex128 [n][res];  fcut: [n] upper grid frequency (the larger of the two waveforms' cuts, signal.py:1853-1858)
+ *   overlap[n] = 4 int Re(h1 conj h2)/Sn df,  snr2_1[n] = 4 int |h1|^2/Sn df,  snr2_2[n] = 4 int |h2|^2/Sn df */
+int gwf_overlap(const double* h1, const double* h2, const double* fcut, int64_t n, int32_t res, double fmin, const gwf_psd* psd,
+                double* overlap, double* snr2_1, double* snr2_2, void* stream);
+
 /* Replaces DetNet.SNR / GWSignal.SNRInteg (network.py:53-81, signal.py:658-777).
  *   snr2_arm: [n_arms][n], the per-arm integrals 4 int (Ap^2+Ac^2)/Sn df (SNR_arm = sqrt of it) */
 int gwf_snr(const gwf_model* model, const gwf_detector* dets, int32_t ndet, const gwf_psd* const* psds, int32_t npsd,

@@ -595,16 +595,22 @@ __global__ void __launch_bounds__(256) overlap_kernel(const double2* __restrict_
     if (lane == 0) { ov[e] = a; s1[e] = b; s2[e] = c; }
 }
 
-// SNR: per-arm integrals, value-only.  Four warps share an event (warp `sub` takes every fourth block of 32 samples), so a
-// CTA of 16 warps stages only four coefficient records and the PSD windows still fit next to them in shared memory.
-constexpr int kSnrSplit = 4, kSnrGroups = kSnrWarps / kSnrSplit;
+// SNR: per-arm integrals, value-only.  kSplit warps share an event (warp `sub` takes every kSplit-th block of 32 samples), so a
+// CTA of 16 warps stages only 16/kSplit coefficient records and the PSD windows still fit next to them in shared memory.
+// Warps per event: two where the staging blocks of eight events still leave room for the PSD windows (measured, prologue + kernel per
+// 1e4 events, 4 -> 2: IMRPhenomD 0.460 -> 0.444 ms, TaylorF2 0.239 -> 0.228 ms), four for IMRPhenomHM (2.62 vs 2.72 ms)
+template <int MODEL> struct SnrMap {
+    static constexpr int kSplit = MODEL == kPhenomHM ? 4 : 2;
+    static constexpr int kGroups = kSnrWarps / kSplit;
+};
 template <int MODEL, int FAST>
 __global__ void __launch_bounds__(kSnrThreads, 1)
-snr_kernel(const typename ModelTraits<MODEL, 4>::Rec* __restrict__ recs, EventsDev ev, long long n, int res, int lin, ModelCfg cfg,
-           const __grid_constant__ NetworkDev net, int narm_out, double* __restrict__ snr2_arm) {
+snr_kernel(const typename ModelTraits<MODEL, 4>::Rec* __restrict__ recs, const EventAux* __restrict__ aux, EventsDev ev, long long n, int res, int lin,
+           ModelCfg cfg, const __grid_constant__ NetworkDev net, int narm_out, double* __restrict__ snr2_arm) {
     typedef typename ModelTraits<MODEL, 4>::Rec Rec;
     typedef PointFns<MODEL, 4> PF;
     typedef WarpSmem<Rec, typename PF::Extra> WS;
+    constexpr int kSnrSplit = SnrMap<MODEL>::kSplit, kSnrGroups = SnrMap<MODEL>::kGroups;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int slot = wid % kSnrGroups, sub = wid / kSnrGroups, gt = sub * 32 + lane;      // gt: thread index inside the group
@@ -620,29 +626,30 @@ snr_kernel(const typename ModelTraits<MODEL, 4>::Rec* __restrict__ recs, EventsD
     const int k0 = gt;
     for (long long e = (long long)blockIdx.x * kSnrGroups + slot; e < n; e += (long long)gridDim.x * kSnrGroups) {
         {
-            // the 128 threads of the group stage the event: coefficient record (coalesced), detector scratch, geometry
+            // the threads of the group stage the event: coefficient record and the prologue's EventAux (geometry, grids) by
+            // coalesced copies, then the detector scratch from the staged geometry
+            constexpr int kGeomDoubles = (int)(sizeof(EvGeom) / sizeof(double)), kGridDoubles = (int)(sizeof(Grid) / sizeof(double));
             const double* src = reinterpret_cast<const double*>(recs + e);
+            const double* asrc = reinterpret_cast<const double*>(aux + e);
             double* dst = reinterpret_cast<double*>(&mine->rec);
+            double* gdst = reinterpret_cast<double*>(&mine->geom);
+            double* qdst = reinterpret_cast<double*>(&mine->grid[0]);
             for (int i = gt; i < kRecDoubles; i += stride) dst[i] = __ldg(src + i);
             if (sub == 0) {
-                EvGeom g0;
-                const EventIn in = load_event(ev, e);
-                g0.set(in);
+                if (lane < kGeomDoubles) gdst[lane] = __ldg(asrc + lane);
+                for (int i = lane; i < kGridDoubles * net.ngroups; i += 32) qdst[i] = __ldg(asrc + kGeomDoubles + i);
+                if (sizeof(typename PF::Extra) > 1 && lane == 31) mine->ex.set(load_event(ev, e));
+                __syncwarp();
                 if (FAST) {
-                    if (lane < net.fnd) scratch_set_fast(mine->sc, net, g0, lane);
-                } else if (lane < net.ndet) scratch_set(mine->sc, net, g0, lane);
-                if (lane == 31) mine->ex.set(in);
-                if (lane == 30) mine->geom = g0;
+                    if (lane < net.fnd) scratch_set_fast(mine->sc, net, mine->geom, lane);
+                } else if (lane < net.ndet) scratch_set(mine->sc, net, mine->geom, lane);
             }
         }
         asm volatile("bar.sync %0, %1;" ::"r"(1 + slot), "r"(stride) : "memory");
         const EvGeom& geom = mine->geom;
         for (int a = 0; a < narm_out; ++a) s2[a * 32] = 0.0;
         for (int g = 0; g < net.ngroups; ++g) {
-            double fcut = rec.fcut_hz;
-            if (net.group_fmax[g] > 0.0 && fcut > net.group_fmax[g]) fcut = net.group_fmax[g];
-            Grid grid;
-            grid.set(net.group_fmin[g], fcut, res, lin != 0, stride);
+            const Grid& grid = mine->grid[g];
             const bool rot = net.group_rot[g] != 0;
             FreqPoint fp;
             if (k0 < res) grid.start(k0, fp);
@@ -880,8 +887,10 @@ template <int MODEL>
 static int run_snr(const gwf_model* model, const gwf_detector* dets, int ndet, const gwf_psd* const* psds, int npsd, const EventsDev& ev,
                    long long n, const gwf_opts* opts, double* snr2_arm, void* ws, size_t ws_bytes, cudaStream_t st) {
     typedef typename ModelTraits<MODEL, 4>::Rec Rec;
-    if (ws_bytes < sizeof(Rec) * (size_t)n) return fail(GWF_ERR_WORKSPACE, "workspace too small");
+    const size_t rec_bytes = (sizeof(Rec) * (size_t)n + 15) & ~(size_t)15;
+    if (ws_bytes < rec_bytes + sizeof(EventAux) * (size_t)n) return fail(GWF_ERR_WORKSPACE, "workspace too small");
     Rec* recs = reinterpret_cast<Rec*>(ws);
+    EventAux* aux = reinterpret_cast<EventAux*>(reinterpret_cast<char*>(ws) + rec_bytes);
     ModelCfg cfg = {model->id, model->flags, model->fcutPar, model->fRef};
     NetworkDev net;
     PsdDev pd[kMaxPsd];
@@ -894,7 +903,13 @@ static int run_snr(const gwf_model* model, const gwf_detector* dets, int ndet, c
     for (int g = 0; g < kMaxGroups; ++g) gi.fmin[g] = net.group_fmin[g];
     const int pb = 128;
     // SNRInteg hands the dict entries straight to the waveform: no Fisher re-parametrisation (signal.py:715-726)
-    prologue_kernel<MODEL, 4><<<(unsigned)((n + pb - 1) / pb), pb, 0, st>>>(ev, n, cfg, 0, g_qnm, gi, recs);
+    const int lin = (opts->flags & GWF_OPT_LIN_GRID) ? 1 : 0;
+    AuxPlan ap;
+    ap.out = aux;
+    for (int g = 0; g < kMaxGroups; ++g) ap.fmax[g] = net.group_fmax[g];
+    constexpr int kSnrSplit = SnrMap<MODEL>::kSplit, kSnrGroups = SnrMap<MODEL>::kGroups;
+    ap.res = opts->res; ap.lin = lin; ap.stride = 32 * kSnrSplit;
+    prologue_kernel<MODEL, 4><<<(unsigned)((n + pb - 1) / pb), pb, 0, st>>>(ev, n, cfg, 0, g_qnm, gi, recs, nullptr, ap);
     GWF_CUDA(cudaGetLastError());
     int dev = 0, sms = 0;
     GWF_CUDA(cudaGetDevice(&dev));
@@ -902,14 +917,13 @@ static int run_snr(const gwf_model* model, const gwf_detector* dets, int ndet, c
     const size_t base = sizeof(WarpSmem<Rec, typename PointFns<MODEL, 4>::Extra>) * kSnrGroups + sizeof(double) * net.narms * (32 * kSnrWarps + kSnrWarps);
     const size_t shmem = plan_psd_cache(net, base, kSmemLimit);
     constexpr bool kHasFast = PointFns<MODEL, 4>::kHasFast;
-    typedef void (*Kern)(const Rec*, EventsDev, long long, int, int, ModelCfg, const NetworkDev, int, double*);
+    typedef void (*Kern)(const Rec*, const EventAux*, EventsDev, long long, int, int, ModelCfg, const NetworkDev, int, double*);
     const Kern kerns[3] = {snr_kernel<MODEL, 0>, kHasFast ? snr_kernel<MODEL, 1> : snr_kernel<MODEL, 0>, kHasFast ? snr_kernel<MODEL, 2> : snr_kernel<MODEL, 0>};
     for (int k = 0; k < 3; ++k) GWF_CUDA(cudaFuncSetAttribute(kerns[k], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem));
     const Kern kern = kerns[(kHasFast && !(opts->flags & GWF_OPT_GENERIC_LOOP)) ? plan_fast(net) : 0];
     const long long want = (n + kSnrGroups - 1) / kSnrGroups;
     const unsigned grid = (unsigned)std::min<long long>(want, (long long)sms);
-    const int lin = (opts->flags & GWF_OPT_LIN_GRID) ? 1 : 0;
-    kern<<<grid, kSnrThreads, shmem, st>>>(recs, ev, n, opts->res, lin, cfg, net, net.narms, snr2_arm);
+    kern<<<grid, kSnrThreads, shmem, st>>>(recs, aux, ev, n, opts->res, lin, cfg, net, net.narms, snr2_arm);
     GWF_CUDA(cudaGetLastError());
     return GWF_OK;
 }

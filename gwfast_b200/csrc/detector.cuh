@@ -316,6 +316,44 @@ GWF_HD double compact_entry(int i, int j, const double* __restrict__ acc, const 
     const int a1 = Ii ? si : sj, a2 = Ii ? sj : si;       // a1 type I, a2 type II
     return (al[a1] * be[a2] + be[a1] * al[a2]) * acc[C::kUV];
 }
+// The same rebuild in table form, for the kernels: entry(i, j) = coef[ka] acc[ia] + coef[kb] acc[ib], where the codes (ia, ib, ka,
+// kb) depend only on (i, j) -- computed once per kernel into shared memory -- and coef is a per-event vector of 58 products of
+// (alpha, beta): 0: 1, 1: 0, 2+s: alpha_s, 6+s: beta_s, 10+4s+t: alpha_s alpha_t, 26+4s+t: beta_s beta_t,
+// 42+4s+t: alpha_s beta_t + beta_s alpha_t.  (compact_entry's chain of selects, run three times per lane, both halves of every
+// event, was 3 % of the Fisher kernel's stall samples, profiles/r01h.)
+constexpr int kCompactCoefs = 58;
+template <int NT>
+GWF_HD void compact_entry_code(int i, int j, unsigned char* code) {
+    typedef Compact<NT> C;
+    const int gi = C::g_of(i), gj = C::g_of(j);
+    int ia, ib, ka, kb;
+    if (gi >= 0 && gj >= 0) {
+        ia = ib = tri(gi > gj ? gi : gj, gi > gj ? gj : gi); ka = 0; kb = 1;
+    } else if (gi >= 0 || gj >= 0) {
+        const int x = gi >= 0 ? gi : gj, sidx = -(gi >= 0 ? gj : gi) - 1, base = C::kGG + 4 * x;
+        if (sidx < 2) { ia = base; ka = 2 + sidx; ib = base + 1; kb = 6 + sidx; }
+        else { ia = base + 2; ka = 6 + sidx; ib = base + 3; kb = 2 + sidx; }
+    } else {
+        const int si = -gi - 1, sj = -gj - 1;
+        const bool Ii = si < 2, Ij = sj < 2;
+        if (Ii == Ij) { ia = C::kUU; ka = 10 + 4 * si + sj; ib = C::kVV; kb = 26 + 4 * si + sj; }
+        else { ia = ib = C::kUV; ka = 42 + 4 * (Ii ? si : sj) + (Ii ? sj : si); kb = 1; }
+    }
+    code[0] = (unsigned char)ia; code[1] = (unsigned char)ib; code[2] = (unsigned char)ka; code[3] = (unsigned char)kb;
+}
+// coefficient k of the per-event vector (see compact_entry_code)
+GWF_HD double compact_coef(int k, const EvGeom& g) {
+    const double al[4] = {-g.K * g.inv_dL, -g.ci * g.si, -2.0 * g.ci, -g.K};
+    const double be[4] = {-g.ci * g.inv_dL, -g.si, 2.0 * g.K, g.ci};
+    if (k < 2) return k == 0 ? 1.0 : 0.0;
+    if (k < 6) return al[k - 2];
+    if (k < 10) return be[k - 6];
+    const int q = (k - 10) & 15, s = q >> 2, t = q & 3;
+    if (k < 26) return al[s] * al[t];
+    if (k < 42) return be[s] * be[t];
+    return al[s] * be[t] + be[s] * al[t];
+}
+
 template <int NT>
 GWF_HD double compact_snr2(const double* __restrict__ acc, const EvGeom& g) {
     return g.K * g.K * acc[Compact<NT>::kUU] + g.ci * g.ci * acc[Compact<NT>::kVV];     // 4 sum w |h|^2 / Sn, signal.py:727

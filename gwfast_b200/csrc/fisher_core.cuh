@@ -592,6 +592,9 @@ template <int MODEL, int NT> struct PointFns {
     }
 #endif
     static GWF_HD double entry(int i, int j, const double* __restrict__ red, const EvGeom& geom) { return compact_entry<NT>(i, j, red, geom); }
+    // table form of entry() for the kernels (compact_entry_code / compact_coef)
+    static constexpr bool kEntryTable = true;
+    static GWF_HD void entry_code(int i, int j, unsigned char* code) { compact_entry_code<NT>(i, j, code); }
     static GWF_HD double snr2(const double* __restrict__ red, const EvGeom& geom) { return compact_snr2<NT>(red, geom); }
     static GWF_HD double snr_deriv(int row, const double* __restrict__ red, const EvGeom& geom) { return compact_snr_deriv<NT>(row, red, geom); }
     static GWF_HD void snr(const Rec& rec, const ModelCfg& cfg, const EvGeom& geom, const NetworkDev& net, const EventScratch& sc, const Extra&, int g,
@@ -623,6 +626,8 @@ template <int NT, bool SD = false> struct PointFnsHM {
     }
 #endif
     static GWF_HD double entry(int i, int j, const double* __restrict__ red, const EvGeom&) { return red[tri(i, j)]; }
+    static constexpr bool kEntryTable = false;      // packed index = accumulator index
+    static GWF_HD void entry_code(int, int, unsigned char*) {}
     static GWF_HD double snr2(const double* __restrict__ red, const EvGeom&) { return red[(NT + 7) * (NT + 8) / 2]; }
     static GWF_HD void snr(const Rec& rec, const ModelCfg& cfg, const EvGeom& geom, const NetworkDev& net, const EventScratch& sc, const Extra& ex, int g,
                            bool rot, const FreqPoint& fp, double* __restrict__ s2) {

@@ -300,6 +300,12 @@ __device__ __forceinline__ void stage_event(WarpSmem<Rec, Extra>* mine, const Re
     __syncwarp();
 }
 
+// Fisher kernel: WarpSmem plus the table form of the entry rebuild
+template <class Rec, class Extra> struct FisherSmem : WarpSmem<Rec, Extra> {
+    double coef[64];                  // per-event coefficient vector (kCompactCoefs used)
+    unsigned char code[4 * 108];      // (ia, ib, ka, kb) per packed entry, filled once per kernel
+};
+
 // Fisher kernel: the record and the prologue's EventAux are copied (coalesced), the detector scratch is then set from the
 // staged geometry by one lane per detector
 template <bool FAST, class Rec, class Extra>
@@ -335,12 +341,20 @@ fisher_kernel(const typename ModelTraits<MODEL, NT>::Rec* __restrict__ recs, con
               int pair) {
     typedef typename ModelTraits<MODEL, NT>::Rec Rec;
     typedef typename PointFnsSel<MODEL, NT, SD>::type PF;
-    typedef WarpSmem<Rec, typename PF::Extra> WS;
+    typedef FisherSmem<Rec, typename PF::Extra> WS;
     constexpr int NP = NT + 7, NPACK = NP * (NP + 1) / 2;
+    static_assert(NPACK <= 108, "entry-code table too small");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     WS* mine = reinterpret_cast<WS*>(smem_raw) + wid;
     const Rec& rec = mine->rec;
+    if (PF::kEntryTable) {
+        for (int p = lane; p < NPACK; p += 32) {
+            int i = 0;
+            while (tri(i + 1, 0) <= p) ++i;                   // row of packed index p
+            PF::entry_code(i, p - tri(i, 0), mine->code + 4 * p);
+        }
+    }
     psd_cache_fill(net, smem_raw);
     // pair mode: warps w and w + kWarpsPerCta/2 take the two halves of an event (every other block of 32 samples each), so the
     // work unit of the persistent loop is half an event and its last round wastes half as much.  The halves never wait for each
@@ -401,10 +415,16 @@ fisher_kernel(const typename ModelTraits<MODEL, NT>::Rec* __restrict__ recs, con
         }
         __syncwarp();
         double* o = out + e * NPACK;
+        if (PF::kEntryTable) {
+            for (int k = lane; k < kCompactCoefs; k += 32) mine->coef[k] = compact_coef(k, geom);
+            __syncwarp();
+        }
         for (int p = lane; p < NPACK; p += 32) {
-            int i = 0;
-            while (tri(i + 1, 0) <= p) ++i;                   // row of packed index p
-            const double v = PF::entry(i, p - tri(i, 0), red, geom);
+            double v;
+            if (PF::kEntryTable) {
+                const uchar4 c = *reinterpret_cast<const uchar4*>(mine->code + 4 * p);
+                v = mine->coef[c.z] * red[c.x] + mine->coef[c.w] * red[c.y];
+            } else v = red[p];
             if (pair) atomicAdd(o + p, v);
             else o[p] = v;
         }
@@ -762,7 +782,7 @@ static int run_fisher(const gwf_model* model, const gwf_detector* dets, int ndet
     GWF_CUDA(cudaGetDevice(&dev));
     GWF_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     // dynamic shared memory: per-warp staging blocks, then the PSD windows (as many tables as fit in 227 KB)
-    const size_t ws_bytes_smem = sizeof(WarpSmem<Rec, typename PointFns<MODEL, NT>::Extra>) * kWarpsPerCta;
+    const size_t ws_bytes_smem = sizeof(FisherSmem<Rec, typename PointFns<MODEL, NT>::Extra>) * kWarpsPerCta;
     const size_t shmem = plan_psd_cache(net, ws_bytes_smem, kSmemLimit);
     // the unrolled form pays off where the waveform leaves registers for it (measured: IMRPhenomD 1.55 -> 1.31 ms, NRTidalv2
     // 3.73 -> 3.21 ms per 1e4 events; TaylorF2's version spills and is 7-20 % slower than the general loop)

@@ -257,6 +257,23 @@ static int plan_fast(NetworkDev& net) {
     net.fast = nrot ? 2 : 1;
     return net.fast;
 }
+// host: shape code of a network in fast form (fisher_core.cuh: base-4 digits = arms per compact detector), or 0 if it has none
+// (a detector with more than 3 arms, or arms that are not consecutive from 0 in net.arm[])
+static int fast_shape(const NetworkDev& net) {
+    if (!net.fast) return 0;
+    int shape = 0, first = 0;
+    for (int i = 0; i < net.fnd; ++i) {
+        const int na = net.fdet[i].arm_end - net.fdet[i].arm_begin;
+        if (na < 1 || na > 3 || net.fdet[i].arm_begin != first) return 0;
+        shape |= na << (2 * i);
+        first += na;
+    }
+    return shape;
+}
+// network shapes with their own kernel instantiation: a single L / T, ET + 2 CE, three and four L (Fisher: a triangle is the
+// (u, v) pair of virtual arms; SNR: its three physical arms)
+#define GWF_FISHER_SHAPES(X) X(1) X(2) X(22) X(21) X(85)
+#define GWF_SNR_SHAPES(X) X(1) X(3) X(23) X(21) X(85)
 
 // device: all threads of the CTA copy the windows; ends with a CTA barrier
 __device__ __forceinline__ void psd_cache_fill(const NetworkDev& net, unsigned char* smem) {
@@ -330,7 +347,7 @@ __device__ __forceinline__ void stage_event_aux(WarpSmem<Rec, Extra>* mine, cons
     __syncwarp();
 }
 
-template <int MODEL, int NT, int FAST, bool SD>
+template <int MODEL, int NT, int FAST, bool SD, int SHAPE = 0>
 #ifdef GWF_FISHER_MAXNREG
 __global__ void __maxnreg__(GWF_FISHER_MAXNREG)
 #else
@@ -394,8 +411,8 @@ fisher_kernel(const typename ModelTraits<MODEL, NT>::Rec* __restrict__ recs, con
                             fp.w = fp.f * (last ? gv->hw_hi : gv->hw_in);
                         }
                     }
-                    if (FAST == 2) PF::template fisher_fast<true>(rec, cfg, geom, net, mine->sc, mine->ex, fp, acc);
-                    else if (FAST == 1) PF::template fisher_fast<false>(rec, cfg, geom, net, mine->sc, mine->ex, fp, acc);
+                    if (FAST == 2) PF::template fisher_fast<true, SHAPE>(rec, cfg, geom, net, mine->sc, mine->ex, fp, acc);
+                    else if (FAST == 1) PF::template fisher_fast<false, SHAPE>(rec, cfg, geom, net, mine->sc, mine->ex, fp, acc);
                     else PF::fisher(rec, cfg, geom, net, mine->sc, mine->ex, g, rot, fp, acc);
                 }
                 if (kUniformLoop && (pair & 4)) asm volatile("bar.sync %0, 64;" ::"r"(1 + slot) : "memory");
@@ -623,7 +640,7 @@ template <int MODEL> struct SnrMap {
     static constexpr int kSplit = MODEL == kPhenomHM ? 4 : 2;
     static constexpr int kGroups = kSnrWarps / kSplit;
 };
-template <int MODEL, int FAST>
+template <int MODEL, int FAST, int SHAPE = 0>
 __global__ void __launch_bounds__(kSnrThreads, 1)
 snr_kernel(const typename ModelTraits<MODEL, 4>::Rec* __restrict__ recs, const EventAux* __restrict__ aux, EventsDev ev, long long n, int res, int lin,
            ModelCfg cfg, const __grid_constant__ NetworkDev net, int narm_out, double* __restrict__ snr2_arm) {
@@ -675,8 +692,8 @@ snr_kernel(const typename ModelTraits<MODEL, 4>::Rec* __restrict__ recs, const E
             if (k0 < res) grid.start(k0, fp);
             for (int k = k0; k < res; k += stride) {
                 if (k != k0) grid.advance(k, fp);
-                if (FAST == 2) PF::template snr_fast<true>(rec, cfg, geom, net, mine->sc, mine->ex, fp, s2);
-                else if (FAST == 1) PF::template snr_fast<false>(rec, cfg, geom, net, mine->sc, mine->ex, fp, s2);
+                if (FAST == 2) PF::template snr_fast<true, SHAPE>(rec, cfg, geom, net, mine->sc, mine->ex, fp, s2);
+                else if (FAST == 1) PF::template snr_fast<false, SHAPE>(rec, cfg, geom, net, mine->sc, mine->ex, fp, s2);
                 else PF::snr(rec, cfg, geom, net, mine->sc, mine->ex, g, rot, fp, s2);
             }
         }
@@ -792,8 +809,15 @@ static int run_fisher(const gwf_model* model, const gwf_detector* dets, int ndet
     // from the compact Gram whenever the output pointer is given
     constexpr bool kSdKernel = MODEL == kPhenomHM;
     const Kern k0 = (kSdKernel && snr_derivs) ? fisher_kernel<MODEL, NT, 0, kSdKernel> : fisher_kernel<MODEL, NT, 0, false>;
-    const Kern kerns[3] = {k0, kHasFast ? fisher_kernel<MODEL, NT, 1, false> : k0, kHasFast ? fisher_kernel<MODEL, NT, 2, false> : k0};
-    for (int k = 0; k < 3; ++k) GWF_CUDA(cudaFuncSetAttribute(kerns[k], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem));
+    // kernel for a fast plan and shape (instantiated shapes only; anything else runs the run-time-bounds form)
+    auto pick = [&](int fast, int shape) -> Kern {
+        if (!kHasFast || fast == 0) return k0;
+#define GWF_PICK(S) if (shape == S) return fast == 2 ? (Kern)fisher_kernel<MODEL, NT, kHasFast ? 2 : 0, false, kHasFast ? S : 0> \
+                                                     : (Kern)fisher_kernel<MODEL, NT, kHasFast ? 1 : 0, false, kHasFast ? S : 0>;
+        GWF_FISHER_SHAPES(GWF_PICK)
+#undef GWF_PICK
+        return fast == 2 ? (Kern)fisher_kernel<MODEL, NT, kHasFast ? 2 : 0, false> : (Kern)fisher_kernel<MODEL, NT, kHasFast ? 1 : 0, false>;
+    };
     const bool allow_fast = kHasFast && !(opts->flags & GWF_OPT_GENERIC_LOOP);
     int fast = allow_fast ? plan_fast(net) : 0;
     const int per_cta = pair ? kWarpsPerCta / 2 : kWarpsPerCta;
@@ -816,7 +840,9 @@ static int run_fisher(const gwf_model* model, const gwf_detector* dets, int ndet
             if (o_s) GWF_CUDA(cudaMemsetAsync(o_s, 0, sizeof(double) * (size_t)n, st));
             if (o_d) GWF_CUDA(cudaMemsetAsync(o_d, 0, sizeof(double) * (size_t)n * NP, st));
         }
-        kerns[fast]<<<grid, kFisherThreads, shmem, st>>>(recs, aux, ev, n, opts->res, lin, cfg, net, o_f, o_s, o_d, pair);
+        const Kern kern = pick(fast, fast_shape(net));
+        GWF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem));
+        kern<<<grid, kFisherThreads, shmem, st>>>(recs, aux, ev, n, opts->res, lin, cfg, net, o_f, o_s, o_d, pair);
         GWF_CUDA(cudaGetLastError());
     }
     return GWF_OK;
@@ -938,9 +964,16 @@ static int run_snr(const gwf_model* model, const gwf_detector* dets, int ndet, c
     const size_t shmem = plan_psd_cache(net, base, kSmemLimit);
     constexpr bool kHasFast = PointFns<MODEL, 4>::kHasFast;
     typedef void (*Kern)(const Rec*, const EventAux*, EventsDev, long long, int, int, ModelCfg, const NetworkDev, int, double*);
-    const Kern kerns[3] = {snr_kernel<MODEL, 0>, kHasFast ? snr_kernel<MODEL, 1> : snr_kernel<MODEL, 0>, kHasFast ? snr_kernel<MODEL, 2> : snr_kernel<MODEL, 0>};
-    for (int k = 0; k < 3; ++k) GWF_CUDA(cudaFuncSetAttribute(kerns[k], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem));
-    const Kern kern = kerns[(kHasFast && !(opts->flags & GWF_OPT_GENERIC_LOOP)) ? plan_fast(net) : 0];
+    const int fast = (kHasFast && !(opts->flags & GWF_OPT_GENERIC_LOOP)) ? plan_fast(net) : 0;
+    auto pick = [&](int shape) -> Kern {
+        if (!kHasFast || fast == 0) return snr_kernel<MODEL, 0>;
+#define GWF_PICK(S) if (shape == S) return fast == 2 ? (Kern)snr_kernel<MODEL, kHasFast ? 2 : 0, kHasFast ? S : 0> : (Kern)snr_kernel<MODEL, kHasFast ? 1 : 0, kHasFast ? S : 0>;
+        GWF_SNR_SHAPES(GWF_PICK)
+#undef GWF_PICK
+        return fast == 2 ? (Kern)snr_kernel<MODEL, kHasFast ? 2 : 0> : (Kern)snr_kernel<MODEL, kHasFast ? 1 : 0>;
+    };
+    const Kern kern = pick(fast_shape(net));
+    GWF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem));
     const long long want = (n + kSnrGroups - 1) / kSnrGroups;
     const unsigned grid = (unsigned)std::min<long long>(want, (long long)sms);
     kern<<<grid, kSnrThreads, shmem, st>>>(recs, aux, ev, n, opts->res, lin, cfg, net, net.narms, snr2_arm);

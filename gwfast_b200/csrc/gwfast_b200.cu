@@ -801,9 +801,9 @@ static int run_fisher(const gwf_model* model, const gwf_detector* dets, int ndet
     // dynamic shared memory: per-warp staging blocks, then the PSD windows (as many tables as fit in 227 KB)
     const size_t ws_bytes_smem = sizeof(FisherSmem<Rec, typename PointFns<MODEL, NT>::Extra>) * kWarpsPerCta;
     const size_t shmem = plan_psd_cache(net, ws_bytes_smem, kSmemLimit);
-    // the unrolled form pays off where the waveform leaves registers for it (measured: IMRPhenomD 1.55 -> 1.31 ms, NRTidalv2
-    // 3.73 -> 3.21 ms per 1e4 events; TaylorF2's version spills and is 7-20 % slower than the general loop)
-    constexpr bool kHasFast = PointFns<MODEL, NT>::kHasFast && MODEL != kTaylorF2;
+    // the unrolled, shape-specialised form (measured per 1e4 events: IMRPhenomD ET+2CE 1.55 -> 1.06 ms, NRTidalv2 3.73 -> 2.26 ms,
+    // TaylorF2 ETSL 0.66 -> 0.55 ms; without the compile-time shape TaylorF2's unrolled loop spilled and lost 7-20 %)
+    constexpr bool kHasFast = PointFns<MODEL, NT>::kHasFast;
     typedef void (*Kern)(const Rec*, const EventAux*, EventsDev, long long, int, int, ModelCfg, const NetworkDev, double*, double*, double*, int);
     // IMRPhenomHM needs extra accumulators for the SNR derivatives (its own instantiation); the other models rebuild them
     // from the compact Gram whenever the output pointer is given

@@ -37,8 +37,8 @@ RES = 1000
 # div/sqrt/transcendental = 1; 4 evaluated arms, 5 Grams, nP = 11, res = 1000
 FLOP_PER_EVENT = 2.676e6
 FP64_NOMINAL_TFLOPS = 148 * 64 * 2 * 1.965e9 / 1e12
-# DRAM traffic of one fisher_kernel launch of this workload, bytes (ncu --set full, profiles/r01h_kernels_ncu.md): 34.71 MB read + 0.42 MB written
-DRAM_BYTES_PER_LAUNCH = 35.13e6
+# DRAM traffic of one fisher_kernel launch of this workload, bytes (ncu --set full, profiles/r01i_kernels_ncu.md): 34.71 MB read + 0.57 MB written
+DRAM_BYTES_PER_LAUNCH = 35.27e6
 
 
 # ----------------------------------------------------------------------------------------------- CPU arm
@@ -304,7 +304,7 @@ def run_engine(args):
                     gpu_launches=launches,
                     roofline=dict(bound='fp64', kernel='fisher_kernel<IMRPhenomD,NT=4>', achieved=achieved, peak=float(peak.value), unit='TFLOP/s',
                                   frac=achieved / float(peak.value) if peak.value > 0 else None, traffic=DRAM_BYTES_PER_LAUNCH,
-                                  traffic_source='dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full capture profiles/r01h (records + EventAux + PSD windows + events in, packed Fisher out)',
+                                  traffic_source='dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full capture profiles/r01i (records + EventAux + PSD windows + events in, packed Fisher out)',
                                   peak_source='measured in this run (gwf_fp64_peak DFMA chain); MEASURED_PEAKS.json has no FP64 entry',
                                   nominal_peak=FP64_NOMINAL_TFLOPS, frac_of_nominal=achieved / FP64_NOMINAL_TFLOPS,
                                   flop_per_event=FLOP_PER_EVENT, kernel_ms=1e3 * t_main / args.steps),

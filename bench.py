@@ -168,7 +168,7 @@ def run_engine(args):
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
-    from gwfast_b200 import waveforms, signal, network, synthetic, _engine, _capi as K
+    from gwfast_b200 import waveforms, signal, network, synthetic, parallel, _engine, _capi as K
     import ctypes as C
 
     # weak scaling: every rank owns its own 10^4-event shard of a world*10^4-event catalog
@@ -251,7 +251,10 @@ def run_engine(args):
         # results are held like in the timed loop, so the pinned-buffer pool reaches its steady state here (the previous
         # step's arrays are still alive when the next call allocates: one extra cudaHostAlloc, ~9 ms, the first time)
         s_ = net.SNR(dict(ev), res=RES)
-        F_ = net.FisherMatr(dict(ev), res=RES)
+        if world > 1:
+            F_, g = parallel.fisher_with_device_gather(net, dict(ev), n * world, dist, res=RES)
+        else:
+            F_ = net.FisherMatr(dict(ev), res=RES)
     barrier()
     t_e2e = 0.0
     h2d = d2h = 0
@@ -260,11 +263,12 @@ def run_engine(args):
         barrier()
         t = time.perf_counter()
         s_ = net.SNR(dict(ev), res=RES)
-        F_ = net.FisherMatr(dict(ev), res=RES)
         if world > 1:
-            # final gather of the results (north star: one NCCL all-gather of Fisher matrices)
-            g = torch.empty((world,) + F_.shape, dtype=torch.float64, device=dev)
-            dist.all_gather_into_tensor(g.view(-1), torch.from_numpy(F_).to(dev).view(-1))
+            # host arrays in, this rank's host arrays out, plus the final gather of the results (north star: one NCCL all-gather
+            # of Fisher matrices) taken from the engine's device-resident result: the full matrix stays in HBM on every rank
+            F_, g = parallel.fisher_with_device_gather(net, dict(ev), n * world, dist, res=RES)
+        else:
+            F_ = net.FisherMatr(dict(ev), res=RES)
         torch.cuda.synchronize()
         t_e2e += time.perf_counter() - t
         if os.environ.get('GWF_BENCH_DEBUG'):

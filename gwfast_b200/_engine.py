@@ -39,6 +39,7 @@ class _State:
                 'gwf_set_qnm_tables')
         self.psds = {}
         self.workspace = None
+        self.last_fisher_device = None
 
 
 def state():
@@ -94,6 +95,10 @@ def _call_arrays(dets, psd_handles):
     parr = (C.c_void_p * len(psd_handles))(*psd_handles)
     return darr, parr
 
+
+# When set, fisher() leaves a reference to its device-resident result (npass, nP, nP, n) in state().last_fisher_device, so that a
+# multi-GPU caller can all-gather it over NVLink without a host round trip (parallel.DistributedDetNet(gather='device')).
+STASH_DEVICE = False
 
 # extra gwf_opts.flags OR-ed into every launch (tests set GWF_OPT_GENERIC_LOOP / GWF_OPT_ONE_WARP_PER_EVENT to compare the
 # kernel variants; production leaves it 0 and the launcher picks the fastest applicable form)
@@ -153,6 +158,7 @@ def fisher(model, dets, psd_handles, ev, n, res, flags, per_arm, want_snr2=True,
             full[..., lo:lo + m] = tmp
             snr2[:, lo:lo + m] = s2
         keep.append((dev_ev, host_ev, packed))
+    st.last_fisher_device = full if STASH_DEVICE else None
     if keep_on_device:
         return full, ((snr2, sder) if want_snr_derivs else snr2), (h2d, 0)
     if want_snr_derivs:

@@ -77,9 +77,36 @@ class DistributedDetNet(object):
         snr = self.net.SNR(local, res=res) if hi > lo else np.zeros(0)
         return all_gather_event_axis(np.asarray(snr, dtype=np.float64), n, self.dist, self._device())
 
-    def FisherMatr(self, evParams, **kwargs):
+    def FisherMatr(self, evParams, gather='host', **kwargs):
+        """``gather='host'`` (default): the full (nP, nP, N) numpy array on every rank.
+        ``gather='device'`` (NCCL): returns ``(F_local, F_all)`` -- this rank's shard as a numpy array, and the full matrix as a
+        device tensor gathered over NVLink straight from the engine's device-resident result (no host round trip); hosts only read
+        their own shard, so the step does not move world x the result through every rank's PCIe link."""
         n = len(np.atleast_1d(evParams['Mc']))
         local, lo, hi = shard_events(evParams, self.dist.get_world_size(), self.dist.get_rank())
         nP = next(iter(self.net.signals.values())).wf_model.nParams
+        if gather == 'device' and self._device() is not None:
+            return fisher_with_device_gather(self.net, local, n, self.dist, **kwargs)
         F = self.net.FisherMatr(local, **kwargs) if hi > lo else np.zeros((nP, nP, 0))
-        return all_gather_event_axis(np.asarray(F, dtype=np.float64), n, self.dist, self._device())
+        full = all_gather_event_axis(np.asarray(F, dtype=np.float64), n, self.dist, self._device())
+        return (F, full) if gather == 'device' else full
+
+
+def fisher_with_device_gather(net, local_events, n_total, dist=None, **kwargs):
+    """``net.FisherMatr(local_events)`` on this rank's shard plus one all-gather of the device-resident result: returns
+    ``(F_local numpy (nP, nP, m), F_all device tensor (nP, nP, n_total))``."""
+    import torch
+    from . import _engine
+    _engine.STASH_DEVICE = True
+    try:
+        F = net.FisherMatr(local_events, **kwargs)
+        dev = _engine.state().last_fisher_device
+    finally:
+        _engine.STASH_DEVICE = False
+        _engine.state().last_fisher_device = None
+    F = np.asarray(F, dtype=np.float64)
+    if dev is not None and dev.shape[0] == 1 and tuple(dev.shape[1:]) == F.shape:
+        local_dev = dev[0]
+    else:       # per-arm / re-indexed results (return_all, duty factors, NewtInspiral): upload the host result
+        local_dev = torch.from_numpy(np.ascontiguousarray(F)).to(_engine.state().device)
+    return F, all_gather_event_axis(local_dev, n_total, dist)

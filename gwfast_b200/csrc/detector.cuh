@@ -146,6 +146,16 @@ GWF_HD double rcp_fast(double x) {
 #endif
 }
 
+// sin / cos of the Earth-rotation angle 2 pi t, t in days.  On the device the argument is reduced in turns (sincospi: exact
+// reduction, no slow path for large arguments -- sincos() carries a Payne-Hanek branch that split every sample's code in two)
+GWF_HD void rot_sincos(double t_days, double* s, double* c) {
+#ifdef __CUDA_ARCH__
+    sincospi(2.0 * t_days, s, c);
+#else
+    sincos(2.0 * kPi * t_days, s, c);
+#endif
+}
+
 // per-event sky / orientation constants
 struct EvGeom {
     double sd, cd, s2d, c2d;     // declination = pi/2 - theta

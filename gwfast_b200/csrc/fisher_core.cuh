@@ -308,7 +308,11 @@ __device__ __forceinline__ void amp_phase_point_fast(const typename ModelTraits<
     if (w.A == 0.0) return;
     const double wA2 = 4.0 * fp.w * w.A * w.A;
     double sBr = 0., cBr = 1.;
-    if (ROT) sincos(2.0 * kPi * fma(-w.tau, kInvDay, geom.tcoal), &sBr, &cBr);
+    // (sincospi where it schedules better: measured per 1e4 events, TaylorF2 0.546 -> 0.536 ms, IMRPhenomD 1.058 -> 1.112 ms)
+    if (ROT) {
+        if (MODEL == kTaylorF2) rot_sincos(fma(-w.tau, kInvDay, geom.tcoal), &sBr, &cBr);
+        else sincos(2.0 * kPi * fma(-w.tau, kInvDay, geom.tcoal), &sBr, &cBr);
+    }
     if constexpr (SHAPE != 0) {
         constexpr int kN = shape_ndet(SHAPE);
 #pragma unroll
@@ -364,7 +368,7 @@ GWF_HD void amp_phase_snr_point(const typename ModelTraits<MODEL, 4>::Rec& rec, 
     if (A == 0.0) return;
     const double wA2 = 4.0 * fp.w * A * A;
     double sBr = 0., cBr = 1.;
-    if (group_rot) sincos(2.0 * kPi * fma(-tau, kInvDay, geom.tcoal), &sBr, &cBr);
+    if (group_rot) rot_sincos(fma(-tau, kInvDay, geom.tcoal), &sBr, &cBr);
     for (int di = 0; di < net.ndet; ++di) {
         const DetDev& d = net.det[di];
         if (d.group != g) continue;
@@ -397,7 +401,7 @@ __device__ __forceinline__ void amp_phase_snr_point_fast(const typename ModelTra
     if (A == 0.0) return;
     const double wA2 = 4.0 * fp.w * A * A;
     double sBr = 0., cBr = 1.;
-    if (ROT) sincos(2.0 * kPi * fma(-tau, kInvDay, geom.tcoal), &sBr, &cBr);
+    if (ROT) rot_sincos(fma(-tau, kInvDay, geom.tcoal), &sBr, &cBr);
     if constexpr (SHAPE != 0) {
         constexpr int kN = shape_ndet(SHAPE);
 #pragma unroll
@@ -586,7 +590,7 @@ GWF_HD void hm_snr_point(const HMRec<4>& rec, const ModelCfg& cfg, const EvGeom&
         double tau, dtau[2];
         const double x13 = cbrt(rec.s.v * f), lpx3 = log(kPi * rec.s.v * f) * (1. / 3.);
         tau_eval(rec.tau, 0.68278406325529568146702083315816 / x13, lpx3, rec.lam, tau, dtau);
-        sincos(2.0 * kPi * fma(-tau, kInvDay, geom.tcoal), &sBr, &cBr);
+        rot_sincos(fma(-tau, kInvDay, geom.tcoal), &sBr, &cBr);
     }
     const double w4 = 4.0 * fp.w;
     for (int di = 0; di < net.ndet; ++di) {

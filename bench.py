@@ -84,7 +84,7 @@ def run_reference(args):
         return
     os.environ.setdefault('OMP_NUM_THREADS', '1')
     cores = os.cpu_count() or 1
-    per_step = 4 * cores                                   # bounded sample: 4 events per core per step
+    per_step = 32 * cores                                  # bounded sample: 32 events per core per step (~1.3 s)
     pool = CpuPool(cores)
     n_tot = t_tot = 0.
     for i in range(args.warmup + args.steps):
@@ -295,7 +295,7 @@ def run_engine(args):
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         pool = CpuPool(cores)
-        ns, dt = pool.run(24 * cores)
+        ns, dt = pool.run(256 * cores)                      # bounded sample: ~10 s of CPU work on all host cores
         pool.close()
         cpu = dict(value=ns / dt, unit='events/s', cores=cores, kind='port',
                    sample='%d events of the C2 catalog (%.1f s wall), multiprocessing.Pool(%d), numpy+dual oracle port' % (ns, dt, cores))

@@ -10,7 +10,9 @@ ET (triangle) + 2 CE per GPU (weak scaling).  Rank 0 prints ONE JSON line.
 
   value     kernel-path events/s, event parameters already resident in HBM (CUDA events, max over ranks; for N>1 the
             final NCCL all-gather of the packed Fisher matrices is inside the timed region)
-  e2e       the same metric through the public API with HOST numpy arrays in and out (H2D/D2H inside the timed region)
+  e2e       the same metric through the public API with HOST numpy arrays in and out (H2D/D2H inside the timed region); for N>1
+            every rank calls the API on its shard and the all-gather is taken from the engine's device-resident Fisher matrices
+            (gwfast_b200.parallel.fisher_with_device_gather): hosts read their own shard, the full matrix stays in HBM
   roofline  FP64 (the path is FP64-FMA/transcendental bound): algorithmic FLOP/event x events / duration of
             the dominant kernel (fisher_kernel, timed alone via GWF_OPT_REUSE_WORKSPACE) against the DFMA peak measured
             in the same run (gwf_fp64_peak) -- nominal 148 SM x 64 lanes x 2 x 1.965 GHz = 37.2 TFLOP/s is also reported

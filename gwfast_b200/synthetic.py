@@ -47,6 +47,12 @@ NETWORKS = {
     'LVK-O4': [('H1', 'H1', 'observing_scenarios_paper/aligo_O4high.txt'), ('L1', 'L1', 'observing_scenarios_paper/aligo_O4high.txt'),
                ('Virgo', 'Virgo', 'observing_scenarios_paper/avirgo_O4high_NEW.txt'),
                ('KAGRA', 'KAGRA', 'observing_scenarios_paper/kagra_80Mpc.txt')],
+    # next-generation layouts with log-uniform PSD tables (they take the shape-specialised kernels): three / four L-shaped detectors,
+    # two triangles (a shape without its own instantiation: run-time loop bounds)
+    '2L-ET+CE': [('ETSL', 'ETSL', 'ET-0000A-18.txt'), ('ETMRL', 'ETMRLpar', 'ET-0000A-18.txt'), ('CE1Id', 'CE1Id', 'ce_strain/cosmic_explorer.txt')],
+    '2L-ET+2CE': [('ETSL', 'ETSL', 'ET-0000A-18.txt'), ('ETMRL', 'ETMRLpar', 'ET-0000A-18.txt'), ('CE1Id', 'CE1Id', 'ce_strain/cosmic_explorer.txt'),
+                  ('CE2NSW', 'CE2NSW', 'ce_strain/cosmic_explorer_20km.txt')],
+    '2ET': [('ETS', 'ETS', 'ET-0000A-18.txt'), ('ETMR', 'ETMR', 'ET-0000A-18.txt')],
 }
 
 

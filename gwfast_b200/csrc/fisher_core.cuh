@@ -324,7 +324,7 @@ __device__ __forceinline__ void amp_phase_point_fast(const typename ModelTraits<
             if (ROT) det_point(sc.ed[i], cBr, sBr, dp);
             else dp = sc.fixed[i];
             DetRows<NT> dr;
-            dr.set(w, dp, ROT, d.no_motion != 0);
+            dr.set(w, dp, ROT, ROT ? false : d.no_motion != 0);       // a detector that follows the rotation is not "noMotion"
             const double wgt = wA2 * rcp_fast(sn_i);
 #pragma unroll
             for (int a = 0; a < shape_arms(SHAPE, i); ++a) arm_rows_accumulate<NT>(w, dp, dr, net.arm[shape_first(SHAPE, i) + a], geom, wgt, acc);

@@ -24,7 +24,7 @@ template <int NT> struct ModelTraits<kTaylorF2, NT> {
             tau_eval(r.tau, p.vm1, p.lpx3, r.lam, tau, dtau);
         }
     }
-    static GWF_HD void prologue(Rec& r, const EventIn& e, const ModelCfg& cfg, int opt_flags, const QnmTables&, const double* fmin_g, int ng) {
+    static GWF_HD void prologue(Rec& r, const EventIn& e, const ModelCfg& cfg, int opt_flags, const QnmTables&, const double* fmin_g, int ng, int = 3) {
         const Intrinsic<NT> p = seed_intrinsic<NT>(e, opt_flags, (cfg.flags & kFlagTidal) != 0);
         tf2_prologue(r, p, e.dL, cfg, e.fcut_host, fmin_g, ng);
     }
@@ -61,9 +61,10 @@ template <int NT> struct ModelTraits<kPhenomD, NT> {
             tau_eval(r.tau, p.xm13 * 0.68278406325529568146702083315816, p.lpx3, r.lam, tau, dtau);
         }
     }
-    static GWF_HD void prologue(Rec& r, const EventIn& e, const ModelCfg& cfg, int opt_flags, const QnmTables& q, const double* fmin_g, int ng) {
+    // parts: the phase (1) and amplitude (2) halves of the record can be computed independently (PhenomDCore::build)
+    static GWF_HD void prologue(Rec& r, const EventIn& e, const ModelCfg& cfg, int opt_flags, const QnmTables& q, const double* fmin_g, int ng, int parts = 3) {
         const Intrinsic<NT> p = seed_intrinsic<NT>(e, opt_flags, false);
-        phenomd_prologue(r, p, e.dL, q, fmin_g, ng, cfg, e.s_host, e.fcut_host);
+        phenomd_prologue(r, p, e.dL, q, fmin_g, ng, cfg, e.s_host, e.fcut_host, parts);
     }
     static GWF_HD void eval(const Rec& r, const ModelCfg& cfg, int g, const FreqPoint& fp, bool need_tau, PointWf<NT>& w) {
         XPow p;
@@ -103,7 +104,7 @@ template <int NT> struct ModelTraits<kNRTidalv2, NT> {
             tau_eval(d.tau, p.xm13 * 0.68278406325529568146702083315816, p.lpx3, d.lam, tau, dtau);
         }
     }
-    static GWF_HD void prologue(Rec& r, const EventIn& e, const ModelCfg& cfg, int opt_flags, const QnmTables& q, const double* fmin_g, int ng) {
+    static GWF_HD void prologue(Rec& r, const EventIn& e, const ModelCfg& cfg, int opt_flags, const QnmTables& q, const double* fmin_g, int ng, int = 3) {
         // NT = 6: Fisher parametrisation (Lambda re-mapped through LambdaTilde/deltaLambda); NT = 4: SNR path, dict values as they are
         const Intrinsic<NT> p = seed_intrinsic<NT>(e, opt_flags, NT >= 6);
         nrtidal_prologue(r, p, e.dL, q, fmin_g, ng, cfg, NT < 6 || (cfg.flags & kFlagLambdaGiven) != 0, e.s_host, e.fcut_host);
@@ -613,7 +614,7 @@ GWF_HD void hm_snr_point(const HMRec<4>& rec, const ModelCfg& cfg, const EvGeom&
 template <int NT> struct ModelTraits<kPhenomHM, NT> {
     typedef HMRec<NT> Rec;
     typedef HMExtra Extra;
-    static GWF_HD void prologue(Rec& r, const EventIn& e, const ModelCfg& cfg, int opt_flags, const QnmTables&, const double* fmin_g, int ng) {
+    static GWF_HD void prologue(Rec& r, const EventIn& e, const ModelCfg& cfg, int opt_flags, const QnmTables&, const double* fmin_g, int ng, int = 3) {
         const Intrinsic<NT> p = seed_intrinsic<NT>(e, opt_flags, false);
         phenomhm_prologue(r, p, e.dL, fmin_g, ng, cfg, e.s_host, e.fcut_host);
     }

@@ -77,8 +77,11 @@ __global__ void __launch_bounds__(128) prologue_kernel(EventsDev ev, long long n
     if (e >= n) return;
     const EventIn in = load_event(ev, e);
     if (fmin_per_event) gi.fmin[0] = fmin_per_event[e];     // stand-alone waveform calls: fRef = min of the user's grid
-    ModelTraits<MODEL, NT>::prologue(recs[e], in, cfg, opt_flags, q, gi.fmin, gi.n);
-    if (aux.out) {
+    // gridDim.y = 2: the blocks with blockIdx.y = 0 / 1 compute the two independent halves of every record (IMRPhenomD: phase /
+    // amplitude) -- the kernel's duration is the instruction-fetch latency of the code one warp walks through
+    const int parts = gridDim.y == 2 ? 1 + (int)blockIdx.y : 3;
+    ModelTraits<MODEL, NT>::prologue(recs[e], in, cfg, opt_flags, q, gi.fmin, gi.n, parts);
+    if (aux.out && (parts & 1)) {
         EventAux& a = aux.out[e];
         a.geom.set(in);
         for (int g = 0; g < gi.n; ++g) {
@@ -792,7 +795,7 @@ static int run_fisher(const gwf_model* model, const gwf_detector* dets, int ndet
         ap.out = aux;
         for (int g = 0; g < kMaxGroups; ++g) ap.fmax[g] = net.group_fmax[g];
         ap.res = opts->res; ap.lin = lin; ap.stride = pair ? 64 : 32;
-        prologue_kernel<MODEL, NT><<<(unsigned)((n + pb - 1) / pb), pb, 0, st>>>(ev, n, cfg, opts->flags, g_qnm, gi, recs, nullptr, ap);
+        prologue_kernel<MODEL, NT><<<dim3((unsigned)((n + pb - 1) / pb), MODEL == kPhenomD ? 2 : 1), pb, 0, st>>>(ev, n, cfg, opts->flags, g_qnm, gi, recs, nullptr, ap);
         GWF_CUDA(cudaGetLastError());
     }
     int dev = 0, sms = 0;
@@ -955,7 +958,7 @@ static int run_snr(const gwf_model* model, const gwf_detector* dets, int ndet, c
     for (int g = 0; g < kMaxGroups; ++g) ap.fmax[g] = net.group_fmax[g];
     constexpr int kSnrSplit = SnrMap<MODEL>::kSplit, kSnrGroups = SnrMap<MODEL>::kGroups;
     ap.res = opts->res; ap.lin = lin; ap.stride = 32 * kSnrSplit;
-    prologue_kernel<MODEL, 4><<<(unsigned)((n + pb - 1) / pb), pb, 0, st>>>(ev, n, cfg, 0, g_qnm, gi, recs, nullptr, ap);
+    prologue_kernel<MODEL, 4><<<dim3((unsigned)((n + pb - 1) / pb), MODEL == kPhenomD ? 2 : 1), pb, 0, st>>>(ev, n, cfg, 0, g_qnm, gi, recs, nullptr, ap);
     GWF_CUDA(cudaGetLastError());
     int dev = 0, sms = 0;
     GWF_CUDA(cudaGetDevice(&dev));

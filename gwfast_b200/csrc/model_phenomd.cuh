@@ -151,34 +151,45 @@ struct PhenomDCore {
     }
 
     // ringdown/damping frequencies from the QNM tables (IMRPhenomD, NRTidalv2; waveforms.py:1034-1035)
-    GWF_HD void build(const D& eta_, const D& chi1, const D& chi2, const D& qm1, const D& qm2, const QnmTables& q) {
+    // parts: 1 = everything the phase needs, 2 = everything the amplitude needs, 3 = both.  The prologue kernel gives the two
+    // halves of an IMRPhenomD event to two different warps: the kernel is ~200 KB of straight-line code that each warp runs
+    // once, so its duration is the instruction-fetch latency of the code a warp walks through (profiles/r01i), and each half
+    // walks through about half of it.  The arithmetic of every quantity is unchanged.
+    GWF_HD void build(const D& eta_, const D& chi1, const D& chi2, const D& qm1, const D& qm2, const QnmTables& q, int parts = 3) {
         const D aeff = final_spin(eta_, chi1, chi2), erad = radiated_energy(eta_, chi1, chi2);
-        build_rd(eta_, chi1, chi2, qm1, qm2, qnm_interp(q, q.fring, aeff) / (1.0 - erad), qnm_interp(q, q.fdamp, aeff) / (1.0 - erad));
+        build_rd(eta_, chi1, chi2, qm1, qm2, qnm_interp(q, q.fring, aeff) / (1.0 - erad), qnm_interp(q, q.fdamp, aeff) / (1.0 - erad), parts);
     }
     // ... or supplied by the caller (IMRPhenomHM uses polynomial fits, waveforms.py:2336-2345)
-    GWF_HD void build_rd(const D& eta_, const D& chi1, const D& chi2, const D& qm1, const D& qm2, const D& fring_, const D& fdamp_) {
+    GWF_HD void build_rd(const D& eta_, const D& chi1, const D& chi2, const D& qm1, const D& qm2, const D& fring_, const D& fdamp_, int parts = 3) {
         eta = eta_;
         fring = fring_;
         fdamp = fdamp_;
         const D e2 = eta * eta, sq = seta_of(eta);
         const D xs = 0.5 * (chi1 + chi2), xa = 0.5 * (chi1 - chi2);
         const D xi = -1.0 + (xs * (1.0 - eta * 76.0 / 113.0) + sq * xa);
-        for (int k = 0; k < kNumFits; ++k) fit[k] = phenomd_fit(k, eta, e2, xi);
-        pn = pn_phase_coeffs(eta, chi1, chi2, qm1, qm2, false);
-        pn.c6 = pn.c6 - pn.ss6;                     // waveforms.py:1077
-        norm = 3. / (128. * eta);
-        // C(1) joins, waveforms.py:1098-1129
-        const D fj(kPhiJoinIns);
-        C2Int = dphi_ins(fj) - dphi_int(fj);
-        C1Int = phi_ins(fj) - phi_int_raw(fj) / eta - C2Int * fj;
+        // fits used by the phase: sigma, beta, alpha (+ gamma2, gamma3 for the peak); by the amplitude: gamma, rho, v2
+        const unsigned need = ((parts & 1) ? ((1u << (ALP5 + 1)) - 1u) | (1u << GAM2) | (1u << GAM3) : 0u) |
+                              ((parts & 2) ? (1u << GAM1) | (1u << GAM2) | (1u << GAM3) | (1u << RHO1) | (1u << RHO2) | (1u << RHO3) | (1u << V2FIT) : 0u);
+        for (int k = 0; k < kNumFits; ++k)
+            if (need & (1u << k)) fit[k] = phenomd_fit(k, eta, e2, xi);
         fMRDJoin = 0.5 * fring;
-        C2MRD = (C2Int + dphi_int(fMRDJoin)) - dphi_mrd(fMRDJoin);
-        C1MRD = (phi_int_raw(fMRDJoin) / eta + C1Int + C2Int * fMRDJoin) - phi_mrd_raw(fMRDJoin) / eta - C2MRD * fMRDJoin;
         // peak frequency, waveforms.py:1134 (phase, |.| on both branches) and :1193 (amplitude)
         const D g2 = fit[GAM2], g3 = fit[GAM3];
         if (g2.v >= 1.0) fpeak_amp = dfabs(fring - (fdamp * g3) / g2);
         else fpeak_amp = fring + (fdamp * (-1.0 + dsqrt(1.0 - g2 * g2)) * g3) / g2;
-        t0 = dphi_mrd(dfabs(fpeak_amp));
+        if (parts & 1) {
+            pn = pn_phase_coeffs(eta, chi1, chi2, qm1, qm2, false);
+            pn.c6 = pn.c6 - pn.ss6;                     // waveforms.py:1077
+            norm = 3. / (128. * eta);
+            // C(1) joins, waveforms.py:1098-1129
+            const D fj(kPhiJoinIns);
+            C2Int = dphi_ins(fj) - dphi_int(fj);
+            C1Int = phi_ins(fj) - phi_int_raw(fj) / eta - C2Int * fj;
+            C2MRD = (C2Int + dphi_int(fMRDJoin)) - dphi_mrd(fMRDJoin);
+            C1MRD = (phi_int_raw(fMRDJoin) / eta + C1Int + C2Int * fMRDJoin) - phi_mrd_raw(fMRDJoin) / eta - C2MRD * fMRDJoin;
+            t0 = dphi_mrd(dfabs(fpeak_amp));
+        }
+        if (!(parts & 2)) return;
         // inspiral amplitude, waveforms.py:1204-1213
         const D sp1 = 1.0 + sq, c12 = chi1 * chi1, c22 = chi2 * chi2;
         const double cp = cbrt(kPi), cp2 = cp * cp;
@@ -210,24 +221,40 @@ struct PhenomDCore {
 // fill the record from the core; xref[g] = dimensionless reference frequency of grid group g
 template <int NT>
 GWF_HD void phenomd_fill(PhenomDRec<NT>& r, const PhenomDCore<NT>& c, const Dual<NT>& M, const Dual<NT>& dL, const double* fmin_g, int ngroups,
-                         const ModelCfg& cfg, double s_host = 0.0, double fcut_host = 0.0) {
+                         const ModelCfg& cfg, double s_host = 0.0, double fcut_host = 0.0, int parts = 3) {
     typedef Dual<NT> D;
     D s = M * kGMsunC3;
     if (s_host > 0.0) s.v = s_host;       // the host's M*GMsun_over_c3: x = s f then rounds like the reference's fgrid
+    if (parts & 2) {
+        ScalePow sp;
+        sp.set(s.v);
+        r.x_peak = c.fpeak_amp.v;
+        // waveforms.py:1248, 1204, 1254
+        const D amp0 = dsqrt(2.0 * c.eta / 3.0) * pow(kPi, -1. / 6.);
+        const D Cc = 2. * sqrt(5. / (64. * kPi)) * M * kGMsunC2Gpc * M * kGMsunC3 / dL * amp0;
+        r.C = Cc.v;
+        r.C76 = Cc.v * (sp.sm13 * sp.sm13 * sp.sm13 * sqrt(sp.sm13));
+#pragma unroll
+        for (int j = 0; j < NT; ++j) r.lnC_d[j] = Cc.d[j] / Cc.v;
+        // amplitude
+        put(r.ains[0], D(1.0));
+        put(r.ains[1], c.A[2]); put(r.ains[2], c.A[3]); put(r.ains[3], c.A[4]); put(r.ains[4], c.A[5]);
+        put(r.ains[5], c.A[6]); put(r.ains[6], c.A[7]); put(r.ains[7], c.A[8]); put(r.ains[8], c.A[9]);
+        for (int k = 0; k < kAInt; ++k) put(r.aint[k], c.e[k]);
+        const D fd3 = c.fdamp * c.fit[GAM3];
+        put(r.amrd[0], c.fring);
+        put(r.amrd[1], c.fit[GAM2] / fd3);
+        put(r.amrd[2], fd3);
+        put(r.amrd[3], fd3 * c.fit[GAM1]);
+        tau_fill(r.tau, s, c.eta);
+    }
+    if (!(parts & 1)) return;
     r.s = s.v;
     r.sp.set(s.v);
 #pragma unroll
     for (int j = 0; j < NT; ++j) r.lam[j] = s.d[j] / s.v;
     r.fcut_hz = fcut_host > 0.0 ? fcut_host : kMfCut / s.v;   // waveforms.py:1333
     r.x_mrd = c.fMRDJoin.v;
-    r.x_peak = c.fpeak_amp.v;
-    // waveforms.py:1248, 1204, 1254
-    const D amp0 = dsqrt(2.0 * c.eta / 3.0) * pow(kPi, -1. / 6.);
-    const D Cc = 2. * sqrt(5. / (64. * kPi)) * M * kGMsunC2Gpc * M * kGMsunC3 / dL * amp0;
-    r.C = Cc.v;
-    r.C76 = Cc.v * (r.sp.sm13 * r.sp.sm13 * r.sp.sm13 * sqrt(r.sp.sm13));
-#pragma unroll
-    for (int j = 0; j < NT; ++j) r.lnC_d[j] = Cc.d[j] / Cc.v;
     const bool apply_cut = !(cfg.flags & kFlagNoFcut);
     for (int g = 0; g < ngroups; ++g) {
         const D xref = (cfg.flags & kFlagHasFRef) ? s * cfg.fRef : s * fmin_g[g];   // waveforms.py:1139-1141
@@ -264,27 +291,16 @@ GWF_HD void phenomd_fill(PhenomDRec<NT>& r, const PhenomDCore<NT>& c, const Dual
     put(r.atn[0], c.fit[ALP4] * ie);
     put(r.atn[1], c.fit[ALP5] * c.fring);
     put(r.atn[2], c.fdamp);
-    // amplitude
-    put(r.ains[0], D(1.0));
-    put(r.ains[1], c.A[2]); put(r.ains[2], c.A[3]); put(r.ains[3], c.A[4]); put(r.ains[4], c.A[5]);
-    put(r.ains[5], c.A[6]); put(r.ains[6], c.A[7]); put(r.ains[7], c.A[8]); put(r.ains[8], c.A[9]);
-    for (int k = 0; k < kAInt; ++k) put(r.aint[k], c.e[k]);
-    const D fd3 = c.fdamp * c.fit[GAM3];
-    put(r.amrd[0], c.fring);
-    put(r.amrd[1], c.fit[GAM2] / fd3);
-    put(r.amrd[2], fd3);
-    put(r.amrd[3], fd3 * c.fit[GAM1]);
-    tau_fill(r.tau, s, c.eta);
 }
 
 template <int NT>
 GWF_HD void phenomd_prologue(PhenomDRec<NT>& r, const Intrinsic<NT>& p, double dL, const QnmTables& q, const double* fmin_g, int ngroups,
-                             const ModelCfg& cfg, double s_host = 0.0, double fcut_host = 0.0) {
+                             const ModelCfg& cfg, double s_host = 0.0, double fcut_host = 0.0, int parts = 3) {
     typedef Dual<NT> D;
     PhenomDCore<NT> c;
-    c.build(p.eta, p.chi1, p.chi2, D(1.0), D(1.0), q);
+    c.build(p.eta, p.chi1, p.chi2, D(1.0), D(1.0), q, parts);
     const D M = p.Mc / dpow(p.eta, 3. / 5.);
-    phenomd_fill(r, c, M, D(dL), fmin_g, ngroups, cfg, s_host, fcut_host);
+    phenomd_fill(r, c, M, D(dL), fmin_g, ngroups, cfg, s_host, fcut_host, parts);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -104,10 +104,10 @@ template <int NT> struct ModelTraits<kNRTidalv2, NT> {
             tau_eval(d.tau, p.xm13 * 0.68278406325529568146702083315816, p.lpx3, d.lam, tau, dtau);
         }
     }
-    static GWF_HD void prologue(Rec& r, const EventIn& e, const ModelCfg& cfg, int opt_flags, const QnmTables& q, const double* fmin_g, int ng, int = 3) {
+    static GWF_HD void prologue(Rec& r, const EventIn& e, const ModelCfg& cfg, int opt_flags, const QnmTables& q, const double* fmin_g, int ng, int parts = 3) {
         // NT = 6: Fisher parametrisation (Lambda re-mapped through LambdaTilde/deltaLambda); NT = 4: SNR path, dict values as they are
         const Intrinsic<NT> p = seed_intrinsic<NT>(e, opt_flags, NT >= 6);
-        nrtidal_prologue(r, p, e.dL, q, fmin_g, ng, cfg, NT < 6 || (cfg.flags & kFlagLambdaGiven) != 0, e.s_host, e.fcut_host);
+        nrtidal_prologue(r, p, e.dL, q, fmin_g, ng, cfg, NT < 6 || (cfg.flags & kFlagLambdaGiven) != 0, e.s_host, e.fcut_host, parts);
     }
     static GWF_HD void eval(const Rec& r, const ModelCfg& cfg, int g, const FreqPoint& fp, bool need_tau, PointWf<NT>& w) {
         const PhenomDRec<NT>& d = r.d;

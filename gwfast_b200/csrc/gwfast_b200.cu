@@ -795,7 +795,7 @@ static int run_fisher(const gwf_model* model, const gwf_detector* dets, int ndet
         ap.out = aux;
         for (int g = 0; g < kMaxGroups; ++g) ap.fmax[g] = net.group_fmax[g];
         ap.res = opts->res; ap.lin = lin; ap.stride = pair ? 64 : 32;
-        prologue_kernel<MODEL, NT><<<dim3((unsigned)((n + pb - 1) / pb), MODEL == kPhenomD ? 2 : 1), pb, 0, st>>>(ev, n, cfg, opts->flags, g_qnm, gi, recs, nullptr, ap);
+        prologue_kernel<MODEL, NT><<<dim3((unsigned)((n + pb - 1) / pb), (MODEL == kPhenomD || MODEL == kNRTidalv2) ? 2 : 1), pb, 0, st>>>(ev, n, cfg, opts->flags, g_qnm, gi, recs, nullptr, ap);
         GWF_CUDA(cudaGetLastError());
     }
     int dev = 0, sms = 0;
@@ -958,7 +958,7 @@ static int run_snr(const gwf_model* model, const gwf_detector* dets, int ndet, c
     for (int g = 0; g < kMaxGroups; ++g) ap.fmax[g] = net.group_fmax[g];
     constexpr int kSnrSplit = SnrMap<MODEL>::kSplit, kSnrGroups = SnrMap<MODEL>::kGroups;
     ap.res = opts->res; ap.lin = lin; ap.stride = 32 * kSnrSplit;
-    prologue_kernel<MODEL, 4><<<dim3((unsigned)((n + pb - 1) / pb), MODEL == kPhenomD ? 2 : 1), pb, 0, st>>>(ev, n, cfg, 0, g_qnm, gi, recs, nullptr, ap);
+    prologue_kernel<MODEL, 4><<<dim3((unsigned)((n + pb - 1) / pb), (MODEL == kPhenomD || MODEL == kNRTidalv2) ? 2 : 1), pb, 0, st>>>(ev, n, cfg, 0, g_qnm, gi, recs, nullptr, ap);
     GWF_CUDA(cudaGetLastError());
     int dev = 0, sms = 0;
     GWF_CUDA(cudaGetDevice(&dev));

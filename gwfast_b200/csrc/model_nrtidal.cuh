@@ -35,27 +35,35 @@ template <class T> GWF_HD T nrt_fmerger(const T& eta, const T& k2T) {           
     return (0.3586 / dsqrt(q)) * (num / den) / (2. * kPi);
 }
 
+// parts: 1 = the phase half of the record, 2 = the amplitude half, 3 = both (see PhenomDCore::build)
 template <int NT>
 GWF_HD void nrtidal_prologue(NRTidalRec<NT>& r, const Intrinsic<NT>& p, double dL, const QnmTables& q, const double* fmin_g, int ngroups,
-                             const ModelCfg& cfg, bool lambda_for_fcut, double s_host = 0.0, double fcut_host = 0.0) {
+                             const ModelCfg& cfg, bool lambda_for_fcut, double s_host = 0.0, double fcut_host = 0.0, int parts = 3) {
     typedef Dual<NT> D;
     const D qm1 = quad_mon(p.L1), qm2 = quad_mon(p.L2);            // waveforms.py:1394-1395
     PhenomDCore<NT> c;
-    c.build(p.eta, p.chi1, p.chi2, qm1, qm2, q);
+    c.build(p.eta, p.chi1, p.chi2, qm1, qm2, q, parts);
     const D M = p.Mc / dpow(p.eta, 3. / 5.);
     ModelCfg cfg_cut = cfg;
     cfg_cut.flags &= ~kFlagNoFcut;                                 // the amplitude always applies the cut (waveforms.py:1673)
-    phenomd_fill(r.d, c, M, D(dL), fmin_g, ngroups, cfg, s_host, 0.0);
+    phenomd_fill(r.d, c, M, D(dL), fmin_g, ngroups, cfg, s_host, 0.0, parts);
     const D sq = seta_of(p.eta);
     const D m1 = 0.5 * (1.0 + sq), m2 = 0.5 * (1.0 - sq);
     const D k2T = nrt_kappa2T(p.eta, p.L1, p.L2);
+    if (parts & 2) {
+        const D amp0 = dsqrt(2.0 * p.eta / 3.0) * pow(kPi, -1. / 6.);
+        put(r.kam, (-9.0 * 2. * sqrt(kPi / 5.)) * k2T / amp0);
+        const D ym = nrt_fmerger(p.eta, k2T);
+        put(r.ym, ym);
+        D s = M * kGMsunC3;
+        if (s_host > 0.0) s.v = s_host;
+        ScalePow sp;
+        sp.set(s.v);
+        const double sm13 = sp.sm13;
+        r.sm76 = sm13 * sm13 * sm13 * sqrt(sm13);
+    }
+    if (!(parts & 1)) return;
     put(r.kph, -k2T * 2.4375 / (m1 * m2));
-    const D amp0 = dsqrt(2.0 * p.eta / 3.0) * pow(kPi, -1. / 6.);
-    put(r.kam, (-9.0 * 2. * sqrt(kPi / 5.)) * k2T / amp0);
-    const D ym = nrt_fmerger(p.eta, k2T);
-    put(r.ym, ym);
-    const double sm13 = r.d.sp.sm13;
-    r.sm76 = sm13 * sm13 * sm13 * sqrt(sm13);
     // fcut uses whatever Lambda the events dict carried when fcut() ran (0 if absent: waveforms.py:1809-1812, SURVEY A-20)
     const double k2T_cut = lambda_for_fcut ? k2T.v : 0.0;
     r.fcut_hz = fcut_host > 0.0 ? fcut_host : 1.2 * nrt_fmerger(p.eta.v, k2T_cut) / r.d.s;

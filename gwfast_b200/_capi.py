@@ -37,6 +37,14 @@ class gwf_opts(C.Structure):
     _fields_ = [('res', C.c_int32), ('flags', C.c_int32), ('per_arm', C.c_int32), ('reserved', C.c_int32)]
 
 
+class gwf_fisher_out(C.Structure):
+    _fields_ = [('fisher_packed', C.c_void_p), ('snr2', C.c_void_p), ('snr2_integ', C.c_void_p), ('snr_derivs', C.c_void_p), ('status', C.c_void_p)]
+
+
+# per-event status bits (gwf_fisher_out.status)
+GWF_EV_NONFINITE_INPUT, GWF_EV_OUT_OF_DOMAIN, GWF_EV_NONFINITE_OUTPUT, GWF_EV_EMPTY_GRID = 1, 2, 4, 8
+
+
 class EngineUnavailable(RuntimeError):
     pass
 
@@ -47,7 +55,7 @@ class EngineError(RuntimeError):
 
 # every symbol include/gwfast_b200.h declares (tests check that the library exports all of them)
 SYMBOLS = ('gwf_version', 'gwf_last_error', 'gwf_num_params', 'gwf_num_arms', 'gwf_workspace_bytes', 'gwf_psd_create',
-           'gwf_psd_destroy', 'gwf_set_qnm_tables', 'gwf_fisher', 'gwf_fisher_ex', 'gwf_strain_derivs', 'gwf_strain', 'gwf_overlap', 'gwf_snr', 'gwf_unpack_fisher', 'gwf_waveform', 'gwf_fp64_peak', 'gwf_covariance', 'gwf_eigen',
+           'gwf_psd_destroy', 'gwf_set_qnm_tables', 'gwf_fisher', 'gwf_fisher_ex', 'gwf_strain_derivs', 'gwf_strain', 'gwf_overlap', 'gwf_snr', 'gwf_unpack_fisher', 'gwf_unpack_fisher_ld', 'gwf_copy_2d', 'gwf_waveform', 'gwf_fp64_peak', 'gwf_covariance', 'gwf_eigen',
            'gwf_inversion_error')
 
 _lib = None
@@ -76,12 +84,14 @@ def load():
     lib.gwf_set_qnm_tables.argtypes = [P(dbl), P(dbl), P(dbl), i32]
     common = [P(gwf_model), P(gwf_detector), i32, P(vp), i32, P(gwf_events), i64, P(gwf_opts)]
     lib.gwf_fisher.argtypes = common + [vp, vp, vp, C.c_size_t, vp]
-    lib.gwf_fisher_ex.argtypes = common + [vp, vp, vp, vp, C.c_size_t, vp]
+    lib.gwf_fisher_ex.argtypes = common + [P(gwf_fisher_out), vp, C.c_size_t, vp]
     lib.gwf_snr.argtypes = common + [vp, vp, C.c_size_t, vp]
     lib.gwf_strain_derivs.argtypes = common + [vp, vp, C.c_size_t, vp]
     lib.gwf_strain.argtypes = common + [vp, vp, C.c_size_t, vp]
     lib.gwf_overlap.argtypes = [vp, vp, vp, i64, i32, dbl, vp, vp, vp, vp, vp]
     lib.gwf_unpack_fisher.argtypes = [vp, i64, i32, vp, vp]
+    lib.gwf_unpack_fisher_ld.argtypes = [vp, i64, i32, vp, i64, vp]
+    lib.gwf_copy_2d.argtypes = [vp, C.c_size_t, vp, C.c_size_t, C.c_size_t, C.c_size_t, vp]
     lib.gwf_waveform.argtypes = [P(gwf_model), P(gwf_events), i64, vp, i32, i32, vp, vp, vp, vp, vp, vp, C.c_size_t, vp]
     lib.gwf_fp64_peak.argtypes = [dbl, P(dbl), vp]
     lib.gwf_covariance.argtypes = [vp, i64, i32, i32, dbl, vp, vp, vp, vp]

@@ -14,65 +14,95 @@ from . import _capi as K
 from ._capi import EngineUnavailable, EngineError  # noqa: F401
 from . import gwfastGlobals as glob
 
-CHUNK_EVENTS = 1 << 18     # events per launch group: bounds the coefficient-record workspace (~2.2 KB/event)
+CHUNK_EVENTS = 1 << 16     # events per launch group: bounds the coefficient-record workspace (2-10 KB/event) and sets the grain of the
+                           # H2D / kernel / D2H pipeline of a large catalog
+MIN_CHUNK = 2048           # a catalog is never cut into groups smaller than this (the persistent kernels want >= 4 events per SM)
+PIPE_DEPTH = 4             # groups a mid-sized batch is cut into so that the D2H of one group hides behind the kernels of the next
+N_STREAMS = 2
 
-_state = None
+_states = {}
 launch_count = 0           # kernels launched through this module (bench.py reports it as gpu_launches)
 
 
 class _State:
-    def __init__(self):
-        try:
-            import torch
-        except ImportError as e:  # pragma: no cover
-            raise EngineUnavailable('torch is required for device memory and streams') from e
+    def __init__(self, torch, index):
         self.torch = torch
         self.lib = K.load()
-        if not torch.cuda.is_available():
-            raise EngineUnavailable('no CUDA device visible: gwfast_b200 has no CPU fallback')
-        self.device = torch.device('cuda', torch.cuda.current_device())
-        torch.cuda.init()
-        torch.zeros(1, device=self.device)   # make sure the primary context exists before the library's first call
-        dp = C.POINTER(C.c_double)
-        tabs = [np.ascontiguousarray(np.loadtxt(os.path.join(glob.WFfilesPath, 'QNMData_%s.txt' % k))) for k in ('a', 'fring', 'fdamp')]
-        K.check(self.lib.gwf_set_qnm_tables(tabs[0].ctypes.data_as(dp), tabs[1].ctypes.data_as(dp), tabs[2].ctypes.data_as(dp), len(tabs[0])),
-                'gwf_set_qnm_tables')
-        self.psds = {}
+        self.device = torch.device('cuda', index)
+        with torch.cuda.device(self.device):
+            torch.zeros(1, device=self.device)   # make sure the primary context exists before the library's first call
         self.workspace = None
+        self.side_ws = {}
+        self.streams = None
         self.last_fisher_device = None
+        self.last_status = None
+
+
+_qnm_set = False
+_psds = {}
 
 
 def state():
-    global _state
-    if _state is None:
-        _state = _State()
-    return _state
+    """engine state of the CURRENT CUDA device (one per device: workspaces, side streams); PSD handles and the QNM tables are
+    process-wide -- the library uploads them to each device on first use."""
+    global _qnm_set
+    try:
+        import torch
+    except ImportError as e:  # pragma: no cover
+        raise EngineUnavailable('torch is required for device memory and streams') from e
+    lib = K.load()
+    if not torch.cuda.is_available():
+        raise EngineUnavailable('no CUDA device visible: gwfast_b200 has no CPU fallback')
+    idx = torch.cuda.current_device()
+    st = _states.get(idx)
+    if st is None:
+        torch.cuda.init()
+        st = _states[idx] = _State(torch, idx)
+    if not _qnm_set:
+        dp = C.POINTER(C.c_double)
+        tabs = [np.ascontiguousarray(np.loadtxt(os.path.join(glob.WFfilesPath, 'QNMData_%s.txt' % k))) for k in ('a', 'fring', 'fdamp')]
+        K.check(lib.gwf_set_qnm_tables(tabs[0].ctypes.data_as(dp), tabs[1].ctypes.data_as(dp), tabs[2].ctypes.data_as(dp), len(tabs[0])),
+                'gwf_set_qnm_tables')
+        _qnm_set = True
+    return st
 
 
 def psd_handle(freq, S):
-    """device PSD table for (strainFreq, noiseCurve); cached on the arrays' content."""
-    st = state()
+    """PSD handle for (strainFreq, noiseCurve); cached on the arrays' content, valid on every device."""
+    lib = K.load()
     freq = np.ascontiguousarray(freq, dtype=np.float64)
     S = np.ascontiguousarray(S, dtype=np.float64)
     key = (freq.shape[0], hash(freq.tobytes()), hash(S.tobytes()))
-    h = st.psds.get(key)
+    h = _psds.get(key)
     if h is None:
         dp = C.POINTER(C.c_double)
         out = C.c_void_p()
-        K.check(st.lib.gwf_psd_create(freq.ctypes.data_as(dp), S.ctypes.data_as(dp), freq.shape[0], C.byref(out)), 'gwf_psd_create')
+        K.check(lib.gwf_psd_create(freq.ctypes.data_as(dp), S.ctypes.data_as(dp), freq.shape[0], C.byref(out)), 'gwf_psd_create')
         h = out.value
-        st.psds[key] = h
+        _psds[key] = h
     return h
 
 
-def _workspace(st, nbytes):
-    if st.workspace is None or st.workspace.numel() < nbytes:
-        st.workspace = st.torch.empty(int(nbytes), dtype=st.torch.uint8, device=st.device)
-    return st.workspace
+def _workspace(st, nbytes, slot=None):
+    """device scratch for the coefficient records: one buffer for the current stream, one per side stream of the pipeline"""
+    if slot is None:
+        if st.workspace is None or st.workspace.numel() < nbytes:
+            st.workspace = st.torch.empty(int(nbytes), dtype=st.torch.uint8, device=st.device)
+        return st.workspace
+    ws = st.side_ws.get(slot)
+    if ws is None or ws.numel() < nbytes:
+        ws = st.side_ws[slot] = st.torch.empty(int(nbytes), dtype=st.torch.uint8, device=st.device)
+    return ws
 
 
-def _upload(st, ev, n, keys):
-    """events dict -> one pinned staging buffer -> one H2D copy; returns (device tensor, gwf_events, bytes)."""
+def _side_streams(st):
+    if st.streams is None:
+        st.streams = [st.torch.cuda.Stream(device=st.device) for _ in range(N_STREAMS)]
+    return st.streams
+
+
+def _stage(st, ev, n, keys):
+    """events dict -> ONE pinned staging table (present keys, n); returns (pinned tensor, present keys)."""
     torch = st.torch
     present = [k for k in keys if k in ev]
     host = torch.empty((len(present), n), dtype=torch.float64, pin_memory=True)
@@ -82,18 +112,38 @@ def _upload(st, ev, n, keys):
         if a.shape != (n,):
             a = np.broadcast_to(np.real(a).astype(np.float64, copy=False), (n,))
         hnp[i] = np.real(a)
-    dev = host.to(st.device, non_blocking=True)
+    return host, present
+
+
+def _events_struct(dev, present, m):
+    """gwf_events over a device table (len(present), m)"""
     evs = K.gwf_events()
-    base, stride = dev.data_ptr(), n * 8
+    base, stride = dev.data_ptr(), m * 8
     for i, k in enumerate(K.EVENT_KEYS):
         evs.p[i] = base + present.index(k) * stride if k in present else None
-    return dev, host, evs, host.numel() * 8
+    return evs
+
+
+def _upload(st, ev, n, keys):
+    """events dict -> one pinned staging buffer -> one H2D copy; returns (device tensor, host tensor, gwf_events, bytes)."""
+    host, present = _stage(st, ev, n, keys)
+    dev = host.to(st.device, non_blocking=True)
+    return dev, host, _events_struct(dev, present, n), host.numel() * 8
 
 
 def _call_arrays(dets, psd_handles):
     darr = (K.gwf_detector * len(dets))(*dets)
     parr = (C.c_void_p * len(psd_handles))(*psd_handles)
     return darr, parr
+
+
+def _groups(n):
+    """launch groups (lo, m) of a batch: one group for a small batch, PIPE_DEPTH groups for a mid-sized one, CHUNK_EVENTS-sized
+    groups for a catalog.  An event's result never depends on the grouping (the kernels' work mapping is fixed per model)."""
+    if n <= 2 * MIN_CHUNK:
+        return [(0, n)]
+    m = min(CHUNK_EVENTS, max(MIN_CHUNK, -(-n // PIPE_DEPTH)))
+    return [(lo, min(m, n - lo)) for lo in range(0, n, m)]
 
 
 # When set, fisher() leaves a reference to its device-resident result (npass, nP, nP, n) in state().last_fisher_device, so that a
@@ -105,12 +155,19 @@ STASH_DEVICE = False
 KERNEL_FLAGS = 0
 
 
-def fisher(model, dets, psd_handles, ev, n, res, flags, per_arm, want_snr2=True, keep_on_device=False, want_snr_derivs=False):
-    """Run gwf_fisher (+ gwf_unpack_fisher) on the current device.
+def fisher(model, dets, psd_handles, ev, n, res, flags, per_arm, want_snr2=True, keep_on_device=False, want_snr_derivs=False,
+           want_snr_integ=False):
+    """Run gwf_fisher_ex (+ gwf_unpack_fisher_ld) on the current device, pipelined over launch groups.
 
     Returns ``(F, snr2, io)`` with ``F`` of shape ``(npass, nP, nP, n)`` and ``snr2`` ``(npass, n)`` as numpy arrays
     (or device tensors if ``keep_on_device``); ``io`` = (h2d_bytes, d2h_bytes).  With ``want_snr_derivs`` the second element
-    is the pair ``(snr2, snr_derivs)`` with ``snr_derivs`` of shape ``(npass, n, nP)`` (gwf_fisher_ex).
+    is the pair ``(snr2, snr_derivs)`` with ``snr_derivs`` of shape ``(npass, n, nP)``; with ``want_snr_integ`` it is the integral
+    SNRInteg forms (gwf_fisher_out.snr2_integ) instead of 4 int |h|^2/Sn.  The per-event status words of the call are left in
+    ``state().last_status`` (numpy int32, or None with ``keep_on_device``).
+
+    Pipeline: the events are staged once in pinned memory; every launch group runs H2D -> prologue -> fisher -> unpack -> D2H on one
+    of two side streams, so the copies of a group overlap the kernels of its neighbours, and the persistent kernel of the next group
+    fills the SMs the previous one's tail leaves idle.  The host waits once, at the end.
     """
     global launch_count
     st = state()
@@ -122,54 +179,84 @@ def fisher(model, dets, psd_handles, ev, n, res, flags, per_arm, want_snr2=True,
     npack = nP * (nP + 1) // 2
     darr, parr = _call_arrays(dets, psd_handles)
     npass = lib.gwf_num_arms(darr, len(dets)) if per_arm else 1
-    stream = torch.cuda.current_stream(st.device)
-    sp = C.c_void_p(stream.cuda_stream)
-    full = torch.empty((npass, nP, nP, n), dtype=torch.float64, device=st.device)
-    snr2 = torch.empty((npass, n), dtype=torch.float64, device=st.device)
-    sder = torch.empty((npass, n, nP), dtype=torch.float64, device=st.device) if want_snr_derivs else None
+    cur = torch.cuda.current_stream(st.device)
+    f64 = torch.float64
+    full = torch.empty((npass, nP, nP, n), dtype=f64, device=st.device)
+    snr2 = torch.empty((npass, n), dtype=f64, device=st.device)
+    sder = torch.empty((npass, n, nP), dtype=f64, device=st.device) if want_snr_derivs else None
+    status = torch.empty((n,), dtype=torch.int32, device=st.device)
     opts = K.gwf_opts(int(res), int(flags) | KERNEL_FLAGS, int(bool(per_arm)), 0)
-    h2d = 0
+    host_ev, present = _stage(st, ev, n, K.EVENT_KEYS)
+    nk = len(present)
+    groups = _groups(n)
+    to_host = not keep_on_device
+    if to_host:
+        out_f = torch.empty(full.shape, dtype=f64, pin_memory=True)
+        out_s = torch.empty(snr2.shape, dtype=f64, pin_memory=True)
+        out_st = torch.empty((n,), dtype=torch.int32, pin_memory=True)
+        out_d = torch.empty(sder.shape, dtype=f64, pin_memory=True) if want_snr_derivs else None
+    piped = len(groups) > 1
+    streams = _side_streams(st) if piped else [cur]
+    if piped:
+        for s_ in streams:
+            s_.wait_stream(cur)
     keep = []
-    for lo in range(0, n, CHUNK_EVENTS):
-        m = min(CHUNK_EVENTS, n - lo)
-        sub = ev if (lo == 0 and m == n) else {k: np.asarray(v)[lo:lo + m] for k, v in ev.items() if k in K.EVENT_KEYS}
-        dev_ev, host_ev, evs, nb = _upload(st, sub, m, K.EVENT_KEYS)
-        h2d += nb
-        ws = _workspace(st, lib.gwf_workspace_bytes(C.byref(model), m))
-        packed = torch.empty((npass, m, npack), dtype=torch.float64, device=st.device)
-        s2 = torch.empty((npass, m), dtype=torch.float64, device=st.device)
-        sd = torch.empty((npass, m, nP), dtype=torch.float64, device=st.device) if want_snr_derivs else None
-        K.check(lib.gwf_fisher_ex(C.byref(model), darr, len(dets), parr, len(psd_handles), C.byref(evs), m, C.byref(opts),
-                                  C.c_void_p(packed.data_ptr()), C.c_void_p(s2.data_ptr()), C.c_void_p(sd.data_ptr()) if want_snr_derivs else None,
-                                  C.c_void_p(ws.data_ptr()), ws.numel(), sp), 'gwf_fisher')
-        if want_snr_derivs:
-            sder[:, lo:lo + m] = sd
-        launch_count += 1 + npass
-        if m == n:
+    for gi, (lo, m) in enumerate(groups):
+        slot = gi % len(streams)
+        stream = streams[slot]
+        sp = C.c_void_p(stream.cuda_stream)
+        with torch.cuda.stream(stream):
+            dev_ev = torch.empty((nk, m), dtype=f64, device=st.device)
+            if m == n:
+                dev_ev.copy_(host_ev, non_blocking=True)
+            else:
+                K.check(lib.gwf_copy_2d(C.c_void_p(dev_ev.data_ptr()), m * 8, C.c_void_p(host_ev.data_ptr() + lo * 8), n * 8, m * 8, nk, sp), 'gwf_copy_2d')
+            evs = _events_struct(dev_ev, present, m)
+            ws = _workspace(st, lib.gwf_workspace_bytes(C.byref(model), m), slot if piped else None)
+            packed = torch.empty((npass, m, npack), dtype=f64, device=st.device)
+            s2 = snr2 if m == n else torch.empty((npass, m), dtype=f64, device=st.device)
+            sd = (sder if m == n else torch.empty((npass, m, nP), dtype=f64, device=st.device)) if want_snr_derivs else None
+            fo = K.gwf_fisher_out(packed.data_ptr(), None if want_snr_integ else s2.data_ptr(), s2.data_ptr() if want_snr_integ else None,
+                                  sd.data_ptr() if want_snr_derivs else None, status.data_ptr() + 4 * lo)
+            K.check(lib.gwf_fisher_ex(C.byref(model), darr, len(dets), parr, len(psd_handles), C.byref(evs), m, C.byref(opts), C.byref(fo),
+                                      C.c_void_p(ws.data_ptr()), ws.numel(), sp), 'gwf_fisher')
+            launch_count += 1 + npass
             for p in range(npass):
-                K.check(lib.gwf_unpack_fisher(C.c_void_p(packed[p].data_ptr()), m, nP, C.c_void_p(full[p].data_ptr()), sp), 'gwf_unpack_fisher')
+                K.check(lib.gwf_unpack_fisher_ld(C.c_void_p(packed[p].data_ptr()), m, nP, C.c_void_p(full[p].data_ptr() + 8 * lo), n, sp), 'gwf_unpack_fisher')
                 launch_count += 1
-            snr2 = s2
-        else:
-            tmp = torch.empty((npass, nP, nP, m), dtype=torch.float64, device=st.device)
-            for p in range(npass):
-                K.check(lib.gwf_unpack_fisher(C.c_void_p(packed[p].data_ptr()), m, nP, C.c_void_p(tmp[p].data_ptr()), sp), 'gwf_unpack_fisher')
-                launch_count += 1
-            full[..., lo:lo + m] = tmp
-            snr2[:, lo:lo + m] = s2
-        keep.append((dev_ev, host_ev, packed))
+            if m != n:
+                snr2[:, lo:lo + m] = s2
+                if want_snr_derivs:
+                    sder[:, lo:lo + m] = sd
+            if to_host:
+                if m == n:
+                    out_f.copy_(full, non_blocking=True)
+                else:
+                    K.check(lib.gwf_copy_2d(C.c_void_p(out_f.data_ptr() + 8 * lo), n * 8, C.c_void_p(full.data_ptr() + 8 * lo), n * 8, m * 8,
+                                            npass * nP * nP, sp), 'gwf_copy_2d')
+        keep.append((dev_ev, packed, s2, sd))
+    if piped:
+        for s_ in streams:
+            cur.wait_stream(s_)
+        for t in (full, snr2, sder, status):                  # allocated on the current stream, written on the side streams
+            if t is not None:
+                for s_ in streams:
+                    t.record_stream(s_)
     st.last_fisher_device = full if STASH_DEVICE else None
+    h2d = host_ev.numel() * 8
     if keep_on_device:
+        st.last_status = None
         return full, ((snr2, sder) if want_snr_derivs else snr2), (h2d, 0)
-    if want_snr_derivs:
-        stream.synchronize()
-        return full.cpu().numpy(), (snr2.cpu().numpy(), sder.cpu().numpy()), (h2d, (full.numel() + snr2.numel() + sder.numel()) * 8)
-    out_f = torch.empty(full.shape, dtype=torch.float64, pin_memory=True)
-    out_s = torch.empty(snr2.shape, dtype=torch.float64, pin_memory=True)
-    out_f.copy_(full, non_blocking=True)
     out_s.copy_(snr2, non_blocking=True)
-    stream.synchronize()
-    return out_f.numpy(), out_s.numpy(), (h2d, (out_f.numel() + out_s.numel()) * 8)
+    out_st.copy_(status, non_blocking=True)
+    if want_snr_derivs:
+        out_d.copy_(sder, non_blocking=True)
+    cur.synchronize()
+    st.last_status = out_st.numpy()
+    d2h = (out_f.numel() + out_s.numel()) * 8 + out_st.numel() * 4
+    if want_snr_derivs:
+        return out_f.numpy(), (out_s.numpy(), out_d.numpy()), (h2d, d2h + out_d.numel() * 8)
+    return out_f.numpy(), out_s.numpy(), (h2d, d2h)
 
 
 def strain_derivs(model, dets, psd_handles, ev, n, res, flags):

@@ -453,32 +453,47 @@ struct HMExtra {
     GWF_HD void set(const EventIn& e) { w.set(e.iota); }
 };
 
-// mode sums of hphc: z_m = A_m exp(-i Phi_m) is folded into h+ / hx (and their iota derivatives) as soon as it is known
+// mode sums of hphc: z_m = A_m exp(-i Phi_m) is folded into h+ / hx (with their intrinsic tangents and iota derivatives) as soon
+// as it is known: d z_m = z_m (d ln A_m - i d Phi_m)
 template <int NT> struct HMStrainSink {
-    typedef Dual<NT> D;
     const HMWeights& w;
-    D hpr, hpi, hcr, hci;
+    double hpr, hpi, hcr, hci;
+    double hpr_d[NT], hpi_d[NT], hcr_d[NT], hci_d[NT];
     double hpr_i, hpi_i, hcr_i, hci_i;
-    GWF_HD explicit HMStrainSink(const HMWeights& w_) : w(w_), hpr(0.0), hpi(0.0), hcr(0.0), hci(0.0), hpr_i(0.), hpi_i(0.), hcr_i(0.), hci_i(0.) {}
-    GWF_HD void operator()(int m, const D& A, const D& ph) {
-        D sn, cs;
-        dsincos(ph, sn, cs);
-        const D zre = A * cs, zim = -(A * sn);
-        hpr = hpr + zre * w.wp[m];
-        hpi = hpi + zim * w.wp[m];
-        hcr = hcr - zim * w.wc[m];
-        hci = hci + zre * w.wc[m];
-        hpr_i = fma(zre.v, w.dwp[m], hpr_i);
-        hpi_i = fma(zim.v, w.dwp[m], hpi_i);
-        hcr_i = fma(-zim.v, w.dwc[m], hcr_i);
-        hci_i = fma(zre.v, w.dwc[m], hci_i);
+    GWF_HD explicit HMStrainSink(const HMWeights& w_) : w(w_), hpr(0.), hpi(0.), hcr(0.), hci(0.), hpr_i(0.), hpi_i(0.), hcr_i(0.), hci_i(0.) {
+#pragma unroll
+        for (int j = 0; j < NT; ++j) hpr_d[j] = hpi_d[j] = hcr_d[j] = hci_d[j] = 0.;
+    }
+    GWF_HD void operator()(int m, double A, double ph, const double* __restrict__ dlnA, const double* __restrict__ dPhi) {
+        if (A == 0.0) return;
+        double sn, cs;
+        sincos(ph, &sn, &cs);
+        const double zre = A * cs, zim = -(A * sn);
+        const double wp = w.wp[m], wc = w.wc[m];
+        hpr = fma(zre, wp, hpr);
+        hpi = fma(zim, wp, hpi);
+        hcr = fma(-zim, wc, hcr);
+        hci = fma(zre, wc, hci);
+        hpr_i = fma(zre, w.dwp[m], hpr_i);
+        hpi_i = fma(zim, w.dwp[m], hpi_i);
+        hcr_i = fma(-zim, w.dwc[m], hcr_i);
+        hci_i = fma(zre, w.dwc[m], hci_i);
+#pragma unroll
+        for (int j = 0; j < NT; ++j) {
+            const double dre = fma(zre, dlnA[j], zim * dPhi[j]), dim = fma(zim, dlnA[j], -zre * dPhi[j]);
+            hpr_d[j] = fma(dre, wp, hpr_d[j]);
+            hpi_d[j] = fma(dim, wp, hpi_d[j]);
+            hcr_d[j] = fma(-dim, wc, hcr_d[j]);
+            hci_d[j] = fma(dre, wc, hci_d[j]);
+        }
     }
 };
 struct HMValueSink {
     const HMWeights& w;
     double hpr, hpi, hcr, hci;
     GWF_HD explicit HMValueSink(const HMWeights& w_) : w(w_), hpr(0.), hpi(0.), hcr(0.), hci(0.) {}
-    GWF_HD void operator()(int m, double A, double ph) {
+    GWF_HD void operator()(int m, double A, double ph, const double*, const double*) {
+        if (A == 0.0) return;
         double sn, cs;
         sincos(ph, &sn, &cs);
         const double zre = A * cs, zim = -(A * sn);
@@ -489,21 +504,27 @@ struct HMValueSink {
     }
 };
 
-// SD: also accumulate (h | d_i h) behind the SNR^2 slot (return_SNR_derivatives)
+// accumulator layout of the IMRPhenomHM Fisher point: packed Gram, then 4 int |h|^2/Sn, then the SNRInteg integral (cross term
+// dropped), then (SD) the (h | d_i h) rows
+template <int NT> struct HMAcc {
+    static constexpr int NP = NT + 7, kSnr2 = NP * (NP + 1) / 2, kSnr2Integ = kSnr2 + 1, kSd = kSnr2 + 2;
+};
+
+// SD: also accumulate (h | d_i h) (return_SNR_derivatives)
 template <int NT, bool SD = false>
 GWF_HD void hm_point(const HMRec<NT>& rec, const ModelCfg& cfg, const EvGeom& geom, const NetworkDev& net, const EventScratch& sc,
                      const HMExtra& ex, int g, bool group_rot, const FreqPoint& fp, double* __restrict__ acc) {
-    typedef Dual<NT> D;
     constexpr int NP = NT + 7;
-    double& snr2 = acc[NP * (NP + 1) / 2];
+    double& snr2 = acc[HMAcc<NT>::kSnr2];
+    double& snr2i = acc[HMAcc<NT>::kSnr2Integ];
     const double f = fp.f, l2f = fp.lnf * 1.4426950408889634073599246810018921;
     const bool cut = !(cfg.flags & kFlagNoFcut);
     // hp = sum z_m Wp_m ; hc = i sum z_m Wc_m ; and their iota derivatives (waveforms.py:2613-2614), summed mode by mode
     HMStrainSink<NT> hs(ex.w);
-    phenomhm_foreach_mode<D, NT>(rec, g, f, cut, hs);
-    const D &hpr = hs.hpr, &hpi = hs.hpi, &hcr = hs.hcr, &hci = hs.hci;
+    phenomhm_foreach_mode<NT, true>(rec, g, fp, cut, hs);
+    if (hs.hpr == 0.0 && hs.hpi == 0.0 && hs.hcr == 0.0 && hs.hci == 0.0) return;
     const double hpr_i = hs.hpr_i, hpi_i = hs.hpi_i, hcr_i = hs.hcr_i, hci_i = hs.hci_i;
-    if (hpr.v == 0.0 && hpi.v == 0.0 && hcr.v == 0.0 && hci.v == 0.0) return;
+    const double hp2 = hs.hpr * hs.hpr + hs.hpi * hs.hpi, hc2 = hs.hcr * hs.hcr + hs.hci * hs.hci;
     PointWf<NT> w;
     w.f = f;
 #pragma unroll
@@ -512,8 +533,8 @@ GWF_HD void hm_point(const HMRec<NT>& rec, const ModelCfg& cfg, const EvGeom& ge
     double sBr = 0., cBr = 1.;
     if (group_rot) {
         double tau, dtau[2];
-        const double x13 = cbrt(rec.s.v * f), lpx3 = log(kPi * rec.s.v * f) * (1. / 3.);
-        tau_eval(rec.tau, 0.68278406325529568146702083315816 / x13, lpx3, rec.lam, tau, dtau);
+        const double xm13 = rec.sp.sm13 * fp.fm13, lpx3 = fma(fp.lnf, 1. / 3., rec.sp.lps3);
+        tau_eval(rec.tau, 0.68278406325529568146702083315816 * xm13, lpx3, rec.lam, tau, dtau);
         w.dtn[0] = -dtau[0] * kInvDay;
         w.dtn[1] = -dtau[1] * kInvDay;
         sincos(2.0 * kPi * fma(-tau, kInvDay, geom.tcoal), &sBr, &cBr);
@@ -537,14 +558,14 @@ GWF_HD void hm_point(const HMRec<NT>& rec, const ModelCfg& cfg, const EvGeom& ge
             const double Fp = av * geom.c2psi + bv * geom.s2psi, Fc = bv * geom.c2psi - av * geom.s2psi;
             const double Fpg = ag * geom.c2psi + bg * geom.s2psi, Fcg = bg * geom.c2psi - ag * geom.s2psi;
             const double Fpd = ad * geom.c2psi + bd * geom.s2psi, Fcd = bd * geom.c2psi - ad * geom.s2psi;
-            const double Hr = hpr.v * Fp + hcr.v * Fc, Hi = hpi.v * Fp + hci.v * Fc;           // signal.py:586-607
-            const double Hgr = hpr.v * Fpg + hcr.v * Fcg, Hgi = hpi.v * Fpg + hci.v * Fcg;
-            const double Hdr = hpr.v * Fpd + hcr.v * Fcd, Hdi = hpi.v * Fpd + hci.v * Fcd;
+            const double Hr = hs.hpr * Fp + hs.hcr * Fc, Hi = hs.hpi * Fp + hs.hci * Fc;           // signal.py:586-607
+            const double Hgr = hs.hpr * Fpg + hs.hcr * Fcg, Hgi = hs.hpi * Fpg + hs.hci * Fcg;
+            const double Hdr = hs.hpr * Fpd + hs.hcr * Fcd, Hdi = hs.hpi * Fpd + hs.hci * Fcd;
             double ra[NP], rb[NP];
 #pragma unroll
             for (int j = 0; j < NT; ++j) {
                 const int row = j < 2 ? j : 7 + j;
-                double re = hpr.d[j] * Fp + hcr.d[j] * Fc - Hi * dr.psi_x[j], im = hpi.d[j] * Fp + hci.d[j] * Fc + Hr * dr.psi_x[j];
+                double re = hs.hpr_d[j] * Fp + hs.hcr_d[j] * Fc - Hi * dr.psi_x[j], im = hs.hpi_d[j] * Fp + hs.hci_d[j] * Fc + Hr * dr.psi_x[j];
                 if (j < 2) {
                     re = fma(Hgr, dr.ang_x[j], re);
                     im = fma(Hgi, dr.ang_x[j], im);
@@ -556,15 +577,16 @@ GWF_HD void hm_point(const HMRec<NT>& rec, const ModelCfg& cfg, const EvGeom& ge
             ra[3] = fma(Hgr, dr.ang_t, -Hdr) - Hi * dr.ph_t;             rb[3] = fma(Hgi, dr.ang_t, -Hdi) + Hr * dr.ph_t;
             ra[4] = fma(Hgr, dr.ang_p, -Hi * dr.ph_p);                   rb[4] = fma(Hgi, dr.ang_p, Hr * dr.ph_p);
             ra[5] = hpr_i * Fp + hcr_i * Fc;                             rb[5] = hpi_i * Fp + hci_i * Fc;     // iota: harmonics only
-            ra[6] = 2.0 * (hpr.v * Fc - hcr.v * Fp);                     rb[6] = 2.0 * (hpi.v * Fc - hci.v * Fp);   // psi: Fp' = 2 Fc, Fc' = -2 Fp
+            ra[6] = 2.0 * (hs.hpr * Fc - hs.hcr * Fp);                   rb[6] = 2.0 * (hs.hpi * Fc - hs.hci * Fp);   // psi: Fp' = 2 Fc, Fc' = -2 Fp
             ra[7] = fma(Hgr, dr.ang_c, -Hi * dr.ph_c);                   rb[7] = fma(Hgi, dr.ang_c, Hr * dr.ph_c);
             ra[8] = Hi;                                                  rb[8] = -Hr;
             const double wg = wgt * a.weight;
             snr2 = fma(wg, Hr * Hr + Hi * Hi, snr2);
+            snr2i = fma(wg, hp2 * Fp * Fp + hc2 * Fc * Fc, snr2i);      // Ap = |hp| Fp, Ac = |hc| Fc (signal.py:457-460, 727)
             if (SD) {
                 const double wr = wg * Hr, wi = wg * Hi;
 #pragma unroll
-                for (int i = 0; i < NP; ++i) acc[NP * (NP + 1) / 2 + 1 + i] = fma(wr, ra[i], fma(wi, rb[i], acc[NP * (NP + 1) / 2 + 1 + i]));
+                for (int i = 0; i < NP; ++i) acc[HMAcc<NT>::kSd + i] = fma(wr, ra[i], fma(wi, rb[i], acc[HMAcc<NT>::kSd + i]));
             }
 #pragma unroll
             for (int i = 0; i < NP; ++i) {
@@ -582,15 +604,15 @@ GWF_HD void hm_snr_point(const HMRec<4>& rec, const ModelCfg& cfg, const EvGeom&
     const double f = fp.f, l2f = fp.lnf * 1.4426950408889634073599246810018921;
     const bool cut = !(cfg.flags & kFlagNoFcut);
     HMValueSink hs(ex.w);
-    phenomhm_foreach_mode<double, 4>(rec, g, f, cut, hs);
+    phenomhm_foreach_mode<4, false>(rec, g, fp, cut, hs);
     const double hpr = hs.hpr, hpi = hs.hpi, hcr = hs.hcr, hci = hs.hci;
     const double hp2 = hpr * hpr + hpi * hpi, hc2 = hcr * hcr + hci * hci;
     if (hp2 == 0.0 && hc2 == 0.0) return;
     double sBr = 0., cBr = 1.;
     if (group_rot) {
         double tau, dtau[2];
-        const double x13 = cbrt(rec.s.v * f), lpx3 = log(kPi * rec.s.v * f) * (1. / 3.);
-        tau_eval(rec.tau, 0.68278406325529568146702083315816 / x13, lpx3, rec.lam, tau, dtau);
+        const double xm13 = rec.sp.sm13 * fp.fm13, lpx3 = fma(fp.lnf, 1. / 3., rec.sp.lps3);
+        tau_eval(rec.tau, 0.68278406325529568146702083315816 * xm13, lpx3, rec.lam, tau, dtau);
         rot_sincos(fma(-tau, kInvDay, geom.tcoal), &sBr, &cBr);
     }
     const double w4 = 4.0 * fp.w;
@@ -648,6 +670,7 @@ template <int MODEL, int NT> struct PointFns {
     static constexpr bool kEntryTable = true;
     static GWF_HD void entry_code(int i, int j, unsigned char* code) { compact_entry_code<NT>(i, j, code); }
     static GWF_HD double snr2(const double* __restrict__ red, const EvGeom& geom) { return compact_snr2<NT>(red, geom); }
+    static GWF_HD double snr2_integ(const double* __restrict__ red, const EvGeom& geom) { return compact_snr2<NT>(red, geom); }
     static GWF_HD double snr_deriv(int row, const double* __restrict__ red, const EvGeom& geom) { return compact_snr_deriv<NT>(row, red, geom); }
     static GWF_HD void snr(const Rec& rec, const ModelCfg& cfg, const EvGeom& geom, const NetworkDev& net, const EventScratch& sc, const Extra&, int g,
                            bool rot, const FreqPoint& fp, double* __restrict__ s2) {
@@ -658,12 +681,12 @@ template <int MODEL, int NT> struct PointFns {
 template <int NT, bool SD = false> struct PointFnsHM {
     typedef HMExtra Extra;
     typedef HMRec<NT> Rec;
-    static constexpr int kAcc = (NT + 7) * (NT + 8) / 2 + 1 + (SD ? NT + 7 : 0);
+    static constexpr int kAcc = HMAcc<NT>::kSd + (SD ? NT + 7 : 0);
     static GWF_HD void fisher(const Rec& rec, const ModelCfg& cfg, const EvGeom& geom, const NetworkDev& net, const EventScratch& sc, const Extra& ex, int g,
                               bool rot, const FreqPoint& fp, double* __restrict__ acc) {
         hm_point<NT, SD>(rec, cfg, geom, net, sc, ex, g, rot, fp, acc);
     }
-    static GWF_HD double snr_deriv(int row, const double* __restrict__ red, const EvGeom&) { return SD ? red[(NT + 7) * (NT + 8) / 2 + 1 + row] : 0.0; }
+    static GWF_HD double snr_deriv(int row, const double* __restrict__ red, const EvGeom&) { return SD ? red[HMAcc<NT>::kSd + row] : 0.0; }
     static constexpr bool kHasFast = false;
 #ifdef __CUDA_ARCH__
     template <bool ROT, int SHAPE = 0>
@@ -680,7 +703,8 @@ template <int NT, bool SD = false> struct PointFnsHM {
     static GWF_HD double entry(int i, int j, const double* __restrict__ red, const EvGeom&) { return red[tri(i, j)]; }
     static constexpr bool kEntryTable = false;      // packed index = accumulator index
     static GWF_HD void entry_code(int, int, unsigned char*) {}
-    static GWF_HD double snr2(const double* __restrict__ red, const EvGeom&) { return red[(NT + 7) * (NT + 8) / 2]; }
+    static GWF_HD double snr2(const double* __restrict__ red, const EvGeom&) { return red[HMAcc<NT>::kSnr2]; }
+    static GWF_HD double snr2_integ(const double* __restrict__ red, const EvGeom&) { return red[HMAcc<NT>::kSnr2Integ]; }
     static GWF_HD void snr(const Rec& rec, const ModelCfg& cfg, const EvGeom& geom, const NetworkDev& net, const EventScratch& sc, const Extra& ex, int g,
                            bool rot, const FreqPoint& fp, double* __restrict__ s2) {
         hm_snr_point(rec, cfg, geom, net, sc, ex, g, rot, fp, s2);
@@ -746,7 +770,7 @@ template <> struct WaveformFns<kPhenomHM> {
     static constexpr int kModes = kHMModes;
     static GWF_HD void eval(const HMRec<4>& r, const ModelCfg& cfg, const HMWeights& w, const FreqPoint& fp, WaveformOut& o) {
         const bool cut = !(cfg.flags & kFlagNoFcut);
-        phenomhm_amp_phase<double, 4>(r, 0, fp.f, cut, o.amp, o.phi);
+        phenomhm_amp_phase<4>(r, 0, fp, cut, o.amp, o.phi);
         o.hp[0] = o.hp[1] = o.hc[0] = o.hc[1] = 0.;
         for (int m = 0; m < kHMModes; ++m) {
             double sn, cs;
@@ -756,7 +780,7 @@ template <> struct WaveformFns<kPhenomHM> {
             o.hc[0] = fma(-zi, w.wc[m], o.hc[0]); o.hc[1] = fma(zr, w.wc[m], o.hc[1]);
         }
         double dtau[2];
-        const double x13 = cbrt(r.s.v * fp.f), lpx3 = log(kPi * r.s.v * fp.f) * (1. / 3.);
+        const double x13 = cbrt(r.s * fp.f), lpx3 = log(kPi * r.s * fp.f) * (1. / 3.);
         tau_eval(r.tau, 0.68278406325529568146702083315816 / x13, lpx3, r.lam, o.tau, dtau);
     }
 };

@@ -16,6 +16,8 @@
 #include <vector>
 #include <algorithm>
 #include <cmath>
+#include <mutex>
+#include <unordered_map>
 
 #include "../../include/gwfast_b200.h"
 #include "fisher_core.cuh"
@@ -69,10 +71,20 @@ struct AuxPlan {
     int res, lin, stride;
 };
 
+// per-event status word (gwf_fisher_out.status / gwf_snr_ex): input checks, done by the prologue
+__device__ __forceinline__ int input_status(const EventIn& in) {
+    const bool finite = isfinite(in.Mc) && isfinite(in.eta) && isfinite(in.dL) && isfinite(in.theta) && isfinite(in.phi) && isfinite(in.iota) &&
+                        isfinite(in.psi) && isfinite(in.tcoal) && isfinite(in.Phicoal) && isfinite(in.chi1z) && isfinite(in.chi2z) &&
+                        isfinite(in.Lambda1) && isfinite(in.Lambda2) && isfinite(in.ecc);
+    const bool domain = in.Mc > 0.0 && in.eta > 0.0 && in.eta <= 0.25 && in.dL > 0.0;
+    return (finite ? 0 : GWF_EV_NONFINITE_INPUT) | ((finite && !domain) ? GWF_EV_OUT_OF_DOMAIN : 0);
+}
+
 template <int MODEL, int NT>
 __global__ void __launch_bounds__(128) prologue_kernel(EventsDev ev, long long n, ModelCfg cfg, int opt_flags, QnmTables q, GroupInfo gi,
                                                       typename ModelTraits<MODEL, NT>::Rec* __restrict__ recs,
-                                                      const double* __restrict__ fmin_per_event = nullptr, AuxPlan aux = AuxPlan()) {
+                                                      const double* __restrict__ fmin_per_event = nullptr, AuxPlan aux = AuxPlan(),
+                                                      int* __restrict__ status = nullptr) {
     const long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (e >= n) return;
     const EventIn in = load_event(ev, e);
@@ -81,6 +93,7 @@ __global__ void __launch_bounds__(128) prologue_kernel(EventsDev ev, long long n
     // amplitude) -- the kernel's duration is the instruction-fetch latency of the code one warp walks through
     const int parts = gridDim.y == 2 ? 1 + (int)blockIdx.y : 3;
     ModelTraits<MODEL, NT>::prologue(recs[e], in, cfg, opt_flags, q, gi.fmin, gi.n, parts);
+    int st = status ? input_status(in) : 0;
     if (aux.out && (parts & 1)) {
         EventAux& a = aux.out[e];
         a.geom.set(in);
@@ -88,8 +101,10 @@ __global__ void __launch_bounds__(128) prologue_kernel(EventsDev ev, long long n
             double fcut = recs[e].fcut_hz;
             if (aux.fmax[g] > 0.0 && fcut > aux.fmax[g]) fcut = aux.fmax[g];   // signal.py:717-718
             a.grid[g].set(gi.fmin[g], fcut, aux.res, aux.lin != 0, aux.stride);
+            if (!(fcut > gi.fmin[g])) st |= GWF_EV_EMPTY_GRID;
         }
     }
+    if (status && (parts & 1)) status[e] = st;
 }
 
 // per-event minimum of a user grid f[res][n] (or the shared f[res])
@@ -350,6 +365,15 @@ __device__ __forceinline__ void stage_event_aux(WarpSmem<Rec, Extra>* mine, cons
     __syncwarp();
 }
 
+// outputs of one Fisher pass (any pointer but `fisher` may be null)
+struct FisherOut {
+    double* fisher;       // [n][NPACK]
+    double* snr2;         // [n]  4 int |h|^2/Sn df of the arms of the pass
+    double* snr2_integ;   // [n]  the integral SNRInteg forms (signal.py:727): = snr2, except IMRPhenomHM (cross term dropped)
+    double* snr_derivs;   // [n][NP]
+    int* status;          // [n]  GWF_EV_* bits; the prologue stores the input bits, the kernel ORs in GWF_EV_NONFINITE_OUTPUT
+};
+
 template <int MODEL, int NT, int FAST, bool SD, int SHAPE = 0>
 #ifdef GWF_FISHER_MAXNREG
 __global__ void __maxnreg__(GWF_FISHER_MAXNREG)
@@ -357,8 +381,10 @@ __global__ void __maxnreg__(GWF_FISHER_MAXNREG)
 __global__ void __launch_bounds__(kFisherThreads, GWF_FISHER_MINBLOCKS)
 #endif
 fisher_kernel(const typename ModelTraits<MODEL, NT>::Rec* __restrict__ recs, const EventAux* __restrict__ aux, EventsDev ev, long long n, int res, int lin,
-              ModelCfg cfg, const __grid_constant__ NetworkDev net, double* __restrict__ out, double* __restrict__ snr2_out, double* __restrict__ sd_out,
-              int pair) {
+              ModelCfg cfg, const __grid_constant__ NetworkDev net, const FisherOut fo, int pair) {
+    double* __restrict__ out = fo.fisher;
+    double* __restrict__ snr2_out = fo.snr2;
+    double* __restrict__ sd_out = fo.snr_derivs;
     typedef typename ModelTraits<MODEL, NT>::Rec Rec;
     typedef typename PointFnsSel<MODEL, NT, SD>::type PF;
     typedef FisherSmem<Rec, typename PF::Extra> WS;
@@ -402,8 +428,10 @@ fisher_kernel(const typename ModelTraits<MODEL, NT>::Rec* __restrict__ recs, con
             // otherwise lanes leave the loop on their own.  Same arithmetic either way; which form the compiler schedules
             // better differs per model (measured per 1e4 events: IMRPhenomD 1.229 -> 1.208 ms, NRTidalv2 3.131 -> 3.287 ms).
             constexpr bool kUniformLoop = MODEL == kPhenomHM || MODEL == kPhenomD;
-            for (int kb = k0 - lane; kUniformLoop ? kb < res : kb + lane < res; kb += stride) {
-                const int k = kb + lane;
+            // kb0 runs over the blocks of `stride` samples; both halves of a pair make the same number of trips (the
+            // block barrier below needs every arrival), the half whose block of 32 lies beyond the grid is predicated off
+            for (int kb0 = 0; kUniformLoop ? kb0 < res : kb0 + k0 < res; kb0 += stride) {
+                const int k = kb0 + k0;
                 if (!kUniformLoop || k < res) {
                     if (k != k0) {
                         if (lin) grid.advance(k, fp);
@@ -439,19 +467,30 @@ fisher_kernel(const typename ModelTraits<MODEL, NT>::Rec* __restrict__ recs, con
             for (int k = lane; k < kCompactCoefs; k += 32) mine->coef[k] = compact_coef(k, geom);
             __syncwarp();
         }
+        bool bad = false;
         for (int p = lane; p < NPACK; p += 32) {
             double v;
             if (PF::kEntryTable) {
                 const uchar4 c = *reinterpret_cast<const uchar4*>(mine->code + 4 * p);
                 v = mine->coef[c.z] * red[c.x] + mine->coef[c.w] * red[c.y];
             } else v = red[p];
+            bad = bad || !isfinite(v);
             if (pair) atomicAdd(o + p, v);
             else o[p] = v;
+        }
+        if (fo.status) {
+            const unsigned anybad = __ballot_sync(0xffffffffu, bad);
+            if (lane == 0 && anybad) atomicOr(fo.status + e, GWF_EV_NONFINITE_OUTPUT);
         }
         if (lane == 0 && snr2_out) {
             const double v = PF::snr2(red, geom);
             if (pair) atomicAdd(snr2_out + e, v);
             else snr2_out[e] = v;
+        }
+        if (lane == 1 && fo.snr2_integ) {
+            const double v = PF::snr2_integ(red, geom);
+            if (pair) atomicAdd(fo.snr2_integ + e, v);
+            else fo.snr2_integ[e] = v;
         }
         if (sd_out && lane < NP) {                            // (h | d_i h), signal.py:938-945
             const double v = PF::snr_deriv(lane, red, geom);
@@ -730,41 +769,111 @@ __global__ void __launch_bounds__(256) dfma_kernel(double* out, int iters, doubl
     if (s == 12345.678) out[0] = s;
 }
 
-__global__ void unpack_kernel(const double* __restrict__ packed, long long n, int nP, double* __restrict__ full) {
-    const long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (e >= n) return;
+// packed [n][npack] -> (nP, nP, ld) planes, event axis fastest; ld >= n lets a chunk of events land in its slice of a larger array.
+// One thread block transposes a tile of 32 events through shared memory: coalesced reads of the packed rows, coalesced plane writes.
+__global__ void __launch_bounds__(256) unpack_kernel(const double* __restrict__ packed, long long n, int nP, double* __restrict__ full, long long ld) {
+    __shared__ double tile[32][109];                 // up to nP = 14 (npack = 105), odd pitch: conflict-free columns
     const int npack = nP * (nP + 1) / 2;
-    const double* src = packed + e * npack;
-    for (int i = 0; i < nP; ++i)
-        for (int j = 0; j <= i; ++j) {
-            const double v = src[tri(i, j)];
-            full[((long long)i * nP + j) * n + e] = v;
-            full[((long long)j * nP + i) * n + e] = v;
-        }
+    const long long e0 = (long long)blockIdx.x * 32;
+    const int ne = (int)((n - e0) < 32 ? (n - e0) : 32);
+    const double* src = packed + e0 * npack;
+    for (int t = threadIdx.x; t < ne * npack; t += blockDim.x) tile[t / npack][t % npack] = src[t];
+    __syncthreads();
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int q = wid; q < nP * nP; q += 8) {
+        const int i = q / nP, j = q % nP;
+        if (lane < ne) full[(long long)q * ld + e0 + lane] = tile[lane][i >= j ? tri(i, j) : tri(j, i)];
+    }
 }
 
 // ------------------------------------------------------------------------------------------- host side
-static QnmTables g_qnm = {nullptr, nullptr, nullptr, 0};
+// Per-device state: SM count, the device copy of the QNM tables, and the largest dynamic shared memory size already
+// requested for each kernel -- looked up once per (device, kernel) instead of on every call.  Tables set with
+// gwf_set_qnm_tables and PSD handles keep a host copy and are uploaded to a device the first time a call runs there.
+struct DeviceCtx {
+    int sms = 0;
+    QnmTables qnm = {nullptr, nullptr, nullptr, 0};
+    int qnm_version = 0;
+    std::unordered_map<const void*, size_t> smem_set;
+};
+static std::mutex g_mu;
+static DeviceCtx g_ctx[kMaxDevices];
+static std::vector<double> g_qnm_host;       // a | fring | fdamp
+static int g_qnm_n = 0, g_qnm_version = 0;
+
+// context of the current device (needs_qnm: make sure the device copy of the QNM tables is current)
+static int device_ctx(bool needs_qnm, DeviceCtx** out, int* dev_out = nullptr) {
+    int dev = 0;
+    GWF_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= kMaxDevices) return fail(GWF_ERR_ARG, "device index out of range");
+    std::lock_guard<std::mutex> lock(g_mu);
+    DeviceCtx& c = g_ctx[dev];
+    if (c.sms == 0) GWF_CUDA(cudaDeviceGetAttribute(&c.sms, cudaDevAttrMultiProcessorCount, dev));
+    if (needs_qnm) {
+        if (g_qnm_n == 0) return fail(GWF_ERR_ARG, "QNM tables not set (gwf_set_qnm_tables)");
+        if (c.qnm_version != g_qnm_version) {
+            if (c.qnm.a) cudaFree(const_cast<double*>(c.qnm.a));
+            double* buf = nullptr;
+            GWF_CUDA(cudaMalloc(&buf, sizeof(double) * 3 * g_qnm_n));
+            GWF_CUDA(cudaMemcpy(buf, g_qnm_host.data(), sizeof(double) * 3 * g_qnm_n, cudaMemcpyHostToDevice));
+            c.qnm.a = buf; c.qnm.fring = buf + g_qnm_n; c.qnm.fdamp = buf + 2 * g_qnm_n; c.qnm.n = g_qnm_n;
+            c.qnm_version = g_qnm_version;
+        }
+    }
+    *out = &c;
+    if (dev_out) *dev_out = dev;
+    return GWF_OK;
+}
+// raise a kernel's dynamic shared memory limit (only when this device has not granted at least `bytes` to it yet)
+template <class Kern> static int ensure_smem(DeviceCtx& c, Kern kern, size_t bytes) {
+    std::lock_guard<std::mutex> lock(g_mu);
+    size_t& have = c.smem_set[reinterpret_cast<const void*>(kern)];
+    if (bytes > have) {
+        GWF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        have = bytes;
+    }
+    return GWF_OK;
+}
 
 static int collect_psds(const gwf_psd* const* psds, int npsd, PsdDev* out) {
     if (npsd < 1 || npsd > kMaxPsd) return fail(GWF_ERR_ARG, "number of PSD tables must be in [1, 8]");
+    int dev = 0;
+    GWF_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= kMaxDevices) return fail(GWF_ERR_ARG, "device index out of range");
     for (int i = 0; i < npsd; ++i) {
         if (!psds[i]) return fail(GWF_ERR_ARG, "null PSD handle");
-        out[i] = reinterpret_cast<const PsdHost*>(psds[i])->dev;
+        PsdHost* h = const_cast<PsdHost*>(reinterpret_cast<const PsdHost*>(psds[i]));
+        {
+            std::lock_guard<std::mutex> lock(g_mu);
+            if (!h->tab[dev]) {           // first use on this device
+                GWF_CUDA(cudaMalloc(&h->tab[dev], sizeof(double4) * h->tab_h.size()));
+                GWF_CUDA(cudaMalloc(&h->bucket[dev], sizeof(int) * h->bucket_h.size()));
+                GWF_CUDA(cudaMemcpy(h->tab[dev], h->tab_h.data(), sizeof(double4) * h->tab_h.size(), cudaMemcpyHostToDevice));
+                GWF_CUDA(cudaMemcpy(h->bucket[dev], h->bucket_h.data(), sizeof(int) * h->bucket_h.size(), cudaMemcpyHostToDevice));
+            }
+        }
+        out[i] = h->dev;
+        out[i].tab = h->tab[dev];
+        out[i].bucket = h->bucket[dev];
     }
     return GWF_OK;
 }
 
 template <int MODEL, int NT>
 static int run_fisher(const gwf_model* model, const gwf_detector* dets, int ndet, const gwf_psd* const* psds, int npsd, const EventsDev& ev,
-                      long long n, const gwf_opts* opts, double* fisher, double* snr2, double* snr_derivs, void* ws, size_t ws_bytes, cudaStream_t st) {
+                      long long n, const gwf_opts* opts, const gwf_fisher_out* outp, void* ws, size_t ws_bytes, cudaStream_t st) {
     typedef typename ModelTraits<MODEL, NT>::Rec Rec;
     constexpr int NP = NT + 7, NPACK = NP * (NP + 1) / 2;
+    double* fisher = outp->fisher_packed;
+    double* snr2 = outp->snr2;
+    double* snr_derivs = outp->snr_derivs;
     const size_t rec_bytes = (sizeof(Rec) * (size_t)n + 15) & ~(size_t)15;
     if (ws_bytes < rec_bytes + sizeof(EventAux) * (size_t)n) return fail(GWF_ERR_WORKSPACE, "workspace too small");
     Rec* recs = reinterpret_cast<Rec*>(ws);
     EventAux* aux = reinterpret_cast<EventAux*>(reinterpret_cast<char*>(ws) + rec_bytes);
     ModelCfg cfg = {model->id, model->flags, model->fcutPar, model->fRef};
+    DeviceCtx* ctx = nullptr;
+    if (int rc0 = device_ctx(MODEL == kPhenomD || MODEL == kNRTidalv2, &ctx)) return rc0;
     NetworkDev net;
     PsdDev pd[kMaxPsd];
     int rc = collect_psds(psds, npsd, pd);
@@ -780,13 +889,9 @@ static int run_fisher(const gwf_model* model, const gwf_detector* dets, int ndet
     // does not depend on the size of the batch it is computed in.  TaylorF2 events are too cheap for the repeated staging
     // (measured 4 % slower), so they keep one warp per event.
     int pair = (MODEL != kTaylorF2 && !(opts->flags & GWF_OPT_ONE_WARP_PER_EVENT)) ? 1 : 0;
-    if (pair) {
-        const char* ls = getenv("GWF_PAIR_LOCKSTEP");
-        // GWF_PAIR_LOCKSTEP (experiments): 0 = free-running halves, 1 = barrier per event, 2 = barrier per block of samples
-        const int mode = ls ? ls[0] - '0' : (MODEL == kPhenomHM ? 2 : 1);
-        if (mode >= 1) pair |= 2;
-        if (mode >= 2) pair |= 4;
-    }
+    // lock step of the two halves: a named barrier per event (bit 1), for IMRPhenomHM per block of samples (bit 2) -- see the
+    // comment at the end of fisher_kernel's event loop for the measurements behind the choice
+    if (pair) pair |= (MODEL == kPhenomHM) ? 6 : 2;
     const int lin = (opts->flags & GWF_OPT_LIN_GRID) ? 1 : 0;
     const int pb = 128;
     if (!(opts->flags & GWF_OPT_REUSE_WORKSPACE)) {
@@ -795,19 +900,17 @@ static int run_fisher(const gwf_model* model, const gwf_detector* dets, int ndet
         ap.out = aux;
         for (int g = 0; g < kMaxGroups; ++g) ap.fmax[g] = net.group_fmax[g];
         ap.res = opts->res; ap.lin = lin; ap.stride = pair ? 64 : 32;
-        prologue_kernel<MODEL, NT><<<dim3((unsigned)((n + pb - 1) / pb), (MODEL == kPhenomD || MODEL == kNRTidalv2) ? 2 : 1), pb, 0, st>>>(ev, n, cfg, opts->flags, g_qnm, gi, recs, nullptr, ap);
+        prologue_kernel<MODEL, NT><<<dim3((unsigned)((n + pb - 1) / pb), (MODEL == kPhenomD || MODEL == kNRTidalv2) ? 2 : 1), pb, 0, st>>>(ev, n, cfg, opts->flags, ctx->qnm, gi, recs, nullptr, ap, outp->status);
         GWF_CUDA(cudaGetLastError());
-    }
-    int dev = 0, sms = 0;
-    GWF_CUDA(cudaGetDevice(&dev));
-    GWF_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    } else if (outp->status) GWF_CUDA(cudaMemsetAsync(outp->status, 0, sizeof(int) * (size_t)n, st));   // the input bits are the prologue's
+    const int sms = ctx->sms;
     // dynamic shared memory: per-warp staging blocks, then the PSD windows (as many tables as fit in 227 KB)
     const size_t ws_bytes_smem = sizeof(FisherSmem<Rec, typename PointFns<MODEL, NT>::Extra>) * kWarpsPerCta;
-    const size_t shmem = plan_psd_cache(net, ws_bytes_smem, kSmemLimit);
+    size_t shmem_pass = plan_psd_cache(net, ws_bytes_smem, kSmemLimit);
     // the unrolled, shape-specialised form (measured per 1e4 events: IMRPhenomD ET+2CE 1.55 -> 1.06 ms, NRTidalv2 3.73 -> 2.26 ms,
     // TaylorF2 ETSL 0.66 -> 0.55 ms; without the compile-time shape TaylorF2's unrolled loop spilled and lost 7-20 %)
     constexpr bool kHasFast = PointFns<MODEL, NT>::kHasFast;
-    typedef void (*Kern)(const Rec*, const EventAux*, EventsDev, long long, int, int, ModelCfg, const NetworkDev, double*, double*, double*, int);
+    typedef void (*Kern)(const Rec*, const EventAux*, EventsDev, long long, int, int, ModelCfg, const NetworkDev, const FisherOut, int);
     // IMRPhenomHM needs extra accumulators for the SNR derivatives (its own instantiation); the other models rebuild them
     // from the compact Gram whenever the output pointer is given
     constexpr bool kSdKernel = MODEL == kPhenomHM;
@@ -831,21 +934,27 @@ static int run_fisher(const gwf_model* model, const gwf_detector* dets, int ndet
         if (opts->per_arm) {
             rc = build_network(dets, ndet, pd, npsd, pass, false, net);
             if (rc) return rc;
-            plan_psd_cache(net, ws_bytes_smem, kSmemLimit);
+            // a table that found no room next to the others in the all-arms plan can fit on its own in a per-arm pass:
+            // the launch is sized for THIS pass's plan
+            shmem_pass = plan_psd_cache(net, ws_bytes_smem, kSmemLimit);
             fast = allow_fast ? plan_fast(net) : 0;
         }
-        double* o_f = fisher + (size_t)pass * n * NPACK;
-        double* o_s = snr2 ? snr2 + (size_t)pass * n : nullptr;
-        double* o_d = snr_derivs ? snr_derivs + (size_t)pass * n * NP : nullptr;
+        FisherOut fo;
+        fo.fisher = fisher + (size_t)pass * n * NPACK;
+        fo.snr2 = snr2 ? snr2 + (size_t)pass * n : nullptr;
+        fo.snr2_integ = outp->snr2_integ ? outp->snr2_integ + (size_t)pass * n : nullptr;
+        fo.snr_derivs = snr_derivs ? snr_derivs + (size_t)pass * n * NP : nullptr;
+        fo.status = outp->status;
         if (pair) {
             // the two halves of an event add their contributions
-            GWF_CUDA(cudaMemsetAsync(o_f, 0, sizeof(double) * (size_t)n * NPACK, st));
-            if (o_s) GWF_CUDA(cudaMemsetAsync(o_s, 0, sizeof(double) * (size_t)n, st));
-            if (o_d) GWF_CUDA(cudaMemsetAsync(o_d, 0, sizeof(double) * (size_t)n * NP, st));
+            GWF_CUDA(cudaMemsetAsync(fo.fisher, 0, sizeof(double) * (size_t)n * NPACK, st));
+            if (fo.snr2) GWF_CUDA(cudaMemsetAsync(fo.snr2, 0, sizeof(double) * (size_t)n, st));
+            if (fo.snr2_integ) GWF_CUDA(cudaMemsetAsync(fo.snr2_integ, 0, sizeof(double) * (size_t)n, st));
+            if (fo.snr_derivs) GWF_CUDA(cudaMemsetAsync(fo.snr_derivs, 0, sizeof(double) * (size_t)n * NP, st));
         }
         const Kern kern = pick(fast, fast_shape(net));
-        GWF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem));
-        kern<<<grid, kFisherThreads, shmem, st>>>(recs, aux, ev, n, opts->res, lin, cfg, net, o_f, o_s, o_d, pair);
+        if (int rcs = ensure_smem(*ctx, kern, shmem_pass)) return rcs;
+        kern<<<grid, kFisherThreads, shmem_pass, st>>>(recs, aux, ev, n, opts->res, lin, cfg, net, fo, pair);
         GWF_CUDA(cudaGetLastError());
     }
     return GWF_OK;
@@ -859,6 +968,8 @@ static int run_derivs(const gwf_model* model, const gwf_detector* dets, int ndet
     if (ws_bytes < sizeof(Rec) * (size_t)n) return fail(GWF_ERR_WORKSPACE, "workspace too small");
     Rec* recs = reinterpret_cast<Rec*>(ws);
     ModelCfg cfg = {model->id, model->flags, model->fcutPar, model->fRef};
+    DeviceCtx* ctx = nullptr;
+    if (int rc0 = device_ctx(MODEL == kPhenomD || MODEL == kNRTidalv2, &ctx)) return rc0;
     NetworkDev net;
     PsdDev pd[kMaxPsd];
     int rc = collect_psds(psds, npsd, pd);
@@ -869,14 +980,12 @@ static int run_derivs(const gwf_model* model, const gwf_detector* dets, int ndet
     gi.n = net.ngroups;
     for (int g = 0; g < kMaxGroups; ++g) gi.fmin[g] = net.group_fmin[g];
     const int pb = 128;
-    prologue_kernel<MODEL, NT><<<(unsigned)((n + pb - 1) / pb), pb, 0, st>>>(ev, n, cfg, opts->flags, g_qnm, gi, recs);
+    prologue_kernel<MODEL, NT><<<(unsigned)((n + pb - 1) / pb), pb, 0, st>>>(ev, n, cfg, opts->flags, ctx->qnm, gi, recs);
     GWF_CUDA(cudaGetLastError());
-    int dev = 0, sms = 0;
-    GWF_CUDA(cudaGetDevice(&dev));
-    GWF_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int sms = ctx->sms;
     const size_t shmem = sizeof(WarpSmem<Rec, typename PointFns<MODEL, NT>::Extra>) * kWarpsPerCta;
     auto kern = derivs_kernel<MODEL, NT>;
-    GWF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem));
+    if (int rcs = ensure_smem(*ctx, kern, shmem)) return rcs;
     const long long want = (n + kWarpsPerCta - 1) / kWarpsPerCta;
     const unsigned grid = (unsigned)std::min<long long>(want, (long long)sms * 2);
     const int lin = (opts->flags & GWF_OPT_LIN_GRID) ? 1 : 0;
@@ -899,6 +1008,8 @@ static int run_strain(const gwf_model* model, const gwf_detector* dets, int ndet
     if (ws_bytes < sizeof(Rec) * (size_t)n) return fail(GWF_ERR_WORKSPACE, "workspace too small");
     Rec* recs = reinterpret_cast<Rec*>(ws);
     ModelCfg cfg = {model->id, model->flags, model->fcutPar, model->fRef};
+    DeviceCtx* ctx = nullptr;
+    if (int rc0 = device_ctx(MODEL == kPhenomD || MODEL == kNRTidalv2, &ctx)) return rc0;
     NetworkDev net;
     PsdDev pd[kMaxPsd];
     int rc = collect_psds(psds, npsd, pd);
@@ -910,14 +1021,12 @@ static int run_strain(const gwf_model* model, const gwf_detector* dets, int ndet
     for (int g = 0; g < kMaxGroups; ++g) gi.fmin[g] = net.group_fmin[g];
     const int pb = 128;
     // GWstrain is handed the dict entries as they are (no Fisher re-parametrisation, signal.py:1871)
-    prologue_kernel<MODEL, 4><<<(unsigned)((n + pb - 1) / pb), pb, 0, st>>>(ev, n, cfg, 0, g_qnm, gi, recs);
+    prologue_kernel<MODEL, 4><<<(unsigned)((n + pb - 1) / pb), pb, 0, st>>>(ev, n, cfg, 0, ctx->qnm, gi, recs);
     GWF_CUDA(cudaGetLastError());
-    int dev = 0, sms = 0;
-    GWF_CUDA(cudaGetDevice(&dev));
-    GWF_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int sms = ctx->sms;
     const size_t shmem = sizeof(WarpSmem<Rec, typename PointFns<MODEL, 4>::Extra>) * kWarpsPerCta;
     auto kern = strain_kernel<MODEL>;
-    GWF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem));
+    if (int rcs = ensure_smem(*ctx, kern, shmem)) return rcs;
     const long long want = (n + kWarpsPerCta - 1) / kWarpsPerCta;
     const unsigned grid = (unsigned)std::min<long long>(want, (long long)sms * 2);
     const int lin = (opts->flags & GWF_OPT_LIN_GRID) ? 1 : 0;
@@ -941,6 +1050,8 @@ static int run_snr(const gwf_model* model, const gwf_detector* dets, int ndet, c
     Rec* recs = reinterpret_cast<Rec*>(ws);
     EventAux* aux = reinterpret_cast<EventAux*>(reinterpret_cast<char*>(ws) + rec_bytes);
     ModelCfg cfg = {model->id, model->flags, model->fcutPar, model->fRef};
+    DeviceCtx* ctx = nullptr;
+    if (int rc0 = device_ctx(MODEL == kPhenomD || MODEL == kNRTidalv2, &ctx)) return rc0;
     NetworkDev net;
     PsdDev pd[kMaxPsd];
     int rc = collect_psds(psds, npsd, pd);
@@ -958,11 +1069,9 @@ static int run_snr(const gwf_model* model, const gwf_detector* dets, int ndet, c
     for (int g = 0; g < kMaxGroups; ++g) ap.fmax[g] = net.group_fmax[g];
     constexpr int kSnrSplit = SnrMap<MODEL>::kSplit, kSnrGroups = SnrMap<MODEL>::kGroups;
     ap.res = opts->res; ap.lin = lin; ap.stride = 32 * kSnrSplit;
-    prologue_kernel<MODEL, 4><<<dim3((unsigned)((n + pb - 1) / pb), (MODEL == kPhenomD || MODEL == kNRTidalv2) ? 2 : 1), pb, 0, st>>>(ev, n, cfg, 0, g_qnm, gi, recs, nullptr, ap);
+    prologue_kernel<MODEL, 4><<<dim3((unsigned)((n + pb - 1) / pb), (MODEL == kPhenomD || MODEL == kNRTidalv2) ? 2 : 1), pb, 0, st>>>(ev, n, cfg, 0, ctx->qnm, gi, recs, nullptr, ap);
     GWF_CUDA(cudaGetLastError());
-    int dev = 0, sms = 0;
-    GWF_CUDA(cudaGetDevice(&dev));
-    GWF_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int sms = ctx->sms;
     const size_t base = sizeof(WarpSmem<Rec, typename PointFns<MODEL, 4>::Extra>) * kSnrGroups + sizeof(double) * net.narms * (32 * kSnrWarps + kSnrWarps);
     const size_t shmem = plan_psd_cache(net, base, kSmemLimit);
     constexpr bool kHasFast = PointFns<MODEL, 4>::kHasFast;
@@ -976,7 +1085,7 @@ static int run_snr(const gwf_model* model, const gwf_detector* dets, int ndet, c
         return fast == 2 ? (Kern)snr_kernel<MODEL, kHasFast ? 2 : 0> : (Kern)snr_kernel<MODEL, kHasFast ? 1 : 0>;
     };
     const Kern kern = pick(fast_shape(net));
-    GWF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem));
+    if (int rcs = ensure_smem(*ctx, kern, shmem)) return rcs;
     const long long want = (n + kSnrGroups - 1) / kSnrGroups;
     const unsigned grid = (unsigned)std::min<long long>(want, (long long)sms);
     kern<<<grid, kSnrThreads, shmem, st>>>(recs, aux, ev, n, opts->res, lin, cfg, net, net.narms, snr2_arm);
@@ -993,6 +1102,8 @@ static int run_waveform(const gwf_model* model, const EventsDev& ev, long long n
     Rec* recs = reinterpret_cast<Rec*>(ws);
     double* fmin_ev = reinterpret_cast<double*>(reinterpret_cast<char*>(ws) + rec_bytes);
     ModelCfg cfg = {model->id, model->flags, model->fcutPar, model->fRef};
+    DeviceCtx* ctx = nullptr;
+    if (int rc0 = device_ctx(MODEL == kPhenomD || MODEL == kNRTidalv2, &ctx)) return rc0;
     GroupInfo gi;
     gi.n = 1;
     for (int g = 0; g < kMaxGroups; ++g) gi.fmin[g] = 1.0;
@@ -1004,14 +1115,12 @@ static int run_waveform(const gwf_model* model, const EventsDev& ev, long long n
         GWF_CUDA(cudaGetLastError());
         fmin_arg = fmin_ev;
     }
-    prologue_kernel<MODEL, 4><<<pg, pb, 0, st>>>(ev, n, cfg, 0, g_qnm, gi, recs, fmin_arg);
+    prologue_kernel<MODEL, 4><<<pg, pb, 0, st>>>(ev, n, cfg, 0, ctx->qnm, gi, recs, fmin_arg);
     GWF_CUDA(cudaGetLastError());
-    int dev = 0, sms = 0;
-    GWF_CUDA(cudaGetDevice(&dev));
-    GWF_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int sms = ctx->sms;
     const size_t shmem = sizeof(WaveBlk<Rec>) * kWarpsPerCta;
     auto kern = waveform_kernel<MODEL>;
-    GWF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem));
+    if (int rcs = ensure_smem(*ctx, kern, shmem)) return rcs;
     const long long want = (n + kWarpsPerCta - 1) / kWarpsPerCta;
     const unsigned grid = (unsigned)std::min<long long>(want, (long long)sms * 4);
     kern<<<grid, kFisherThreads, shmem, st>>>(recs, ev, n, f, res, f2d, cfg, phi, ampl, tau, hphc, fcut);
@@ -1056,43 +1165,37 @@ size_t gwf_workspace_bytes(const gwf_model* model, int64_t n) {
 
 int gwf_psd_create(const double* f, const double* S, int32_t n, gwf_psd** out) {
     if (!out) return fail(GWF_ERR_ARG, "gwf_psd_create: null output");
-    std::vector<double4> tab;
-    std::vector<int> bucket;
     PsdHost* h = new PsdHost;
-    int rc = build_psd_tables(f, S, n, tab, bucket, h->dev);
+    int rc = build_psd_tables(f, S, n, h->tab_h, h->bucket_h, h->dev);
     if (rc) { delete h; return rc; }
-    if (cudaMalloc(&h->tab, sizeof(double4) * tab.size()) != cudaSuccess || cudaMalloc(&h->bucket, sizeof(int) * bucket.size()) != cudaSuccess) {
-        delete h;
-        return fail(GWF_ERR_CUDA, "gwf_psd_create: cudaMalloc failed");
-    }
-    GWF_CUDA(cudaMemcpy(h->tab, tab.data(), sizeof(double4) * tab.size(), cudaMemcpyHostToDevice));
-    GWF_CUDA(cudaMemcpy(h->bucket, bucket.data(), sizeof(int) * bucket.size(), cudaMemcpyHostToDevice));
-    h->dev.tab = h->tab;
-    h->dev.bucket = h->bucket;
-    *out = reinterpret_cast<gwf_psd*>(h);
+    *out = reinterpret_cast<gwf_psd*>(h);     // device copies are made by the first call that uses the handle on a device
     return GWF_OK;
 }
 
 void gwf_psd_destroy(gwf_psd* psd) {
     if (!psd) return;
     PsdHost* h = reinterpret_cast<PsdHost*>(psd);
-    cudaFree(h->tab);
-    cudaFree(h->bucket);
+    int cur = 0;
+    cudaGetDevice(&cur);
+    for (int d = 0; d < kMaxDevices; ++d)
+        if (h->tab[d]) {
+            cudaSetDevice(d);
+            cudaFree(h->tab[d]);
+            cudaFree(h->bucket[d]);
+        }
+    cudaSetDevice(cur);
     delete h;
 }
 
 int gwf_set_qnm_tables(const double* a, const double* fring, const double* fdamp, int32_t n) {
     if (!a || !fring || !fdamp || n < 2) return fail(GWF_ERR_ARG, "gwf_set_qnm_tables: bad arguments");
-    double* buf = nullptr;
-    GWF_CUDA(cudaMalloc(&buf, sizeof(double) * 3 * n));
-    GWF_CUDA(cudaMemcpy(buf, a, sizeof(double) * n, cudaMemcpyHostToDevice));
-    GWF_CUDA(cudaMemcpy(buf + n, fring, sizeof(double) * n, cudaMemcpyHostToDevice));
-    GWF_CUDA(cudaMemcpy(buf + 2 * n, fdamp, sizeof(double) * n, cudaMemcpyHostToDevice));
-    if (g_qnm.a) cudaFree(const_cast<double*>(g_qnm.a));
-    g_qnm.a = buf;
-    g_qnm.fring = buf + n;
-    g_qnm.fdamp = buf + 2 * n;
-    g_qnm.n = n;
+    std::lock_guard<std::mutex> lock(g_mu);
+    g_qnm_host.resize(3 * (size_t)n);
+    std::memcpy(g_qnm_host.data(), a, sizeof(double) * n);
+    std::memcpy(g_qnm_host.data() + n, fring, sizeof(double) * n);
+    std::memcpy(g_qnm_host.data() + 2 * n, fdamp, sizeof(double) * n);
+    g_qnm_n = n;
+    ++g_qnm_version;                           // every device re-uploads on its next call
     return GWF_OK;
 }
 
@@ -1103,17 +1206,16 @@ static int check_common(const gwf_model* model, const gwf_detector* dets, const 
     if (opts->res < 2) return fail(GWF_ERR_ARG, "res must be at least 2");
     for (int i = 0; i < 11; ++i)
         if (!events->p[i] && n > 0) return fail(GWF_ERR_ARG, "missing event parameter array");
-    if ((model->id == GWF_IMRPHENOMD || model->id == GWF_IMRPHENOMD_NRTIDALV2) && !g_qnm.a)
+    if ((model->id == GWF_IMRPHENOMD || model->id == GWF_IMRPHENOMD_NRTIDALV2) && g_qnm_n == 0)
         return fail(GWF_ERR_ARG, "QNM tables not set (gwf_set_qnm_tables)");
     return GWF_OK;
 }
 
 int gwf_fisher_ex(const gwf_model* model, const gwf_detector* dets, int32_t ndet, const gwf_psd* const* psds, int32_t npsd, const gwf_events* events,
-                  int64_t n, const gwf_opts* opts, double* fisher_packed, double* snr2, double* snr_derivs, void* workspace, size_t workspace_bytes,
-                  void* stream) {
+                  int64_t n, const gwf_opts* opts, const gwf_fisher_out* out, void* workspace, size_t workspace_bytes, void* stream) {
     int rc = check_common(model, dets, psds, events, n, opts);
     if (rc) return rc;
-    if (!fisher_packed) return fail(GWF_ERR_ARG, "null output");
+    if (!out || !out->fisher_packed) return fail(GWF_ERR_ARG, "null output");
     if (n == 0) return GWF_OK;
     EventsDev ev;
     for (int i = 0; i < GWF_NPARAM_IN; ++i) ev.p[i] = events->p[i];
@@ -1124,19 +1226,19 @@ int gwf_fisher_ex(const gwf_model* model, const gwf_detector* dets, int32_t ndet
             if (ecc && !ev.p[15]) return fail(GWF_ERR_ARG, "eccentric model needs ecc");
             if (model->flags & GWF_MODEL_TIDAL) {
                 if (!ev.p[11] || !ev.p[12]) return fail(GWF_ERR_ARG, "tidal model needs Lambda1, Lambda2");
-                if (ecc) return run_fisher<kTaylorF2, 7>(model, dets, ndet, psds, npsd, ev, n, opts, fisher_packed, snr2, snr_derivs, workspace, workspace_bytes, st);
-                return run_fisher<kTaylorF2, 6>(model, dets, ndet, psds, npsd, ev, n, opts, fisher_packed, snr2, snr_derivs, workspace, workspace_bytes, st);
+                if (ecc) return run_fisher<kTaylorF2, 7>(model, dets, ndet, psds, npsd, ev, n, opts, out, workspace, workspace_bytes, st);
+                return run_fisher<kTaylorF2, 6>(model, dets, ndet, psds, npsd, ev, n, opts, out, workspace, workspace_bytes, st);
             }
-            if (ecc) return run_fisher<kTaylorF2, 5>(model, dets, ndet, psds, npsd, ev, n, opts, fisher_packed, snr2, snr_derivs, workspace, workspace_bytes, st);
-            return run_fisher<kTaylorF2, 4>(model, dets, ndet, psds, npsd, ev, n, opts, fisher_packed, snr2, snr_derivs, workspace, workspace_bytes, st);
+            if (ecc) return run_fisher<kTaylorF2, 5>(model, dets, ndet, psds, npsd, ev, n, opts, out, workspace, workspace_bytes, st);
+            return run_fisher<kTaylorF2, 4>(model, dets, ndet, psds, npsd, ev, n, opts, out, workspace, workspace_bytes, st);
         }
         case GWF_IMRPHENOMD:
-            return run_fisher<kPhenomD, 4>(model, dets, ndet, psds, npsd, ev, n, opts, fisher_packed, snr2, snr_derivs, workspace, workspace_bytes, st);
+            return run_fisher<kPhenomD, 4>(model, dets, ndet, psds, npsd, ev, n, opts, out, workspace, workspace_bytes, st);
         case GWF_IMRPHENOMD_NRTIDALV2:
             if (!ev.p[11] || !ev.p[12]) return fail(GWF_ERR_ARG, "tidal model needs Lambda1, Lambda2");
-            return run_fisher<kNRTidalv2, 6>(model, dets, ndet, psds, npsd, ev, n, opts, fisher_packed, snr2, snr_derivs, workspace, workspace_bytes, st);
+            return run_fisher<kNRTidalv2, 6>(model, dets, ndet, psds, npsd, ev, n, opts, out, workspace, workspace_bytes, st);
         case GWF_IMRPHENOMHM:
-            return run_fisher<kPhenomHM, 4>(model, dets, ndet, psds, npsd, ev, n, opts, fisher_packed, snr2, snr_derivs, workspace, workspace_bytes, st);
+            return run_fisher<kPhenomHM, 4>(model, dets, ndet, psds, npsd, ev, n, opts, out, workspace, workspace_bytes, st);
         default:
             return fail(GWF_ERR_UNSUPPORTED, "model not built yet");
     }
@@ -1144,7 +1246,11 @@ int gwf_fisher_ex(const gwf_model* model, const gwf_detector* dets, int32_t ndet
 
 int gwf_fisher(const gwf_model* model, const gwf_detector* dets, int32_t ndet, const gwf_psd* const* psds, int32_t npsd, const gwf_events* events,
                int64_t n, const gwf_opts* opts, double* fisher_packed, double* snr2, void* workspace, size_t workspace_bytes, void* stream) {
-    return gwf_fisher_ex(model, dets, ndet, psds, npsd, events, n, opts, fisher_packed, snr2, nullptr, workspace, workspace_bytes, stream);
+    gwf_fisher_out out;
+    std::memset(&out, 0, sizeof(out));
+    out.fisher_packed = fisher_packed;
+    out.snr2 = snr2;
+    return gwf_fisher_ex(model, dets, ndet, psds, npsd, events, n, opts, &out, workspace, workspace_bytes, stream);
 }
 
 int gwf_strain_derivs(const gwf_model* model, const gwf_detector* dets, int32_t ndet, const gwf_psd* const* psds, int32_t npsd, const gwf_events* events,
@@ -1241,12 +1347,22 @@ int gwf_overlap(const double* h1, const double* h2, const double* fcut, int64_t 
     return GWF_OK;
 }
 
-int gwf_unpack_fisher(const double* packed, int64_t n, int32_t nP, double* full, void* stream) {
-    if (!packed || !full || nP < 1) return fail(GWF_ERR_ARG, "gwf_unpack_fisher: bad arguments");
+int gwf_unpack_fisher_ld(const double* packed, int64_t n, int32_t nP, double* full, int64_t ld, void* stream) {
+    if (!packed || !full || nP < 1 || nP > 14 || ld < n) return fail(GWF_ERR_ARG, "gwf_unpack_fisher: bad arguments");
     if (n == 0) return GWF_OK;
-    const int tb = 256;
-    unpack_kernel<<<(unsigned)((n + tb - 1) / tb), tb, 0, reinterpret_cast<cudaStream_t>(stream)>>>(packed, n, nP, full);
+    unpack_kernel<<<(unsigned)((n + 31) / 32), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(packed, n, nP, full, ld);
     GWF_CUDA(cudaGetLastError());
+    return GWF_OK;
+}
+
+int gwf_unpack_fisher(const double* packed, int64_t n, int32_t nP, double* full, void* stream) {
+    return gwf_unpack_fisher_ld(packed, n, nP, full, n, stream);
+}
+
+int gwf_copy_2d(void* dst, size_t dst_pitch, const void* src, size_t src_pitch, size_t width_bytes, size_t height, void* stream) {
+    if (!dst || !src) return fail(GWF_ERR_ARG, "gwf_copy_2d: null pointer");
+    if (width_bytes == 0 || height == 0) return GWF_OK;
+    GWF_CUDA(cudaMemcpy2DAsync(dst, dst_pitch, src, src_pitch, width_bytes, height, cudaMemcpyDefault, reinterpret_cast<cudaStream_t>(stream)));
     return GWF_OK;
 }
 
@@ -1288,7 +1404,7 @@ int gwf_waveform(const gwf_model* model, const gwf_events* events, int64_t n, co
     if (n < 0 || res < 0 || (res > 0 && !f)) return fail(GWF_ERR_ARG, "gwf_waveform: bad grid");
     for (int i = 0; i < 11; ++i)
         if (!events->p[i] && n > 0) return fail(GWF_ERR_ARG, "missing event parameter array");
-    if ((model->id == GWF_IMRPHENOMD || model->id == GWF_IMRPHENOMD_NRTIDALV2) && !g_qnm.a) return fail(GWF_ERR_ARG, "QNM tables not set (gwf_set_qnm_tables)");
+    if ((model->id == GWF_IMRPHENOMD || model->id == GWF_IMRPHENOMD_NRTIDALV2) && g_qnm_n == 0) return fail(GWF_ERR_ARG, "QNM tables not set (gwf_set_qnm_tables)");
     if (hphc_out && model->id != GWF_IMRPHENOMHM) return fail(GWF_ERR_UNSUPPORTED, "hphc is only defined for IMRPhenomHM");
     if (n == 0) return GWF_OK;
     EventsDev ev;

@@ -59,10 +59,15 @@ static int build_psd_tables(const double* f, const double* S, int n, std::vector
     return GWF_OK;
 }
 
+// A PSD handle keeps the host copy of its tables and uploads them to a device the first time a call runs there, so one
+// process can drive several devices with the same handles (SURVEY.md 8(b) threading contract).
+constexpr int kMaxDevices = 64;
 struct PsdHost {
-    double4* tab = nullptr;
-    int* bucket = nullptr;
-    PsdDev dev;
+    std::vector<double4> tab_h;
+    std::vector<int> bucket_h;
+    double4* tab[kMaxDevices] = {};
+    int* bucket[kMaxDevices] = {};
+    PsdDev dev;      // descriptor with null table pointers; collect_psds fills in the current device's
 };
 
 static int model_nt(const gwf_model& m) {

@@ -16,6 +16,7 @@ class DetNet(object):
         # signals: {'detector_name': GWSignal}
         self.signals = signals
         self.verbose = verbose
+        self.last_status = None
 
     def _clear_cache(self):
         for d in self.signals.keys():
@@ -31,8 +32,12 @@ class DetNet(object):
                 print('\nSeed for detector %s is %s' % (d, self.signals[d].seedUse))
 
     def _fusable(self):
+        """one fused launch needs a common waveform object and a network inside the C side's limits (8 detectors, 16 arms,
+        4 distinct (fmin, fmax) pairs); anything else runs one launch per detector"""
         sigs = list(self.signals.values())
-        return all(s.wf_model is sigs[0].wf_model for s in sigs) and len(sigs) <= 8
+        groups = {(float(s.fmin), None if s.fmax is None else float(s.fmax)) for s in sigs}
+        arms = sum(s._narms() for s in sigs)
+        return all(s.wf_model is sigs[0].wf_model for s in sigs) and len(sigs) <= 8 and arms <= 16 and len(groups) <= 4
 
     # ------------------------------------------------------------------ SNR
     def SNR(self, evParams, res=1000, return_all=False):
@@ -70,11 +75,34 @@ class DetNet(object):
         return net_snr
 
     # ------------------------------------------------------------------ Fisher
-    def FisherMatr(self, evParams, return_all=False, return_derivatives=False, return_SNR_derivatives=False, **kwargs):
-        """Total Fisher matrix, shape (nParams, nParams, N); with ``return_all`` a dict per detector/arm plus 'net'."""
+    def FisherMatr(self, evParams, return_all=False, return_derivatives=False, return_SNR_derivatives=False, return_SNR=False, **kwargs):
+        """Total Fisher matrix, shape (nParams, nParams, N); with ``return_all`` a dict per detector/arm plus 'net'.
+
+        ``return_SNR=True`` (an addition to the reference's keywords): returns ``(F, SNR)`` where ``SNR`` is what ``self.SNR`` returns
+        for the same events and ``res`` -- taken from the same fused launch when the network is fusable and no per-arm output or duty
+        factor is involved (the Fisher kernel integrates |h|^2/Sn anyway), otherwise from a separate ``SNR`` call.  After the call
+        ``self.last_status`` holds the per-event status words (``_capi.GWF_EV_*``; 0 = clean)."""
         utils.check_evparams(evParams)
         names = list(self.signals.keys())
         sigs = [self.signals[d] for d in names]
+        if return_SNR:
+            fused = self._fusable() and not (return_all or return_derivatives or return_SNR_derivatives) and \
+                all(s.DutyFactor is None for s in sigs) and not (kwargs.get('df') is not None and kwargs.get('res', 1000) is None)
+            if not fused:
+                snr = self.SNR(evParams, res=kwargs.get('res', 1000) or 1000, return_all=return_all)
+                return self.FisherMatr(evParams, return_all=return_all, return_derivatives=return_derivatives,
+                                       return_SNR_derivatives=return_SNR_derivatives, **kwargs), snr
+            for s in sigs:
+                s._prepare_snr(evParams)                      # the dict bookkeeping DetNet.SNR would have done first
+            kw = dict(kwargs)
+            res = kw.pop('res', 1000)
+            lambdas = None
+            for s in sigs:
+                lambdas, res_s = s._prepare_fisher(evParams, res, kw.get('df'), kw.get('computeDerivFinDiff', False), False, False)
+            F, s2, _ = _sig.hot_fisher(sigs, evParams, lambdas, res_s, kw.get('spacing', 'geom'), kw.get('use_m1m2', False),
+                                       kw.get('use_chi1chi2', True), False, want_snr_integ=True)
+            self.last_status = _sig._engine.state().last_status
+            return F[0], onp.sqrt(s2[0])
         if return_derivatives or return_SNR_derivatives:
             # network.py:124-152: per-detector calls, every arm separately; 'net' of the SNR derivatives = sum over arms / network SNR
             SNRs_net = kwargs.pop('SNRs', None)
@@ -143,6 +171,7 @@ class DetNet(object):
                 print('Computing Fisher for %s...' % d)
         per_arm = return_all or duty
         F, _, _ = _sig.hot_fisher(sigs, evParams, lambdas, res_s, spacing, use_m1m2, use_chi1chi2, per_arm)
+        self.last_status = _sig._engine.state().last_status
         if self.verbose:
             print('Done.')
         if not per_arm:

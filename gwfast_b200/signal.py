@@ -98,25 +98,18 @@ def hot_strain_derivs(signals, evParams, lambdas, res, spacing, use_m1m2, use_ch
     return D if rows is None else onp.ascontiguousarray(D[:, rows])
 
 
-def hot_fisher(signals, evParams, lambdas, res, spacing, use_m1m2, use_chi1chi2, per_arm, want_snr_derivs=False):
-    """Fisher matrices for a list of GWSignal sharing one waveform model: ONE prologue + one launch per block."""
+def hot_fisher(signals, evParams, lambdas, res, spacing, use_m1m2, use_chi1chi2, per_arm, want_snr_derivs=False, want_snr_integ=False):
+    """Fisher matrices for a list of GWSignal sharing one waveform model: ONE prologue + one launch per block.  With
+    ``want_snr_integ`` the second return value is the integral SNRInteg forms for the same arms (the fused SNR + Fisher launch)."""
     wf = signals[0].wf_model
     n = _num_events(evParams)
-    flags = 0
-    if use_m1m2:
-        flags |= K.GWF_OPT_M1M2
-    if not use_chi1chi2:
-        flags |= K.GWF_OPT_CHIS_CHIA
-    if spacing == 'lin':
-        flags |= K.GWF_OPT_LIN_GRID
-    elif spacing != 'geom':
-        raise ValueError("spacing has to be 'geom' or 'lin'")
+    flags = _fisher_flags(spacing, use_m1m2, use_chi1chi2)
     dets, handles = [], []
     for s in signals:
         dets.append(s._detector_struct(len(handles)))
         handles.append(s._psd_handle())
     F, snr2, io = _engine.fisher(wf._descriptor(evParams), dets, handles, _engine_events(wf, evParams, lambdas, use_m1m2), n, res, flags, per_arm,
-                                 want_snr_derivs=want_snr_derivs)
+                                 want_snr_derivs=want_snr_derivs, want_snr_integ=want_snr_integ)
     rows = getattr(wf, '_engine_rows', None)
     if rows is not None:
         # NewtInspiral: the engine's eta / spin rows are identically zero and are not part of the model's 8 parameters
@@ -169,6 +162,7 @@ class GWSignal(object):
         self.seedUse = onp.random.randint(2 ** 32 - 1, size=1)
         self.jitCompileDerivs = jitCompileDerivs   # accepted for compatibility; there is nothing to jit
         self._psd = None
+        self.last_status = None                    # per-event status words of the last FisherMatr call (_capi.GWF_EV_*)
 
     # ------------------------------------------------------------------ engine hooks
     def _psd_handle(self):
@@ -252,11 +246,26 @@ class GWSignal(object):
 
     def FisherMatr(self, evParams, res=1000, df=None, spacing='geom', use_m1m2=False, use_chi1chi2=True, use_prec_ang=True,
                    computeDerivFinDiff=False, computeAnalyticalDeriv=True, return_all=False, return_derivatives=False,
-                   return_SNR_derivatives=False, **kwargs):
+                   return_SNR_derivatives=False, return_SNR=False, **kwargs):
         """Fisher matrix, shape (nParams, nParams, N) (list per arm with ``return_all``); signal.py:782-1098.
 
         ``computeAnalyticalDeriv`` is accepted for compatibility: the engine's derivatives are exact either way.
+        ``return_SNR=True`` (an addition to the reference's keywords) returns ``(F, SNR)`` with the SNR ``SNRInteg`` would give for
+        the same events, from the same launch -- the Fisher kernel already integrates |h|^2/Sn, so ``SNRInteg`` followed by
+        ``FisherMatr`` costs one launch instead of two.  After the call ``self.last_status`` holds the per-event status words
+        (``_capi.GWF_EV_*``; 0 = clean).
         """
+        if return_SNR:
+            if return_all or return_derivatives or return_SNR_derivatives or self.DutyFactor is not None:
+                snr = self.SNRInteg(evParams, res=res if res is not None else 1000)
+                return self.FisherMatr(evParams, res=res, df=df, spacing=spacing, use_m1m2=use_m1m2, use_chi1chi2=use_chi1chi2,
+                                       computeDerivFinDiff=computeDerivFinDiff, return_all=return_all, return_derivatives=return_derivatives,
+                                       return_SNR_derivatives=return_SNR_derivatives, **kwargs), snr
+            self._prepare_snr(evParams)                       # the dict bookkeeping SNRInteg would have done first
+            lambdas, res = self._prepare_fisher(evParams, res, df, computeDerivFinDiff, False, False)
+            F, s2, _ = hot_fisher([self], evParams, lambdas, res, spacing, use_m1m2, use_chi1chi2, False, want_snr_integ=True)
+            self.last_status = _engine.state().last_status
+            return F[0], onp.sqrt(s2[0])
         if self.DutyFactor is not None:
             onp.random.seed(self.seedUse)
         lambdas, res = self._prepare_fisher(evParams, res, df, computeDerivFinDiff, return_derivatives, return_SNR_derivatives)
@@ -277,6 +286,7 @@ class GWSignal(object):
             return allF, [onp.ascontiguousarray(sd[i].T) for i in range(sd.shape[0])]
         per_arm = return_all or (self.DutyFactor is not None)
         F, _, _ = hot_fisher([self], evParams, lambdas, res, spacing, use_m1m2, use_chi1chi2, per_arm)
+        self.last_status = _engine.state().last_status
         if self.DutyFactor is not None:
             masks = self._duty_masks(n)
             F = F * onp.array(masks)[:, None, None, :]

@@ -122,12 +122,28 @@ int gwf_fisher(const gwf_model* model, const gwf_detector* dets, int32_t ndet, c
                const gwf_events* events, int64_t n, const gwf_opts* opts, double* fisher_packed, double* snr2,
                void* workspace, size_t workspace_bytes, void* stream);
 
-/* gwf_fisher with the return_SNR_derivatives output of GWSignal.FisherMatr (signal.py:938-945, network.py:124-152):
- *   snr_derivs: NULL, or [n] (per_arm=0) / [n_arms][n] blocks of nP doubles: 4 Re int conj(d_i h) h / Sn df of the arms in the block,
- *               rows in ParNums order (the tcoal row per second like the Fisher).  The reference returns this per arm
- *               (per_arm=1) and divides the sum over arms by the network SNR on the host (network.py:143). */
+/* Per-event status word (SURVEY.md 5 "failure detection"): a bad event gives NaN rows in the reference; here it is also flagged. */
+#define GWF_EV_NONFINITE_INPUT 1   /* a parameter of the event is NaN or infinite */
+#define GWF_EV_OUT_OF_DOMAIN 2     /* Mc <= 0, dL <= 0 or eta outside (0, 0.25] */
+#define GWF_EV_NONFINITE_OUTPUT 4  /* a Fisher element (or SNR^2) of the event came out NaN or infinite */
+#define GWF_EV_EMPTY_GRID 8        /* fcut <= fmin for some detector: the frequency grid of the event is degenerate */
+
+/* Outputs of gwf_fisher_ex; every pointer except fisher_packed may be NULL.  "blocks" = 1 (per_arm=0) or n_arms (per_arm=1). */
+typedef struct {
+    double* fisher_packed; /* [blocks][n][nP(nP+1)/2], as gwf_fisher */
+    double* snr2;          /* [blocks][n]: 4 int |h|^2/Sn df of the arms in the block */
+    double* snr2_integ;    /* [blocks][n]: the integral GWSignal.SNRInteg forms for the same arms (signal.py:725-728), so that one launch
+                              serves DetNet.SNR and DetNet.FisherMatr of the same events: equal to snr2 except for IMRPhenomHM, whose
+                              SNR drops the +/x cross term (signal.py:457-460) */
+    double* snr_derivs;    /* [blocks][n][nP]: 4 Re int conj(d_i h) h / Sn df, rows in ParNums order, the tcoal row per second like the
+                              Fisher (return_SNR_derivatives, signal.py:938-945; the reference divides the sum over arms by the network
+                              SNR on the host, network.py:143) */
+    int32_t* status;       /* [n]: GWF_EV_* bits, 0 = clean */
+} gwf_fisher_out;
+
+/* gwf_fisher with all optional outputs (return_SNR_derivatives of GWSignal.FisherMatr, the SNR of the same launch, status words). */
 int gwf_fisher_ex(const gwf_model* model, const gwf_detector* dets, int32_t ndet, const gwf_psd* const* psds, int32_t npsd,
-                  const gwf_events* events, int64_t n, const gwf_opts* opts, double* fisher_packed, double* snr2, double* snr_derivs,
+                  const gwf_events* events, int64_t n, const gwf_opts* opts, const gwf_fisher_out* out,
                   void* workspace, size_t workspace_bytes, void* stream);
 
 /* The return_derivatives output of GWSignal.FisherMatr (signal.py:917-945, network.py:124-141): the derivative strain itself,
@@ -161,6 +177,12 @@ int gwf_snr(const gwf_model* model, const gwf_detector* dets, int32_t ndet, cons
 
 /* packed lower triangle [n][nP(nP+1)/2] -> the reference's (nP, nP, N) layout, event axis fastest (signal.py:924) */
 int gwf_unpack_fisher(const double* packed, int64_t n, int32_t nP, double* full, void* stream);
+/* the same into a slice of a larger (nP, nP, ld) array: plane (i, j) of the chunk starts at full + (i nP + j) ld; ld >= n.  Lets the
+ * chunks of a catalog land in the one array DetNet.FisherMatr returns (network.py:118) */
+int gwf_unpack_fisher_ld(const double* packed, int64_t n, int32_t nP, double* full, int64_t ld, void* stream);
+/* stream-ordered 2-D copy (cudaMemcpy2DAsync, direction from the pointers): moves a chunk's (nP nP) x n planes between the device
+ * array and the pinned host array the caller returns, while the next chunk computes */
+int gwf_copy_2d(void* dst, size_t dst_pitch, const void* src, size_t src_pitch, size_t width_bytes, size_t height, void* stream);
 
 /* Replaces WaveFormModel.Phi / Ampl / tau_star / fcut (and IMRPhenomHM.hphc) evaluated on a user grid (waveforms.py:149-199,
  * 2256-2616), with the dict entries handed straight to the waveform (no Fisher re-parametrisation).

@@ -150,6 +150,10 @@ def _groups(n):
 # multi-GPU caller can all-gather it over NVLink without a host round trip (parallel.DistributedDetNet(gather='device')).
 STASH_DEVICE = False
 
+# When set (parallel.PeerGather), fisher() hands the packed rows of every launch group to gwf_unpack_gather instead of
+# gwf_unpack_fisher_ld: the unpack kernel also stores them into this rank's slot of every peer's gathered buffer over NVLink.
+PEER = None
+
 # extra gwf_opts.flags OR-ed into every launch (tests set GWF_OPT_GENERIC_LOOP / GWF_OPT_ONE_WARP_PER_EVENT to compare the
 # kernel variants; production leaves it 0 and the launcher picks the fastest applicable form)
 KERNEL_FLAGS = 0
@@ -222,7 +226,11 @@ def fisher(model, dets, psd_handles, ev, n, res, flags, per_arm, want_snr2=True,
                                       C.c_void_p(ws.data_ptr()), ws.numel(), sp), 'gwf_fisher')
             launch_count += 1 + npass
             for p in range(npass):
-                K.check(lib.gwf_unpack_fisher_ld(C.c_void_p(packed[p].data_ptr()), m, nP, C.c_void_p(full[p].data_ptr() + 8 * lo), n, sp), 'gwf_unpack_fisher')
+                if PEER is not None and npass == 1:
+                    K.check(lib.gwf_unpack_gather(C.c_void_p(packed[p].data_ptr()), m, nP, C.c_void_p(full[p].data_ptr() + 8 * lo), n,
+                                                  PEER.slots(lo), PEER.world, sp), 'gwf_unpack_gather')
+                else:
+                    K.check(lib.gwf_unpack_fisher_ld(C.c_void_p(packed[p].data_ptr()), m, nP, C.c_void_p(full[p].data_ptr() + 8 * lo), n, sp), 'gwf_unpack_fisher')
                 launch_count += 1
             if m != n:
                 snr2[:, lo:lo + m] = s2

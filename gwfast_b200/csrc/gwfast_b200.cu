@@ -786,6 +786,49 @@ __global__ void __launch_bounds__(256) unpack_kernel(const double* __restrict__ 
     }
 }
 
+// Multi-GPU: the same transposition fused with the write side of an all-gather over NVLink peer memory.  The packed rows of this
+// rank's events are also stored into this rank's slot of every peer's gathered buffer (peer pointers obtained by the caller through
+// CUDA IPC): plain coalesced 16-byte stores that the NVSwitch fabric routes to the peers while the tile is transposed -- no
+// separate collective kernel, no copy of the result through a communication buffer, and the stores of one tile overlap the
+// loads of the next.  The caller synchronises the ranks (any barrier) before the gathered buffers are read.
+struct PeerSlots {
+    double* p[kMaxPeers];
+    int n;
+};
+__global__ void __launch_bounds__(256) unpack_gather_kernel(const double* __restrict__ packed, long long n, int nP, double* __restrict__ full, long long ld,
+                                                            const PeerSlots peers) {
+    __shared__ __align__(16) double tile[32][110];   // even pitch: rows stay 16-byte aligned for the vector stores
+    const int npack = nP * (nP + 1) / 2;
+    const long long e0 = (long long)blockIdx.x * 32;
+    const int ne = (int)((n - e0) < 32 ? (n - e0) : 32);
+    const double* src = packed + e0 * npack;
+    const int total = ne * npack;
+    for (int t = threadIdx.x; t < total; t += blockDim.x) {
+        const double v = src[t];
+        tile[t / npack][t % npack] = v;
+    }
+    // the tile's rows are contiguous in the packed array: forward them to the peers as they are
+    if (((e0 * npack) & 1) == 0) {
+        const double2* s2 = reinterpret_cast<const double2*>(src);
+        for (int q = 0; q < peers.n; ++q) {
+            double2* d2 = reinterpret_cast<double2*>(peers.p[q] + e0 * npack);
+            for (int t = threadIdx.x; t < total / 2; t += blockDim.x) d2[t] = s2[t];
+            if ((total & 1) && threadIdx.x == 0) peers.p[q][e0 * npack + total - 1] = src[total - 1];
+        }
+    } else {
+        for (int q = 0; q < peers.n; ++q)
+            for (int t = threadIdx.x; t < total; t += blockDim.x) peers.p[q][e0 * npack + t] = src[t];
+    }
+    __syncthreads();
+    if (full) {
+        const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+        for (int q = wid; q < nP * nP; q += 8) {
+            const int i = q / nP, j = q % nP;
+            if (lane < ne) full[(long long)q * ld + e0 + lane] = tile[lane][i >= j ? tri(i, j) : tri(j, i)];
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------- host side
 // Per-device state: SM count, the device copy of the QNM tables, and the largest dynamic shared memory size already
 // requested for each kernel -- looked up once per (device, kernel) instead of on every call.  Tables set with
@@ -1337,7 +1380,8 @@ int gwf_overlap(const double* h1, const double* h2, const double* fcut, int64_t 
     if (!h1 || !h2 || !fcut || !psd || !overlap || !snr2_1 || !snr2_2) return fail(GWF_ERR_ARG, "gwf_overlap: null argument");
     if (n < 0 || res < 2 || !(fmin > 0.0)) return fail(GWF_ERR_ARG, "gwf_overlap: bad grid");
     if (n == 0) return GWF_OK;
-    PsdDev pd = reinterpret_cast<const PsdHost*>(psd)->dev;
+    PsdDev pd;                                  // the handle's table on the CURRENT device (uploaded on first use)
+    if (int rc = collect_psds(&psd, 1, &pd)) return rc;
     pd.c_off = -1;
     const int tb = 256;
     const long long threads = (long long)n * 32;
@@ -1351,6 +1395,20 @@ int gwf_unpack_fisher_ld(const double* packed, int64_t n, int32_t nP, double* fu
     if (!packed || !full || nP < 1 || nP > 14 || ld < n) return fail(GWF_ERR_ARG, "gwf_unpack_fisher: bad arguments");
     if (n == 0) return GWF_OK;
     unpack_kernel<<<(unsigned)((n + 31) / 32), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(packed, n, nP, full, ld);
+    GWF_CUDA(cudaGetLastError());
+    return GWF_OK;
+}
+
+int gwf_unpack_gather(const double* packed, int64_t n, int32_t nP, double* full, int64_t ld, double* const* peer_slots, int32_t npeers, void* stream) {
+    if (!packed || nP < 1 || nP > 14 || (full && ld < n)) return fail(GWF_ERR_ARG, "gwf_unpack_gather: bad arguments");
+    if (npeers < 0 || npeers > kMaxPeers || (npeers > 0 && !peer_slots)) return fail(GWF_ERR_ARG, "gwf_unpack_gather: at most 8 peer slots");
+    if (n == 0) return GWF_OK;
+    PeerSlots ps;
+    ps.n = npeers;
+    for (int i = 0; i < kMaxPeers; ++i) ps.p[i] = i < npeers ? peer_slots[i] : nullptr;
+    for (int i = 0; i < npeers; ++i)
+        if (!ps.p[i]) return fail(GWF_ERR_ARG, "gwf_unpack_gather: null peer slot");
+    unpack_gather_kernel<<<(unsigned)((n + 31) / 32), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(packed, n, nP, full, ld, ps);
     GWF_CUDA(cudaGetLastError());
     return GWF_OK;
 }

@@ -62,6 +62,7 @@ static int build_psd_tables(const double* f, const double* S, int n, std::vector
 // A PSD handle keeps the host copy of its tables and uploads them to a device the first time a call runs there, so one
 // process can drive several devices with the same handles (SURVEY.md 8(b) threading contract).
 constexpr int kMaxDevices = 64;
+constexpr int kMaxPeers = 8;      // GPUs of one NVSwitch box
 struct PsdHost {
     std::vector<double4> tab_h;
     std::vector<int> bucket_h;

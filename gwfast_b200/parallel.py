@@ -86,27 +86,137 @@ class DistributedDetNet(object):
         local, lo, hi = shard_events(evParams, self.dist.get_world_size(), self.dist.get_rank())
         nP = next(iter(self.net.signals.values())).wf_model.nParams
         if gather == 'device' and self._device() is not None:
-            return fisher_with_device_gather(self.net, local, n, self.dist, **kwargs)
+            import torch
+            out, buf = fisher_with_device_gather(self.net, local, n, self.dist, **kwargs)
+            world = self.dist.get_world_size()
+            sizes = [shard_bounds(n, world, r)[1] - shard_bounds(n, world, r)[0] for r in range(world)]
+            full = buf[0] if world == 1 else torch.cat([buf[r][..., :sizes[r]] for r in range(world)], dim=-1)
+            return out, full
         F = self.net.FisherMatr(local, **kwargs) if hi > lo else np.zeros((nP, nP, 0))
         full = all_gather_event_axis(np.asarray(F, dtype=np.float64), n, self.dist, self._device())
         return (F, full) if gather == 'device' else full
 
 
-def fisher_with_device_gather(net, local_events, n_total, dist=None, **kwargs):
-    """``net.FisherMatr(local_events)`` on this rank's shard plus one all-gather of the device-resident result: returns
-    ``(F_local numpy (nP, nP, m), F_all device tensor (nP, nP, n_total))``."""
+_gather_buffers = {}
+
+
+def fisher_with_device_gather(net, local_events, n_total, dist=None, peer=None, **kwargs):
+    """``net.FisherMatr(local_events, **kwargs)`` on this rank's shard plus the gather of the device-resident result.
+
+    Returns ``(result, gathered)``: ``result`` is whatever ``FisherMatr`` returns for the shard (host numpy; a tuple with
+    ``return_SNR=True``), ``gathered`` the Fisher matrices of ALL ranks as a device tensor that never crossed PCIe:
+
+    * ``peer`` = a :class:`PeerGather`: packed rows ``(world, n_max, nP(nP+1)/2)``, stored into every rank's buffer by the engine's
+      own unpack kernels over NVLink (``gwf_unpack_gather``) while the shard is still being computed group by group;
+    * otherwise one ``all_gather_into_tensor`` (NCCL) of the engine's device-resident ``(nP, nP, m)`` result into a preallocated
+      ``(world, nP, nP, m_max)`` buffer (uneven shards: rank r's events are ``gathered[r, :, :, :m_r]``).
+    """
     import torch
     from . import _engine
+    if dist is None:
+        import torch.distributed as dist
+    if peer is not None:
+        _engine.PEER = peer
+        try:
+            out = net.FisherMatr(local_events, **kwargs)
+        finally:
+            _engine.PEER = None
+        return out, peer.finish()
     _engine.STASH_DEVICE = True
     try:
-        F = net.FisherMatr(local_events, **kwargs)
+        out = net.FisherMatr(local_events, **kwargs)
         dev = _engine.state().last_fisher_device
     finally:
         _engine.STASH_DEVICE = False
         _engine.state().last_fisher_device = None
-    F = np.asarray(F, dtype=np.float64)
+    F = np.asarray(out[0] if isinstance(out, tuple) else out, dtype=np.float64)
     if dev is not None and dev.shape[0] == 1 and tuple(dev.shape[1:]) == F.shape:
         local_dev = dev[0]
     else:       # per-arm / re-indexed results (return_all, duty factors, NewtInspiral): upload the host result
         local_dev = torch.from_numpy(np.ascontiguousarray(F)).to(_engine.state().device)
-    return F, all_gather_event_axis(local_dev, n_total, dist)
+    world, rank = dist.get_world_size(), dist.get_rank()
+    m_max = max(shard_bounds(n_total, world, r)[1] - shard_bounds(n_total, world, r)[0] for r in range(world))
+    lead = tuple(local_dev.shape[:-1])
+    key = (world, lead, m_max, local_dev.device)
+    buf = _gather_buffers.get(key)
+    if buf is None:
+        _gather_buffers.clear()
+        buf = _gather_buffers[key] = torch.zeros((world,) + lead + (m_max,), dtype=torch.float64, device=local_dev.device)
+    if local_dev.shape[-1] == m_max:
+        src = local_dev.contiguous()
+    else:
+        src = torch.zeros(lead + (m_max,), dtype=torch.float64, device=local_dev.device)
+        src[..., :local_dev.shape[-1]] = local_dev
+    dist.all_gather_into_tensor(buf.view(-1), src.view(-1))
+    return out, buf
+
+
+class PeerGather(object):
+    """Write-based all-gather of the packed Fisher matrices over NVLink peer memory (``gwf_unpack_gather``).
+
+    Every rank owns a ``gathered`` buffer ``(world, n_max, npack)`` in its HBM and maps the buffers of the other ranks into its
+    address space through CUDA IPC (one exchange of handles at construction, over the process group).  A rank's unpack kernel then
+    stores its packed rows into its own slot of every peer's buffer while it transposes them for the caller: the gather costs no
+    extra kernel, no NCCL launch and no staging copy, and the remote stores ride behind the transposition.  ``finish()`` is the
+    rendezvous (a barrier on the process group) after which ``gathered`` holds every rank's rows.
+
+    Only for the one-process-per-GPU layout of a single NVSwitch box (``world <= 8``, NCCL backend); ``available()`` says whether
+    the peers could be mapped -- callers fall back to ``dist.all_gather_into_tensor`` otherwise.
+    """
+
+    def __init__(self, n_max, npack, dist=None):
+        import torch
+        from torch.multiprocessing.reductions import reduce_tensor
+        if dist is None:
+            import torch.distributed as dist
+        self.dist, self.torch = dist, torch
+        self.world, self.rank = dist.get_world_size(), dist.get_rank()
+        self.n_max, self.npack = int(n_max), int(npack)
+        if self.world > 8:
+            raise ValueError('PeerGather is for the GPUs of one box (world <= 8)')
+        dev = torch.device('cuda', torch.cuda.current_device())
+        # its own allocation (not a slice of a cached block): the IPC handle covers the whole underlying allocation
+        self.gathered = torch.zeros((self.world, self.n_max, self.npack), dtype=torch.float64, device=dev)
+        self._peers = None
+        try:
+            fn, args = reduce_tensor(self.gathered)
+            handles = [None] * self.world
+            dist.all_gather_object(handles, (fn, args))
+            peers = []
+            for r, (f, a) in enumerate(handles):
+                peers.append(self.gathered if r == self.rank else f(*a))
+            self._peers = peers
+        except Exception as e:          # pragma: no cover - depends on the box (IPC / peer access)
+            self._error = e
+        ok = torch.tensor([1 if self._peers is not None else 0], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok.item()) == 0:
+            self._peers = None
+        self._slot_cache = {}
+
+    def available(self):
+        return self._peers is not None
+
+    def slots(self, lo=0):
+        """ctypes array of this rank's slot in every rank's buffer, advanced to event `lo` of the shard"""
+        import ctypes as C
+        key = int(lo)
+        arr = self._slot_cache.get(key)
+        if arr is None:
+            slot_bytes = self.n_max * self.npack * 8
+            arr = self._slot_cache[key] = (C.c_void_p * self.world)(*[p.data_ptr() + self.rank * slot_bytes + key * self.npack * 8 for p in self._peers])
+        return arr
+
+    def unpack_and_scatter(self, packed, n, nP, full, ld, stream):
+        """gwf_unpack_gather on `stream`: `packed` (n, npack) device tensor of this rank; `full` (nP, nP, ld) device tensor or None"""
+        import ctypes as C
+        from . import _capi as K
+        lib = K.load()
+        K.check(lib.gwf_unpack_gather(C.c_void_p(packed.data_ptr()), int(n), int(nP), C.c_void_p(full.data_ptr()) if full is not None else None,
+                                      int(ld), self.slots(0), self.world, C.c_void_p(stream.cuda_stream)), 'gwf_unpack_gather')
+
+    def finish(self):
+        """rendezvous: after it returns (stream-ordered on the current stream) every rank's rows are in ``gathered``"""
+        self.torch.cuda.current_stream().synchronize()
+        self.dist.barrier()
+        return self.gathered

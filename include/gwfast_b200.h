@@ -180,6 +180,14 @@ int gwf_unpack_fisher(const double* packed, int64_t n, int32_t nP, double* full,
 /* the same into a slice of a larger (nP, nP, ld) array: plane (i, j) of the chunk starts at full + (i nP + j) ld; ld >= n.  Lets the
  * chunks of a catalog land in the one array DetNet.FisherMatr returns (network.py:118) */
 int gwf_unpack_fisher_ld(const double* packed, int64_t n, int32_t nP, double* full, int64_t ld, void* stream);
+/* Multi-GPU (events sharded over the GPUs of one box, one final all-gather of the Fisher matrices; the reference's
+ * counterpart is the result files its batch pool writes, run/calculate_forecasts_from_catalog.py:900-1024): gwf_unpack_fisher_ld
+ * fused with the write side of an all-gather over NVLink peer memory.  peer_slots[q] (q < npeers <= 8) points at THIS rank's slot
+ * [n][nP(nP+1)/2] inside peer q's gathered buffer (a device pointer of another GPU mapped into this process with CUDA IPC, or of
+ * this GPU); the kernel stores the packed rows there while it transposes them into `full` (which may be NULL).  The ranks must
+ * synchronise (any barrier) before the gathered buffers are read. */
+int gwf_unpack_gather(const double* packed, int64_t n, int32_t nP, double* full, int64_t ld, double* const* peer_slots, int32_t npeers,
+                      void* stream);
 /* stream-ordered 2-D copy (cudaMemcpy2DAsync, direction from the pointers): moves a chunk's (nP nP) x n planes between the device
  * array and the pinned host array the caller returns, while the next chunk computes */
 int gwf_copy_2d(void* dst, size_t dst_pitch, const void* src, size_t src_pitch, size_t width_bytes, size_t height, void* stream);

@@ -217,6 +217,17 @@ def _abs(a):
     return Dual(np.abs(a.v), _ex(np.sign(a.v)) * a.d)
 
 
+def _sqrt(a):
+    """d sqrt(x) = dx / (2 sqrt(x)).  Where x = 0 AND dx = 0 exactly -- the constant branch of
+    ``sqrt(where(eta < 0.25, 1 - 4 eta, 0.))`` at eta >= 0.25 (gwfast/waveforms.py:759, 1013) -- the tangent is 0, which is what
+    ``jax.jacrev`` returns there: the cotangent g / (2 * 0) that reaches the ``where`` is dropped by the select's transpose (the
+    unselected branch receives zeros, nothing is multiplied by 0), so the reference differentiates Seta to 0 at eta = 0.25."""
+    v = np.sqrt(a.v)
+    with np.errstate(all='ignore'):
+        d = _ex(0.5 / v) * a.d
+    return Dual(v, np.where(_ex(v == 0) & (a.d == 0), 0.0, d))
+
+
 def _unary(fun, dfun):
     def g(a):
         v = fun(a.v)
@@ -258,7 +269,7 @@ _UFUNCS = {
     np.conjugate: lambda a: a.conj(),
     np.exp: _unary(np.exp, lambda x, v: v),
     np.log: _unary(np.log, lambda x, v: 1.0 / x),
-    np.sqrt: _unary(np.sqrt, lambda x, v: 0.5 / v),
+    np.sqrt: _sqrt,
     np.cbrt: _unary(np.cbrt, lambda x, v: v / (3.0 * x)),
     np.sin: _unary(np.sin, lambda x, v: np.cos(x)),
     np.cos: _unary(np.cos, lambda x, v: -np.sin(x)),

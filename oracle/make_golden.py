@@ -315,7 +315,79 @@ def fx_wfvalues():
     save('wf_values', dict(note='per-model events stored as ev__<cls>__<key>'), evs, out)
 
 
-ALL = {'init': fx_init, 'c1': fx_c1, 'c1b': fx_c1b, 'c2': fx_c2, 'var': fx_variants, 'c3': fx_c3, 'c4': fx_c4, 'gw170817': fx_gw170817, 'wf': fx_wfvalues, 'newt': fx_newt, 'ecc': fx_ecc}
+def _run_chunk(args):
+    """worker of fx_c4big / fx_edge: SNR + Fisher of the unmodified reference on a slice of events"""
+    cfg, ev = args
+    warnings.filterwarnings('ignore')
+    out = run_network(cfg, ev, want_all=False)
+    return out['snr'], out['fisher']
+
+
+def run_network_pool(cfg, ev, chunk=16, procs=None):
+    """run_network(..., want_all=False) over slices of `chunk` events in a process pool (the reference under the shim does ~1 IMRPhenomHM
+    event per second and core)"""
+    import multiprocessing as mp
+    n = len(ev['Mc'])
+    jobs = [(cfg, {k: v[lo:lo + chunk] for k, v in ev.items()}) for lo in range(0, n, chunk)]
+    with mp.get_context('spawn').Pool(procs or min(len(jobs), os.cpu_count() or 1)) as pool:
+        parts = pool.map(_run_chunk, jobs)
+    return {'snr': np.concatenate([p[0] for p in parts]), 'fisher': np.concatenate([p[1] for p in parts], axis=-1)}
+
+
+def fx_c4big():
+    """IMRPhenomHM on the LVK-O4 network, the first 256 events of the C4 catalog (BASELINE.md 3.3 size)."""
+    cfg = dict(model=dict(cls='IMRPhenomHM'), network='LVK-O4', rot=False, fmin=10.)
+    ev = take(synthetic.bbh_catalog(100000, synthetic.SEEDS['C4']), 256)
+    save('c4_phenomhm_lvk_256', cfg, ev, run_network_pool(cfg, ev))
+
+
+def fx_edge():
+    """SURVEY.md 8(c) edge sets.  Forward-mode convention (what the shim's duals and the engine compute; JAX's reverse mode can
+    NaN-poison through the unselected branch of a where):
+      * eta = 0.25 exactly: Seta = sqrt(where(eta < 0.25, 1 - 4 eta, 0)) has value 0; its tangent is 0 (oracle/dual.py:_sqrt: what
+        jax.jacrev gives -- the select's transpose drops the infinite cotangent of sqrt at 0), so every entry is finite.
+      * |chi| in [0.9, 0.99] aligned: gamma2 >= 1, fpeak takes the fabs branch (waveforms.py:1134, 1193).
+      * Lambda = 0 and 0 < Lambda < 1: polynomial branch of the spin-induced quadrupole (waveforms.py:1394), kappa2T = 0."""
+    fx_edge_eta()
+    fx_edge_rest()
+
+
+def fx_edge_eta():
+    bbh = take(synthetic.bbh_catalog(10000, synthetic.SEEDS['C2'] + 50), 16)
+    q = _copy(bbh)
+    q['eta'][::2] = 0.25
+    for tag, cfg in (('phenomd_et2ce', dict(model=dict(cls='IMRPhenomD'), network='ET+2CE', rot=True, fmin=2.)),
+                     ('phenomhm_lvk', dict(model=dict(cls='IMRPhenomHM'), network='LVK-O4', rot=False, fmin=10.))):
+        save('edge_eta_quarter_' + tag, cfg, q, run_network_pool(cfg, q, chunk=4))
+    bns = take(synthetic.bns_catalog(100, synthetic.SEEDS['C1'] + 50, tidal=True), 16)
+    qb = {k: v for k, v in _copy(bns).items() if not k.startswith('Lambda')}
+    qb['eta'][::2] = 0.25
+    cfg = dict(model=dict(cls='TaylorF2_RestrictedPN', kw=dict(use_3p5PN_SpinHO=True)), network='ETSL', rot=True, fmin=2.)
+    save('edge_eta_quarter_tf2_etsl', cfg, qb, run_network_pool(cfg, qb, chunk=4))
+
+
+def fx_edge_rest():
+    rng = np.random.default_rng(909)
+    hs = take(synthetic.bbh_catalog(10000, synthetic.SEEDS['C2'] + 51), 32)
+    hs['chi1z'] = rng.uniform(0.9, 0.99, 32) * np.where(np.arange(32) % 4 == 3, -1., 1.)
+    hs['chi2z'] = rng.uniform(0.9, 0.99, 32) * np.where(np.arange(32) % 4 == 2, -1., 1.)
+    for tag, cfg in (('phenomd_et2ce', dict(model=dict(cls='IMRPhenomD'), network='ET+2CE', rot=True, fmin=2.)),
+                     ('phenomhm_lvk', dict(model=dict(cls='IMRPhenomHM'), network='LVK-O4', rot=False, fmin=10.))):
+        save('edge_highspin_' + tag, cfg, hs, run_network_pool(cfg, hs, chunk=4))
+    lz = take(synthetic.bns_catalog(100, synthetic.SEEDS['C3'] + 50, tidal=True), 16)
+    lz['Lambda1'][0:4] = 0.
+    lz['Lambda2'][2:6] = 0.
+    lz['Lambda1'][6:9] = rng.uniform(0.05, 0.95, 3)
+    lz['Lambda2'][8:11] = rng.uniform(0.05, 0.95, 3)
+    cfg = dict(model=dict(cls='IMRPhenomD_NRTidalv2'), network='ET+2CE', rot=True, fmin=2.)
+    out = run_network_pool(cfg, lz, chunk=4)
+    out.update(masked_last_sample(cfg, lz))
+    save('edge_lambda_zero_nrtidal_et2ce', cfg, lz, out)
+    cfg = dict(model=dict(cls='TaylorF2_RestrictedPN', kw=dict(is_tidal=True, use_QuadMonTid=True, use_3p5PN_SpinHO=True)), network='ETSL', rot=True, fmin=2.)
+    save('edge_lambda_zero_tf2_etsl', cfg, lz, run_network_pool(cfg, lz, chunk=4))
+
+
+ALL = {'init': fx_init, 'c1': fx_c1, 'c1b': fx_c1b, 'c2': fx_c2, 'var': fx_variants, 'c3': fx_c3, 'c4': fx_c4, 'gw170817': fx_gw170817, 'wf': fx_wfvalues, 'newt': fx_newt, 'ecc': fx_ecc, 'c4big': fx_c4big, 'edge': fx_edge, 'edge_eta': fx_edge_eta}
 
 if __name__ == '__main__':
     warnings.filterwarnings('ignore')

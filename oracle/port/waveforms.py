@@ -23,7 +23,7 @@ EULER = np.euler_gamma
 
 
 def _seta(eta):
-    # waveforms.py:759 (and everywhere): sqrt(where(eta<0.25, 1-4 eta, 0))
+    # waveforms.py:759 (and everywhere): sqrt(where(eta<0.25, 1-4 eta, 0)); at eta >= 0.25 value 0 and tangent 0 (oracle/dual.py:_sqrt)
     return np.sqrt(np.where(eta < 0.25, 1.0 - 4.0 * eta, 0.))
 
 

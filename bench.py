@@ -14,7 +14,7 @@ DetNet.FisherMatr(return_SNR=True)): the Fisher kernel integrates |h|^2/S_n anyw
             peers' gathered buffers over NVLink (gwf_unpack_gather, peer memory mapped with CUDA IPC); if the peers cannot be mapped
             it falls back to dist.all_gather_into_tensor and says so in config.gather
   e2e       the same metric through the public API with HOST numpy arrays in and out (H2D/D2H inside the timed region); for N>1
-            every rank calls the API on its shard and the gather is taken from the engine's device-resident Fisher matrices
+            every rank calls the API on its shard and the gather is done by the engine's own unpack kernels (peer stores over NVLink)
   roofline  FP64 (the path is FP64-FMA/transcendental bound): algorithmic FLOP/event x events / duration of
             the dominant kernel (fisher_kernel, timed alone via GWF_OPT_REUSE_WORKSPACE) against the DFMA peak measured
             in the same run (gwf_fp64_peak) -- nominal 148 SM x 64 lanes x 2 x 1.965 GHz = 37.2 TFLOP/s is also reported
@@ -347,7 +347,7 @@ def run_engine(args):
         if world > 1:
             # host arrays in, this rank's host arrays out, plus the final gather of the results taken from the engine's
             # device-resident Fisher matrices: the full matrix stays in HBM on every rank
-            return parallel.fisher_with_device_gather(net, dict(ev), n * world, dist, res=RES, return_SNR=True)
+            return parallel.fisher_with_device_gather(net, dict(ev), n * world, dist, peer=peer, res=RES, return_SNR=True)
         return net.FisherMatr(dict(ev), res=RES, return_SNR=True)
 
     for _ in range(warm):
@@ -431,7 +431,7 @@ def run_engine(args):
 
             def astep():
                 if world > 1:
-                    return parallel.fisher_with_device_gather(c.net, dict(sub), n_tot, dist, res=RES, return_SNR=True)
+                    return parallel.fisher_with_device_gather(c.net, dict(sub), n_tot, dist, peer=pgc, res=RES, return_SNR=True)
                 return c.net.FisherMatr(dict(sub), res=RES, return_SNR=True)
 
             for _ in range(2):
@@ -456,6 +456,8 @@ def run_engine(args):
                                gather=('gwf_unpack_gather (NVLink peer stores)' if pgc is not None else ('NCCL all-gather' if gat is not None else 'none'))
                                if world > 1 else 'none (one GPU)')
             c.release()
+            if pgc is not None:
+                pgc.close()
             c = pgc = gat = None
             torch.cuda.empty_cache()
 
@@ -495,6 +497,9 @@ def run_engine(args):
             line['cpu_baseline'] = cpu
         print(json.dumps(line))
     if world > 1:
+        if peer is not None:
+            gathered = None
+            peer.close()
         dist.barrier()
         dist.destroy_process_group()
 

@@ -55,7 +55,7 @@ class EngineError(RuntimeError):
 
 # every symbol include/gwfast_b200.h declares (tests check that the library exports all of them)
 SYMBOLS = ('gwf_version', 'gwf_last_error', 'gwf_num_params', 'gwf_num_arms', 'gwf_workspace_bytes', 'gwf_psd_create',
-           'gwf_psd_destroy', 'gwf_set_qnm_tables', 'gwf_fisher', 'gwf_fisher_ex', 'gwf_strain_derivs', 'gwf_strain', 'gwf_overlap', 'gwf_snr', 'gwf_unpack_fisher', 'gwf_unpack_fisher_ld', 'gwf_unpack_gather', 'gwf_copy_2d', 'gwf_waveform', 'gwf_fp64_peak', 'gwf_covariance', 'gwf_eigen',
+           'gwf_psd_destroy', 'gwf_set_qnm_tables', 'gwf_fisher', 'gwf_fisher_ex', 'gwf_strain_derivs', 'gwf_strain', 'gwf_overlap', 'gwf_snr', 'gwf_unpack_fisher', 'gwf_unpack_fisher_ld', 'gwf_unpack_gather', 'gwf_peer_alloc', 'gwf_peer_open', 'gwf_peer_close', 'gwf_peer_free', 'gwf_copy_2d', 'gwf_waveform', 'gwf_fp64_peak', 'gwf_covariance', 'gwf_eigen',
            'gwf_inversion_error')
 
 _lib = None
@@ -91,6 +91,10 @@ def load():
     lib.gwf_overlap.argtypes = [vp, vp, vp, i64, i32, dbl, vp, vp, vp, vp, vp]
     lib.gwf_unpack_fisher.argtypes = [vp, i64, i32, vp, vp]
     lib.gwf_unpack_fisher_ld.argtypes = [vp, i64, i32, vp, i64, vp]
+    lib.gwf_peer_alloc.argtypes = [C.c_size_t, P(vp), C.c_char_p]
+    lib.gwf_peer_open.argtypes = [C.c_char_p, P(vp)]
+    lib.gwf_peer_close.argtypes = [vp]
+    lib.gwf_peer_free.argtypes = [vp]
     lib.gwf_unpack_gather.argtypes = [vp, i64, i32, vp, i64, P(vp), i32, vp]
     lib.gwf_copy_2d.argtypes = [vp, C.c_size_t, vp, C.c_size_t, C.c_size_t, C.c_size_t, vp]
     lib.gwf_waveform.argtypes = [P(gwf_model), P(gwf_events), i64, vp, i32, i32, vp, vp, vp, vp, vp, vp, C.c_size_t, vp]

@@ -290,6 +290,7 @@ GWF_HD void amp_phase_point(const typename ModelTraits<MODEL, NT>::Rec& rec, con
 // NRTidalv2 3.011 -> 2.327 ms).  SHAPE = 0: bounds read from the network at run time.
 GWF_HD constexpr int shape_arms(int shape, int i) { return (shape >> (2 * i)) & 3; }
 GWF_HD constexpr int shape_ndet(int shape) { return (shape_arms(shape, 0) != 0) + (shape_arms(shape, 1) != 0) + (shape_arms(shape, 2) != 0) + (shape_arms(shape, 3) != 0); }
+GWF_HD constexpr int shape_total(int shape) { return shape_arms(shape, 0) + shape_arms(shape, 1) + shape_arms(shape, 2) + shape_arms(shape, 3); }
 GWF_HD constexpr int shape_first(int shape, int i) { return (i > 0 ? shape_arms(shape, 0) : 0) + (i > 1 ? shape_arms(shape, 1) : 0) + (i > 2 ? shape_arms(shape, 2) : 0); }
 
 #ifdef __CUDA_ARCH__
@@ -413,12 +414,15 @@ __device__ __forceinline__ void amp_phase_snr_point_fast(const typename ModelTra
             const double wgt = wA2 * rcp_fast(sn[i]);
 #pragma unroll
             for (int a = 0; a < shape_arms(SHAPE, i); ++a) {
+                // shape-specialised form: snr2_arm is a per-lane REGISTER array indexed by compile-time constants -- in SNR mode
+                // the arms of a network are its physical arms in order, each with weight 1 and output slot = its index
+                // (host_build.h:build_network), so neither arm.out nor arm.weight is read
                 const ArmDev& arm = net.arm[shape_first(SHAPE, i) + a];
                 double Fp, Fc;
                 arm_pattern(dp, arm, geom, Fp, Fc);
                 const double Gr = Fp * geom.K, Gi = Fc * geom.ci;
-                double& slot = snr2_arm[GWF_SNR_SLOT(arm.out)];
-                slot = fma(wgt * arm.weight, Gr * Gr + Gi * Gi, slot);
+                double& slot = snr2_arm[shape_first(SHAPE, i) + a];
+                slot = fma(wgt, fma(Gr, Gr, Gi * Gi), slot);
             }
         }
     } else {

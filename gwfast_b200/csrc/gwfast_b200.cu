@@ -726,7 +726,14 @@ snr_kernel(const typename ModelTraits<MODEL, 4>::Rec* __restrict__ recs, const E
         }
         asm volatile("bar.sync %0, %1;" ::"r"(1 + slot), "r"(stride) : "memory");
         const EvGeom& geom = mine->geom;
-        for (int a = 0; a < narm_out; ++a) s2[a * 32] = 0.0;
+        // per-arm sums: registers when the shape (hence every arm index) is a compile-time constant, else [arm][lane] in shared memory
+        constexpr bool kRegSums = FAST != 0 && SHAPE != 0;
+        constexpr int kRegArms = kRegSums ? shape_total(SHAPE) : 1;
+        double s2r[kRegArms];
+#pragma unroll
+        for (int a = 0; a < kRegArms; ++a) s2r[a] = 0.0;
+        if (!kRegSums)
+            for (int a = 0; a < narm_out; ++a) s2[a * 32] = 0.0;
         for (int g = 0; g < net.ngroups; ++g) {
             const Grid& grid = mine->grid[g];
             const bool rot = net.group_rot[g] != 0;
@@ -734,14 +741,22 @@ snr_kernel(const typename ModelTraits<MODEL, 4>::Rec* __restrict__ recs, const E
             if (k0 < res) grid.start(k0, fp);
             for (int k = k0; k < res; k += stride) {
                 if (k != k0) grid.advance(k, fp);
-                if (FAST == 2) PF::template snr_fast<true, SHAPE>(rec, cfg, geom, net, mine->sc, mine->ex, fp, s2);
-                else if (FAST == 1) PF::template snr_fast<false, SHAPE>(rec, cfg, geom, net, mine->sc, mine->ex, fp, s2);
+                if (FAST == 2) PF::template snr_fast<true, SHAPE>(rec, cfg, geom, net, mine->sc, mine->ex, fp, kRegSums ? s2r : s2);
+                else if (FAST == 1) PF::template snr_fast<false, SHAPE>(rec, cfg, geom, net, mine->sc, mine->ex, fp, kRegSums ? s2r : s2);
                 else PF::snr(rec, cfg, geom, net, mine->sc, mine->ex, g, rot, fp, s2);
             }
         }
-        for (int a = 0; a < narm_out; ++a) {
-            const double v = warp_sum(s2[a * 32]);
-            if (lane == 0) comb[sub * narm_out + a] = v;
+        if (kRegSums) {
+#pragma unroll
+            for (int a = 0; a < kRegArms; ++a) {
+                const double v = warp_sum(s2r[a]);
+                if (lane == 0) comb[sub * narm_out + a] = v;
+            }
+        } else {
+            for (int a = 0; a < narm_out; ++a) {
+                const double v = warp_sum(s2[a * 32]);
+                if (lane == 0) comb[sub * narm_out + a] = v;
+            }
         }
         // all warps of the group are done with the record and have left their totals
         asm volatile("bar.sync %0, %1;" ::"r"(1 + slot), "r"(stride) : "memory");
@@ -1396,6 +1411,39 @@ int gwf_unpack_fisher_ld(const double* packed, int64_t n, int32_t nP, double* fu
     if (n == 0) return GWF_OK;
     unpack_kernel<<<(unsigned)((n + 31) / 32), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(packed, n, nP, full, ld);
     GWF_CUDA(cudaGetLastError());
+    return GWF_OK;
+}
+
+int gwf_peer_alloc(size_t bytes, void** ptr_out, unsigned char* handle_out) {
+    if (!ptr_out || !handle_out || bytes == 0) return fail(GWF_ERR_ARG, "gwf_peer_alloc: bad arguments");
+    void* p = nullptr;
+    GWF_CUDA(cudaMalloc(&p, bytes));                 // its own allocation: the IPC handle names exactly this buffer
+    GWF_CUDA(cudaMemset(p, 0, bytes));
+    cudaIpcMemHandle_t h;
+    const cudaError_t e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) { cudaFree(p); return fail(GWF_ERR_CUDA, std::string("cudaIpcGetMemHandle: ") + cudaGetErrorString(e)); }
+    static_assert(sizeof(h) == GWF_IPC_HANDLE_BYTES, "cudaIpcMemHandle_t is 64 bytes");
+    std::memcpy(handle_out, &h, sizeof(h));
+    *ptr_out = p;
+    return GWF_OK;
+}
+
+int gwf_peer_open(const unsigned char* handle, void** ptr_out) {
+    if (!handle || !ptr_out) return fail(GWF_ERR_ARG, "gwf_peer_open: bad arguments");
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle, sizeof(h));
+    // opened with THIS rank's device current: the lazy-peer-access flag maps the exporter's memory for this device's kernels
+    GWF_CUDA(cudaIpcOpenMemHandle(ptr_out, h, cudaIpcMemLazyEnablePeerAccess));
+    return GWF_OK;
+}
+
+int gwf_peer_close(void* ptr) {
+    if (ptr) GWF_CUDA(cudaIpcCloseMemHandle(ptr));
+    return GWF_OK;
+}
+
+int gwf_peer_free(void* ptr) {
+    if (ptr) GWF_CUDA(cudaFree(ptr));
     return GWF_OK;
 }
 

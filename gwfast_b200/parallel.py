@@ -165,8 +165,9 @@ class PeerGather(object):
     """
 
     def __init__(self, n_max, npack, dist=None):
+        import ctypes as C
         import torch
-        from torch.multiprocessing.reductions import reduce_tensor
+        from . import _capi as K
         if dist is None:
             import torch.distributed as dist
         self.dist, self.torch = dist, torch
@@ -175,27 +176,58 @@ class PeerGather(object):
         if self.world > 8:
             raise ValueError('PeerGather is for the GPUs of one box (world <= 8)')
         dev = torch.device('cuda', torch.cuda.current_device())
-        # its own allocation (not a slice of a cached block): the IPC handle covers the whole underlying allocation
-        self.gathered = torch.zeros((self.world, self.n_max, self.npack), dtype=torch.float64, device=dev)
-        self._peers = None
-        try:
-            fn, args = reduce_tensor(self.gathered)
-            handles = [None] * self.world
-            dist.all_gather_object(handles, (fn, args))
-            peers = []
-            for r, (f, a) in enumerate(handles):
-                peers.append(self.gathered if r == self.rank else f(*a))
-            self._peers = peers
-        except Exception as e:          # pragma: no cover - depends on the box (IPC / peer access)
-            self._error = e
-        ok = torch.tensor([1 if self._peers is not None else 0], device=dev)
-        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
-        if int(ok.item()) == 0:
-            self._peers = None
+        self._lib = lib = K.load()
+        self._base = self._opened = None
         self._slot_cache = {}
+        nbytes = self.world * self.n_max * self.npack * 8
+        handle = C.create_string_buffer(64)
+        base = C.c_void_p()
+        ok_local = lib.gwf_peer_alloc(nbytes, C.byref(base), handle) == 0
+        handles = [None] * self.world
+        dist.all_gather_object(handles, bytes(handle.raw) if ok_local else None)
+        ptrs = None
+        if ok_local and all(h is not None for h in handles):
+            self._base = base.value
+            ptrs, opened = [], []
+            for r, h in enumerate(handles):
+                if r == self.rank:
+                    ptrs.append(self._base)
+                    continue
+                p = C.c_void_p()
+                if lib.gwf_peer_open(h, C.byref(p)) != 0:
+                    ptrs = None
+                    break
+                ptrs.append(p.value)
+                opened.append(p.value)
+            self._opened = opened
+        ok = torch.tensor([1 if ptrs is not None else 0], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        self._ptrs = ptrs if int(ok.item()) == 1 else None
+        self.gathered = None
+        if self._ptrs is not None:
+            # this rank's buffer as a tensor (zero-copy view of the cudaMalloc'ed block through __cuda_array_interface__)
+            class _View(object):
+                pass
+            v = _View()
+            v.__cuda_array_interface__ = dict(shape=(self.world, self.n_max, self.npack), typestr='<f8', data=(self._base, False), version=2, strides=None)
+            self.gathered = torch.as_tensor(v, device=dev)
+            self._view = v
+
+    def close(self):
+        """unmap the peers' buffers and free this rank's (collective: every rank must be done reading)"""
+        if self._base is None:
+            return
+        self.torch.cuda.synchronize()
+        self.dist.barrier()
+        for p in (self._opened or []):
+            self._lib.gwf_peer_close(p)
+        self.gathered = None
+        self.dist.barrier()
+        self._lib.gwf_peer_free(self._base)
+        self._base = self._ptrs = self._opened = None
 
     def available(self):
-        return self._peers is not None
+        return self._ptrs is not None
 
     def slots(self, lo=0):
         """ctypes array of this rank's slot in every rank's buffer, advanced to event `lo` of the shard"""
@@ -204,7 +236,7 @@ class PeerGather(object):
         arr = self._slot_cache.get(key)
         if arr is None:
             slot_bytes = self.n_max * self.npack * 8
-            arr = self._slot_cache[key] = (C.c_void_p * self.world)(*[p.data_ptr() + self.rank * slot_bytes + key * self.npack * 8 for p in self._peers])
+            arr = self._slot_cache[key] = (C.c_void_p * self.world)(*[p + self.rank * slot_bytes + key * self.npack * 8 for p in self._ptrs])
         return arr
 
     def unpack_and_scatter(self, packed, n, nP, full, ld, stream):

@@ -186,6 +186,14 @@ int gwf_unpack_fisher_ld(const double* packed, int64_t n, int32_t nP, double* fu
  * [n][nP(nP+1)/2] inside peer q's gathered buffer (a device pointer of another GPU mapped into this process with CUDA IPC, or of
  * this GPU); the kernel stores the packed rows there while it transposes them into `full` (which may be NULL).  The ranks must
  * synchronise (any barrier) before the gathered buffers are read. */
+/* the gathered buffer of a rank and its peers' views of it: gwf_peer_alloc = cudaMalloc (zero-filled) + cudaIpcGetMemHandle; the 64-byte
+ * handle travels to the other ranks by any means (the process group), which map it with gwf_peer_open (cudaIpcOpenMemHandle with lazy peer
+ * access, opened on the importing rank's own device so that its kernels can store into it).  gwf_peer_close / gwf_peer_free undo them. */
+#define GWF_IPC_HANDLE_BYTES 64
+int gwf_peer_alloc(size_t bytes, void** ptr_out, unsigned char* handle_out);
+int gwf_peer_open(const unsigned char* handle, void** ptr_out);
+int gwf_peer_close(void* ptr);
+int gwf_peer_free(void* ptr);
 int gwf_unpack_gather(const double* packed, int64_t n, int32_t nP, double* full, int64_t ld, double* const* peer_slots, int32_t npeers,
                       void* stream);
 /* stream-ordered 2-D copy (cudaMemcpy2DAsync, direction from the pointers): moves a chunk's (nP nP) x n planes between the device

@@ -12,7 +12,7 @@ LIB_PATH = os.environ.get('GWFAST_B200_LIB', os.path.join(_HERE, 'lib', 'libgwfa
 GWF_TAYLORF2, GWF_IMRPHENOMD, GWF_IMRPHENOMD_NRTIDALV2, GWF_IMRPHENOMHM = 0, 1, 2, 3
 GWF_MODEL_TIDAL, GWF_MODEL_3P5PN_SPINHO, GWF_MODEL_PHIREF_VLSO, GWF_MODEL_QUADMON_TID = 1, 2, 4, 8
 GWF_MODEL_KERR_ISCO, GWF_MODEL_NO_FCUT, GWF_MODEL_HAS_FREF, GWF_MODEL_LAMBDA_GIVEN, GWF_MODEL_NEWTONIAN, GWF_MODEL_ECCENTRIC = 16, 32, 64, 128, 256, 512
-GWF_OPT_M1M2, GWF_OPT_CHIS_CHIA, GWF_OPT_LIN_GRID, GWF_OPT_REUSE_WORKSPACE, GWF_OPT_GENERIC_LOOP, GWF_OPT_ONE_WARP_PER_EVENT = 1, 2, 4, 8, 16, 32
+GWF_OPT_M1M2, GWF_OPT_CHIS_CHIA, GWF_OPT_LIN_GRID, GWF_OPT_REUSE_WORKSPACE, GWF_OPT_GENERIC_LOOP, GWF_OPT_ONE_WARP_PER_EVENT, GWF_OPT_HM_BLOCK_PAIRS = 1, 2, 4, 8, 16, 32, 64
 GWF_NPARAM_IN = 16
 # order of gwf_events.p[]
 EVENT_KEYS = ('Mc', 'eta', 'dL', 'theta', 'phi', 'iota', 'psi', 'tcoal', 'Phicoal', 'chi1z', 'chi2z', 'Lambda1', 'Lambda2',
@@ -41,6 +41,10 @@ class gwf_fisher_out(C.Structure):
     _fields_ = [('fisher_packed', C.c_void_p), ('snr2', C.c_void_p), ('snr2_integ', C.c_void_p), ('snr_derivs', C.c_void_p), ('status', C.c_void_p)]
 
 
+class gwf_signal_out(C.Structure):
+    _fields_ = [(k, C.c_void_p) for k in ('Ap', 'Ac', 'psi', 'strain', 'Fp', 'Fc', 'dt')]
+
+
 # per-event status bits (gwf_fisher_out.status)
 GWF_EV_NONFINITE_INPUT, GWF_EV_OUT_OF_DOMAIN, GWF_EV_NONFINITE_OUTPUT, GWF_EV_EMPTY_GRID = 1, 2, 4, 8
 
@@ -55,7 +59,7 @@ class EngineError(RuntimeError):
 
 # every symbol include/gwfast_b200.h declares (tests check that the library exports all of them)
 SYMBOLS = ('gwf_version', 'gwf_last_error', 'gwf_num_params', 'gwf_num_arms', 'gwf_workspace_bytes', 'gwf_psd_create',
-           'gwf_psd_destroy', 'gwf_set_qnm_tables', 'gwf_fisher', 'gwf_fisher_ex', 'gwf_strain_derivs', 'gwf_strain', 'gwf_overlap', 'gwf_snr', 'gwf_unpack_fisher', 'gwf_unpack_fisher_ld', 'gwf_unpack_gather', 'gwf_peer_alloc', 'gwf_peer_open', 'gwf_peer_close', 'gwf_peer_free', 'gwf_copy_2d', 'gwf_waveform', 'gwf_fp64_peak', 'gwf_covariance', 'gwf_eigen',
+           'gwf_psd_destroy', 'gwf_set_qnm_tables', 'gwf_fisher', 'gwf_fisher_ex', 'gwf_strain_derivs', 'gwf_strain', 'gwf_overlap', 'gwf_snr', 'gwf_unpack_fisher', 'gwf_unpack_fisher_ld', 'gwf_unpack_gather', 'gwf_peer_alloc', 'gwf_peer_open', 'gwf_peer_close', 'gwf_peer_free', 'gwf_copy_2d', 'gwf_waveform', 'gwf_signal_grid', 'gwf_pattern', 'gwf_fp64_peak', 'gwf_covariance', 'gwf_eigen',
            'gwf_inversion_error')
 
 _lib = None
@@ -98,6 +102,8 @@ def load():
     lib.gwf_unpack_gather.argtypes = [vp, i64, i32, vp, i64, P(vp), i32, vp]
     lib.gwf_copy_2d.argtypes = [vp, C.c_size_t, vp, C.c_size_t, C.c_size_t, C.c_size_t, vp]
     lib.gwf_waveform.argtypes = [P(gwf_model), P(gwf_events), i64, vp, i32, i32, vp, vp, vp, vp, vp, vp, C.c_size_t, vp]
+    lib.gwf_signal_grid.argtypes = [P(gwf_model), P(gwf_detector), dbl, P(gwf_events), i64, vp, i32, i32, P(gwf_signal_out), vp, C.c_size_t, vp]
+    lib.gwf_pattern.argtypes = [P(gwf_detector), dbl, vp, vp, vp, vp, i64, vp, vp, vp, vp]
     lib.gwf_fp64_peak.argtypes = [dbl, P(dbl), vp]
     lib.gwf_covariance.argtypes = [vp, i64, i32, i32, dbl, vp, vp, vp, vp]
     lib.gwf_eigen.argtypes = [vp, i64, i32, vp, vp, vp, vp]

@@ -131,21 +131,6 @@ __device__ __forceinline__ double psd_lookup_fast(const PsdDev& p, double f, dou
 }
 #endif
 
-// reciprocal for the per-sample weights: MUFU seed + two Newton steps (error < 1 ulp; no denormal/special-case branch
-// of the IEEE division -- the arguments here are PSD values and amplitude denominators, always normal and positive)
-GWF_HD double rcp_fast(double x) {
-#ifdef __CUDA_ARCH__
-    double r;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
-    double e = fma(-x, r, 1.0);
-    r = fma(r, e, r);
-    e = fma(-x, r, 1.0);
-    return fma(r, e, r);          // seed 2^-23 -> 2^-46 -> rounding level
-#else
-    return 1.0 / x;
-#endif
-}
-
 // sin / cos of the Earth-rotation angle 2 pi t, t in days.  On the device the argument is reduced in turns (sincospi: exact
 // reduction, no slow path for large arguments -- sincos() carries a Payne-Hanek branch that split every sample's code in two)
 GWF_HD void rot_sincos(double t_days, double* s, double* c) {
@@ -210,6 +195,8 @@ struct DetPoint {
     double dt;                    // Delta t [s]
 };
 
+// a/b basis at ang = (ra - lon) - 2 pi t given as (c1, s1) = cos/sin(ang)  (signal.py:360-376)
+GWF_HD void det_basis(const EvDet& e, double c1, double s1, DetPoint& o);
 // (cB, sB) = cos/sin(2 pi tn), tn = time in days BEFORE the Earth-centre->site delay is added (signal.py:444-453)
 GWF_HD void det_point(const EvDet& e, double cB, double sB, DetPoint& o) {
     // ang0 = (ra - lon) - 2 pi tn
@@ -222,6 +209,9 @@ GWF_HD void det_point(const EvDet& e, double cB, double sB, DetPoint& o) {
     const double del = (2.0 * kPi * kInvDay) * o.dt;
     const double cdl = 1.0 - 0.5 * del * del, sdl = del * (1.0 - del * del * (1. / 6.));
     const double c1 = c0 * cdl + s0 * sdl, s1 = s0 * cdl - c0 * sdl;
+    det_basis(e, c1, s1, o);
+}
+GWF_HD void det_basis(const EvDet& e, double c1, double s1, DetPoint& o) {
     const double c2 = c1 * c1 - s1 * s1, s2 = 2.0 * s1 * c1;
     o.aS = e.p[0] * c2 + e.p[1] * c1 + e.p[2];
     o.aC = -(e.p[3] * s2 + e.p[4] * s1);

@@ -468,6 +468,26 @@ template <int NT> struct HMStrainSink {
 #pragma unroll
         for (int j = 0; j < NT; ++j) hpr_d[j] = hpi_d[j] = hcr_d[j] = hci_d[j] = 0.;
     }
+    // partial sums over a subset of the modes, exchanged between the two warps of a pair: kWords doubles per lane, laid out [word][lane]
+    static constexpr int kWords = 8 + 4 * NT;
+    GWF_HD void store(double* __restrict__ x, int lane) const {
+        x[0 * 32 + lane] = hpr; x[1 * 32 + lane] = hpi; x[2 * 32 + lane] = hcr; x[3 * 32 + lane] = hci;
+        x[4 * 32 + lane] = hpr_i; x[5 * 32 + lane] = hpi_i; x[6 * 32 + lane] = hcr_i; x[7 * 32 + lane] = hci_i;
+#pragma unroll
+        for (int j = 0; j < NT; ++j) {
+            x[(8 + 4 * j) * 32 + lane] = hpr_d[j]; x[(9 + 4 * j) * 32 + lane] = hpi_d[j];
+            x[(10 + 4 * j) * 32 + lane] = hcr_d[j]; x[(11 + 4 * j) * 32 + lane] = hci_d[j];
+        }
+    }
+    GWF_HD void add(const double* __restrict__ x, int lane) {
+        hpr += x[0 * 32 + lane]; hpi += x[1 * 32 + lane]; hcr += x[2 * 32 + lane]; hci += x[3 * 32 + lane];
+        hpr_i += x[4 * 32 + lane]; hpi_i += x[5 * 32 + lane]; hcr_i += x[6 * 32 + lane]; hci_i += x[7 * 32 + lane];
+#pragma unroll
+        for (int j = 0; j < NT; ++j) {
+            hpr_d[j] += x[(8 + 4 * j) * 32 + lane]; hpi_d[j] += x[(9 + 4 * j) * 32 + lane];
+            hcr_d[j] += x[(10 + 4 * j) * 32 + lane]; hci_d[j] += x[(11 + 4 * j) * 32 + lane];
+        }
+    }
     GWF_HD void operator()(int m, double A, double ph, const double* __restrict__ dlnA, const double* __restrict__ dPhi) {
         if (A == 0.0) return;
         double sn, cs;
@@ -514,6 +534,40 @@ template <int NT> struct HMAcc {
     static constexpr int NP = NT + 7, kSnr2 = NP * (NP + 1) / 2, kSnr2Integ = kSnr2 + 1, kSd = kSnr2 + 2;
 };
 
+// rows of d h / d p_i (ParNums order) of one arm at one sample, without the carrier e^{i (2 pi f tcoal 86400 - Phicoal + 2 pi f Delta t)}
+// (it cancels in the Gram): h = hp Fp + hc Fc (signal.py:584-607); H = (Hr, Hi) is the strain itself in the same convention
+template <int NT>
+GWF_HD void hm_arm_rows(const HMStrainSink<NT>& hs, const DetPoint& dp, const DetRows<NT>& dr, const ArmDev& a, const EvGeom& geom,
+                        double* __restrict__ ra, double* __restrict__ rb, double& Hr, double& Hi, double& Fp, double& Fc) {
+    const double av = a.S2 * dp.aS + a.C2 * dp.aC, bv = a.C2 * dp.bC + a.S2 * dp.bS;
+    const double ag = a.S2 * dp.aS_g + a.C2 * dp.aC_g, bg = a.C2 * dp.bC_g + a.S2 * dp.bS_g;
+    const double ad = a.S2 * dp.aS_d + a.C2 * dp.aC_d, bd = a.C2 * dp.bC_d + a.S2 * dp.bS_d;
+    Fp = av * geom.c2psi + bv * geom.s2psi; Fc = bv * geom.c2psi - av * geom.s2psi;
+    const double Fpg = ag * geom.c2psi + bg * geom.s2psi, Fcg = bg * geom.c2psi - ag * geom.s2psi;
+    const double Fpd = ad * geom.c2psi + bd * geom.s2psi, Fcd = bd * geom.c2psi - ad * geom.s2psi;
+    Hr = hs.hpr * Fp + hs.hcr * Fc; Hi = hs.hpi * Fp + hs.hci * Fc;           // signal.py:586-607
+    const double Hgr = hs.hpr * Fpg + hs.hcr * Fcg, Hgi = hs.hpi * Fpg + hs.hci * Fcg;
+    const double Hdr = hs.hpr * Fpd + hs.hcr * Fcd, Hdi = hs.hpi * Fpd + hs.hci * Fcd;
+#pragma unroll
+    for (int j = 0; j < NT; ++j) {
+        const int row = j < 2 ? j : 7 + j;
+        double re = hs.hpr_d[j] * Fp + hs.hcr_d[j] * Fc - Hi * dr.psi_x[j], im = hs.hpi_d[j] * Fp + hs.hci_d[j] * Fc + Hr * dr.psi_x[j];
+        if (j < 2) {
+            re = fma(Hgr, dr.ang_x[j], re);
+            im = fma(Hgi, dr.ang_x[j], im);
+        }
+        ra[row] = re;
+        rb[row] = im;
+    }
+    ra[2] = -Hr * geom.inv_dL;                                   rb[2] = -Hi * geom.inv_dL;
+    ra[3] = fma(Hgr, dr.ang_t, -Hdr) - Hi * dr.ph_t;             rb[3] = fma(Hgi, dr.ang_t, -Hdi) + Hr * dr.ph_t;
+    ra[4] = fma(Hgr, dr.ang_p, -Hi * dr.ph_p);                   rb[4] = fma(Hgi, dr.ang_p, Hr * dr.ph_p);
+    ra[5] = hs.hpr_i * Fp + hs.hcr_i * Fc;                       rb[5] = hs.hpi_i * Fp + hs.hci_i * Fc;     // iota: harmonics only
+    ra[6] = 2.0 * (hs.hpr * Fc - hs.hcr * Fp);                   rb[6] = 2.0 * (hs.hpi * Fc - hs.hci * Fp);   // psi: Fp' = 2 Fc, Fc' = -2 Fp
+    ra[7] = fma(Hgr, dr.ang_c, -Hi * dr.ph_c);                   rb[7] = fma(Hgi, dr.ang_c, Hr * dr.ph_c);
+    ra[8] = Hi;                                                  rb[8] = -Hr;
+}
+
 // SD: also accumulate (h | d_i h) (return_SNR_derivatives)
 template <int NT, bool SD = false>
 GWF_HD void hm_point(const HMRec<NT>& rec, const ModelCfg& cfg, const EvGeom& geom, const NetworkDev& net, const EventScratch& sc,
@@ -527,7 +581,6 @@ GWF_HD void hm_point(const HMRec<NT>& rec, const ModelCfg& cfg, const EvGeom& ge
     HMStrainSink<NT> hs(ex.w);
     phenomhm_foreach_mode<NT, true>(rec, g, fp, cut, hs);
     if (hs.hpr == 0.0 && hs.hpi == 0.0 && hs.hcr == 0.0 && hs.hci == 0.0) return;
-    const double hpr_i = hs.hpr_i, hpi_i = hs.hpi_i, hcr_i = hs.hcr_i, hci_i = hs.hci_i;
     const double hp2 = hs.hpr * hs.hpr + hs.hpi * hs.hpi, hc2 = hs.hcr * hs.hcr + hs.hci * hs.hci;
     PointWf<NT> w;
     w.f = f;
@@ -556,34 +609,8 @@ GWF_HD void hm_point(const HMRec<NT>& rec, const ModelCfg& cfg, const EvGeom& ge
         const double wgt = w4 / Sn;
         for (int ai = d.arm_begin; ai < d.arm_end; ++ai) {
             const ArmDev& a = net.arm[ai];
-            const double av = a.S2 * dp.aS + a.C2 * dp.aC, bv = a.C2 * dp.bC + a.S2 * dp.bS;
-            const double ag = a.S2 * dp.aS_g + a.C2 * dp.aC_g, bg = a.C2 * dp.bC_g + a.S2 * dp.bS_g;
-            const double ad = a.S2 * dp.aS_d + a.C2 * dp.aC_d, bd = a.C2 * dp.bC_d + a.S2 * dp.bS_d;
-            const double Fp = av * geom.c2psi + bv * geom.s2psi, Fc = bv * geom.c2psi - av * geom.s2psi;
-            const double Fpg = ag * geom.c2psi + bg * geom.s2psi, Fcg = bg * geom.c2psi - ag * geom.s2psi;
-            const double Fpd = ad * geom.c2psi + bd * geom.s2psi, Fcd = bd * geom.c2psi - ad * geom.s2psi;
-            const double Hr = hs.hpr * Fp + hs.hcr * Fc, Hi = hs.hpi * Fp + hs.hci * Fc;           // signal.py:586-607
-            const double Hgr = hs.hpr * Fpg + hs.hcr * Fcg, Hgi = hs.hpi * Fpg + hs.hci * Fcg;
-            const double Hdr = hs.hpr * Fpd + hs.hcr * Fcd, Hdi = hs.hpi * Fpd + hs.hci * Fcd;
-            double ra[NP], rb[NP];
-#pragma unroll
-            for (int j = 0; j < NT; ++j) {
-                const int row = j < 2 ? j : 7 + j;
-                double re = hs.hpr_d[j] * Fp + hs.hcr_d[j] * Fc - Hi * dr.psi_x[j], im = hs.hpi_d[j] * Fp + hs.hci_d[j] * Fc + Hr * dr.psi_x[j];
-                if (j < 2) {
-                    re = fma(Hgr, dr.ang_x[j], re);
-                    im = fma(Hgi, dr.ang_x[j], im);
-                }
-                ra[row] = re;
-                rb[row] = im;
-            }
-            ra[2] = -Hr * geom.inv_dL;                                   rb[2] = -Hi * geom.inv_dL;
-            ra[3] = fma(Hgr, dr.ang_t, -Hdr) - Hi * dr.ph_t;             rb[3] = fma(Hgi, dr.ang_t, -Hdi) + Hr * dr.ph_t;
-            ra[4] = fma(Hgr, dr.ang_p, -Hi * dr.ph_p);                   rb[4] = fma(Hgi, dr.ang_p, Hr * dr.ph_p);
-            ra[5] = hpr_i * Fp + hcr_i * Fc;                             rb[5] = hpi_i * Fp + hci_i * Fc;     // iota: harmonics only
-            ra[6] = 2.0 * (hs.hpr * Fc - hs.hcr * Fp);                   rb[6] = 2.0 * (hs.hpi * Fc - hs.hci * Fp);   // psi: Fp' = 2 Fc, Fc' = -2 Fp
-            ra[7] = fma(Hgr, dr.ang_c, -Hi * dr.ph_c);                   rb[7] = fma(Hgi, dr.ang_c, Hr * dr.ph_c);
-            ra[8] = Hi;                                                  rb[8] = -Hr;
+            double ra[NP], rb[NP], Hr, Hi, Fp, Fc;
+            hm_arm_rows<NT>(hs, dp, dr, a, geom, ra, rb, Hr, Hi, Fp, Fc);
             const double wg = wgt * a.weight;
             snr2 = fma(wg, Hr * Hr + Hi * Hi, snr2);
             snr2i = fma(wg, hp2 * Fp * Fp + hc2 * Fc * Fc, snr2i);      // Ap = |hp| Fp, Ac = |hc| Fc (signal.py:457-460, 727)
@@ -601,6 +628,107 @@ GWF_HD void hm_point(const HMRec<NT>& rec, const ModelCfg& cfg, const EvGeom& ge
         }
     }
 }
+
+#ifdef __CUDACC__
+// ---- IMRPhenomHM with the work of one block of 32 samples SPLIT over the two warps of a pair ------------------------------------
+// The full point above keeps 68 accumulators (136 registers) alive while the six modes are evaluated and spilled ~600 local loads
+// and stores per warp-sample (profiles/r02b: FP64 pipe 24 %, long_scoreboard 3.1 cycles per issue).  Here both warps of a pair work on
+// the SAME samples: warp `half` evaluates modes 3 half .. 3 half + 2, the partial mode sums (8 + 4 NT doubles per lane) are exchanged
+// through shared memory, and each warp then forms the rows of every arm but accumulates only the packed entries it owns (p & 1 ==
+// half): 34 accumulators per lane instead of 68, no mode work done twice, only the row assembly (~10 % of the sample) is duplicated.
+template <int NT, bool SD> struct HMSplitAcc {
+    static constexpr int NP = NT + 7, NPACK = NP * (NP + 1) / 2;
+    static_assert(NPACK % 2 == 0, "entries are dealt out alternately");
+    static constexpr int kSnr = NPACK / 2;             // half 0: 4 int |h|^2/Sn ; half 1: the SNRInteg integral
+    static constexpr int kSd = kSnr + 1;               // (h | d_i h) of the rows i with (i & 1) == half, at kSd + (i >> 1)
+    static constexpr int kAcc = kSd + (SD ? (NP + 1) / 2 : 0);
+};
+template <int NT, bool SD, int HALF>
+__device__ __forceinline__ void hm_gram_half(double wg, const double* __restrict__ ra, const double* __restrict__ rb, double Hr, double Hi,
+                                             double* __restrict__ acc) {
+    constexpr int NP = NT + 7;
+    if (SD) {
+        const double wr = wg * Hr, wi = wg * Hi;
+#pragma unroll
+        for (int i = HALF; i < NP; i += 2) acc[HMSplitAcc<NT, SD>::kSd + (i >> 1)] = fma(wr, ra[i], fma(wi, rb[i], acc[HMSplitAcc<NT, SD>::kSd + (i >> 1)]));
+    }
+#pragma unroll
+    for (int i = 0; i < NP; ++i) {
+        const double wa = wg * ra[i], wb = wg * rb[i];
+#pragma unroll
+        for (int j = 0; j <= i; ++j)
+            if ((tri(i, j) & 1) == HALF) acc[tri(i, j) >> 1] = fma(wa, ra[j], fma(wb, rb[j], acc[tri(i, j) >> 1]));
+    }
+}
+// xbuf: [2 halves][kWords][32] doubles of the pair; bar_id: the pair's named barrier (64 threads).  Every lane of both warps must call
+// this for every block (inactive lanes -- beyond the grid -- only take part in the exchange).
+template <int NT, bool SD>
+__device__ __forceinline__ void hm_point_split(const HMRec<NT>& rec, const ModelCfg& cfg, const EvGeom& geom, const NetworkDev& net, const EventScratch& sc,
+                                               const HMExtra& ex, int g, bool group_rot, const FreqPoint& fp, double* __restrict__ acc, int half,
+                                               double* __restrict__ xbuf, int bar_id, int lane, bool active) {
+    constexpr int NP = NT + 7;
+    typedef HMSplitAcc<NT, SD> L;
+    constexpr int kW = HMStrainSink<NT>::kWords;
+    HMStrainSink<NT> hs(ex.w);
+    PointWf<NT> w;
+    double sBr = 0., cBr = 1.;
+    // PSD rows of the first detectors are requested before the modes are evaluated: tables that found no room in shared memory are
+    // read through L1/L2 (two dependent loads), and that latency then hides behind the mode arithmetic instead of stalling the detector loop
+    constexpr int kPre = 4;
+    double sn_pre[kPre];
+    const double f = fp.f, l2f = fp.lnf * 1.4426950408889634073599246810018921;
+#pragma unroll
+    for (int di = 0; di < kPre; ++di)
+        sn_pre[di] = (active && di < net.ndet && net.det[di].group == g && net.det[di].arm_begin != net.det[di].arm_end)
+                         ? psd_lookup(net.psd[net.det[di].psd], f, l2f) : 1.0;
+    if (active) {
+        phenomhm_foreach_mode<NT, true>(rec, g, fp, !(cfg.flags & kFlagNoFcut), hs, 3 * half, 3 * half + 3);
+        w.f = fp.f;
+#pragma unroll
+        for (int j = 0; j < NT; ++j) w.phi_d[j] = 0.;
+        w.dtn[0] = w.dtn[1] = 0.;
+        if (group_rot) {                      // every read of the staged record happens before the exchange barrier
+            double tau, dtau[2];
+            const double xm13 = rec.sp.sm13 * fp.fm13, lpx3 = fma(fp.lnf, 1. / 3., rec.sp.lps3);
+            tau_eval(rec.tau, 0.68278406325529568146702083315816 * xm13, lpx3, rec.lam, tau, dtau);
+            w.dtn[0] = -dtau[0] * kInvDay;
+            w.dtn[1] = -dtau[1] * kInvDay;
+            sincos(2.0 * kPi * fma(-tau, kInvDay, geom.tcoal), &sBr, &cBr);
+        }
+    }
+    hs.store(xbuf + half * (kW * 32), lane);
+    asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
+    hs.add(xbuf + (1 - half) * (kW * 32), lane);
+    asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");     // the partner has read this warp's words: the slot may be rewritten
+    if (!active || (hs.hpr == 0.0 && hs.hpi == 0.0 && hs.hcr == 0.0 && hs.hci == 0.0)) return;
+    const double hp2 = hs.hpr * hs.hpr + hs.hpi * hs.hpi, hc2 = hs.hcr * hs.hcr + hs.hci * hs.hci;
+    const double w4 = 4.0 * fp.w;
+    for (int di = 0; di < net.ndet; ++di) {
+        const DetDev& d = net.det[di];
+        if (d.group != g || d.arm_begin == d.arm_end) continue;
+        const double Sn = di == 0 ? sn_pre[0] : (di == 1 ? sn_pre[1] : (di == 2 ? sn_pre[2] : (di == 3 ? sn_pre[3] : psd_lookup(net.psd[d.psd], f, l2f))));
+        DetPoint dp;
+        if (d.use_rot) det_point(sc.ed[di], cBr, sBr, dp);
+        else dp = sc.fixed[di];
+        DetRows<NT> dr;
+        dr.set(w, dp, d.use_rot != 0, d.no_motion != 0);
+        const double wgt = w4 * rcp_fast(Sn);
+        for (int ai = d.arm_begin; ai < d.arm_end; ++ai) {
+            const ArmDev& a = net.arm[ai];
+            double ra[NP], rb[NP], Hr, Hi, Fp, Fc;
+            hm_arm_rows<NT>(hs, dp, dr, a, geom, ra, rb, Hr, Hi, Fp, Fc);
+            const double wg = wgt * a.weight;
+            if (half == 0) {
+                acc[L::kSnr] = fma(wg, Hr * Hr + Hi * Hi, acc[L::kSnr]);
+                hm_gram_half<NT, SD, 0>(wg, ra, rb, Hr, Hi, acc);
+            } else {
+                acc[L::kSnr] = fma(wg, hp2 * Fp * Fp + hc2 * Fc * Fc, acc[L::kSnr]);      // Ap = |hp| Fp, Ac = |hc| Fc (signal.py:457-460, 727)
+                hm_gram_half<NT, SD, 1>(wg, ra, rb, Hr, Hi, acc);
+            }
+        }
+    }
+}
+#endif
 
 // HM SNR as the reference defines it: Ap = |hp| Fp, Ac = |hc| Fc (the +/x cross term is dropped, signal.py:457-460, 727)
 GWF_HD void hm_snr_point(const HMRec<4>& rec, const ModelCfg& cfg, const EvGeom& geom, const NetworkDev& net, const EventScratch& sc,

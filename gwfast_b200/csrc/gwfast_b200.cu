@@ -166,6 +166,106 @@ waveform_kernel(const typename ModelTraits<MODEL, 4>::Rec* __restrict__ recs, Ev
     }
 }
 
+// GWSignal.GWAmplitudes / GWPhase / GWstrain on a USER grid (signal.py:425-655) for one detector and one arm orientation
+// (xax + rot): one warp per event, lanes over the grid samples.  Any output may be null.
+struct SignalOut {
+    double *Ap, *Ac, *psi, *strain, *Fp, *Fc, *dt;
+};
+template <int MODEL>
+__global__ void __launch_bounds__(kFisherThreads)
+signal_grid_kernel(const typename ModelTraits<MODEL, 4>::Rec* __restrict__ recs, EventsDev ev, long long n, const double* __restrict__ f, int res, int f2d,
+                   ModelCfg cfg, DetDev det, ArmDev arm, SignalOut out) {
+    typedef typename ModelTraits<MODEL, 4>::Rec Rec;
+    typedef WaveformFns<MODEL> WF;
+    constexpr int kRecDoubles = (int)(sizeof(Rec) / sizeof(double));
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    typedef WaveBlk<Rec> Blk;
+    Blk* mine = reinterpret_cast<Blk*>(smem_raw) + wid;
+    const long long nwarps = (long long)gridDim.x * kWarpsPerCta;
+    for (long long e = (long long)blockIdx.x * kWarpsPerCta + wid; e < n; e += nwarps) {
+        const double* src = reinterpret_cast<const double*>(recs + e);
+        double* dst = reinterpret_cast<double*>(&mine->rec);
+        __syncwarp();
+        for (int i = lane; i < kRecDoubles; i += 32) dst[i] = __ldg(src + i);
+        const EventIn in = load_event(ev, e);
+        if (lane == 0) mine->w.set(in.iota);
+        __syncwarp();
+        EvGeom geom;
+        geom.set(in);
+        EvDet ed;
+        ed.set(det, geom);
+        const bool rot = det.use_rot != 0;
+        for (int k = lane; k < res; k += 32) {
+            FreqPoint fp;
+            fp.from_f(f2d ? f[(long long)k * n + e] : f[k]);
+            fp.w = 0.;
+            WaveformOut o;
+            WF::eval(mine->rec, cfg, mine->w, fp, o);
+            // time the response is evaluated at (signal.py:444-453, 564-580), before the Earth-centre -> site delay is added
+            double sB = 0., cB = 1.;
+            if (!det.no_motion) sincos(2.0 * kPi * (rot ? fma(-o.tau, kInvDay, geom.tcoal) : geom.tcoal), &sB, &cB);
+            DetPoint dp;
+            det_point(ed, cB, sB, dp);
+            double Fp, Fc;
+            arm_pattern(dp, arm, geom, Fp, Fc);
+            const long long at = (long long)k * n + e;
+            const double W2 = 2.0 * kPi * fp.f;
+            const double carrier = W2 * (geom.tcoal * 3600. * 24.) - in.Phicoal;                 // signal.py:484
+            double Ap, Ac, hr, hi;
+            if (MODEL == kPhenomHM) {
+                // Ap = |hp| Fp, Ac = |hc| Fc (signal.py:457-460); strain = (hp Fp + hc Fc) e^{i (phiL + carrier)} (signal.py:584-607)
+                Ap = sqrt(o.hp[0] * o.hp[0] + o.hp[1] * o.hp[1]) * Fp;
+                Ac = sqrt(o.hc[0] * o.hc[0] + o.hc[1] * o.hc[1]) * Fc;
+                double sP, cP;
+                sincos(fma(W2, dp.dt, carrier), &sP, &cP);
+                const double zr = o.hp[0] * Fp + o.hc[0] * Fc, zi = o.hp[1] * Fp + o.hc[1] * Fc;
+                hr = zr * cP - zi * sP; hi = zr * sP + zi * cP;
+            } else {
+                Ap = o.amp[0] * Fp * geom.K;                                                      // signal.py:463-464
+                Ac = o.amp[0] * Fc * geom.ci;
+                double sP, cP;
+                sincos((carrier - o.phi[0]) + W2 * dp.dt, &sP, &cP);                              // Psi + phiL, signal.py:580, 641
+                hr = Ap * cP - Ac * sP; hi = Ap * sP + Ac * cP;
+            }
+            if (out.Ap) out.Ap[at] = Ap;
+            if (out.Ac) out.Ac[at] = Ac;
+            if (out.psi) out.psi[at] = carrier - o.phi[0];
+            if (out.strain) reinterpret_cast<double2*>(out.strain)[at] = make_double2(hr, hi);
+            if (out.Fp) out.Fp[at] = Fp;
+            if (out.Fc) out.Fc[at] = Fc;
+            if (out.dt) out.dt[at] = dp.dt;
+        }
+    }
+}
+
+// GWSignal._PatternFunction / _DeltLoc (signal.py:342-423), element-wise over m points: the pattern functions at EXACTLY the given
+// time (no delay added) and the Earth-centre -> site delay at that time
+__global__ void __launch_bounds__(256) pattern_kernel(DetDev det, ArmDev arm, const double* __restrict__ theta, const double* __restrict__ phi,
+                                                      const double* __restrict__ t, const double* __restrict__ psi, long long m,
+                                                      double* __restrict__ Fp, double* __restrict__ Fc, double* __restrict__ dt) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    EventIn in = EventIn();
+    in.theta = theta[i]; in.phi = phi[i]; in.psi = psi ? psi[i] : 0.0; in.dL = 1.0;
+    EvGeom geom;
+    geom.set(in);
+    EvDet ed;
+    ed.set(det, geom);
+    double sB, cB;
+    sincos(2.0 * kPi * t[i], &sB, &cB);
+    const double c1 = ed.cA * cB + ed.sA * sB, s1 = ed.sA * cB - ed.cA * sB;
+    if (dt) dt[i] = -kRc * (ed.kc * c1 + ed.k0);                                                  // signal.py:417-421
+    if (Fp || Fc) {
+        DetPoint dp;
+        det_basis(ed, c1, s1, dp);
+        double p, c;
+        arm_pattern(dp, arm, geom, p, c);
+        if (Fp) Fp[i] = p;
+        if (Fc) Fc[i] = c;
+    }
+}
+
 // ------------------------------------------------------------------------------------------- K2
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -505,6 +605,87 @@ fisher_kernel(const typename ModelTraits<MODEL, NT>::Rec* __restrict__ recs, con
     }
 }
 
+// IMRPhenomHM, pair mode: the two warps of a pair share ONE staged event and work on the same blocks of 32 samples (hm_point_split:
+// three modes each, exchanged partial sums, half of the packed entries each).  Outputs are added to the zero-initialised arrays like
+// fisher_kernel's pair mode does; an entry is only ever added by the warp that owns it.
+template <int NT, bool SD>
+__global__ void __launch_bounds__(kFisherThreads, 1)
+fisher_hm_split_kernel(const HMRec<NT>* __restrict__ recs, const EventAux* __restrict__ aux, EventsDev ev, long long n, int res, int lin, ModelCfg cfg,
+                       const __grid_constant__ NetworkDev net, const FisherOut fo) {
+    typedef HMRec<NT> Rec;
+    typedef HMSplitAcc<NT, SD> L;
+    typedef WarpSmem<Rec, HMExtra> WS;
+    constexpr int NP = NT + 7, NPACK = NP * (NP + 1) / 2;
+    constexpr int kPairs = kWarpsPerCta / 2, kW = HMStrainSink<NT>::kWords;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int half = wid / kPairs, slot = wid % kPairs;          // warps w and w + kPairs sit on the same scheduler
+    WS* mine = reinterpret_cast<WS*>(smem_raw) + slot;
+    double* xbuf = reinterpret_cast<double*>(smem_raw + sizeof(WS) * kPairs) + slot * (2 * kW * 32);
+    const Rec& rec = mine->rec;
+    const int bar_id = 1 + slot;
+    psd_cache_fill(net, smem_raw);
+    for (long long e = (long long)blockIdx.x * kPairs + slot; e < n; e += (long long)gridDim.x * kPairs) {
+        // both warps stage the event into the shared block (identical values; neither reads before its own copy is complete)
+        stage_event_aux<false>(mine, recs, aux, ev, e, net, lane);
+        const EvGeom& geom = mine->geom;
+        double acc[L::kAcc];
+#pragma unroll
+        for (int p = 0; p < L::kAcc; ++p) acc[p] = 0.0;
+        for (int g = 0; g < net.ngroups; ++g) {
+            const Grid& grid = mine->grid[g];
+            const bool rot = net.group_rot[g] != 0;
+            const volatile Grid* gv = &mine->grid[g];
+            FreqPoint fp;
+            if (lane < res) grid.start(lane, fp);
+            for (int kb0 = 0; kb0 < res; kb0 += 32) {
+                const int k = kb0 + lane;
+                const bool active = k < res;
+                if (active && kb0 != 0) {
+                    if (lin) grid.advance(k, fp);
+                    else {
+                        const bool last = k == res - 1;
+                        fp.f = last ? gv->fcut : fp.f * gv->r;
+                        fp.f13 *= gv->r13; fp.fm13 *= gv->rm13; fp.fm76 *= gv->rm76; fp.lnf += gv->dln;
+                        fp.w = fp.f * (last ? gv->hw_hi : gv->hw_in);
+                    }
+                }
+                hm_point_split<NT, SD>(rec, cfg, geom, net, mine->sc, mine->ex, g, rot, fp, acc, half, xbuf, bar_id, lane, active);
+            }
+        }
+        // both warps are past the last exchange: nothing reads the record any more, its space takes the reduced accumulators
+        typedef Fold<L::kAcc> F;
+        F::run(acc, lane);
+        double* red = reinterpret_cast<double*>(&mine->rec) + half * 64;
+        static_assert(L::kAcc <= 64 && sizeof(Rec) >= sizeof(double) * 128, "reduced accumulators of the two halves live in the record's space");
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < F::kOut; ++i) {
+            const int idx = F::index(lane, i);
+            if (idx >= 0) red[idx] = acc[i];
+        }
+        __syncwarp();
+        double* o = fo.fisher + e * NPACK;
+        bool bad = false;
+        for (int p = 2 * lane + half; p < NPACK; p += 64) {
+            const double v = red[p >> 1];
+            bad = bad || !isfinite(v);
+            atomicAdd(o + p, v);
+        }
+        if (fo.status) {
+            const unsigned anybad = __ballot_sync(0xffffffffu, bad);
+            if (lane == 0 && anybad) atomicOr(fo.status + e, GWF_EV_NONFINITE_OUTPUT);
+        }
+        if (lane == 0) {
+            double* dst = half == 0 ? fo.snr2 : fo.snr2_integ;
+            if (dst) atomicAdd(dst + e, red[L::kSnr]);
+        }
+        if (SD && fo.snr_derivs && lane < NP && (lane & 1) == half) atomicAdd(fo.snr_derivs + e * NP + lane, red[L::kSd + (lane >> 1)]);
+        // the shared block is restaged for the next event only when both warps are done with this one
+        asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
+    }
+}
+
 // return_derivatives (signal.py:917-945): the derivative strain d h / d p_i of ONE arm (a per-arm pass network) written out as
 // complex128 [nP][n][res] -- the array the Fisher kernel deliberately never materialises.  Same rows as arm_rows / Compact, times
 // A e^{i Psi} with Psi = 2 pi f tcoal 86400 - Phicoal - Phi(f) + 2 pi f Delta t (signal.py:484, 580, 641); HBM-write bound.
@@ -546,12 +727,45 @@ derivs_kernel(const typename ModelTraits<MODEL, NT>::Rec* __restrict__ recs, Eve
         for (int k = lane; k < res; k += 32) {
             FreqPoint fp;
             grid.start(k, fp);
-            PointWf<NT> w;
-            ModelTraits<MODEL, NT>::eval(rec, cfg, g, fp, rot, w);
-            w.f = fp.f;
             double2 row[NP];
 #pragma unroll
             for (int i = 0; i < NP; ++i) row[i] = make_double2(0.0, 0.0);
+            if constexpr (MODEL == kPhenomHM) {
+                // rows of hm_arm_rows times the carrier e^{i (2 pi f tcoal 86400 - Phicoal + 2 pi f Delta t)} (signal.py:584-607, 1378-1380)
+                HMStrainSink<NT> hs(mine->ex.w);
+                phenomhm_foreach_mode<NT, true>(rec, g, fp, !(cfg.flags & kFlagNoFcut), hs);
+                if (!(hs.hpr == 0.0 && hs.hpi == 0.0 && hs.hcr == 0.0 && hs.hci == 0.0)) {
+                    PointWf<NT> w;
+                    w.f = fp.f;
+#pragma unroll
+                    for (int j = 0; j < NT; ++j) w.phi_d[j] = 0.;
+                    w.dtn[0] = w.dtn[1] = 0.;
+                    double sBr = 0., cBr = 1.;
+                    if (rot) {
+                        double tau, dtau[2];
+                        const double xm13 = rec.sp.sm13 * fp.fm13, lpx3 = fma(fp.lnf, 1. / 3., rec.sp.lps3);
+                        tau_eval(rec.tau, 0.68278406325529568146702083315816 * xm13, lpx3, rec.lam, tau, dtau);
+                        w.dtn[0] = -dtau[0] * kInvDay;
+                        w.dtn[1] = -dtau[1] * kInvDay;
+                        sincos(2.0 * kPi * fma(-tau, kInvDay, geom.tcoal), &sBr, &cBr);
+                    }
+                    DetPoint dp;
+                    if (rot) det_point(mine->sc.ed[di], cBr, sBr, dp);
+                    else dp = mine->sc.fixed[di];
+                    DetRows<NT> dr;
+                    dr.set(w, dp, rot, d.no_motion != 0);
+                    double ra[NP], rb[NP], Hr, Hi, Fp, Fc;
+                    hm_arm_rows<NT>(hs, dp, dr, arm, geom, ra, rb, Hr, Hi, Fp, Fc);
+                    const double W2 = 2.0 * kPi * fp.f;
+                    double sP, cP;
+                    sincos(fma(W2, dp.dt, W2 * (geom.tcoal * 3600. * 24.) - phicoal), &sP, &cP);
+#pragma unroll
+                    for (int i = 0; i < NP; ++i) row[i] = make_double2(ra[i] * cP - rb[i] * sP, ra[i] * sP + rb[i] * cP);
+                }
+            } else {
+            PointWf<NT> w;
+            ModelTraits<MODEL, NT>::eval(rec, cfg, g, fp, rot, w);
+            w.f = fp.f;
             if (w.A != 0.0) {
                 double sBr = 0., cBr = 1.;
                 if (rot) sincos(2.0 * kPi * fma(-w.tau, kInvDay, geom.tcoal), &sBr, &cBr);
@@ -581,6 +795,7 @@ derivs_kernel(const typename ModelTraits<MODEL, NT>::Rec* __restrict__ recs, Eve
                     }
                     row[i] = make_double2(a * zr - b * zi, a * zi + b * zr);
                 }
+            }
             }
 #pragma unroll
             for (int i = 0; i < NP; ++i) out[((long long)i * n + e) * res + k] = row[i];
@@ -627,9 +842,33 @@ strain_kernel(const typename ModelTraits<MODEL, 4>::Rec* __restrict__ recs, Even
         for (int k = lane; k < res; k += 32) {
             FreqPoint fp;
             grid.start(k, fp);
+            double2 h = make_double2(0.0, 0.0);
+            if constexpr (MODEL == kPhenomHM) {
+                // h = (hp Fp + hc Fc) e^{i (2 pi f Delta t + 2 pi f tcoal 86400 - Phicoal)}, signal.py:584-607
+                HMValueSink hs(mine->ex.w);
+                phenomhm_foreach_mode<NT, false>(rec, g, fp, !(cfg.flags & kFlagNoFcut), hs);
+                if (!(hs.hpr == 0.0 && hs.hpi == 0.0 && hs.hcr == 0.0 && hs.hci == 0.0)) {
+                    double sBr = 0., cBr = 1.;
+                    if (rot) {
+                        double tau, dtau[2];
+                        const double xm13 = rec.sp.sm13 * fp.fm13, lpx3 = fma(fp.lnf, 1. / 3., rec.sp.lps3);
+                        tau_eval(rec.tau, 0.68278406325529568146702083315816 * xm13, lpx3, rec.lam, tau, dtau);
+                        sincos(2.0 * kPi * fma(-tau, kInvDay, geom.tcoal), &sBr, &cBr);
+                    }
+                    DetPoint dp;
+                    if (rot) det_point(mine->sc.ed[di], cBr, sBr, dp);
+                    else dp = mine->sc.fixed[di];
+                    double Fp, Fc;
+                    arm_pattern(dp, arm, geom, Fp, Fc);
+                    const double W2 = 2.0 * kPi * fp.f;
+                    double sP, cP;
+                    sincos(fma(W2, dp.dt, W2 * (geom.tcoal * 3600. * 24.) - phicoal), &sP, &cP);
+                    const double zr = hs.hpr * Fp + hs.hcr * Fc, zi = hs.hpi * Fp + hs.hci * Fc;
+                    h = make_double2(zr * cP - zi * sP, zr * sP + zi * cP);
+                }
+            } else {
             PointWf<NT> w;
             ModelTraits<MODEL, NT>::eval(rec, cfg, g, fp, rot, w);
-            double2 h = make_double2(0.0, 0.0);
             if (w.A != 0.0) {
                 double sBr = 0., cBr = 1.;
                 if (rot) sincos(2.0 * kPi * fma(-w.tau, kInvDay, geom.tcoal), &sBr, &cBr);
@@ -644,6 +883,7 @@ strain_kernel(const typename ModelTraits<MODEL, 4>::Rec* __restrict__ recs, Even
                 sincos(Psi, &sP, &cP);
                 const double ar = w.A * geom.K * Fp, ai = w.A * geom.ci * Fc;                            // Ap, Ac (signal.py:463-464)
                 h = make_double2(ar * cP - ai * sP, ar * sP + ai * cP);
+            }
             }
             out[e * res + k] = h;
         }
@@ -947,6 +1187,9 @@ static int run_fisher(const gwf_model* model, const gwf_detector* dets, int ndet
     // does not depend on the size of the batch it is computed in.  TaylorF2 events are too cheap for the repeated staging
     // (measured 4 % slower), so they keep one warp per event.
     int pair = (MODEL != kTaylorF2 && !(opts->flags & GWF_OPT_ONE_WARP_PER_EVENT)) ? 1 : 0;
+    // IMRPhenomHM pairs split the modes and the packed entries of the SAME samples (fisher_hm_split_kernel) instead of taking
+    // alternate blocks of samples
+    constexpr bool kSplitPair = MODEL == kPhenomHM;
     // lock step of the two halves: a named barrier per event (bit 1), for IMRPhenomHM per block of samples (bit 2) -- see the
     // comment at the end of fisher_kernel's event loop for the measurements behind the choice
     if (pair) pair |= (MODEL == kPhenomHM) ? 6 : 2;
@@ -957,7 +1200,7 @@ static int run_fisher(const gwf_model* model, const gwf_detector* dets, int ndet
         AuxPlan ap;
         ap.out = aux;
         for (int g = 0; g < kMaxGroups; ++g) ap.fmax[g] = net.group_fmax[g];
-        ap.res = opts->res; ap.lin = lin; ap.stride = pair ? 64 : 32;
+        ap.res = opts->res; ap.lin = lin; ap.stride = (pair && !(kSplitPair && !(opts->flags & GWF_OPT_HM_BLOCK_PAIRS))) ? 64 : 32;
         prologue_kernel<MODEL, NT><<<dim3((unsigned)((n + pb - 1) / pb), (MODEL == kPhenomD || MODEL == kNRTidalv2) ? 2 : 1), pb, 0, st>>>(ev, n, cfg, opts->flags, ctx->qnm, gi, recs, nullptr, ap, outp->status);
         GWF_CUDA(cudaGetLastError());
     } else if (outp->status) GWF_CUDA(cudaMemsetAsync(outp->status, 0, sizeof(int) * (size_t)n, st));   // the input bits are the prologue's
@@ -1009,6 +1252,18 @@ static int run_fisher(const gwf_model* model, const gwf_detector* dets, int ndet
             if (fo.snr2) GWF_CUDA(cudaMemsetAsync(fo.snr2, 0, sizeof(double) * (size_t)n, st));
             if (fo.snr2_integ) GWF_CUDA(cudaMemsetAsync(fo.snr2_integ, 0, sizeof(double) * (size_t)n, st));
             if (fo.snr_derivs) GWF_CUDA(cudaMemsetAsync(fo.snr_derivs, 0, sizeof(double) * (size_t)n * NP, st));
+        }
+        if constexpr (kSplitPair) {
+            if (pair && !(opts->flags & GWF_OPT_HM_BLOCK_PAIRS)) {
+                typedef WarpSmem<Rec, HMExtra> WSs;
+                const size_t base = sizeof(WSs) * (kWarpsPerCta / 2) + sizeof(double) * (kWarpsPerCta / 2) * 2 * HMStrainSink<NT>::kWords * 32;
+                const size_t shmem_split = plan_psd_cache(net, base, kSmemLimit);
+                auto ks = snr_derivs ? fisher_hm_split_kernel<NT, true> : fisher_hm_split_kernel<NT, false>;
+                if (int rcs = ensure_smem(*ctx, ks, shmem_split)) return rcs;
+                ks<<<grid, kFisherThreads, shmem_split, st>>>(recs, aux, ev, n, opts->res, lin, cfg, net, fo);
+                GWF_CUDA(cudaGetLastError());
+                continue;
+            }
         }
         const Kern kern = pick(fast, fast_shape(net));
         if (int rcs = ensure_smem(*ctx, kern, shmem_pass)) return rcs;
@@ -1147,6 +1402,53 @@ static int run_snr(const gwf_model* model, const gwf_detector* dets, int ndet, c
     const long long want = (n + kSnrGroups - 1) / kSnrGroups;
     const unsigned grid = (unsigned)std::min<long long>(want, (long long)sms);
     kern<<<grid, kSnrThreads, shmem, st>>>(recs, aux, ev, n, opts->res, lin, cfg, net, net.narms, snr2_arm);
+    GWF_CUDA(cudaGetLastError());
+    return GWF_OK;
+}
+
+// DetDev / ArmDev of one gwf_detector at the arm orientation xax + rot_deg (signal.py:342-387: rot in degrees)
+static void single_arm(const gwf_detector& d, double rot_deg, DetDev& o, ArmDev& a) {
+    std::memset(&o, 0, sizeof(o));
+    o.sl = std::sin(d.lat_rad); o.cl = std::cos(d.lat_rad);
+    o.s2l = std::sin(2.0 * d.lat_rad); o.c2l = std::cos(2.0 * d.lat_rad);
+    o.slon = std::sin(d.long_rad); o.clon = std::cos(d.long_rad);
+    o.fmin = d.fmin; o.fmax = d.fmax > 0.0 ? d.fmax : 0.0;
+    o.no_motion = d.no_motion != 0;
+    o.use_rot = (d.use_earth_motion != 0) && !o.no_motion;
+    const double sarm = d.shape == 0 ? 1.0 : std::sin(kPi / 3.);
+    const double x = d.xax_rad + rot_deg * kPi / 180.;
+    a.S2 = sarm * std::sin(2.0 * x); a.C2 = sarm * std::cos(2.0 * x); a.weight = 1.0; a.out = 0; a.pad = 0;
+}
+
+template <int MODEL>
+static int run_signal_grid(const gwf_model* model, const gwf_detector* det, double rot_deg, const EventsDev& ev, long long n, const double* f, int res,
+                           int f2d, const SignalOut& out, void* ws, size_t ws_bytes, cudaStream_t st) {
+    typedef typename ModelTraits<MODEL, 4>::Rec Rec;
+    const size_t rec_bytes = (sizeof(Rec) * (size_t)n + 15) & ~(size_t)15;
+    if (ws_bytes < rec_bytes + sizeof(double) * (size_t)n) return fail(GWF_ERR_WORKSPACE, "workspace too small");
+    Rec* recs = reinterpret_cast<Rec*>(ws);
+    double* fmin_ev = reinterpret_cast<double*>(reinterpret_cast<char*>(ws) + rec_bytes);
+    ModelCfg cfg = {model->id, model->flags, model->fcutPar, model->fRef};
+    DeviceCtx* ctx = nullptr;
+    if (int rc0 = device_ctx(MODEL == kPhenomD || MODEL == kNRTidalv2, &ctx)) return rc0;
+    GroupInfo gi;
+    gi.n = 1;
+    for (int g = 0; g < kMaxGroups; ++g) gi.fmin[g] = 1.0;
+    const int pb = 128;
+    const unsigned pg = (unsigned)((n + pb - 1) / pb);
+    grid_min_kernel<<<pg, pb, 0, st>>>(f, res, n, f2d, fmin_ev);                 // fRef = min of the user's grid (waveforms.py:1139)
+    GWF_CUDA(cudaGetLastError());
+    prologue_kernel<MODEL, 4><<<pg, pb, 0, st>>>(ev, n, cfg, 0, ctx->qnm, gi, recs, fmin_ev);
+    GWF_CUDA(cudaGetLastError());
+    DetDev d;
+    ArmDev a;
+    single_arm(*det, rot_deg, d, a);
+    const size_t shmem = sizeof(WaveBlk<Rec>) * kWarpsPerCta;
+    auto kern = signal_grid_kernel<MODEL>;
+    if (int rcs = ensure_smem(*ctx, kern, shmem)) return rcs;
+    const long long want = (n + kWarpsPerCta - 1) / kWarpsPerCta;
+    const unsigned grid = (unsigned)std::min<long long>(want, (long long)ctx->sms * 4);
+    kern<<<grid, kFisherThreads, shmem, st>>>(recs, ev, n, f, res, f2d, cfg, d, a, out);
     GWF_CUDA(cudaGetLastError());
     return GWF_OK;
 }
@@ -1337,8 +1639,10 @@ int gwf_strain_derivs(const gwf_model* model, const gwf_detector* dets, int32_t 
         case GWF_IMRPHENOMD_NRTIDALV2:
             if (!ev.p[11] || !ev.p[12]) return fail(GWF_ERR_ARG, "tidal model needs Lambda1, Lambda2");
             return run_derivs<kNRTidalv2, 6>(model, dets, ndet, psds, npsd, ev, n, opts, derivs, workspace, workspace_bytes, st);
+        case GWF_IMRPHENOMHM:
+            return run_derivs<kPhenomHM, 4>(model, dets, ndet, psds, npsd, ev, n, opts, derivs, workspace, workspace_bytes, st);
         default:
-            return fail(GWF_ERR_UNSUPPORTED, "gwf_strain_derivs: not built for this model (IMRPhenomHM: use the Fisher / SNR-derivative outputs)");
+            return fail(GWF_ERR_UNSUPPORTED, "gwf_strain_derivs: model not built");
     }
 }
 
@@ -1385,8 +1689,10 @@ int gwf_strain(const gwf_model* model, const gwf_detector* dets, int32_t ndet, c
         case GWF_IMRPHENOMD_NRTIDALV2:
             if (!ev.p[11] || !ev.p[12]) return fail(GWF_ERR_ARG, "tidal model needs Lambda1, Lambda2");
             return run_strain<kNRTidalv2>(model, dets, ndet, psds, npsd, ev, n, opts, strain, workspace, workspace_bytes, st);
+        case GWF_IMRPHENOMHM:
+            return run_strain<kPhenomHM>(model, dets, ndet, psds, npsd, ev, n, opts, strain, workspace, workspace_bytes, st);
         default:
-            return fail(GWF_ERR_UNSUPPORTED, "gwf_strain: not built for this model (IMRPhenomHM)");
+            return fail(GWF_ERR_UNSUPPORTED, "gwf_strain: model not built");
     }
 }
 
@@ -1525,6 +1831,49 @@ int gwf_waveform(const gwf_model* model, const gwf_events* events, int64_t n, co
         case GWF_IMRPHENOMHM: return run_waveform<kPhenomHM>(model, ev, n, f, res, f_is_2d, phi_out, ampl_out, tau_out, hphc_out, fcut_out, workspace, workspace_bytes, st);
         default: return fail(GWF_ERR_ARG, "unknown model");
     }
+}
+
+int gwf_signal_grid(const gwf_model* model, const gwf_detector* det, double rot_deg, const gwf_events* events, int64_t n, const double* f, int32_t res,
+                    int32_t f_is_2d, const gwf_signal_out* outp, void* workspace, size_t workspace_bytes, void* stream) {
+    if (!model || !det || !events || !outp || !f) return fail(GWF_ERR_ARG, "gwf_signal_grid: null argument");
+    if (n < 0 || res < 1) return fail(GWF_ERR_ARG, "gwf_signal_grid: bad grid");
+    if (det->shape != 0 && det->shape != 1) return fail(GWF_ERR_ARG, "Enter valid detector configuration");
+    for (int i = 0; i < 11; ++i)
+        if (!events->p[i] && n > 0) return fail(GWF_ERR_ARG, "missing event parameter array");
+    if ((model->id == GWF_IMRPHENOMD || model->id == GWF_IMRPHENOMD_NRTIDALV2) && g_qnm_n == 0) return fail(GWF_ERR_ARG, "QNM tables not set (gwf_set_qnm_tables)");
+    if (outp->psi && model->id == GWF_IMRPHENOMHM) return fail(GWF_ERR_UNSUPPORTED, "GWPhase is not defined for IMRPhenomHM (its Phi is per mode)");
+    if (n == 0) return GWF_OK;
+    EventsDev ev;
+    for (int i = 0; i < GWF_NPARAM_IN; ++i) ev.p[i] = events->p[i];
+    const SignalOut out = {outp->Ap, outp->Ac, outp->psi, outp->strain, outp->Fp, outp->Fc, outp->dt};
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    switch (model->id) {
+        case GWF_TAYLORF2:
+            if ((model->flags & GWF_MODEL_ECCENTRIC) && !ev.p[15]) return fail(GWF_ERR_ARG, "eccentric model needs ecc");
+            if ((model->flags & GWF_MODEL_TIDAL) && (!ev.p[11] || !ev.p[12])) return fail(GWF_ERR_ARG, "tidal model needs Lambda1, Lambda2");
+            return run_signal_grid<kTaylorF2>(model, det, rot_deg, ev, n, f, res, f_is_2d, out, workspace, workspace_bytes, st);
+        case GWF_IMRPHENOMD: return run_signal_grid<kPhenomD>(model, det, rot_deg, ev, n, f, res, f_is_2d, out, workspace, workspace_bytes, st);
+        case GWF_IMRPHENOMD_NRTIDALV2:
+            if (!ev.p[11] || !ev.p[12]) return fail(GWF_ERR_ARG, "tidal model needs Lambda1, Lambda2");
+            return run_signal_grid<kNRTidalv2>(model, det, rot_deg, ev, n, f, res, f_is_2d, out, workspace, workspace_bytes, st);
+        case GWF_IMRPHENOMHM: return run_signal_grid<kPhenomHM>(model, det, rot_deg, ev, n, f, res, f_is_2d, out, workspace, workspace_bytes, st);
+        default: return fail(GWF_ERR_ARG, "unknown model");
+    }
+}
+
+int gwf_pattern(const gwf_detector* det, double rot_deg, const double* theta, const double* phi, const double* t, const double* psi, int64_t m,
+                double* Fp, double* Fc, double* dt, void* stream) {
+    if (!det || !theta || !phi || !t) return fail(GWF_ERR_ARG, "gwf_pattern: null argument");
+    if ((Fp || Fc) && !psi) return fail(GWF_ERR_ARG, "gwf_pattern: the pattern functions need psi");
+    if (det->shape != 0 && det->shape != 1) return fail(GWF_ERR_ARG, "Enter valid detector configuration");
+    if (m < 0) return fail(GWF_ERR_ARG, "negative count");
+    if (m == 0) return GWF_OK;
+    DetDev d;
+    ArmDev a;
+    single_arm(*det, rot_deg, d, a);
+    pattern_kernel<<<(unsigned)((m + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(d, a, theta, phi, t, psi, m, Fp, Fc, dt);
+    GWF_CUDA(cudaGetLastError());
+    return GWF_OK;
 }
 
 int gwf_covariance(const double* fisher, int64_t n, int32_t nP, int32_t method, double thresh, double* cov, double* inv_err, int32_t* status,

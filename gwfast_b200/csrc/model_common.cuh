@@ -38,6 +38,21 @@ struct ModelCfg {
 };
 
 // plain per-event inputs as the events dict carries them
+// reciprocal for the per-sample weights: MUFU seed + two Newton steps (error < 1 ulp; no denormal/special-case branch
+// of the IEEE division -- the arguments here are PSD values and amplitude denominators, always normal and positive)
+GWF_HD double rcp_fast(double x) {
+#ifdef __CUDA_ARCH__
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.0);
+    return fma(r, e, r);          // seed 2^-23 -> 2^-46 -> rounding level
+#else
+    return 1.0 / x;
+#endif
+}
+
 struct EventIn {
     double Mc, eta, dL, theta, phi, iota, psi, tcoal, Phicoal, chi1z, chi2z, Lambda1, Lambda2;
     double fcut_host, s_host;   // optional host-computed wf_model.fcut and M*GMsun_over_c3 (0 = compute on the device)

@@ -396,7 +396,7 @@ struct HMX {
 // as soon as it is known, so callers that only need sums over the modes keep nothing per mode.  The mode loop is rolled: the six
 // modes run the same code on different rows of the record (the kernel's instruction footprint stays that of one mode).
 template <int NT, bool TAN, class Sink>
-GWF_HD void phenomhm_foreach_mode(const HMRec<NT>& r, int g, const FreqPoint& fp, bool apply_cut, Sink& sink) {
+GWF_HD void phenomhm_foreach_mode(const HMRec<NT>& r, int g, const FreqPoint& fp, bool apply_cut, Sink& sink, int m_begin = 0, int m_end = kHMModes) {
     HMX X;
     X.set(r.s, r.sp, r.ln_s, fp);
     const double x = X.x;
@@ -408,7 +408,7 @@ GWF_HD void phenomhm_foreach_mode(const HMRec<NT>& r, int g, const FreqPoint& fp
         for (int j = 0; j < NT; ++j) dL0[j] = fma(-fma(r.t0[0], r.lam[j], r.t0[1 + j]), x, r.pc0[g][1 + j]);
     }
 #pragma unroll 1
-    for (int m = 0; m < kHMModes; ++m) {
+    for (int m = m_begin; m < m_end; ++m) {
         const HMModeRec<NT>& o = r.mode[m];
         const int mm = hm_mm(m);
         double A = 0.0, dlnA[NT];
@@ -420,7 +420,7 @@ GWF_HD void phenomhm_foreach_mode(const HMRec<NT>& r, int g, const FreqPoint& fp
             const double* Ma = o.amap[ra][0];
             const double* Mb = o.amap[ra][1];
             const double y = fma(Ma[0], x, Mb[0]);
-            const double iy = 1.0 / y;
+            const double iy = rcp_fast(y);
             double dlny[NT];
             if (TAN) {
 #pragma unroll
@@ -445,7 +445,7 @@ GWF_HD void phenomhm_foreach_mode(const HMRec<NT>& r, int g, const FreqPoint& fp
             } else if (!apply_cut || y < kMfCut) {
                 // exp(-(y-fr) g) * P / ((y-fr)^2 + w^2);  amrd = {fr, g, w, P}
                 const double u = y - r.amrd[0][0], gg = r.amrd[1][0], w = r.amrd[2][0], P = r.amrd[3][0];
-                const double iden = 1.0 / (u * u + w * w), iP = 1.0 / P;
+                const double iden = rcp_fast(u * u + w * w), iP = rcp_fast(P);
                 v = exp(-u * gg) * P * iden;
                 const double ku = -gg - 2. * u * iden;
                 dx = v * ku * y;
@@ -457,7 +457,7 @@ GWF_HD void phenomhm_foreach_mode(const HMRec<NT>& r, int g, const FreqPoint& fp
             } else on = false;
             if (on && v != 0.0) {
                 const double ym76 = iy * rsqrt(y13);
-                const double iv = 1.0 / v;
+                const double iv = rcp_fast(v);
                 if (m == 0) {
                     // (2,1): |H(v1)| |H(vS)| / |H(v2)| with v1 = (2 pi x)^(1/3), v2 = (4 pi x)^(1/3), vS = (2 pi y)^(1/3)
                     const double c2p = 1.84527014864402841909680387958898802678;      // (2 pi)^(1/3)
@@ -472,7 +472,7 @@ GWF_HD void phenomhm_foreach_mode(const HMRec<NT>& r, int g, const FreqPoint& fp
                         const double n2 = Pq * Pq + Qq * Qq;
                         habs[q] = (1.4142135623730951 / 3.0) * vq * sqrt(n2);
                         if (TAN && n2 != 0.0) {
-                            const double in2 = 1.0 / n2;
+                            const double in2 = rcp_fast(n2);
                             const double vPv = fma(3.0 * r.h21[3][0], v3, fma(2.0 * r.h21[2][0], v2, r.h21[1][0] * vq));   // v dP/dv
                             const double vQv = 3.0 * Qq;
                             // d ln v: lam/3 for v1, v2; dlny/3 for vS
@@ -489,7 +489,7 @@ GWF_HD void phenomhm_foreach_mode(const HMRec<NT>& r, int g, const FreqPoint& fp
                         }
                     }
                     if (habs[1] != 0.0) {                     // nan_to_num of 0/0 (waveforms.py:2582)
-                        A = r.Camp * ym76 * v * (habs[0] * habs[2] / habs[1]);
+                        A = r.Camp * ym76 * v * (habs[0] * habs[2] * rcp_fast(habs[1]));
                         if (TAN) {
 #pragma unroll
                             for (int j = 0; j < NT; ++j)
@@ -517,7 +517,7 @@ GWF_HD void phenomhm_foreach_mode(const HMRec<NT>& r, int g, const FreqPoint& fp
             const double* Mo = o.pmap[rp][2];
             const double* Ms = o.pmap[rp][3];
             const double y = fma(Ma[0], x, Mb[0]);
-            const double iy = 1.0 / y;
+            const double iy = rcp_fast(y);
             double dlny[NT];
             if (TAN) {
 #pragma unroll
@@ -556,9 +556,9 @@ GWF_HD void phenomhm_foreach_mode(const HMRec<NT>& r, int g, const FreqPoint& fp
                 const double* tc = o.mrd[2];
                 const double* ta = o.mrd[3];
                 const double* tw = o.mrd[4];
-                const double iw = 1.0 / tw[0];
+                const double iw = rcp_fast(tw[0]);
                 const double u = (y - ta[0]) * iw;
-                const double at = atan(u), wq = tc[0] / (1.0 + u * u) * iw;     // at_c d(atan)/du / at_w
+                const double at = atan(u), wq = tc[0] * rcp_fast(1.0 + u * u) * iw;     // at_c d(atan)/du / at_w
                 v += fma(tc[0], at, fma(c2[0], y, c1[0]));
                 dx += (wq + c2[0]) * y;
                 if (TAN) {

@@ -190,6 +190,103 @@ class GWSignal(object):
         """one Bernoulli mask per arm from numpy's global RNG, drawn in the reference's order (signal.py:729-762)."""
         return [onp.random.choice([0, 1], n, p=[1. - self.DutyFactor, self.DutyFactor]) for _ in range(self._narms())]
 
+    # ------------------------------------------------------------------ strain-level methods (signal.py:342-655)
+    def _this_detector(self):
+        return K.gwf_detector(self.det_lat_rad, self.det_long_rad, self.det_xax_rad, 0 if self.detector_shape == 'L' else 1,
+                              int(bool(self.useEarthMotion)), int(bool(self.noMotion)), 0, float(self.fmin),
+                              float(self.fmax) if self.fmax is not None else 0.)
+
+    def _ra_dec_from_th_phi(self, theta, phi):
+        """signal.py:389-399."""
+        return utils.ra_dec_from_th_phi_rad(theta, phi)
+
+    def _PatternFunction(self, theta, phi, t, psi, rot=0.):
+        """Plus and cross pattern functions of the detector (arXiv:gr-qc/9804014 eq. 10-13) for sky positions, times (GMST, days) and
+        polarisation angles of any mutually broadcastable shapes; ``rot`` in degrees (signal.py:342-387).  Evaluated by ``gwf_pattern``."""
+        from . import _elementwise
+        r = _elementwise.pattern(self._this_detector(), rot, theta, phi, t, psi, ('Fp', 'Fc'))
+        return r['Fp'], r['Fc']
+
+    def _DeltLoc(self, theta, phi, t):
+        """Time (s) to go from the Earth's centre to the detector for sky positions and times (GMST, days) (signal.py:401-423)."""
+        from . import _elementwise
+        return _elementwise.pattern(self._this_detector(), 0., theta, phi, t, None, ('dt',))['dt']
+
+    def GWAmplitudes(self, evParams, f, rot=0.):
+        """Plus and cross amplitudes at the detector on the grid ``f`` (``(res,)`` or ``(res, N)``); signal.py:425-466."""
+        from . import _elementwise
+        r = _elementwise.signal_grid(self.wf_model, self._this_detector(), rot, f, evParams, ('Ap', 'Ac'))
+        return r['Ap'], r['Ac']
+
+    def GWPhase(self, evParams, f):
+        """Complete signal phase 2 pi f tcoal 86400 - Phicoal - Phi(f) on the grid ``f``; signal.py:468-484."""
+        if self.wf_model.is_HigherModes:
+            raise TypeError('GWPhase is not defined for a higher-mode waveform: its Phi is a dictionary of mode phases (waveforms.py:2075)')
+        from . import _elementwise
+        return _elementwise.signal_grid(self.wf_model, self._this_detector(), 0., f, evParams, ('psi',))['psi']
+
+    def GWstrain(self, f, Mc, eta, dL, theta, phi, iota, psi, tcoal, Phicoal, chiS, chiA, chi1x, chi2x, chi1y, chi2y, LambdaTilde, deltaLambda,
+                 ecc, rot=0., is_m1m2=False, is_chi1chi2=False, is_prec_ang=False, is_Lam1Lam2=False, return_single_comp=None):
+        """Full complex strain at the detector on the grid ``f`` as a function of the parameters (signal.py:486-655): the same
+        re-parametrisation switches (``is_m1m2``, ``is_chi1chi2``, ``is_Lam1Lam2``) and ``return_single_comp`` values
+        ('Ap', 'Ac', 'Psip', 'Psic', 'At', 'Psit')."""
+        from . import _elementwise
+        if is_m1m2:
+            McUse, etaUse = utils.Mceta_from_m1m2(Mc, eta)
+        else:
+            McUse, etaUse = Mc, eta
+        if is_chi1chi2:
+            chi1z, chi2z = chiS, chiA
+        else:
+            chi1z, chi2z = chiS + chiA, chiS - chiA
+        ev = {'Mc': McUse, 'dL': dL, 'theta': theta, 'phi': phi, 'iota': iota, 'psi': psi, 'tcoal': tcoal, 'eta': etaUse, 'Phicoal': Phicoal,
+              'chi1z': chi1z, 'chi2z': chi2z}
+        if self.wf_model.is_tidal:
+            if not is_Lam1Lam2:
+                ev['Lambda1'], ev['Lambda2'] = utils.Lam12_from_Lamt_delLam(LambdaTilde, deltaLambda, etaUse)
+            else:
+                ev['Lambda1'], ev['Lambda2'] = LambdaTilde, deltaLambda
+        if self.wf_model.is_eccentric:
+            ev['ecc'] = ecc
+        det = self._this_detector()
+        if return_single_comp is None:
+            return _elementwise.signal_grid(self.wf_model, det, rot, f, ev, ('strain',))['strain']
+        if return_single_comp not in ('Ap', 'Ac', 'Psip', 'Psic', 'At', 'Psit'):
+            raise ValueError('Single component to return has to be among Ap, Ac, Psip, Psic')
+        if self.wf_model.is_HigherModes:
+            # signal.py:590-603: moduli and unwrapped phases of the two polarisation terms hp Fp e^{i...}, hc Fc e^{i...}
+            r = _elementwise.signal_grid(self.wf_model, det, rot, f, ev, ('strain', 'Fp', 'Fc', 'dt'))
+            hp, hc = self.wf_model.hphc(f, **ev)
+            fa = onp.asarray(f, dtype=float)
+            ph = onp.exp(1j * (2. * onp.pi * fa * r['dt'] + 2. * onp.pi * fa * (onp.asarray(tcoal) * 3600. * 24.) - onp.asarray(Phicoal)))
+            hp, hc = hp * r['Fp'] * ph, hc * r['Fc'] * ph
+            return {'Ap': lambda: onp.abs(hp), 'Ac': lambda: onp.abs(hc), 'Psip': lambda: onp.unwrap(onp.angle(hp)),
+                    'Psic': lambda: onp.unwrap(onp.angle(hc)), 'At': lambda: onp.abs(hp + hc), 'Psit': lambda: onp.unwrap(onp.angle(hp + hc))}[return_single_comp]()
+        r = _elementwise.signal_grid(self.wf_model, det, rot, f, ev, ('Ap', 'Ac', 'psi', 'dt'))
+        Psi = r['psi'] + 2. * onp.pi * onp.asarray(f, dtype=float) * r['dt']
+        if return_single_comp == 'Ap':
+            return r['Ap']
+        if return_single_comp == 'Ac':
+            return r['Ac']
+        if return_single_comp == 'Psip':
+            return Psi
+        if return_single_comp == 'Psic':
+            return Psi + onp.pi * 0.5
+        if return_single_comp == 'At':
+            return onp.abs(r['Ap'] + 1j * r['Ac'])
+        return Psi + onp.arctan2(r['Ac'], r['Ap'])
+
+    def optimal_location(self, tcoal, is_tGPS=False):
+        """Optimal (theta, phi) for a signal to be seen by the detector at a given GMST (psi = 0); signal.py:1586-1614."""
+        from scipy.optimize import minimize
+        if is_tGPS:
+            tcoal = utils.GPSt_to_LMST(tcoal, lat=0., long=0.)
+
+        def pattern_fixedtpsi(pars, tc=tcoal):
+            Fp, Fc = self._PatternFunction(pars[0], pars[1], t=tc, psi=0)
+            return -onp.sqrt(Fp ** 2 + Fc ** 2)
+        return minimize(pattern_fixedtpsi, [1., 1.], bounds=((0., onp.pi), (0., 2. * onp.pi))).x
+
     # ------------------------------------------------------------------ SNR
     def _prepare_snr(self, evParams):
         utils.check_evparams(evParams)
@@ -233,8 +330,6 @@ class GWSignal(object):
         if computeDerivFinDiff:
             raise NotImplementedError('finite-difference derivatives (numdifftools) are only used by the LAL/TEOBResumS wrappers of the reference; '
                                       'this engine always differentiates exactly')
-        if return_derivatives and self.wf_model.is_HigherModes:
-            raise NotImplementedError('return_derivatives is not built for IMRPhenomHM (return_SNR_derivatives is)')
         if res is None and df is not None:
             fcut = self.wf_model.fcut(**evParams)
             if self.fmax is not None:
@@ -300,8 +395,6 @@ class GWSignal(object):
         returns the arrays the engine consumes."""
         if WF.is_Precessing:
             raise NotImplementedError('precessing waveforms exist in the reference only through the LAL wrapper')
-        if WF.is_HigherModes:
-            raise NotImplementedError('WFOverlap is not built for IMRPhenomHM (gwf_strain)')
         zeros = onp.zeros_like(evParams['Mc'])
         if 'chi1z' in evParams:
             evParams['chi1x'], evParams['chi1y'], evParams['chi2x'], evParams['chi2y'] = zeros, zeros.copy(), zeros.copy(), zeros.copy()

@@ -94,6 +94,8 @@ typedef struct {
                                      form with all PSD windows in shared memory (tests compare the two kernels) */
 #define GWF_OPT_ONE_WARP_PER_EVENT 32 /* never split an event over two warps (the launcher does that when it shortens the
                                      persistent loop of a small catalog; tests compare the two mappings) */
+#define GWF_OPT_HM_BLOCK_PAIRS 64 /* IMRPhenomHM: the two warps of a pair take alternate blocks of 32 samples (the mapping of the other models)
+                                     instead of splitting the modes and the packed entries of the same samples (tests compare the two) */
 typedef struct {
     int32_t res;    /* frequency samples per event (res=1000) */
     int32_t flags;  /* GWF_OPT_* */
@@ -209,6 +211,27 @@ int gwf_copy_2d(void* dst, size_t dst_pitch, const void* src, size_t src_pitch, 
 int gwf_waveform(const gwf_model* model, const gwf_events* events, int64_t n, const double* f, int32_t res, int32_t f_is_2d,
                  double* phi_out, double* ampl_out, double* tau_out, double* hphc_out, double* fcut_out,
                  void* workspace, size_t workspace_bytes, void* stream);
+
+/* Replaces GWSignal.GWAmplitudes / GWPhase / GWstrain (gwfast/signal.py:425-655) on a USER frequency grid, for one detector at the arm
+ * orientation xax + rot_deg (the `rot` argument, degrees; the triangle's arms are rot = 0, 60 and -(1+2)).  The dict entries go
+ * straight to the waveform (GWstrain's own re-parametrisation flags -- is_m1m2, is_chi1chi2, is_Lam1Lam2 -- are applied by the caller).
+ *   f: [res][n] if f_is_2d else [res];  every output is [res][n] and may be NULL:
+ *   Ap, Ac   GWAmplitudes (A Fp (1+cos^2 iota)/2, A Fc cos iota; IMRPhenomHM: |hp| Fp, |hc| Fc, signal.py:457-464)
+ *   psi      GWPhase = 2 pi f tcoal 86400 - Phicoal - Phi(f)   (signal.py:484; not for IMRPhenomHM)
+ *   strain   complex128 (re, im): (Ap + i Ac) exp(i (psi + 2 pi f Delta t))   (IMRPhenomHM: (hp Fp + hc Fc) exp(i(...)), signal.py:584-607)
+ *   Fp, Fc   the pattern functions at the time the response uses (t = tcoal - tau(f)/86400 with useEarthMotion, + Delta t/86400)
+ *   dt       Delta t_loc in seconds at that time (signal.py:401-423) */
+typedef struct {
+    double *Ap, *Ac, *psi, *strain, *Fp, *Fc, *dt;
+} gwf_signal_out;
+int gwf_signal_grid(const gwf_model* model, const gwf_detector* det, double rot_deg, const gwf_events* events, int64_t n, const double* f,
+                    int32_t res, int32_t f_is_2d, const gwf_signal_out* out, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Replaces GWSignal._PatternFunction(theta, phi, t, psi, rot) and GWSignal._DeltLoc(theta, phi, t) (signal.py:342-423), element-wise over
+ * m points (device arrays): the pattern functions at exactly the time t (GMST, days) and the Earth-centre -> site delay in seconds.
+ * Fp, Fc, dt may be NULL; psi may be NULL if only dt is wanted. */
+int gwf_pattern(const gwf_detector* det, double rot_deg, const double* theta, const double* phi, const double* t, const double* psi, int64_t m,
+                double* Fp, double* Fc, double* dt, void* stream);
 
 /* Replaces fisherTools.CovMatr (gwfast/fisherTools.py:32-196): per event, normalise by the diagonal (ws F ws), invert, symmetrise,
  * undo the normalisation; double-double arithmetic on the device instead of the reference's per-event mpmath loop.

@@ -138,9 +138,12 @@ class Dual:
 
     def __truediv__(self, o):
         if isinstance(o, Dual):
-            inv = 1.0 / o.v
-            q = self.v * inv
-            return Dual(q, (self.d - _ex(q) * o.d) * _ex(inv))
+            # the VALUE is the plain quotient, bit for bit what the undifferentiated code computes: comparisons such as
+            # `fgrid < fcutPar` at the last grid sample (Mf = 0.2 up to the last bit, waveforms.py:2290, 2178) must take the same branch
+            # in the derivative pass as in the value pass (a reciprocal-multiply here switched IMRPhenomHM's (2,2) mode on in the
+            # derivative of a sample whose value had it off)
+            q = self.v / o.v
+            return Dual(q, (self.d - _ex(q) * o.d) / _ex(o.v))
         o = np.asarray(o)
         return Dual(self.v / o, self.d / _ex(o))
 

@@ -31,7 +31,20 @@ def run(cfg, ev, derivs=True):
     return out
 
 
+def hm_strain_derivs():
+    """IMRPhenomHM return_derivatives (signal.py:917-945 with the hphc branch of the analytic derivatives, :1378-1380): LVK without and the
+    ET triangle with Earth rotation"""
+    cfg = dict(model=dict(cls='IMRPhenomHM'), network='LVK-O4', rot=False, fmin=10., res=300)
+    ev = take(synthetic.bbh_catalog(10000, synthetic.SEEDS['C4']), 4)
+    save('deriv_hm_strain_lvk', cfg, ev, run(cfg, ev))
+    cfg = dict(model=dict(cls='IMRPhenomHM'), network='ET', rot=True, fmin=2., res=200)
+    save('deriv_hm_strain_et', cfg, take(ev, 3), run(cfg, take(ev, 3)))
+
+
 if __name__ == '__main__':
+    if len(sys.argv) > 1 and sys.argv[1] == 'hm':
+        hm_strain_derivs()
+        sys.exit(0)
     cfg = dict(model=dict(cls='IMRPhenomD'), network='ET+2CE', rot=True, fmin=2., res=200)
     ev = take(synthetic.bbh_catalog(10000, synthetic.SEEDS['C2']), 6)
     save('deriv_c2', cfg, ev, run(cfg, ev))
@@ -45,6 +58,7 @@ if __name__ == '__main__':
     cfg = dict(model=dict(cls='IMRPhenomHM'), network='LVK-O4', rot=False, fmin=10., res=300)
     ev = take(synthetic.bbh_catalog(10000, synthetic.SEEDS['C4']), 4)
     save('deriv_hm_lvk', cfg, ev, run(cfg, ev, derivs=False))
+    hm_strain_derivs()
     cfg = dict(model=dict(cls='IMRPhenomD_NRTidalv2'), network='ET', rot=True, fmin=2., res=200)
     ev = take(synthetic.bns_catalog(10000, synthetic.SEEDS['C3'], tidal=True), 4)
     save('deriv_nrtidal', cfg, ev, run(cfg, ev))

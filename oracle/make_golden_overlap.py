@@ -57,7 +57,22 @@ def save(name, cfg, ev1, ev2, out):
     print('wrote %s (%.1f KB)' % (path, os.path.getsize(path) / 1024.), {k: v for k, v in out.items() if k.startswith('overlap')})
 
 
+def hm_cases():
+    """IMRPhenomHM against itself at nearby parameters (LVK), and against IMRPhenomD (ET triangle with rotation): GWstrain's hp Fp + hc Fc"""
+    rng = np.random.default_rng(20260097)
+    cfg = dict(model1=dict(cls='IMRPhenomHM'), model2=dict(cls='IMRPhenomHM'), network='LVK-O4', rot=False, fmin=10., res=500)
+    ev1 = take(synthetic.bbh_catalog(10000, synthetic.SEEDS['C4']), 5)
+    ev2 = perturb(ev1, rng)
+    save('wfo_hm_lvk', cfg, ev1, ev2, run(cfg, ev1, ev2))
+    cfg = dict(model1=dict(cls='IMRPhenomHM'), model2=dict(cls='IMRPhenomD'), network='ET', rot=True, fmin=2., res=400)
+    ev1 = take(ev1, 4)
+    save('wfo_hm_phenomd_et', cfg, ev1, _copy(ev1), run(cfg, ev1, _copy(ev1)))
+
+
 if __name__ == '__main__':
+    if len(sys.argv) > 1 and sys.argv[1] == 'hm':
+        hm_cases()
+        sys.exit(0)
     rng = np.random.default_rng(20260099)
     # same model, nearby parameters, ET triangle + 2 CE with Earth rotation
     cfg = dict(model1=dict(cls='IMRPhenomD'), model2=dict(cls='IMRPhenomD'), network='ET+2CE', rot=True, fmin=2., res=600)

@@ -27,7 +27,7 @@ sp = C.c_void_p(torch.cuda.current_stream().cuda_stream)
 def call(flags):
     o = K.gwf_opts(res, flags, 0, 0)
     K.check(lib.gwf_fisher(C.byref(model), darr, len(dets), parr, len(handles), C.byref(evs), n, C.byref(o), C.c_void_p(packed.data_ptr()), C.c_void_p(snr2.data_ptr()), C.c_void_p(ws.data_ptr()), ws.numel(), sp), 'f')
-for extra, tag in ((0, 'fast+pair'), (16, 'generic+pair'), (32, 'fast, 1 warp/event'), (48, 'generic, 1 warp/event')):
+for extra, tag in ((0, 'fast+pair'), (16, 'generic+pair'), (32, 'fast, 1 warp/event'), (48, 'generic, 1 warp/event'), (64, 'HM: pairs take alternate blocks')):
     for _ in range(3): call(extra)
     ref = packed.clone()
     ts = []

@@ -76,7 +76,7 @@ def test_engine_snr_derivatives_match_reference(name):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize('name', ['deriv_c2', 'deriv_tf2tidal', 'deriv_m1m2_lvk', 'deriv_nrtidal'])
+@pytest.mark.parametrize('name', ['deriv_c2', 'deriv_tf2tidal', 'deriv_m1m2_lvk', 'deriv_nrtidal', 'deriv_hm_strain_lvk', 'deriv_hm_strain_et'])
 def test_engine_strain_derivatives_match_reference(name):
     cfg, ev, out = load_golden(name)
     net = make_network('engine', cfg)
@@ -105,7 +105,7 @@ def test_engine_strain_derivatives_match_reference(name):
 
 @pytest.mark.gpu
 def test_single_detector_derivative_api():
-    """GWSignal.FisherMatr returns (allFishers, allDerivs) lists, one entry per arm; HM strain derivatives are not built."""
+    """GWSignal.FisherMatr returns (allFishers, allDerivs) lists, one entry per arm (IMRPhenomHM included)."""
     from gwfast_b200 import waveforms, signal, synthetic
     ev = synthetic.bbh_catalog(5, 77)
     s = synthetic.build_network(signal.GWSignal, waveforms.IMRPhenomD(), 'ET')['ET']
@@ -117,5 +117,5 @@ def test_single_detector_derivative_api():
     for a, b in zip(Fs, Fs2):
         assert np.array_equal(a, b)
     hm = synthetic.build_network(signal.GWSignal, waveforms.IMRPhenomHM(), 'ET')['ET']
-    with pytest.raises(NotImplementedError):
-        hm.FisherMatr(copy_events(ev), res=64, return_derivatives=True)
+    Fh, Dh = hm.FisherMatr(copy_events(ev), res=64, return_derivatives=True)
+    assert len(Dh) == 3 and Dh[0].shape == (11, 5, 64) and np.allclose(Dh[2], -(Dh[0] + Dh[1]), rtol=1e-9, atol=1e-12 * np.abs(Dh[0]).max())

@@ -16,7 +16,7 @@ import pytest
 from conftest import GOLD, SNR_RTOL, copy_events
 
 OV_TOL = 2e-6
-CASES = ['wfo_phenomd_et2ce', 'wfo_phenomd_tf2_lvk', 'wfo_tidal_etsl_fmax']
+CASES = ['wfo_phenomd_et2ce', 'wfo_phenomd_tf2_lvk', 'wfo_tidal_etsl_fmax', 'wfo_hm_lvk', 'wfo_hm_phenomd_et']
 
 
 def _load(name):
@@ -99,5 +99,6 @@ def test_overlap_identities_and_bookkeeping():
         sel = wf.fcut(**ev) >= wf.fcut(**ev2)
         assert np.max(np.abs(a1[sel] / snr[sel] - 1)) < 1e-9
         assert np.all(np.abs(o12 / (a1 * a2)) <= 1 + 1e-12)
-    with pytest.raises(NotImplementedError):
-        sigs['ET'].WFOverlap(waveforms.IMRPhenomHM(), wf, copy_events(ev), copy_events(ev))
+    # IMRPhenomHM against itself: overlap 1
+    hm = waveforms.IMRPhenomHM()
+    assert np.max(np.abs(sigs['ET'].WFOverlap(hm, hm, copy_events(ev), copy_events(ev)) - 1)) < 1e-12

@@ -59,7 +59,7 @@ class EngineError(RuntimeError):
 
 # every symbol include/gwfast_b200.h declares (tests check that the library exports all of them)
 SYMBOLS = ('gwf_version', 'gwf_last_error', 'gwf_num_params', 'gwf_num_arms', 'gwf_workspace_bytes', 'gwf_psd_create',
-           'gwf_psd_destroy', 'gwf_set_qnm_tables', 'gwf_fisher', 'gwf_fisher_ex', 'gwf_strain_derivs', 'gwf_strain', 'gwf_overlap', 'gwf_snr', 'gwf_unpack_fisher', 'gwf_unpack_fisher_ld', 'gwf_unpack_gather', 'gwf_peer_alloc', 'gwf_peer_open', 'gwf_peer_close', 'gwf_peer_free', 'gwf_copy_2d', 'gwf_waveform', 'gwf_signal_grid', 'gwf_pattern', 'gwf_fp64_peak', 'gwf_covariance', 'gwf_eigen',
+           'gwf_psd_destroy', 'gwf_set_qnm_tables', 'gwf_fisher', 'gwf_fisher_ex', 'gwf_fisher_range', 'gwf_round_events', 'gwf_strain_derivs', 'gwf_strain', 'gwf_overlap', 'gwf_snr', 'gwf_unpack_fisher', 'gwf_unpack_fisher_ld', 'gwf_unpack_gather', 'gwf_peer_alloc', 'gwf_peer_open', 'gwf_peer_close', 'gwf_peer_free', 'gwf_copy_2d', 'gwf_waveform', 'gwf_signal_grid', 'gwf_pattern', 'gwf_fp64_peak', 'gwf_covariance', 'gwf_eigen',
            'gwf_inversion_error')
 
 _lib = None
@@ -89,6 +89,9 @@ def load():
     common = [P(gwf_model), P(gwf_detector), i32, P(vp), i32, P(gwf_events), i64, P(gwf_opts)]
     lib.gwf_fisher.argtypes = common + [vp, vp, vp, C.c_size_t, vp]
     lib.gwf_fisher_ex.argtypes = common + [P(gwf_fisher_out), vp, C.c_size_t, vp]
+    lib.gwf_fisher_range.argtypes = [P(gwf_model), P(gwf_detector), i32, P(vp), i32, P(gwf_events), i64, i64, i64, i32, P(gwf_opts), P(gwf_fisher_out), vp, C.c_size_t, vp]
+    lib.gwf_round_events.argtypes = [P(gwf_model)]
+    lib.gwf_round_events.restype = i64
     lib.gwf_snr.argtypes = common + [vp, vp, C.c_size_t, vp]
     lib.gwf_strain_derivs.argtypes = common + [vp, vp, C.c_size_t, vp]
     lib.gwf_strain.argtypes = common + [vp, vp, C.c_size_t, vp]

@@ -16,8 +16,6 @@ from . import gwfastGlobals as glob
 
 CHUNK_EVENTS = 1 << 16     # events per launch group: bounds the coefficient-record workspace (2-10 KB/event) and sets the grain of the
                            # H2D / kernel / D2H pipeline of a large catalog
-MIN_CHUNK = 2048           # a catalog is never cut into groups smaller than this (the persistent kernels want >= 4 events per SM)
-PIPE_DEPTH = 4             # groups a mid-sized batch is cut into so that the D2H of one group hides behind the kernels of the next
 N_STREAMS = 2
 
 _states = {}
@@ -137,15 +135,6 @@ def _call_arrays(dets, psd_handles):
     return darr, parr
 
 
-def _groups(n):
-    """launch groups (lo, m) of a batch: one group for a small batch, PIPE_DEPTH groups for a mid-sized one, CHUNK_EVENTS-sized
-    groups for a catalog.  An event's result never depends on the grouping (the kernels' work mapping is fixed per model)."""
-    if n <= 2 * MIN_CHUNK:
-        return [(0, n)]
-    m = min(CHUNK_EVENTS, max(MIN_CHUNK, -(-n // PIPE_DEPTH)))
-    return [(lo, min(m, n - lo)) for lo in range(0, n, m)]
-
-
 # When set, fisher() leaves a reference to its device-resident result (npass, nP, nP, n) in state().last_fisher_device, so that a
 # multi-GPU caller can all-gather it over NVLink without a host round trip (parallel.DistributedDetNet(gather='device')).
 STASH_DEVICE = False
@@ -159,9 +148,29 @@ PEER = None
 KERNEL_FLAGS = 0
 
 
+MAX_GROUPS = 4             # launch groups of a single-chunk batch (D2H of one group behind the kernels of the next)
+
+
+def _round_groups(m, round_events, max_groups=None):
+    """Cut [0, m) into at most `max_groups` launch groups whose boundaries are multiples of `round_events` (what one round of the
+    persistent Fisher grid takes): every CTA stays equally loaded, so the cut costs no ragged extra round, and the device->host copy of a
+    group hides behind the kernels of the next.  The last group (whose copy is exposed) is the smallest and holds the partial round."""
+    rounds = -(-m // round_events)
+    g = max(1, min(MAX_GROUPS if max_groups is None else max_groups, rounds // 2))
+    if g == 1:
+        return [(0, m)]
+    q, r = divmod(rounds, g)
+    out, lo = [], 0
+    for k in range(g):
+        hi = min(m, lo + (q + (1 if k < r else 0)) * round_events)
+        out.append((lo, hi - lo))
+        lo = hi
+    return [t for t in out if t[1] > 0]
+
+
 def fisher(model, dets, psd_handles, ev, n, res, flags, per_arm, want_snr2=True, keep_on_device=False, want_snr_derivs=False,
            want_snr_integ=False):
-    """Run gwf_fisher_ex (+ gwf_unpack_fisher_ld) on the current device, pipelined over launch groups.
+    """Run the Fisher kernels (+ unpack) on the current device, pipelined.
 
     Returns ``(F, snr2, io)`` with ``F`` of shape ``(npass, nP, nP, n)`` and ``snr2`` ``(npass, n)`` as numpy arrays
     (or device tensors if ``keep_on_device``); ``io`` = (h2d_bytes, d2h_bytes).  With ``want_snr_derivs`` the second element
@@ -169,9 +178,10 @@ def fisher(model, dets, psd_handles, ev, n, res, flags, per_arm, want_snr2=True,
     SNRInteg forms (gwf_fisher_out.snr2_integ) instead of 4 int |h|^2/Sn.  The per-event status words of the call are left in
     ``state().last_status`` (numpy int32, or None with ``keep_on_device``).
 
-    Pipeline: the events are staged once in pinned memory; every launch group runs H2D -> prologue -> fisher -> unpack -> D2H on one
-    of two side streams, so the copies of a group overlap the kernels of its neighbours, and the persistent kernel of the next group
-    fills the SMs the previous one's tail leaves idle.  The host waits once, at the end.
+    The events are staged once in pinned memory.  A batch of up to CHUNK_EVENTS events is ONE H2D copy and ONE prologue, followed by a
+    few launch groups cut at multiples of the persistent grid's round (``gwf_fisher_range``): while a group's kernels run, the Fisher
+    matrices of the previous group are unpacked and copied to the host on a side stream.  A larger catalog is cut into chunks of
+    CHUNK_EVENTS, each running H2D -> prologue -> kernels -> unpack -> D2H on one of two side streams.  The host waits once, at the end.
     """
     global launch_count
     st = state()
@@ -182,79 +192,124 @@ def fisher(model, dets, psd_handles, ev, n, res, flags, per_arm, want_snr2=True,
         raise EngineError('unknown model')
     npack = nP * (nP + 1) // 2
     darr, parr = _call_arrays(dets, psd_handles)
-    npass = lib.gwf_num_arms(darr, len(dets)) if per_arm else 1
+    ndet, npsd = len(dets), len(psd_handles)
+    npass = lib.gwf_num_arms(darr, ndet) if per_arm else 1
     cur = torch.cuda.current_stream(st.device)
     f64 = torch.float64
+    # the input copy goes first: it is in flight while the host allocates the outputs
+    host_ev, present = _stage(st, ev, n, K.EVENT_KEYS)
+    nk = len(present)
+    chunks = [(lo, min(CHUNK_EVENTS, n - lo)) for lo in range(0, n, CHUNK_EVENTS)]
+    multi = len(chunks) > 1
+    dev_all = None
+    if not multi:
+        dev_all = torch.empty((nk, n), dtype=f64, device=st.device)
+        dev_all.copy_(host_ev, non_blocking=True)
     full = torch.empty((npass, nP, nP, n), dtype=f64, device=st.device)
     snr2 = torch.empty((npass, n), dtype=f64, device=st.device)
     sder = torch.empty((npass, n, nP), dtype=f64, device=st.device) if want_snr_derivs else None
     status = torch.empty((n,), dtype=torch.int32, device=st.device)
     opts = K.gwf_opts(int(res), int(flags) | KERNEL_FLAGS, int(bool(per_arm)), 0)
-    host_ev, present = _stage(st, ev, n, K.EVENT_KEYS)
-    nk = len(present)
-    groups = _groups(n)
     to_host = not keep_on_device
-    if to_host:
-        out_f = torch.empty(full.shape, dtype=f64, pin_memory=True)
-        out_s = torch.empty(snr2.shape, dtype=f64, pin_memory=True)
-        out_st = torch.empty((n,), dtype=torch.int32, pin_memory=True)
-        out_d = torch.empty(sder.shape, dtype=f64, pin_memory=True) if want_snr_derivs else None
-    piped = len(groups) > 1
-    streams = _side_streams(st) if piped else [cur]
-    if piped:
-        for s_ in streams:
-            s_.wait_stream(cur)
+    host_out = []
+
+    def pinned_outputs():
+        # allocated when the first copy is about to be queued: by then the kernels are already running
+        if not host_out:
+            host_out.extend([torch.empty(full.shape, dtype=f64, pin_memory=True), torch.empty(snr2.shape, dtype=f64, pin_memory=True),
+                             torch.empty((n,), dtype=torch.int32, pin_memory=True),
+                             torch.empty(sder.shape, dtype=f64, pin_memory=True) if want_snr_derivs else None])
+        return host_out
+    side = _side_streams(st)
+    for s_ in side:
+        s_.wait_stream(cur)
+    copy_stream = side[-1]
+    round_events = max(1, int(lib.gwf_round_events(C.byref(model))))
     keep = []
-    for gi, (lo, m) in enumerate(groups):
-        slot = gi % len(streams)
-        stream = streams[slot]
+
+    def outputs(packed, s2, sd, lo):
+        return K.gwf_fisher_out(packed.data_ptr(), None if want_snr_integ else s2, s2 if want_snr_integ else None, sd, status.data_ptr() + 4 * lo)
+
+    def unpack(packed, lo, m, sp):
+        global launch_count
+        for p in range(npass):
+            if PEER is not None and npass == 1:
+                K.check(lib.gwf_unpack_gather(C.c_void_p(packed[p].data_ptr()), m, nP, C.c_void_p(full[p].data_ptr() + 8 * lo), n,
+                                              PEER.slots(lo), PEER.world, sp), 'gwf_unpack_gather')
+            else:
+                K.check(lib.gwf_unpack_fisher_ld(C.c_void_p(packed[p].data_ptr()), m, nP, C.c_void_p(full[p].data_ptr() + 8 * lo), n, sp), 'gwf_unpack_fisher')
+            launch_count += 1
+
+    def to_host_copy(lo, m, sp):
+        out_f = pinned_outputs()[0]
+        if m == n:
+            out_f.copy_(full, non_blocking=True)
+        else:
+            K.check(lib.gwf_copy_2d(C.c_void_p(out_f.data_ptr() + 8 * lo), n * 8, C.c_void_p(full.data_ptr() + 8 * lo), n * 8, m * 8,
+                                    npass * nP * nP, sp), 'gwf_copy_2d')
+
+    for ci, (clo, cm) in enumerate(chunks):
+        stream = side[ci % len(side)] if multi else cur
         sp = C.c_void_p(stream.cuda_stream)
         with torch.cuda.stream(stream):
-            dev_ev = torch.empty((nk, m), dtype=f64, device=st.device)
-            if m == n:
-                dev_ev.copy_(host_ev, non_blocking=True)
+            dev_ev = dev_all if dev_all is not None else torch.empty((nk, cm), dtype=f64, device=st.device)
+            if dev_all is not None:
+                pass
             else:
-                K.check(lib.gwf_copy_2d(C.c_void_p(dev_ev.data_ptr()), m * 8, C.c_void_p(host_ev.data_ptr() + lo * 8), n * 8, m * 8, nk, sp), 'gwf_copy_2d')
-            evs = _events_struct(dev_ev, present, m)
-            ws = _workspace(st, lib.gwf_workspace_bytes(C.byref(model), m), slot if piped else None)
-            packed = torch.empty((npass, m, npack), dtype=f64, device=st.device)
-            s2 = snr2 if m == n else torch.empty((npass, m), dtype=f64, device=st.device)
-            sd = (sder if m == n else torch.empty((npass, m, nP), dtype=f64, device=st.device)) if want_snr_derivs else None
-            fo = K.gwf_fisher_out(packed.data_ptr(), None if want_snr_integ else s2.data_ptr(), s2.data_ptr() if want_snr_integ else None,
-                                  sd.data_ptr() if want_snr_derivs else None, status.data_ptr() + 4 * lo)
-            K.check(lib.gwf_fisher_ex(C.byref(model), darr, len(dets), parr, len(psd_handles), C.byref(evs), m, C.byref(opts), C.byref(fo),
-                                      C.c_void_p(ws.data_ptr()), ws.numel(), sp), 'gwf_fisher')
-            launch_count += 1 + npass
-            for p in range(npass):
-                if PEER is not None and npass == 1:
-                    K.check(lib.gwf_unpack_gather(C.c_void_p(packed[p].data_ptr()), m, nP, C.c_void_p(full[p].data_ptr() + 8 * lo), n,
-                                                  PEER.slots(lo), PEER.world, sp), 'gwf_unpack_gather')
-                else:
-                    K.check(lib.gwf_unpack_fisher_ld(C.c_void_p(packed[p].data_ptr()), m, nP, C.c_void_p(full[p].data_ptr() + 8 * lo), n, sp), 'gwf_unpack_fisher')
+                K.check(lib.gwf_copy_2d(C.c_void_p(dev_ev.data_ptr()), cm * 8, C.c_void_p(host_ev.data_ptr() + clo * 8), n * 8, cm * 8, nk, sp), 'gwf_copy_2d')
+            evs = _events_struct(dev_ev, present, cm)
+            ws = _workspace(st, lib.gwf_workspace_bytes(C.byref(model), cm), (ci % len(side)) if multi else None)
+            wsp, wsn = C.c_void_p(ws.data_ptr()), ws.numel()
+            groups = [(0, cm)] if multi else _round_groups(cm, round_events)
+            if len(groups) > 1:
+                # one prologue for the chunk, then the groups
+                fo = K.gwf_fisher_out(None, None, None, None, status.data_ptr() + 4 * clo)
+                K.check(lib.gwf_fisher_range(C.byref(model), darr, ndet, parr, npsd, C.byref(evs), cm, 0, cm, 1, C.byref(opts), C.byref(fo), wsp, wsn, sp),
+                        'gwf_fisher_range')
                 launch_count += 1
-            if m != n:
-                snr2[:, lo:lo + m] = s2
-                if want_snr_derivs:
-                    sder[:, lo:lo + m] = sd
-            if to_host:
-                if m == n:
-                    out_f.copy_(full, non_blocking=True)
+            for (glo, gm) in groups:
+                lo = clo + glo
+                packed = torch.empty((npass, gm, npack), dtype=f64, device=st.device)
+                direct = npass == 1
+                s2 = None if direct else torch.empty((npass, gm), dtype=f64, device=st.device)
+                sd = None if (direct or not want_snr_derivs) else torch.empty((npass, gm, nP), dtype=f64, device=st.device)
+                s2p = snr2.data_ptr() + 8 * lo if direct else s2.data_ptr()
+                sdp = (sder.data_ptr() + 8 * nP * lo if direct else sd.data_ptr()) if want_snr_derivs else None
+                fo = outputs(packed, s2p, sdp, lo)
+                if len(groups) > 1:
+                    K.check(lib.gwf_fisher_range(C.byref(model), darr, ndet, parr, npsd, C.byref(evs), cm, glo, gm, 2, C.byref(opts), C.byref(fo), wsp, wsn, sp),
+                            'gwf_fisher_range')
+                    launch_count += npass
                 else:
-                    K.check(lib.gwf_copy_2d(C.c_void_p(out_f.data_ptr() + 8 * lo), n * 8, C.c_void_p(full.data_ptr() + 8 * lo), n * 8, m * 8,
-                                            npass * nP * nP, sp), 'gwf_copy_2d')
-        keep.append((dev_ev, packed, s2, sd))
-    if piped:
-        for s_ in streams:
-            cur.wait_stream(s_)
-        for t in (full, snr2, sder, status):                  # allocated on the current stream, written on the side streams
-            if t is not None:
-                for s_ in streams:
-                    t.record_stream(s_)
+                    K.check(lib.gwf_fisher_ex(C.byref(model), darr, ndet, parr, npsd, C.byref(evs), cm, C.byref(opts), C.byref(fo), wsp, wsn, sp), 'gwf_fisher')
+                    launch_count += 1 + npass
+                unpack(packed, lo, gm, sp)
+                if not direct:
+                    snr2[:, lo:lo + gm] = s2
+                    if want_snr_derivs:
+                        sder[:, lo:lo + gm] = sd
+                if to_host:
+                    if multi or len(groups) == 1:
+                        to_host_copy(lo, gm, sp)                     # same stream: the chunk pipeline overlaps it with the other stream's kernels
+                    else:
+                        done = torch.cuda.Event()
+                        done.record(stream)
+                        copy_stream.wait_event(done)
+                        to_host_copy(lo, gm, C.c_void_p(copy_stream.cuda_stream))
+                keep.append((packed, s2, sd))
+            keep.append((dev_ev,))
+    for s_ in side:
+        cur.wait_stream(s_)
+    for t in (full, snr2, sder, status):                  # allocated on the current stream, touched on the side streams
+        if t is not None:
+            for s_ in side:
+                t.record_stream(s_)
     st.last_fisher_device = full if STASH_DEVICE else None
     h2d = host_ev.numel() * 8
     if keep_on_device:
         st.last_status = None
         return full, ((snr2, sder) if want_snr_derivs else snr2), (h2d, 0)
+    out_f, out_s, out_st, out_d = pinned_outputs()
     out_s.copy_(snr2, non_blocking=True)
     out_st.copy_(status, non_blocking=True)
     if want_snr_derivs:

@@ -1157,18 +1157,31 @@ static int collect_psds(const gwf_psd* const* psds, int npsd, PsdDev* out) {
     return GWF_OK;
 }
 
+// which part of a Fisher call to run, on which events: the workspace (records + EventAux) is laid out for n_total events; the
+// prologue (phase bit 1) always covers all of them, the kernels (phase bit 2) the events [lo, lo + m) -- outputs then refer to that range
+struct FisherRange {
+    long long lo, m;
+    int phases;
+};
 template <int MODEL, int NT>
-static int run_fisher(const gwf_model* model, const gwf_detector* dets, int ndet, const gwf_psd* const* psds, int npsd, const EventsDev& ev,
-                      long long n, const gwf_opts* opts, const gwf_fisher_out* outp, void* ws, size_t ws_bytes, cudaStream_t st) {
+static int run_fisher(const gwf_model* model, const gwf_detector* dets, int ndet, const gwf_psd* const* psds, int npsd, const EventsDev& ev_all,
+                      long long n_total, const FisherRange& range, const gwf_opts* opts, const gwf_fisher_out* outp, void* ws, size_t ws_bytes,
+                      cudaStream_t st) {
     typedef typename ModelTraits<MODEL, NT>::Rec Rec;
     constexpr int NP = NT + 7, NPACK = NP * (NP + 1) / 2;
     double* fisher = outp->fisher_packed;
     double* snr2 = outp->snr2;
     double* snr_derivs = outp->snr_derivs;
-    const size_t rec_bytes = (sizeof(Rec) * (size_t)n + 15) & ~(size_t)15;
-    if (ws_bytes < rec_bytes + sizeof(EventAux) * (size_t)n) return fail(GWF_ERR_WORKSPACE, "workspace too small");
-    Rec* recs = reinterpret_cast<Rec*>(ws);
-    EventAux* aux = reinterpret_cast<EventAux*>(reinterpret_cast<char*>(ws) + rec_bytes);
+    const size_t rec_bytes = (sizeof(Rec) * (size_t)n_total + 15) & ~(size_t)15;
+    if (ws_bytes < rec_bytes + sizeof(EventAux) * (size_t)n_total) return fail(GWF_ERR_WORKSPACE, "workspace too small");
+    Rec* recs_all = reinterpret_cast<Rec*>(ws);
+    EventAux* aux_all = reinterpret_cast<EventAux*>(reinterpret_cast<char*>(ws) + rec_bytes);
+    // the kernels' view: the events of the range
+    const long long n = range.m;
+    Rec* recs = recs_all + range.lo;
+    EventAux* aux = aux_all + range.lo;
+    EventsDev ev;
+    for (int i = 0; i < GWF_NPARAM_IN; ++i) ev.p[i] = ev_all.p[i] ? ev_all.p[i] + range.lo : nullptr;
     ModelCfg cfg = {model->id, model->flags, model->fcutPar, model->fRef};
     DeviceCtx* ctx = nullptr;
     if (int rc0 = device_ctx(MODEL == kPhenomD || MODEL == kNRTidalv2, &ctx)) return rc0;
@@ -1195,15 +1208,19 @@ static int run_fisher(const gwf_model* model, const gwf_detector* dets, int ndet
     if (pair) pair |= (MODEL == kPhenomHM) ? 6 : 2;
     const int lin = (opts->flags & GWF_OPT_LIN_GRID) ? 1 : 0;
     const int pb = 128;
-    if (!(opts->flags & GWF_OPT_REUSE_WORKSPACE)) {
-        // the prologue also leaves the per-event geometry and grids (EventAux) for the Fisher kernel
-        AuxPlan ap;
-        ap.out = aux;
-        for (int g = 0; g < kMaxGroups; ++g) ap.fmax[g] = net.group_fmax[g];
-        ap.res = opts->res; ap.lin = lin; ap.stride = (pair && !(kSplitPair && !(opts->flags & GWF_OPT_HM_BLOCK_PAIRS))) ? 64 : 32;
-        prologue_kernel<MODEL, NT><<<dim3((unsigned)((n + pb - 1) / pb), (MODEL == kPhenomD || MODEL == kNRTidalv2) ? 2 : 1), pb, 0, st>>>(ev, n, cfg, opts->flags, ctx->qnm, gi, recs, nullptr, ap, outp->status);
-        GWF_CUDA(cudaGetLastError());
-    } else if (outp->status) GWF_CUDA(cudaMemsetAsync(outp->status, 0, sizeof(int) * (size_t)n, st));   // the input bits are the prologue's
+    if (range.phases & 1) {
+        if (!(opts->flags & GWF_OPT_REUSE_WORKSPACE)) {
+            // the prologue also leaves the per-event geometry and grids (EventAux) for the Fisher kernel
+            AuxPlan ap;
+            ap.out = aux_all;
+            for (int g = 0; g < kMaxGroups; ++g) ap.fmax[g] = net.group_fmax[g];
+            ap.res = opts->res; ap.lin = lin; ap.stride = (pair && !(kSplitPair && !(opts->flags & GWF_OPT_HM_BLOCK_PAIRS))) ? 64 : 32;
+            prologue_kernel<MODEL, NT><<<dim3((unsigned)((n_total + pb - 1) / pb), (MODEL == kPhenomD || MODEL == kNRTidalv2) ? 2 : 1), pb, 0, st>>>(
+                ev_all, n_total, cfg, opts->flags, ctx->qnm, gi, recs_all, nullptr, ap, outp->status);
+            GWF_CUDA(cudaGetLastError());
+        } else if (outp->status) GWF_CUDA(cudaMemsetAsync(outp->status, 0, sizeof(int) * (size_t)n_total, st));   // the input bits are the prologue's
+    }
+    if (!(range.phases & 2) || n == 0) return GWF_OK;
     const int sms = ctx->sms;
     // dynamic shared memory: per-warp staging blocks, then the PSD windows (as many tables as fit in 227 KB)
     const size_t ws_bytes_smem = sizeof(FisherSmem<Rec, typename PointFns<MODEL, NT>::Extra>) * kWarpsPerCta;
@@ -1571,11 +1588,31 @@ static int check_common(const gwf_model* model, const gwf_detector* dets, const 
     return GWF_OK;
 }
 
+static int fisher_dispatch(const gwf_model* model, const gwf_detector* dets, int32_t ndet, const gwf_psd* const* psds, int32_t npsd, const gwf_events* events,
+                           int64_t n, const FisherRange& range, const gwf_opts* opts, const gwf_fisher_out* out, void* workspace, size_t workspace_bytes,
+                           void* stream);
+
 int gwf_fisher_ex(const gwf_model* model, const gwf_detector* dets, int32_t ndet, const gwf_psd* const* psds, int32_t npsd, const gwf_events* events,
                   int64_t n, const gwf_opts* opts, const gwf_fisher_out* out, void* workspace, size_t workspace_bytes, void* stream) {
+    const FisherRange all = {0, n, 3};
+    if (!out || !out->fisher_packed) return fail(GWF_ERR_ARG, "null output");
+    return fisher_dispatch(model, dets, ndet, psds, npsd, events, n, all, opts, out, workspace, workspace_bytes, stream);
+}
+
+int gwf_fisher_range(const gwf_model* model, const gwf_detector* dets, int32_t ndet, const gwf_psd* const* psds, int32_t npsd, const gwf_events* events,
+                     int64_t n_total, int64_t lo, int64_t m, int32_t phases, const gwf_opts* opts, const gwf_fisher_out* out, void* workspace,
+                     size_t workspace_bytes, void* stream) {
+    if (lo < 0 || m < 0 || lo + m > n_total || !(phases & 3)) return fail(GWF_ERR_ARG, "gwf_fisher_range: bad range or phases");
+    if (!out || ((phases & 2) && !out->fisher_packed)) return fail(GWF_ERR_ARG, "null output");
+    const FisherRange r = {lo, m, phases & 3};
+    return fisher_dispatch(model, dets, ndet, psds, npsd, events, n_total, r, opts, out, workspace, workspace_bytes, stream);
+}
+
+static int fisher_dispatch(const gwf_model* model, const gwf_detector* dets, int32_t ndet, const gwf_psd* const* psds, int32_t npsd, const gwf_events* events,
+                           int64_t n, const FisherRange& range, const gwf_opts* opts, const gwf_fisher_out* out, void* workspace, size_t workspace_bytes,
+                           void* stream) {
     int rc = check_common(model, dets, psds, events, n, opts);
     if (rc) return rc;
-    if (!out || !out->fisher_packed) return fail(GWF_ERR_ARG, "null output");
     if (n == 0) return GWF_OK;
     EventsDev ev;
     for (int i = 0; i < GWF_NPARAM_IN; ++i) ev.p[i] = events->p[i];
@@ -1586,22 +1623,29 @@ int gwf_fisher_ex(const gwf_model* model, const gwf_detector* dets, int32_t ndet
             if (ecc && !ev.p[15]) return fail(GWF_ERR_ARG, "eccentric model needs ecc");
             if (model->flags & GWF_MODEL_TIDAL) {
                 if (!ev.p[11] || !ev.p[12]) return fail(GWF_ERR_ARG, "tidal model needs Lambda1, Lambda2");
-                if (ecc) return run_fisher<kTaylorF2, 7>(model, dets, ndet, psds, npsd, ev, n, opts, out, workspace, workspace_bytes, st);
-                return run_fisher<kTaylorF2, 6>(model, dets, ndet, psds, npsd, ev, n, opts, out, workspace, workspace_bytes, st);
+                if (ecc) return run_fisher<kTaylorF2, 7>(model, dets, ndet, psds, npsd, ev, n, range, opts, out, workspace, workspace_bytes, st);
+                return run_fisher<kTaylorF2, 6>(model, dets, ndet, psds, npsd, ev, n, range, opts, out, workspace, workspace_bytes, st);
             }
-            if (ecc) return run_fisher<kTaylorF2, 5>(model, dets, ndet, psds, npsd, ev, n, opts, out, workspace, workspace_bytes, st);
-            return run_fisher<kTaylorF2, 4>(model, dets, ndet, psds, npsd, ev, n, opts, out, workspace, workspace_bytes, st);
+            if (ecc) return run_fisher<kTaylorF2, 5>(model, dets, ndet, psds, npsd, ev, n, range, opts, out, workspace, workspace_bytes, st);
+            return run_fisher<kTaylorF2, 4>(model, dets, ndet, psds, npsd, ev, n, range, opts, out, workspace, workspace_bytes, st);
         }
         case GWF_IMRPHENOMD:
-            return run_fisher<kPhenomD, 4>(model, dets, ndet, psds, npsd, ev, n, opts, out, workspace, workspace_bytes, st);
+            return run_fisher<kPhenomD, 4>(model, dets, ndet, psds, npsd, ev, n, range, opts, out, workspace, workspace_bytes, st);
         case GWF_IMRPHENOMD_NRTIDALV2:
             if (!ev.p[11] || !ev.p[12]) return fail(GWF_ERR_ARG, "tidal model needs Lambda1, Lambda2");
-            return run_fisher<kNRTidalv2, 6>(model, dets, ndet, psds, npsd, ev, n, opts, out, workspace, workspace_bytes, st);
+            return run_fisher<kNRTidalv2, 6>(model, dets, ndet, psds, npsd, ev, n, range, opts, out, workspace, workspace_bytes, st);
         case GWF_IMRPHENOMHM:
-            return run_fisher<kPhenomHM, 4>(model, dets, ndet, psds, npsd, ev, n, opts, out, workspace, workspace_bytes, st);
+            return run_fisher<kPhenomHM, 4>(model, dets, ndet, psds, npsd, ev, n, range, opts, out, workspace, workspace_bytes, st);
         default:
             return fail(GWF_ERR_UNSUPPORTED, "model not built yet");
     }
+}
+
+int64_t gwf_round_events(const gwf_model* model) {
+    if (!model) return 0;
+    DeviceCtx* ctx = nullptr;
+    if (device_ctx(false, &ctx)) return 0;
+    return (int64_t)ctx->sms * (model->id == GWF_TAYLORF2 ? kWarpsPerCta : kWarpsPerCta / 2);
 }
 
 int gwf_fisher(const gwf_model* model, const gwf_detector* dets, int32_t ndet, const gwf_psd* const* psds, int32_t npsd, const gwf_events* events,

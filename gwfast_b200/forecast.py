@@ -136,11 +136,57 @@ def _batch_file(fout, a, b):
     return os.path.join(fout, 'batch_%d_to_%d.npz' % (a, b))
 
 
+REFERENCE_FILES = ('snrs', 'fishers', 'covs', 'sky_area', 'errors', 'inversion_errors', 'cond_numbers', 'idxs_det')
+
+
+def to_reference_files(fout, a, b, snrs, totF, eps, cov, sky, errs, idxs, cond):
+    """One batch in the reference's own files (run script to_file :224-247 and the snrs-only branch :784-788): ``snrs_<a>_to_<b>.txt``
+    for every batch -- the file ``--resume_run`` looks for (:738-741) -- and, when Fisher matrices were computed, ``fishers``/``covs``
+    ``.npy`` plus ``sky_area``, ``errors``, ``inversion_errors``, ``cond_numbers``, ``idxs_det`` ``.txt`` with the same suffix, so that the
+    reference script can resume or concatenate a run started here (and vice versa)."""
+    suff = '_%d_to_%d' % (a, b)
+    np.savetxt(os.path.join(fout, 'snrs' + suff + '.txt'), np.atleast_1d(snrs))
+    if totF is None or np.all(np.isnan(totF)):
+        return
+    np.save(os.path.join(fout, 'fishers' + suff + '.npy'), totF)
+    np.save(os.path.join(fout, 'covs' + suff + '.npy'), cov)
+    np.savetxt(os.path.join(fout, 'sky_area' + suff + '.txt'), np.atleast_1d(sky))
+    np.savetxt(os.path.join(fout, 'errors' + suff + '.txt'), errs)
+    np.savetxt(os.path.join(fout, 'inversion_errors' + suff + '.txt'), np.atleast_1d(eps))
+    np.savetxt(os.path.join(fout, 'cond_numbers' + suff + '.txt'), np.atleast_1d(cond))
+    np.savetxt(os.path.join(fout, 'idxs_det' + suff + '.txt'), idxs)
+
+
+def concatenate_reference_files(fout, ranges):
+    """The reference's ``--concatenate`` step (run script :1034-1170) over batches written by to_reference_files: one array per quantity
+    in catalog order (batches without detections contribute their SNRs only)."""
+    out = {k: [] for k in ('snrs', 'fishers', 'covs', 'sky_area', 'errors', 'inversion_errors', 'cond_numbers', 'idxs_det')}
+    for a, b in ranges:
+        suff = '_%d_to_%d' % (a, b)
+        out['snrs'].append(np.atleast_1d(np.loadtxt(os.path.join(fout, 'snrs' + suff + '.txt'))))
+        if not os.path.exists(os.path.join(fout, 'fishers' + suff + '.npy')):
+            continue
+        out['fishers'].append(np.load(os.path.join(fout, 'fishers' + suff + '.npy')))
+        out['covs'].append(np.load(os.path.join(fout, 'covs' + suff + '.npy')))
+        for k in ('sky_area', 'inversion_errors', 'cond_numbers', 'idxs_det'):
+            out[k].append(np.atleast_1d(np.loadtxt(os.path.join(fout, k + suff + '.txt'))))
+        e = np.loadtxt(os.path.join(fout, 'errors' + suff + '.txt'))
+        out['errors'].append(e[:, None] if e.ndim == 1 else e)
+    res = {'snrs': np.concatenate(out['snrs'])}
+    if out['fishers']:
+        res.update(fishers=np.concatenate(out['fishers'], axis=-1), covs=np.concatenate(out['covs'], axis=-1), errors=np.concatenate(out['errors'], axis=-1))
+        for k in ('sky_area', 'inversion_errors', 'cond_numbers', 'idxs_det'):
+            res[k] = np.concatenate(out[k])
+    return res
+
+
 def run_catalog(events, net, fout, batch_size=100000, snr_th=12., duty_factor=None, seeds=None, params_fix=(), resume=False,
-                idx_in=0, idx_f=None, rank=0, world=1, save_fishers=False, verbose=True):
+                idx_in=0, idx_f=None, rank=0, world=1, save_fishers=False, verbose=True, reference_files=False):
     """Process a catalog in batches; rank ``rank`` of ``world`` takes every ``world``-th batch.  Each batch is written to
-    ``fout/batch_<a>_to_<b>.npz`` as soon as it is done, ``resume`` skips batches whose file exists (run script :738).  Returns the
-    list of batch files of this rank."""
+    ``fout/batch_<a>_to_<b>.npz`` as soon as it is done, ``resume`` skips batches whose file exists (run script :738).  With
+    ``reference_files`` the batches are written in the reference's own layout instead (``snrs_<a>_to_<b>.txt``, ``fishers_...npy``, ...:
+    to_reference_files) and ``resume`` looks for ``snrs_<a>_to_<b>.txt`` exactly like the reference's ``--resume_run``.  Returns the list
+    of batch files of this rank."""
     os.makedirs(fout, exist_ok=True)
     n = len(events[list(events.keys())[0]])
     wf = net.signals[list(net.signals.keys())[0]].wf_model
@@ -148,7 +194,7 @@ def run_catalog(events, net, fout, batch_size=100000, snr_th=12., duty_factor=No
     for bi, (a, b) in enumerate(batch_ranges(n, batch_size, idx_in, idx_f)):
         if bi % world != rank:
             continue
-        path = _batch_file(fout, a, b)
+        path = os.path.join(fout, 'snrs_%d_to_%d.txt' % (a, b)) if reference_files else _batch_file(fout, a, b)
         if resume and os.path.exists(path):
             done.append(path)
             continue
@@ -157,6 +203,13 @@ def run_catalog(events, net, fout, batch_size=100000, snr_th=12., duty_factor=No
         snrs_all, Fres, eps, cov, sky, cond, idxs = compute_errs(sub, net, snr_th=snr_th, duty_factor=duty_factor, seeds=seeds,
                                                                  params_fix=params_fix, i_in=a, i_f=b)
         errs = np.sqrt(np.einsum('iin->in', cov)) if cov.size else np.zeros((cov.shape[0], 0))
+        if reference_files:
+            totF = Fres['net'] if isinstance(Fres, dict) else Fres
+            to_reference_files(fout, a, b, snrs_all['net'], totF, eps, cov, sky, errs, idxs, cond)
+            done.append(path)
+            if verbose:
+                print('[rank %d] events %d-%d: %d detected (SNR > %s) in %.2f s' % (rank, a, b, len(np.ravel(idxs)), snr_th, time.time() - t0))
+            continue
         data = dict(snrs=snrs_all['net'], errors=errs, sky_area_90=sky, cond_numbers=cond, eps=eps, idxs_detected=np.ravel(idxs),
                     par_names=np.array([k for k in wf.ParNums if k not in params_fix]))
         for k, v in snrs_all.items():
@@ -205,6 +258,7 @@ def main(argv=None):
     ap.add_argument('--idx_f', type=int, default=None)
     ap.add_argument('--resume_run', action='store_true')
     ap.add_argument('--save_fishers', action='store_true')
+    ap.add_argument('--reference_files', action='store_true', help="write the batches in the reference script's own files (snrs_<a>_to_<b>.txt, fishers_...npy, ...)")
     args = ap.parse_args(argv)
     rank, world = int(os.environ.get('RANK', '0')), int(os.environ.get('WORLD_SIZE', '1'))
     if world > 1:
@@ -221,7 +275,7 @@ def main(argv=None):
         with open(os.path.join(args.fout, 'config.json'), 'w') as fh:
             json.dump(vars(args), fh, indent=1)
     run_catalog(events, net, args.fout, batch_size=args.batch_size, snr_th=args.snr_th, duty_factor=args.duty_factor, params_fix=tuple(args.params_fix),
-                resume=args.resume_run, idx_in=args.idx_in, idx_f=args.idx_f, rank=rank, world=world, save_fishers=args.save_fishers)
+                resume=args.resume_run, idx_in=args.idx_in, idx_f=args.idx_f, rank=rank, world=world, save_fishers=args.save_fishers, reference_files=args.reference_files)
 
 
 if __name__ == '__main__':

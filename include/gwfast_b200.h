@@ -148,6 +148,17 @@ int gwf_fisher_ex(const gwf_model* model, const gwf_detector* dets, int32_t ndet
                   const gwf_events* events, int64_t n, const gwf_opts* opts, const gwf_fisher_out* out,
                   void* workspace, size_t workspace_bytes, void* stream);
 
+/* gwf_fisher_ex in two parts, so that a caller can overlap the device->host copy of one group of events with the kernels of the next
+ * without paying one prologue launch and one ragged last round of the persistent kernel per group: the workspace is laid out for
+ * n_total events;  phases & 1: the prologue over ALL n_total events (out->status: [n_total], other outputs unused);
+ * phases & 2: the Fisher kernels on the events [lo, lo + m) -- every pointer of `out` then refers to that range ([blocks][m][...],
+ * status + lo).  Group boundaries at multiples of gwf_round_events() keep every CTA of the persistent grid equally loaded. */
+int gwf_fisher_range(const gwf_model* model, const gwf_detector* dets, int32_t ndet, const gwf_psd* const* psds, int32_t npsd,
+                     const gwf_events* events, int64_t n_total, int64_t lo, int64_t m, int32_t phases, const gwf_opts* opts,
+                     const gwf_fisher_out* out, void* workspace, size_t workspace_bytes, void* stream);
+/* events one round of the persistent Fisher grid takes on the current device (SMs x events per CTA for this model) */
+int64_t gwf_round_events(const gwf_model* model);
+
 /* The return_derivatives output of GWSignal.FisherMatr (signal.py:917-945, network.py:124-141): the derivative strain itself,
  *   derivs: complex128 (re, im) [n_arms][nP][n][res], one block per arm (triangle arms 0, 60 deg, -(1+2)), rows in ParNums order, the
  *           tcoal row per second (signal.py:920); samples beyond the waveform cut are 0.  TaylorF2, IMRPhenomD, IMRPhenomD_NRTidalv2.

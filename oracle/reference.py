@@ -32,6 +32,8 @@ def load():
     import numpy as onp
     if not hasattr(onp, "trapz"):             # gwfast/signal.py:929
         onp.trapz = onp.trapezoid
+    if "NaN" not in onp.__dict__:             # gwfast/fisherTools.py:371 (removed in numpy 2.0)
+        onp.NaN = onp.nan
     with contextlib.redirect_stdout(io.StringIO()):
         from gwfast import waveforms, signal, network
         from gwfast import gwfastUtils as utils

@@ -88,3 +88,78 @@ def test_run_catalog_batches_resume_and_collect(tmp_path):
     mt = os.path.getmtime(f0[0])
     fc.run_catalog(copy_events(ev), net, fout2, batch_size=100, snr_th=8., resume=True, verbose=False)
     assert os.path.getmtime(f0[0]) == mt
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('name', ['forecast_c2_200', 'forecast_lvk_duty_fix'])
+def test_compute_errs_matches_the_reference_run_script(name):
+    """forecast.compute_errs against the UNMODIFIED reference's compute_errs (run/calculate_forecasts_from_catalog.py:410-635, golden from
+    oracle/make_golden_forecast.py): SNRs per arm and network, detected indices, per-arm and network Fisher matrices, and -- through
+    the covariance of the network Fisher -- parameter errors, 90 % sky areas, condition numbers and inversion errors.
+
+    Tolerances: SNR 1e-9 and Fisher 1e-6 (north star).  The covariance is the inverse of a matrix whose (diagonal-normalised) condition
+    number is 1e6-1e12 here, so the Fisher tolerance does not carry over directly: errors and sky areas are held to 1e-5 relative on the events whose normalised
+    condition number is below 5e7 (a perturbation bound of 1e-9 * cond < 5 %; the Fisher matrices themselves agree to ~1e-10); the
+    rest is too ill-conditioned for a meaningful comparison and is left out (at least half of the events must remain)."""
+    from conftest import load_golden, fisher_err
+    from gwfast_b200 import forecast as fc
+    cfg, ev, out = load_golden(name)
+    net = make_network('engine', cfg)
+    res = fc.compute_errs(copy_events(ev), net, snr_th=cfg['snr_th'], duty_factor=cfg['duty_factor'], seeds=cfg['seeds'], params_fix=tuple(cfg['params_fix']))
+    snrs_all, Fres, eps, cov, sky, cond, idxs = res
+    for k in snrs_all:
+        ref = out['snr__' + k]
+        assert np.array_equal(ref == 0, snrs_all[k] == 0), k                      # duty-factor masks: same draws, same order
+        nz = ref != 0
+        assert np.max(np.abs(snrs_all[k][nz] / ref[nz] - 1)) < 1e-9, k
+    assert np.array_equal(np.ravel(idxs), out['idxs_detected'])
+    assert set(Fres) == {k[len('fisher__'):] for k in out if k.startswith('fisher__')}
+    for k in Fres:
+        ref = out['fisher__' + k]
+        assert Fres[k].shape == ref.shape
+        live = np.einsum('iin->n', np.abs(ref)) > 0                               # arms switched off by the duty factor are all-zero
+        assert np.array_equal(Fres[k][..., ~live], ref[..., ~live])
+        if live.any():
+            assert fisher_err(Fres[k][..., live], ref[..., live]) < 1e-6, k
+    # conditioning of the diagonal-normalised network Fisher, per event
+    F = out['fisher__net']
+    dg = np.sqrt(np.einsum('iin->in', F))
+    with np.errstate(all='ignore'):
+        condn = np.array([np.linalg.cond(F[..., i] / np.outer(dg[:, i], dg[:, i])) if np.all(dg[:, i] > 0) else np.inf for i in range(F.shape[-1])])
+    tol = 1e-9 * condn
+    err = np.sqrt(np.einsum('iin->in', cov))
+    ok = np.isfinite(out['errors']).all(axis=0) & np.isfinite(out['sky_area_90']) & (tol < 5e-2)
+    assert ok.sum() >= 0.5 * len(ok)                                             # the rest is too ill-conditioned for any comparison
+    d_err = np.max(np.abs(err[:, ok] / out['errors'][:, ok] - 1), axis=0)
+    d_sky = np.abs(sky[ok] / out['sky_area_90'][ok] - 1)
+    print('%s: %d of %d events compared; max |d sigma/sigma| / (1e-9 cond) = %.3g, sky = %.3g; worst |d sigma/sigma| = %.2e' % (
+        name, ok.sum(), len(ok), np.max(d_err / tol[ok]), np.max(d_sky / tol[ok]), np.max(d_err)))
+    assert np.all(d_err < 1e-5) and np.all(d_sky < 1e-5)                          # measured on B200: 2.5e-8 / 1.2e-7 (errors), 2.5e-8 (sky areas)
+    assert np.all(np.abs(np.log10(cond[ok] / out['cond_numbers'][ok])) < 1e-3 + tol[ok])
+    assert cov.shape == out['cov'].shape and eps.shape == out['eps'].shape
+
+
+@pytest.mark.gpu
+def test_run_catalog_in_the_reference_file_layout(tmp_path):
+    """--reference_files: the per-batch files of the reference script (snrs_<a>_to_<b>.txt, fishers/covs .npy, sky_area, errors,
+    inversion_errors, cond_numbers, idxs_det .txt; run script :224-247, :784-788), the name --resume_run looks for (:738-741), and their
+    concatenation equal to the .npz run."""
+    from gwfast_b200 import forecast as fc, synthetic
+    cfg = dict(model=dict(cls='TaylorF2_RestrictedPN', kw=dict(use_3p5PN_SpinHO=True)), network='ET', rot=True, fmin=2.)
+    net = make_network('engine', cfg)
+    ev = synthetic.bns_catalog(250, 5)
+    fout = str(tmp_path / 'ref')
+    th = 8.
+    files = fc.run_catalog(copy_events(ev), net, fout, batch_size=100, snr_th=th, verbose=False, reference_files=True)
+    assert [os.path.basename(f) for f in files] == ['snrs_0_to_100.txt', 'snrs_100_to_200.txt', 'snrs_200_to_250.txt']
+    for stem in fc.REFERENCE_FILES:
+        assert os.path.exists(os.path.join(fout, '%s_0_to_100.%s' % (stem, 'npy' if stem in ('fishers', 'covs') else 'txt'))), stem
+    cat = fc.concatenate_reference_files(fout, fc.batch_ranges(250, 100))
+    other = str(tmp_path / 'npz')
+    fc.run_catalog(copy_events(ev), net, other, batch_size=100, snr_th=th, verbose=False)
+    one = fc.collect(other)
+    assert np.allclose(cat['snrs'], one['snrs'], rtol=1e-15) and np.array_equal(cat['idxs_det'].astype(int), one['idxs_detected'])
+    assert np.allclose(cat['errors'], one['errors'], rtol=1e-15) and cat['fishers'].shape == (11, 11, len(one['idxs_detected']))
+    mt = os.path.getmtime(files[0])
+    fc.run_catalog(copy_events(ev), net, fout, batch_size=100, snr_th=th, verbose=False, reference_files=True, resume=True)
+    assert os.path.getmtime(files[0]) == mt

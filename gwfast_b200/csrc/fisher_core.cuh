@@ -133,7 +133,7 @@ template <int NT> struct ModelTraits<kNRTidalv2, NT> {
         const double B = fma(xm76, v, r.kam[0] * Q);
         w.A = d.C * B * T;
         if (w.A == 0.0) return;
-        const double iB = 1.0 / B, tT = Ty / T;
+        const double iB = rcp_fast(B), tT = Ty * rcp_fast(T);
 #pragma unroll
         for (int j = 0; j < NT; ++j) {
             const double dB = xm76 * (dv[j] - (7. / 6.) * d.lam[j] * v) + r.kam[1 + j] * Q + r.kam[0] * xQp * d.lam[j];

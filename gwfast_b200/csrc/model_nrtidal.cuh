@@ -91,7 +91,7 @@ GWF_HD void nrt_phase_shape(double p13, double& R, double& xRp) {
     const double pN = (2. / 3.) * (-12.615214237993088 * p23) + (19.0537346970349 * p) + (4. / 3.) * (-21.166863146081035 * p43) +
                       (5. / 3.) * (90.55082156324926 * p53) + 2. * (-60.25357801943598 * p2);
     const double pD = (2. / 3.) * (-15.11120782773667 * p23) + (22.195327350624694 * p) + (4. / 3.) * (8.064109635305156 * p43);
-    const double iN = 1.0 / N, iD = 1.0 / Dn;
+    const double iN = rcp_fast(N), iD = rcp_fast(Dn);
     R = p53 * N * iD;
     xRp = R * (5. / 3. + pN * iN - pD * iD);
 }

@@ -363,9 +363,9 @@ GWF_HD void phenomd_phase(const PhenomDRec<NT>& r, int g, const XPow& p, bool ap
         const double bx[kPMrd] = {0., x, -xm1, 0.75 * x34, 2. / 3. * p.x23};
         expand<kPMrd, NT>(r.pmrd, b, bx, v, d, dx);
         // alpha4/eta * atan((x - alpha5 fring)/fdamp)
-        const double ifd = 1.0 / r.atn[2][0];
+        const double ifd = rcp_fast(r.atn[2][0]);
         const double u = (x - r.atn[1][0]) * ifd;
-        const double at = atan(u), w = r.atn[0][0] / (1.0 + u * u) * ifd;   // c * d(atan)/du * (1/fd)
+        const double at = atan(u), w = r.atn[0][0] * rcp_fast(1.0 + u * u) * ifd;   // c * d(atan)/du * (1/fd)
         v = fma(r.atn[0][0], at, v);
         dx = fma(w, x, dx);
 #pragma unroll
@@ -402,7 +402,7 @@ GWF_HD bool phenomd_amp_core(const PhenomDRec<NT>& r, const XPow& p, bool apply_
     } else if (!apply_cut || x < kMfCut) {
         // exp(-(x-fr) g) * P / ((x-fr)^2 + w^2);  amrd = {fr, g, w, P}
         const double u = x - r.amrd[0][0], g = r.amrd[1][0], w = r.amrd[2][0], P = r.amrd[3][0];
-        const double iden = 1.0 / (u * u + w * w), iP = 1.0 / P;
+        const double iden = rcp_fast(u * u + w * w), iP = rcp_fast(P);
         v = exp(-u * g) * P * iden;
         // d ln v = -(du) g - u dg + dP/P - (2 u du + 2 w dw)/den, with du_j = x lam_j - dfr_j
         const double ku = -g - 2. * u * iden;
@@ -437,7 +437,7 @@ GWF_HD double phenomd_amp_value(const PhenomDRec<NT>& r, const XPow& p, bool app
     }
     if (!apply_cut || x < kMfCut) {
         const double u = x - r.amrd[0][0], w = r.amrd[2][0];
-        return exp(-u * r.amrd[1][0]) * r.amrd[3][0] / (u * u + w * w);
+        return exp(-u * r.amrd[1][0]) * r.amrd[3][0] * rcp_fast(u * u + w * w);
     }
     return 0.0;
 }
@@ -453,7 +453,7 @@ GWF_HD void phenomd_amp(const PhenomDRec<NT>& r, const XPow& p, bool apply_cut, 
         return;
     }
     A = r.C76 * p.fm76 * v;
-    const double iv = 1.0 / v;
+    const double iv = rcp_fast(v);
 #pragma unroll
     for (int j = 0; j < NT; ++j) lnA_d[j] = fma(dv[j], iv, fma(-7. / 6., r.lam[j], r.lnC_d[j]));
 }

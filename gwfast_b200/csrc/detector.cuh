@@ -375,12 +375,14 @@ GWF_HD double compact_snr_deriv(int row, const double* __restrict__ acc, const E
 
 // general rows of d h / d p (divided by A e^{i Psi}) for one arm: ra + i rb for the NG general parameters, and the
 // pattern functions Fp, Fc that generate the four fixed-combination rows (see Compact)
-template <int NT>
+// UNIT: the arm's coefficient pair is known at compile time -- 1: (S2, C2) = (1, 0), 2: (0, 1), the two virtual arms of a summed
+// triangle (host_build.h:build_network) -- and the six linear combinations below are plain selections
+template <int NT, int UNIT = 0>
 GWF_HD void arm_rows(const PointWf<NT>& w, const DetPoint& p, const DetRows<NT>& dr, const ArmDev& a, const EvGeom& g,
                      double* __restrict__ ra, double* __restrict__ rb, double& Fp, double& Fc) {
-    const double av = a.S2 * p.aS + a.C2 * p.aC, bv = a.C2 * p.bC + a.S2 * p.bS;
-    const double ag = a.S2 * p.aS_g + a.C2 * p.aC_g, bg = a.C2 * p.bC_g + a.S2 * p.bS_g;
-    const double ad = a.S2 * p.aS_d + a.C2 * p.aC_d, bd = a.C2 * p.bC_d + a.S2 * p.bS_d;
+    const double av = UNIT == 1 ? p.aS : (UNIT == 2 ? p.aC : a.S2 * p.aS + a.C2 * p.aC), bv = UNIT == 1 ? p.bS : (UNIT == 2 ? p.bC : a.C2 * p.bC + a.S2 * p.bS);
+    const double ag = UNIT == 1 ? p.aS_g : (UNIT == 2 ? p.aC_g : a.S2 * p.aS_g + a.C2 * p.aC_g), bg = UNIT == 1 ? p.bS_g : (UNIT == 2 ? p.bC_g : a.C2 * p.bC_g + a.S2 * p.bS_g);
+    const double ad = UNIT == 1 ? p.aS_d : (UNIT == 2 ? p.aC_d : a.S2 * p.aS_d + a.C2 * p.aC_d), bd = UNIT == 1 ? p.bS_d : (UNIT == 2 ? p.bC_d : a.C2 * p.bC_d + a.S2 * p.bS_d);
     Fp = av * g.c2psi + bv * g.s2psi;
     Fc = bv * g.c2psi - av * g.s2psi;
     const double Gr = Fp * g.K, Gi = Fc * g.ci;                                       // signal.py:463-464
@@ -429,11 +431,11 @@ GWF_HD void gram_accumulate(double wg, double Fp, double Fc, const double* __res
     }
 }
 
-template <int NT>
+template <int NT, int UNIT = 0>
 GWF_HD void arm_rows_accumulate(const PointWf<NT>& w, const DetPoint& p, const DetRows<NT>& dr, const ArmDev& a, const EvGeom& g, double wgt,
                                 double* __restrict__ acc) {
     double ra[Compact<NT>::NG], rb[Compact<NT>::NG], Fp, Fc;
-    arm_rows<NT>(w, p, dr, a, g, ra, rb, Fp, Fc);
+    arm_rows<NT, UNIT>(w, p, dr, a, g, ra, rb, Fp, Fc);
     gram_accumulate<NT>(wgt * a.weight, Fp, Fc, ra, rb, acc);
 }
 

@@ -1,6 +1,7 @@
 // Per-(event, frequency) work of the fused Fisher/SNR path, independent of the thread mapping:
 // frequency grid + trapezoid weights (gwfast/signal.py:715-723, 884-901, 929), model dispatch, detector loop.
 #pragma once
+#include <type_traits>
 #include "detector.cuh"
 #include "model_phenomd.cuh"
 #include "model_tf2.cuh"
@@ -293,6 +294,15 @@ GWF_HD constexpr int shape_ndet(int shape) { return (shape_arms(shape, 0) != 0) 
 GWF_HD constexpr int shape_total(int shape) { return shape_arms(shape, 0) + shape_arms(shape, 1) + shape_arms(shape, 2) + shape_arms(shape, 3); }
 GWF_HD constexpr int shape_first(int shape, int i) { return (i > 0 ? shape_arms(shape, 0) : 0) + (i > 1 ? shape_arms(shape, 1) : 0) + (i > 2 ? shape_arms(shape, 2) : 0); }
 
+// compile-time loop: f(std::integral_constant<int, I>) for I = BEGIN .. END - 1
+template <int I, int END, class F>
+__host__ __device__ __forceinline__ void static_for(F&& f) {
+    if constexpr (I < END) {
+        f(std::integral_constant<int, I>{});
+        static_for<I + 1, END>(f);
+    }
+}
+
 #ifdef __CUDA_ARCH__
 // The same point for a network in "fast" form (NetworkDev::fast): fully unrolled detector loop over net.fdet[i] / net.fpsd[i]
 // with compile-time i, ROT = every active detector follows the Earth rotation (else none does).  sc.ed / sc.fixed are
@@ -317,8 +327,8 @@ __device__ __forceinline__ void amp_phase_point_fast(const typename ModelTraits<
     }
     if constexpr (SHAPE != 0) {
         constexpr int kN = shape_ndet(SHAPE);
-#pragma unroll
-        for (int i = 0; i < kN; ++i) {
+        static_for<0, kN>([&](auto ic) {
+            constexpr int i = decltype(ic)::value;
             const DetDev& d = net.fdet[i];
             const double sn_i = sn_next;
             if (i + 1 < kN) sn_next = psd_lookup_fast(net.fpsd[i + 1 < kN ? i + 1 : 0], f, l2f);
@@ -328,9 +338,16 @@ __device__ __forceinline__ void amp_phase_point_fast(const typename ModelTraits<
             DetRows<NT> dr;
             dr.set(w, dp, ROT, ROT ? false : d.no_motion != 0);       // a detector that follows the rotation is not "noMotion"
             const double wgt = wA2 * rcp_fast(sn_i);
+            constexpr int na = shape_arms(SHAPE, i), first = shape_first(SHAPE, i);
+            if constexpr (na == 2) {
+                // a summed triangle: the unit pair (1, 0), (0, 1) (host_build.h:build_network)
+                arm_rows_accumulate<NT, 1>(w, dp, dr, net.arm[first], geom, wgt, acc);
+                arm_rows_accumulate<NT, 2>(w, dp, dr, net.arm[first + 1], geom, wgt, acc);
+            } else {
 #pragma unroll
-            for (int a = 0; a < shape_arms(SHAPE, i); ++a) arm_rows_accumulate<NT>(w, dp, dr, net.arm[shape_first(SHAPE, i) + a], geom, wgt, acc);
-        }
+                for (int a = 0; a < na; ++a) arm_rows_accumulate<NT>(w, dp, dr, net.arm[first + a], geom, wgt, acc);
+            }
+        });
     } else {
 #pragma unroll
         for (int i = 0; i < kMaxFastDet; ++i) {

@@ -133,9 +133,15 @@ static int build_network(const gwf_detector* dets, int ndet, const PsdDev* psds,
             push(s2, c2, 1.0, flat + 1);
             push(-(s1 + s2), -(c1 + c2), 1.0, flat + 2);                      // signal.py:751
         } else if (pass < 0) {
-            // G(r1)+G(r2)+G(r1+r2) = 3/2 G(r1+r2) + 1/2 G(r1-r2)
-            push(s1 + s2, c1 + c2, 1.5, 0);
-            push(s1 - s2, c1 - c2, 0.5, 0);
+            // The rows of an arm are linear in its pair (S2, C2) = sin(60 deg) (sin, cos)(2 (xax + rot)), and the three arms sit at
+            // 2 xax + {0, 120, 240} deg: sum S2^2 = sum C2^2 = 3/2 sin^2(60 deg) = 9/8 and sum S2 C2 = 0, so
+            //     G(r1) + G(r2) + G(-(r1 + r2)) = 9/8 [ G(r_S) + G(r_C) ]
+            // with the unit arms r_S: (S2, C2) = (1, 0) and r_C: (0, 1) -- two Grams instead of three, whatever xax is, and rows that
+            // need no linear combination at all (detector.cuh:arm_rows<NT, UNIT>; the shape-specialised kernels rely on a two-arm
+            // detector being exactly this pair, in this order)
+            (void)s1; (void)c1; (void)s2; (void)c2;
+            push(1.0, 0.0, 1.125, 0);
+            push(0.0, 1.0, 1.125, 0);
         } else {
             if (pass == flat) push(s1, c1, 1.0, 0);
             if (pass == flat + 1) push(s2, c2, 1.0, 0);

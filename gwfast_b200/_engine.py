@@ -5,6 +5,7 @@ torch is used for what it is good at here -- device/pinned memory with caching a
 CUDA kernel behind the C ABI (``include/gwfast_b200.h``).  There is no CPU path: without the library or without a
 CUDA device every call raises :class:`EngineUnavailable`.
 """
+import contextlib
 import ctypes as C
 import os
 
@@ -19,6 +20,7 @@ CHUNK_EVENTS = 1 << 16     # events per launch group: bounds the coefficient-rec
 N_STREAMS = 2
 
 _states = {}
+_NULL_CTX = contextlib.nullcontext()
 launch_count = 0           # kernels launched through this module (bench.py reports it as gpu_launches)
 
 
@@ -34,6 +36,7 @@ class _State:
         self.streams = None
         self.last_fisher_device = None
         self.last_status = None
+        self.round_events = {}
 
 
 _qnm_set = False
@@ -107,18 +110,21 @@ def _stage(st, ev, n, keys):
     hnp = host.numpy()
     for i, k in enumerate(present):
         a = np.asarray(ev[k])
-        if a.shape != (n,):
+        if a.dtype != np.float64 or a.shape != (n,):
             a = np.broadcast_to(np.real(a).astype(np.float64, copy=False), (n,))
-        hnp[i] = np.real(a)
+        np.copyto(hnp[i], a)
     return host, present
+
+
+_KEY_SLOT = {k: i for i, k in enumerate(K.EVENT_KEYS)}
 
 
 def _events_struct(dev, present, m):
     """gwf_events over a device table (len(present), m)"""
     evs = K.gwf_events()
     base, stride = dev.data_ptr(), m * 8
-    for i, k in enumerate(K.EVENT_KEYS):
-        evs.p[i] = base + present.index(k) * stride if k in present else None
+    for row, k in enumerate(present):
+        evs.p[_KEY_SLOT[k]] = base + row * stride
     return evs
 
 
@@ -221,10 +227,13 @@ def fisher(model, dets, psd_handles, ev, n, res, flags, per_arm, want_snr2=True,
                              torch.empty(sder.shape, dtype=f64, pin_memory=True) if want_snr_derivs else None])
         return host_out
     side = _side_streams(st)
-    for s_ in side:
-        s_.wait_stream(cur)
     copy_stream = side[-1]
-    round_events = max(1, int(lib.gwf_round_events(C.byref(model))))
+    used = side if multi else [copy_stream]         # a single-chunk batch computes on the current stream and only copies on a side stream
+    for s_ in used:
+        s_.wait_stream(cur)
+    round_events = st.round_events.get(model.id)
+    if round_events is None:
+        round_events = st.round_events[model.id] = max(1, int(lib.gwf_round_events(C.byref(model))))
     keep = []
 
     def outputs(packed, s2, sd, lo):
@@ -251,7 +260,7 @@ def fisher(model, dets, psd_handles, ev, n, res, flags, per_arm, want_snr2=True,
     for ci, (clo, cm) in enumerate(chunks):
         stream = side[ci % len(side)] if multi else cur
         sp = C.c_void_p(stream.cuda_stream)
-        with torch.cuda.stream(stream):
+        with (torch.cuda.stream(stream) if multi else _NULL_CTX):
             dev_ev = dev_all if dev_all is not None else torch.empty((nk, cm), dtype=f64, device=st.device)
             if dev_all is not None:
                 pass
@@ -298,11 +307,11 @@ def fisher(model, dets, psd_handles, ev, n, res, flags, per_arm, want_snr2=True,
                         to_host_copy(lo, gm, C.c_void_p(copy_stream.cuda_stream))
                 keep.append((packed, s2, sd))
             keep.append((dev_ev,))
-    for s_ in side:
+    for s_ in used:
         cur.wait_stream(s_)
-    for t in (full, snr2, sder, status):                  # allocated on the current stream, touched on the side streams
+    for t in ((full, snr2, sder, status) if multi else (full,)):     # allocated on the current stream, touched on the side streams
         if t is not None:
-            for s_ in side:
+            for s_ in used:
                 t.record_stream(s_)
     st.last_fisher_device = full if STASH_DEVICE else None
     h2d = host_ev.numel() * 8

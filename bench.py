@@ -10,11 +10,11 @@ ET (triangle) + 2 CE per GPU (weak scaling).  Both results come from ONE fused l
 DetNet.FisherMatr(return_SNR=True)): the Fisher kernel integrates |h|^2/S_n anyway.  Rank 0 prints ONE JSON line.
 
   value     kernel-path events/s, event parameters already resident in HBM (CUDA events, max over ranks).  For N>1 the final gather
-            of the packed Fisher matrices is inside the timed region: the unpack kernel stores every rank's rows straight into the
-            peers' gathered buffers over NVLink (gwf_unpack_gather, peer memory mapped with CUDA IPC); if the peers cannot be mapped
-            it falls back to dist.all_gather_into_tensor and says so in config.gather
+            of the packed Fisher matrices is inside the timed region: the Fisher kernel stores every finished row straight into the
+            peers' gathered buffers over NVLink (gwf_fisher_out.peer_fisher, peer memory mapped with CUDA IPC), so the gather overlaps
+            the computation; if the peers cannot be mapped it falls back to dist.all_gather_into_tensor and says so in config.gather
   e2e       the same metric through the public API with HOST numpy arrays in and out (H2D/D2H inside the timed region); for N>1
-            every rank calls the API on its shard and the gather is done by the engine's own unpack kernels (peer stores over NVLink)
+            every rank calls the API on its shard and the gather is done by the engine's own Fisher kernels (peer stores over NVLink)
   roofline  FP64 (the path is FP64-FMA/transcendental bound): algorithmic FLOP/event x events / duration of
             the dominant kernel (fisher_kernel, timed alone via GWF_OPT_REUSE_WORKSPACE) against the DFMA peak measured
             in the same run (gwf_fp64_peak) -- nominal 148 SM x 64 lanes x 2 x 1.965 GHz = 37.2 TFLOP/s is also reported
@@ -47,8 +47,8 @@ RES = 1000
 FLOP_PER_EVENT = 2.676e6
 FLOP_MODEL = {'C1': 0.674e6, 'C2': 2.676e6, 'C3': 3.444e6, 'C4': 4.176e6, 'C5': 2.676e6}
 FP64_NOMINAL_TFLOPS = 148 * 64 * 2 * 1.965e9 / 1e12
-# DRAM traffic of one fisher_kernel launch of this workload, bytes (ncu --set full, profiles/r01i_kernels_ncu.md): 34.71 MB read + 0.57 MB written
-DRAM_BYTES_PER_LAUNCH = 35.27e6
+# DRAM traffic of one fisher_kernel launch of this workload, bytes (ncu --set full, profiles/r02_kernels_ncu.md): 34.70 MB read + 0.32 MB written
+DRAM_BYTES_PER_LAUNCH = 35.02e6
 
 
 # ----------------------------------------------------------------------------------------------- CPU arm
@@ -216,6 +216,11 @@ class Case:
         self.K.check(self.lib.gwf_fisher_ex(*self._common(self.opts_reuse if reuse else self.opts), C.byref(self.fo), C.c_void_p(self.ws.data_ptr()),
                                             self.ws.numel(), self.sp), 'gwf_fisher_ex')
 
+    def set_peer(self, pg):
+        """multi-GPU: the Fisher kernel stores every finished packed row into this rank's slot of every rank's gathered buffer"""
+        self.fo.peer_fisher = C.cast(pg.slots(0), C.c_void_p)
+        self.fo.npeers = pg.world
+
     def unpack(self, peer=None):
         if peer is not None:
             peer.unpack_and_scatter(self.packed, self.n, self.nP, self.full, self.n, self.stream)
@@ -293,13 +298,14 @@ def run_engine(args):
             if pg.available():
                 peer = pg
                 gathered = pg.gathered
-                gather_kind = 'gwf_unpack_gather: packed rows stored into the peers\' buffers over NVLink by the unpack kernel (CUDA IPC peer memory)'
+                case.set_peer(pg)
+                gather_kind = 'fused into fisher_kernel: every finished packed row is stored into the peers\' gathered buffers over NVLink (gwf_fisher_out.peer_fisher, CUDA IPC peer memory)'
         if peer is None:
             gathered = torch.empty((world, n, case.npack), dtype=torch.float64, device=dev)
 
     def kernel_step():
         case.fisher()
-        case.unpack(peer)
+        case.unpack()
         if world > 1 and peer is None:
             dist.all_gather_into_tensor(gathered.view(-1), case.packed.view(-1))
         return 3                                                                    # prologue, fisher, unpack(+gather)
@@ -417,9 +423,12 @@ def run_engine(args):
                     pgc = None
             gat = torch.empty((world, m, c.npack), dtype=torch.float64, device=dev) if (world > 1 and pgc is None and scaling == 'weak') else None
 
+            if pgc is not None:
+                c.set_peer(pgc)
+
             def kstep():
                 c.fisher()
-                c.unpack(pgc)
+                c.unpack()
                 if gat is not None:
                     dist.all_gather_into_tensor(gat.view(-1), c.packed.view(-1))
 
@@ -453,7 +462,7 @@ def run_engine(args):
                                ms_per_step=1e3 * tk / osteps, e2e=n_tot * osteps / te, fisher_kernel_ms=1e3 * tm / osteps,
                                fisher_kernel_ms_per_1e4=1e3 * tm / osteps * 1e4 / m, flop_per_event=FLOP_MODEL[tag], achieved_tflops=ach,
                                frac=ach / peak_tf if peak_tf > 0 else None, frac_of_nominal=ach / FP64_NOMINAL_TFLOPS, finite=ok,
-                               gather=('gwf_unpack_gather (NVLink peer stores)' if pgc is not None else ('NCCL all-gather' if gat is not None else 'none'))
+                               gather=('fused into the Fisher kernel (NVLink peer stores)' if pgc is not None else ('NCCL all-gather' if gat is not None else 'none'))
                                if world > 1 else 'none (one GPU)')
             c.release()
             if pgc is not None:
@@ -481,7 +490,7 @@ def run_engine(args):
                     gpu_launches=launches,
                     roofline=dict(bound='fp64', kernel='fisher_kernel<IMRPhenomD,NT=4>', achieved=achieved, peak=peak_tf, unit='TFLOP/s',
                                   frac=achieved / peak_tf if peak_tf > 0 else None, traffic=DRAM_BYTES_PER_LAUNCH,
-                                  traffic_source='dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full capture (records + EventAux + PSD windows + events in, packed Fisher out)',
+                                  traffic_source='dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full capture profiles/r02d_fisher_d_ncu_raw.csv (records + EventAux + PSD windows + events in, packed Fisher out)',
                                   peak_source='measured in this run (gwf_fp64_peak DFMA chain); MEASURED_PEAKS.json has no FP64 entry',
                                   nominal_peak=FP64_NOMINAL_TFLOPS, frac_of_nominal=achieved / FP64_NOMINAL_TFLOPS,
                                   flop_per_event=FLOP_PER_EVENT, kernel_ms=1e3 * t_main / args.steps),

@@ -38,7 +38,8 @@ class gwf_opts(C.Structure):
 
 
 class gwf_fisher_out(C.Structure):
-    _fields_ = [('fisher_packed', C.c_void_p), ('snr2', C.c_void_p), ('snr2_integ', C.c_void_p), ('snr_derivs', C.c_void_p), ('status', C.c_void_p)]
+    _fields_ = [('fisher_packed', C.c_void_p), ('snr2', C.c_void_p), ('snr2_integ', C.c_void_p), ('snr_derivs', C.c_void_p), ('status', C.c_void_p),
+                ('peer_fisher', C.c_void_p), ('npeers', C.c_int32), ('reserved', C.c_int32)]
 
 
 class gwf_signal_out(C.Structure):

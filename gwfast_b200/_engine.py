@@ -145,8 +145,8 @@ def _call_arrays(dets, psd_handles):
 # multi-GPU caller can all-gather it over NVLink without a host round trip (parallel.DistributedDetNet(gather='device')).
 STASH_DEVICE = False
 
-# When set (parallel.PeerGather), fisher() hands the packed rows of every launch group to gwf_unpack_gather instead of
-# gwf_unpack_fisher_ld: the unpack kernel also stores them into this rank's slot of every peer's gathered buffer over NVLink.
+# When set (parallel.PeerGather), fisher() passes this rank's slots in the peers' gathered buffers to the Fisher kernels
+# (gwf_fisher_out.peer_fisher): every finished packed row is stored there over NVLink while the rest of the batch is still computing.
 PEER = None
 
 # extra gwf_opts.flags OR-ed into every launch (tests set GWF_OPT_GENERIC_LOOP / GWF_OPT_ONE_WARP_PER_EVENT to compare the
@@ -237,16 +237,17 @@ def fisher(model, dets, psd_handles, ev, n, res, flags, per_arm, want_snr2=True,
     keep = []
 
     def outputs(packed, s2, sd, lo):
-        return K.gwf_fisher_out(packed.data_ptr(), None if want_snr_integ else s2, s2 if want_snr_integ else None, sd, status.data_ptr() + 4 * lo)
+        fo = K.gwf_fisher_out(packed.data_ptr(), None if want_snr_integ else s2, s2 if want_snr_integ else None, sd, status.data_ptr() + 4 * lo)
+        if PEER is not None and npass == 1:
+            # multi-GPU: the Fisher kernel itself stores every finished row into this rank's slot of the peers' gathered buffers
+            fo.peer_fisher = C.cast(PEER.slots(lo), C.c_void_p)
+            fo.npeers = PEER.world
+        return fo
 
     def unpack(packed, lo, m, sp):
         global launch_count
         for p in range(npass):
-            if PEER is not None and npass == 1:
-                K.check(lib.gwf_unpack_gather(C.c_void_p(packed[p].data_ptr()), m, nP, C.c_void_p(full[p].data_ptr() + 8 * lo), n,
-                                              PEER.slots(lo), PEER.world, sp), 'gwf_unpack_gather')
-            else:
-                K.check(lib.gwf_unpack_fisher_ld(C.c_void_p(packed[p].data_ptr()), m, nP, C.c_void_p(full[p].data_ptr() + 8 * lo), n, sp), 'gwf_unpack_fisher')
+            K.check(lib.gwf_unpack_fisher_ld(C.c_void_p(packed[p].data_ptr()), m, nP, C.c_void_p(full[p].data_ptr() + 8 * lo), n, sp), 'gwf_unpack_fisher')
             launch_count += 1
 
     def to_host_copy(lo, m, sp):

@@ -436,10 +436,13 @@ __device__ __forceinline__ void stage_event(WarpSmem<Rec, Extra>* mine, const Re
 }
 
 // Fisher kernel: WarpSmem plus the table form of the entry rebuild
+constexpr int kXferDoubles = 128;     // packed entries (<= 108) + the two SNR sums + (h | d_i h) (<= 14)
 template <class Rec, class Extra> struct FisherSmem : WarpSmem<Rec, Extra> {
     double coef[64];                  // per-event coefficient vector (kCompactCoefs used)
     unsigned char code[4 * 108];      // (ia, ib, ka, kb) per packed entry, filled once per kernel
 };
+// pair mode: behind the per-warp blocks, two hand-over slots per pair (the second warp's entries on their way to the first, used alternately)
+constexpr size_t kXferBytes = sizeof(double) * (kFisherThreads / 64) * 2 * kXferDoubles;
 
 // Fisher kernel: the record and the prologue's EventAux are copied (coalesced), the detector scratch is then set from the
 // staged geometry by one lane per detector
@@ -466,13 +469,27 @@ __device__ __forceinline__ void stage_event_aux(WarpSmem<Rec, Extra>* mine, cons
 }
 
 // outputs of one Fisher pass (any pointer but `fisher` may be null)
+// this rank's slot in the gathered buffer of every rank of the box (device pointers, peers mapped through CUDA IPC)
+struct PeerSlots {
+    double* p[kMaxPeers];
+    int n;
+};
 struct FisherOut {
     double* fisher;       // [n][NPACK]
     double* snr2;         // [n]  4 int |h|^2/Sn df of the arms of the pass
     double* snr2_integ;   // [n]  the integral SNRInteg forms (signal.py:727): = snr2, except IMRPhenomHM (cross term dropped)
     double* snr_derivs;   // [n][NP]
     int* status;          // [n]  GWF_EV_* bits; the prologue stores the input bits, the kernel ORs in GWF_EV_NONFINITE_OUTPUT
+    PeerSlots peers;      // multi-GPU: the finished packed row of every event is also stored into these [n][NPACK] slots (n = 0: none)
 };
+
+// Multi-GPU gather fused into the Fisher kernel: the finished packed row of event e goes to this rank's slot of every rank's
+// gathered buffer as soon as the event is done -- 8-byte stores over NVLink spread over the whole lifetime of the kernel, so the
+// exchange step of the path (one all-gather of the Fisher matrices) costs no time of its own.
+__device__ __forceinline__ void forward_row(const PeerSlots& peers, long long e, int npack, int p, double v) {
+#pragma unroll 1
+    for (int q = 0; q < peers.n; ++q) peers.p[q][e * npack + p] = v;
+}
 
 template <int MODEL, int NT, int FAST, bool SD, int SHAPE = 0>
 #ifdef GWF_FISHER_MAXNREG
@@ -503,13 +520,13 @@ fisher_kernel(const typename ModelTraits<MODEL, NT>::Rec* __restrict__ recs, con
     }
     psd_cache_fill(net, smem_raw);
     // pair mode: warps w and w + kWarpsPerCta/2 take the two halves of an event (every other block of 32 samples each), so the
-    // work unit of the persistent loop is half an event and its last round wastes half as much.  The halves never wait for each
-    // other: each rebuilds the Fisher entries of its own partial sums (the entries are linear in the accumulators) and adds
-    // them to the zero-initialised output with one atomic per entry -- two commutative additions, so the result is
-    // deterministic.  (A named-barrier hand-over of the partial sums cost 4.3 % of the kernel in barrier stalls.)
+    // work unit of the persistent loop is half an event and its last round wastes half as much.  Each half rebuilds the Fisher
+    // entries of its own partial sums (the entries are linear in the accumulators); the second warp hands its entries to the
+    // first through shared memory at the pair's per-event barrier (see the end of the event loop).
     constexpr int kHalfWarps = kWarpsPerCta / 2;
     const int half = pair ? wid / kHalfWarps : 0, slot = pair ? wid % kHalfWarps : wid;
     const int per_cta = pair ? kHalfWarps : kWarpsPerCta, stride = pair ? 64 : 32, k0 = lane + 32 * half;
+    int xpar = 0;
     for (long long e = (long long)blockIdx.x * per_cta + slot; e < n; e += (long long)gridDim.x * per_cta) {
         stage_event_aux<FAST != 0>(mine, recs, aux, ev, e, net, lane);
         const EvGeom& geom = mine->geom;
@@ -567,41 +584,72 @@ fisher_kernel(const typename ModelTraits<MODEL, NT>::Rec* __restrict__ recs, con
             for (int k = lane; k < kCompactCoefs; k += 32) mine->coef[k] = compact_coef(k, geom);
             __syncwarp();
         }
-        bool bad = false;
-        for (int p = lane; p < NPACK; p += 32) {
-            double v;
-            if (PF::kEntryTable) {
-                const uchar4 c = *reinterpret_cast<const uchar4*>(mine->code + 4 * p);
-                v = mine->coef[c.z] * red[c.x] + mine->coef[c.w] * red[c.y];
-            } else v = red[p];
-            bad = bad || !isfinite(v);
-            if (pair) atomicAdd(o + p, v);
-            else o[p] = v;
+        // Every lane rebuilds its share of the packed entries from this warp's sums (the entries are linear in the accumulators).
+        // One warp per event: they are the result.  Pair mode: the second warp of the pair leaves its entries (and its SNR sums) in
+        // the first warp's hand-over slot, the pair meets at its per-event barrier -- which also keeps the two warps in the same
+        // stretch of code: they sit on the same scheduler and share its instruction fetches (measured per 1e4 events, free-running
+        // -> lock step per event: IMRPhenomD 1.251 -> 1.229 ms, NRTidalv2 3.166 -> 3.131 ms) -- and the first warp adds its own and
+        // writes the event out: plain stores, no atomics, no zero-initialised output, and in a multi-GPU run the finished row goes to
+        // the peers from registers.  a + b is commutative: the result is bitwise what two atomic additions to zero gave.
+        constexpr int kVals = (NPACK + 31) / 32;
+        constexpr int kXSnr = NPACK, kXInteg = NPACK + 1, kXSd = NPACK + 2;          // layout of a hand-over slot
+        static_assert(kXSd + NP <= kXferDoubles, "hand-over slot too small");
+        double vals[kVals];
+#pragma unroll
+        for (int i = 0; i < kVals; ++i) {
+            const int p = lane + 32 * i;
+            double v = 0.0;
+            if (p < NPACK) {
+                if (PF::kEntryTable) {
+                    const uchar4 c = *reinterpret_cast<const uchar4*>(mine->code + 4 * p);
+                    v = mine->coef[c.z] * red[c.x] + mine->coef[c.w] * red[c.y];
+                } else v = red[p];
+            }
+            vals[i] = v;
         }
-        if (fo.status) {
-            const unsigned anybad = __ballot_sync(0xffffffffu, bad);
-            if (lane == 0 && anybad) atomicOr(fo.status + e, GWF_EV_NONFINITE_OUTPUT);
+        double s_snr = (lane == 0 && snr2_out) ? PF::snr2(red, geom) : 0.0;
+        double s_integ = (lane == 1 && fo.snr2_integ) ? PF::snr2_integ(red, geom) : 0.0;
+        double s_sd = (sd_out && lane < NP) ? PF::snr_deriv(lane, red, geom) : 0.0;      // (h | d_i h), signal.py:938-945
+        if (pair) {
+            double* slot_x = reinterpret_cast<double*>(smem_raw + sizeof(WS) * kWarpsPerCta) + (slot * 2 + xpar) * kXferDoubles;
+            if (half == 1) {
+#pragma unroll
+                for (int i = 0; i < kVals; ++i)
+                    if (lane + 32 * i < NPACK) slot_x[lane + 32 * i] = vals[i];
+                if (lane == 0) slot_x[kXSnr] = s_snr;
+                if (lane == 1) slot_x[kXInteg] = s_integ;
+                if (lane < NP) slot_x[kXSd + lane] = s_sd;
+            }
+            asm volatile("bar.sync %0, 64;" ::"r"(1 + slot) : "memory");
+            if (half == 0) {
+#pragma unroll
+                for (int i = 0; i < kVals; ++i)
+                    if (lane + 32 * i < NPACK) vals[i] += slot_x[lane + 32 * i];
+                if (lane == 0) s_snr += slot_x[kXSnr];
+                if (lane == 1) s_integ += slot_x[kXInteg];
+                if (lane < NP) s_sd += slot_x[kXSd + lane];
+            }
+            xpar ^= 1;      // two slots: the second warp's next hand-over cannot overtake this read (it passes the next barrier first)
         }
-        if (lane == 0 && snr2_out) {
-            const double v = PF::snr2(red, geom);
-            if (pair) atomicAdd(snr2_out + e, v);
-            else snr2_out[e] = v;
+        if (!pair || half == 0) {
+            bool bad = false;
+#pragma unroll
+            for (int i = 0; i < kVals; ++i) {
+                const int p = lane + 32 * i;
+                if (p < NPACK) {
+                    bad = bad || !isfinite(vals[i]);
+                    o[p] = vals[i];
+                    if (fo.peers.n) forward_row(fo.peers, e, NPACK, p, vals[i]);
+                }
+            }
+            if (fo.status) {
+                const unsigned anybad = __ballot_sync(0xffffffffu, bad);
+                if (lane == 0 && anybad) atomicOr(fo.status + e, GWF_EV_NONFINITE_OUTPUT);
+            }
+            if (lane == 0 && snr2_out) snr2_out[e] = s_snr;
+            if (lane == 1 && fo.snr2_integ) fo.snr2_integ[e] = s_integ;
+            if (sd_out && lane < NP) sd_out[e * NP + lane] = s_sd;
         }
-        if (lane == 1 && fo.snr2_integ) {
-            const double v = PF::snr2_integ(red, geom);
-            if (pair) atomicAdd(fo.snr2_integ + e, v);
-            else fo.snr2_integ[e] = v;
-        }
-        if (sd_out && lane < NP) {                            // (h | d_i h), signal.py:938-945
-            const double v = PF::snr_deriv(lane, red, geom);
-            if (pair) atomicAdd(sd_out + e * NP + lane, v);
-            else sd_out[e * NP + lane] = v;
-        }
-        // lock step of the two halves (no data dependence): the two warps of a pair sit on the same scheduler, and keeping them
-        // in the same stretch of code shares its instruction fetches -- the kernels are 90-300 KB of SASS (measured per 1e4
-        // events, free-running -> per event -> per block of samples: IMRPhenomD 1.251 -> 1.229 -> 1.236 ms, NRTidalv2
-        // 3.166 -> 3.131 -> 3.197 ms, IMRPhenomHM 22.1 -> 19.7 -> 17.6 ms)
-        if (pair & 2) asm volatile("bar.sync %0, 64;" ::"r"(1 + slot) : "memory");
     }
 }
 
@@ -665,12 +713,14 @@ fisher_hm_split_kernel(const HMRec<NT>* __restrict__ recs, const EventAux* __res
             if (idx >= 0) red[idx] = acc[i];
         }
         __syncwarp();
+        // every entry has exactly one owner: plain stores (and, in a multi-GPU run, the same value to the peers)
         double* o = fo.fisher + e * NPACK;
         bool bad = false;
         for (int p = 2 * lane + half; p < NPACK; p += 64) {
             const double v = red[p >> 1];
             bad = bad || !isfinite(v);
-            atomicAdd(o + p, v);
+            o[p] = v;
+            if (fo.peers.n) forward_row(fo.peers, e, NPACK, p, v);
         }
         if (fo.status) {
             const unsigned anybad = __ballot_sync(0xffffffffu, bad);
@@ -678,9 +728,9 @@ fisher_hm_split_kernel(const HMRec<NT>* __restrict__ recs, const EventAux* __res
         }
         if (lane == 0) {
             double* dst = half == 0 ? fo.snr2 : fo.snr2_integ;
-            if (dst) atomicAdd(dst + e, red[L::kSnr]);
+            if (dst) dst[e] = red[L::kSnr];
         }
-        if (SD && fo.snr_derivs && lane < NP && (lane & 1) == half) atomicAdd(fo.snr_derivs + e * NP + lane, red[L::kSd + (lane >> 1)]);
+        if (SD && fo.snr_derivs && lane < NP && (lane & 1) == half) fo.snr_derivs[e * NP + lane] = red[L::kSd + (lane >> 1)];
         // the shared block is restaged for the next event only when both warps are done with this one
         asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
     }
@@ -1046,10 +1096,6 @@ __global__ void __launch_bounds__(256) unpack_kernel(const double* __restrict__ 
 // CUDA IPC): plain coalesced 16-byte stores that the NVSwitch fabric routes to the peers while the tile is transposed -- no
 // separate collective kernel, no copy of the result through a communication buffer, and the stores of one tile overlap the
 // loads of the next.  The caller synchronises the ranks (any barrier) before the gathered buffers are read.
-struct PeerSlots {
-    double* p[kMaxPeers];
-    int n;
-};
 __global__ void __launch_bounds__(256) unpack_gather_kernel(const double* __restrict__ packed, long long n, int nP, double* __restrict__ full, long long ld,
                                                             const PeerSlots peers) {
     __shared__ __align__(16) double tile[32][110];   // even pitch: rows stay 16-byte aligned for the vector stores
@@ -1223,7 +1269,7 @@ static int run_fisher(const gwf_model* model, const gwf_detector* dets, int ndet
     if (!(range.phases & 2) || n == 0) return GWF_OK;
     const int sms = ctx->sms;
     // dynamic shared memory: per-warp staging blocks, then the PSD windows (as many tables as fit in 227 KB)
-    const size_t ws_bytes_smem = sizeof(FisherSmem<Rec, typename PointFns<MODEL, NT>::Extra>) * kWarpsPerCta;
+    const size_t ws_bytes_smem = sizeof(FisherSmem<Rec, typename PointFns<MODEL, NT>::Extra>) * kWarpsPerCta + (pair ? kXferBytes : 0);
     size_t shmem_pass = plan_psd_cache(net, ws_bytes_smem, kSmemLimit);
     // the unrolled, shape-specialised form (measured per 1e4 events: IMRPhenomD ET+2CE 1.55 -> 1.06 ms, NRTidalv2 3.73 -> 2.26 ms,
     // TaylorF2 ETSL 0.66 -> 0.55 ms; without the compile-time shape TaylorF2's unrolled loop spilled and lost 7-20 %)
@@ -1263,12 +1309,15 @@ static int run_fisher(const gwf_model* model, const gwf_detector* dets, int ndet
         fo.snr2_integ = outp->snr2_integ ? outp->snr2_integ + (size_t)pass * n : nullptr;
         fo.snr_derivs = snr_derivs ? snr_derivs + (size_t)pass * n * NP : nullptr;
         fo.status = outp->status;
-        if (pair) {
-            // the two halves of an event add their contributions
-            GWF_CUDA(cudaMemsetAsync(fo.fisher, 0, sizeof(double) * (size_t)n * NPACK, st));
-            if (fo.snr2) GWF_CUDA(cudaMemsetAsync(fo.snr2, 0, sizeof(double) * (size_t)n, st));
-            if (fo.snr2_integ) GWF_CUDA(cudaMemsetAsync(fo.snr2_integ, 0, sizeof(double) * (size_t)n, st));
-            if (fo.snr_derivs) GWF_CUDA(cudaMemsetAsync(fo.snr_derivs, 0, sizeof(double) * (size_t)n * NP, st));
+        fo.peers.n = 0;
+        for (int q = 0; q < kMaxPeers; ++q) fo.peers.p[q] = nullptr;
+        if (outp->npeers > 0 && !opts->per_arm) {
+            if (outp->npeers > kMaxPeers || !outp->peer_fisher) return fail(GWF_ERR_ARG, "gwf_fisher_out: at most 8 peer slots");
+            fo.peers.n = outp->npeers;
+            for (int q = 0; q < outp->npeers; ++q) {
+                if (!outp->peer_fisher[q]) return fail(GWF_ERR_ARG, "gwf_fisher_out: null peer slot");
+                fo.peers.p[q] = outp->peer_fisher[q];
+            }
         }
         if constexpr (kSplitPair) {
             if (pair && !(opts->flags & GWF_OPT_HM_BLOCK_PAIRS)) {

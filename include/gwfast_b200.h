@@ -141,6 +141,12 @@ typedef struct {
                               Fisher (return_SNR_derivatives, signal.py:938-945; the reference divides the sum over arms by the network
                               SNR on the host, network.py:143) */
     int32_t* status;       /* [n]: GWF_EV_* bits, 0 = clean */
+    double* const* peer_fisher; /* multi-GPU (per_arm = 0 only): npeers device pointers [n][nP(nP+1)/2], this rank's slot in the gathered
+                              buffer of every rank of the box (peers mapped with gwf_peer_open); the kernel stores the finished packed
+                              row of every event there as soon as the event is done, so the all-gather of the Fisher matrices
+                               overlaps the computation.  The ranks synchronise before reading.  NULL / 0: none */
+    int32_t npeers;
+    int32_t reserved;
 } gwf_fisher_out;
 
 /* gwf_fisher with all optional outputs (return_SNR_derivatives of GWSignal.FisherMatr, the SNR of the same launch, status words). */

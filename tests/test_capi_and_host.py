@@ -97,3 +97,36 @@ def test_events_dict_side_effects_and_errors():
     lt, dl = U.Lamt_delLam_from_Lam12(L1, L2, np.array([0.245]))
     r1, r2 = U.Lam12_from_Lamt_delLam(lt, dl, np.array([0.245]))
     assert abs(r1[0] / 400. - 1) < 1e-9 and abs(r2[0] / 700. - 1) < 1e-9
+
+
+def test_round_two_entry_points_check_their_arguments_before_any_cuda_call():
+    K = _built()
+    lib = K.load()
+    m = K.gwf_model(1, 0, 0.2, 0.)
+    det = K.gwf_detector(0.7, 0.1, 0., 1, 1, 0, 0, 2., 0.)
+    opts = K.gwf_opts(1000, 0, 0, 0)
+    fo = K.gwf_fisher_out(None, None, None, None, None)
+    # gwf_fisher_range: the range must lie inside the workspace's events and a phase must be selected
+    assert lib.gwf_fisher_range(C.byref(m), None, 0, None, 0, None, 10, 8, 4, 2, C.byref(opts), C.byref(fo), None, 0, None) == -1
+    assert b'range' in lib.gwf_last_error()
+    assert lib.gwf_fisher_range(C.byref(m), None, 0, None, 0, None, 10, 0, 10, 0, C.byref(opts), C.byref(fo), None, 0, None) == -1
+    assert lib.gwf_unpack_gather(None, 4, 11, None, 4, None, 0, None) == -1
+    slots = (C.c_void_p * 9)()
+    assert lib.gwf_unpack_gather(C.c_void_p(8), 4, 11, None, 4, slots, 9, None) == -1 and b'8 peer' in lib.gwf_last_error()
+    assert lib.gwf_pattern(C.byref(det), 0., None, None, None, None, 4, None, None, None, None) == -1
+    so = K.gwf_signal_out(None, None, None, None, None, None, None)
+    assert lib.gwf_signal_grid(C.byref(m), C.byref(det), 0., None, 4, None, 10, 0, C.byref(so), None, 0, None) == -1
+    assert lib.gwf_peer_open(None, None) == -1 and lib.gwf_peer_alloc(0, None, None) == -1
+    assert C.sizeof(K.gwf_fisher_out) == 7 * 8 and C.sizeof(K.gwf_signal_out) == 7 * 8
+
+
+def test_launch_groups_are_cut_at_multiples_of_the_persistent_round():
+    from gwfast_b200 import _engine
+    for m in (1, 591, 592, 1000, 2500, 10000, 65536):
+        for rnd in (592, 1184):
+            g = _engine._round_groups(m, rnd)
+            assert g[0][0] == 0 and sum(x[1] for x in g) == m and all(a[0] + a[1] == b[0] for a, b in zip(g, g[1:]))
+            assert all(lo % rnd == 0 for lo, _ in g) and len(g) <= _engine.MAX_GROUPS
+            assert all(x[1] >= 2 * rnd or len(g) == 1 or x is g[-1] for x in g)        # every group but the last holds whole rounds, at least two
+    assert _engine._round_groups(10000, 592) == [(0, 2960), (2960, 2368), (5328, 2368), (7696, 2304)]
+    assert _engine._round_groups(1000, 592) == [(0, 1000)]

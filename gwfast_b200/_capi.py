@@ -9,7 +9,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get('GWFAST_B200_LIB', os.path.join(_HERE, 'lib', 'libgwfast_b200.so'))   # override: kernel experiments
 
-GWF_TAYLORF2, GWF_IMRPHENOMD, GWF_IMRPHENOMD_NRTIDALV2, GWF_IMRPHENOMHM = 0, 1, 2, 3
+GWF_TAYLORF2, GWF_IMRPHENOMD, GWF_IMRPHENOMD_NRTIDALV2, GWF_IMRPHENOMHM, GWF_IMRPHENOMNSBH = 0, 1, 2, 3, 4
 GWF_MODEL_TIDAL, GWF_MODEL_3P5PN_SPINHO, GWF_MODEL_PHIREF_VLSO, GWF_MODEL_QUADMON_TID = 1, 2, 4, 8
 GWF_MODEL_KERR_ISCO, GWF_MODEL_NO_FCUT, GWF_MODEL_HAS_FREF, GWF_MODEL_LAMBDA_GIVEN, GWF_MODEL_NEWTONIAN, GWF_MODEL_ECCENTRIC = 16, 32, 64, 128, 256, 512
 GWF_OPT_M1M2, GWF_OPT_CHIS_CHIA, GWF_OPT_LIN_GRID, GWF_OPT_REUSE_WORKSPACE, GWF_OPT_GENERIC_LOOP, GWF_OPT_ONE_WARP_PER_EVENT, GWF_OPT_HM_BLOCK_PAIRS = 1, 2, 4, 8, 16, 32, 64
@@ -60,7 +60,7 @@ class EngineError(RuntimeError):
 
 # every symbol include/gwfast_b200.h declares (tests check that the library exports all of them)
 SYMBOLS = ('gwf_version', 'gwf_last_error', 'gwf_num_params', 'gwf_num_arms', 'gwf_workspace_bytes', 'gwf_psd_create',
-           'gwf_psd_destroy', 'gwf_set_qnm_tables', 'gwf_fisher', 'gwf_fisher_ex', 'gwf_fisher_range', 'gwf_round_events', 'gwf_strain_derivs', 'gwf_strain', 'gwf_overlap', 'gwf_snr', 'gwf_unpack_fisher', 'gwf_unpack_fisher_ld', 'gwf_unpack_gather', 'gwf_peer_alloc', 'gwf_peer_open', 'gwf_peer_close', 'gwf_peer_free', 'gwf_copy_2d', 'gwf_waveform', 'gwf_signal_grid', 'gwf_pattern', 'gwf_fp64_peak', 'gwf_covariance', 'gwf_eigen',
+           'gwf_psd_destroy', 'gwf_set_qnm_tables', 'gwf_xitide_table', 'gwf_fisher', 'gwf_fisher_ex', 'gwf_fisher_range', 'gwf_round_events', 'gwf_strain_derivs', 'gwf_strain', 'gwf_overlap', 'gwf_snr', 'gwf_unpack_fisher', 'gwf_unpack_fisher_ld', 'gwf_unpack_gather', 'gwf_peer_alloc', 'gwf_peer_open', 'gwf_peer_close', 'gwf_peer_free', 'gwf_copy_2d', 'gwf_waveform', 'gwf_signal_grid', 'gwf_pattern', 'gwf_fp64_peak', 'gwf_covariance', 'gwf_eigen',
            'gwf_inversion_error')
 
 _lib = None
@@ -87,6 +87,7 @@ def load():
     lib.gwf_psd_destroy.argtypes = [vp]
     lib.gwf_psd_destroy.restype = None
     lib.gwf_set_qnm_tables.argtypes = [P(dbl), P(dbl), P(dbl), i32]
+    lib.gwf_xitide_table.argtypes = [vp]
     common = [P(gwf_model), P(gwf_detector), i32, P(vp), i32, P(gwf_events), i64, P(gwf_opts)]
     lib.gwf_fisher.argtypes = common + [vp, vp, vp, C.c_size_t, vp]
     lib.gwf_fisher_ex.argtypes = common + [P(gwf_fisher_out), vp, C.c_size_t, vp]

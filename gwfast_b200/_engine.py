@@ -68,6 +68,15 @@ def state():
     return st
 
 
+def xitide_table():
+    """the (200, 200, 200) xi_tide table of IMRPhenomNSBH as the current device tabulated it (gwf_xitide_table; the reference reads it
+    from WFfiles/xiTide_Table_200.h5 or tabulates it with numpy.roots, waveforms.py:3286-3373)."""
+    state()
+    tab = np.empty((200, 200, 200))
+    K.check(K.load().gwf_xitide_table(tab.ctypes.data_as(C.c_void_p)), 'gwf_xitide_table')
+    return tab
+
+
 def psd_handle(freq, S):
     """PSD handle for (strainFreq, noiseCurve); cached on the arrays' content, valid on every device."""
     lib = K.load()

@@ -7,6 +7,7 @@
 #include "model_tf2.cuh"
 #include "model_nrtidal.cuh"
 #include "model_phenomhm.cuh"
+#include "model_nsbh.cuh"
 
 namespace gwf {
 
@@ -155,6 +156,73 @@ template <int NT> struct ModelTraits<kNRTidalv2, NT> {
             double tau, dtau[2];
             const double cpm1 = 0.68278406325529568146702083315816;   // pi^(-1/3)
             tau_eval(d.tau, p.xm13 * cpm1, p.lpx3, d.lam, tau, dtau);
+            w.tau = tau;
+            w.dtn[0] = -dtau[0] * kInvDay;
+            w.dtn[1] = -dtau[1] * kInvDay;
+        }
+    }
+};
+
+template <int NT> struct ModelTraits<kNSBH, NT> {
+    typedef NSBHRec<NT> Rec;
+    static GWF_HD void eval_amp(const Rec& r, const ModelCfg& cfg, const FreqPoint& fp, bool need_tau, double& A, double& tau) {
+        const PhenomDRec<NT>& d = r.d;
+        XPow p;
+        p.set(d.s, d.sp, fp);
+        A = 0.;
+        tau = 0.;
+        if ((cfg.flags & kFlagNoFcut) || p.x < kMfCut) {
+            NsbhPowers np;
+            nsbh_powers(np, p, r.sm76);
+            double c[kNsbhCoef];
+#pragma unroll
+            for (int k = 0; k < kNsbhCoef; ++k) c[k] = r.amp[k][0];
+            A = r.C * nsbh_amp_shape<double>(c, np, nullptr);
+        }
+        if (need_tau) {
+            double dtau[2];
+            tau_eval(d.tau, p.xm13 * 0.68278406325529568146702083315816, p.lpx3, d.lam, tau, dtau);
+        }
+    }
+    static GWF_HD void prologue(Rec& r, const EventIn& e, const ModelCfg& cfg, int opt_flags, const QnmTables& q, const double* fmin_g, int ng, int = 3) {
+        // NT = 6: Fisher parametrisation (Lambda re-mapped through LambdaTilde/deltaLambda, signal.py:871, 554); NT = 4: dict values as they are
+        const Intrinsic<NT> p = seed_intrinsic<NT>(e, opt_flags, NT >= 6);
+        nsbh_prologue(r, p, e.dL, q, fmin_g, e.fmax_g, e.fmax_exact, ng, cfg, e.s_host, e.fcut_host);
+    }
+    static GWF_HD void eval(const Rec& r, const ModelCfg& cfg, int g, const FreqPoint& fp, bool need_tau, PointWf<NT>& w) {
+        const PhenomDRec<NT>& d = r.d;
+        XPow p;
+        p.set(d.s, d.sp, fp);
+        w.dtn[0] = w.dtn[1] = 0.;
+        w.tau = 0.;
+        const bool cut = !(cfg.flags & kFlagNoFcut);
+        phenomd_phase(d, g, p, cut, w.phi, w.phi_d);
+        w.A = 0.;
+#pragma unroll
+        for (int j = 0; j < NT; ++j) w.lnA_d[j] = 0.;
+        if (!cut || p.x < kMfCut) {
+            // - t0_g x and the Pade tidal term (waveforms.py:3008-3033)
+            double R, xRp;
+            nrt_phase_shape(1.4645918875615232630201425272637904 * p.x13, R, xRp);
+            const double t0 = r.t0[g][0];
+            w.phi += r.kph[0] * R - t0 * p.x;
+#pragma unroll
+            for (int j = 0; j < NT; ++j)
+                w.phi_d[j] += r.kph[1 + j] * R + (r.kph[0] * xRp - t0 * p.x) * d.lam[j] - r.t0[g][1 + j] * p.x;
+            NsbhPowers np;
+            nsbh_powers(np, p, r.sm76);
+            Dual<NT> c[kNsbhCoef];
+#pragma unroll
+            for (int k = 0; k < kNsbhCoef; ++k) c[k] = get<NT>(r.amp[k]);
+            const Dual<NT> a = nsbh_amp_shape<Dual<NT>>(c, np, d.lam);
+            w.A = r.C * a.v;
+            const double ia = 1.0 / a.v;
+#pragma unroll
+            for (int j = 0; j < NT; ++j) w.lnA_d[j] = fma(a.d[j], ia, r.lnC_d[j]);
+        }
+        if (need_tau) {
+            double tau, dtau[2];
+            tau_eval(d.tau, p.xm13 * 0.68278406325529568146702083315816, p.lpx3, d.lam, tau, dtau);
             w.tau = tau;
             w.dtn[0] = -dtau[0] * kInvDay;
             w.dtn[1] = -dtau[1] * kInvDay;
@@ -801,7 +869,7 @@ template <int MODEL, int NT> struct PointFns {
                               bool rot, const FreqPoint& fp, double* __restrict__ acc) {
         amp_phase_point<MODEL, NT>(rec, cfg, geom, net, sc, g, rot, fp, acc);
     }
-    static constexpr bool kHasFast = true;
+    static constexpr bool kHasFast = MODEL != kNSBH;   // IMRPhenomNSBH runs the run-time-bounds form only (one instantiation per kernel)
 #ifdef __CUDA_ARCH__
     template <bool ROT, int SHAPE = 0>
     static __device__ __forceinline__ void fisher_fast(const Rec& rec, const ModelCfg& cfg, const EvGeom& geom, const NetworkDev& net, const EventScratch& sc,
@@ -913,6 +981,16 @@ template <> struct WaveformFns<kNRTidalv2> {
         nrt_amp_shape(p13, p.lpx3, Q, xQp);
         o.amp[0] = d.C * fma(r.sm76 * fp.fm76, v, r.kam[0] * Q) * T;
         tau_eval(d.tau, p.xm13 * 0.68278406325529568146702083315816, p.lpx3, d.lam, o.tau, dtau);
+    }
+};
+template <> struct WaveformFns<kNSBH> {
+    static constexpr int kModes = 1;
+    static GWF_HD void eval(const NSBHRec<4>& r, const ModelCfg& cfg, const HMWeights&, const FreqPoint& fp, WaveformOut& o) {
+        PointWf<4> w;
+        ModelTraits<kNSBH, 4>::eval(r, cfg, 0, fp, true, w);
+        o.phi[0] = w.phi;
+        o.amp[0] = w.A;
+        o.tau = w.tau;
     }
 };
 template <> struct WaveformFns<kPhenomHM> {

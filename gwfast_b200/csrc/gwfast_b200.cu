@@ -61,7 +61,31 @@ constexpr int kSnrThreads = 512, kSnrWarps = kSnrThreads / 32;     // SNR kernel
 struct GroupInfo {
     int n;
     double fmin[kMaxGroups];
+    double fmax[kMaxGroups];    // upper end of the group's band in Hz (0 = none); IMRPhenomNSBH needs the last grid sample in its prologue
+    int fmax_exact;             // fmax[0] is the last sample of a user grid, not a clip
 };
+static GroupInfo group_info(const NetworkDev& net) {
+    GroupInfo gi;
+    gi.n = net.ngroups;
+    gi.fmax_exact = 0;
+    for (int g = 0; g < kMaxGroups; ++g) {
+        gi.fmin[g] = net.group_fmin[g];
+        gi.fmax[g] = net.group_fmax[g];
+    }
+    return gi;
+}
+static GroupInfo group_info_user_grid() {
+    GroupInfo gi;
+    gi.n = 1;
+    gi.fmax_exact = 0;
+    for (int g = 0; g < kMaxGroups; ++g) {
+        gi.fmin[g] = 1.0;
+        gi.fmax[g] = 0.0;
+    }
+    return gi;
+}
+// which device tables a model's prologue reads: 1 = QNM ringdown tables, 2 = the xi_tide table of IMRPhenomNSBH
+template <int MODEL> constexpr int model_tables() { return (MODEL == kPhenomD || MODEL == kNRTidalv2) ? 1 : (MODEL == kNSBH ? 3 : 0); }
 
 // ------------------------------------------------------------------------------------------- K1
 // what the Fisher launch needs to know to fill EventAux (out == nullptr: not wanted)
@@ -87,8 +111,14 @@ __global__ void __launch_bounds__(128) prologue_kernel(EventsDev ev, long long n
                                                       int* __restrict__ status = nullptr) {
     const long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (e >= n) return;
-    const EventIn in = load_event(ev, e);
-    if (fmin_per_event) gi.fmin[0] = fmin_per_event[e];     // stand-alone waveform calls: fRef = min of the user's grid
+    EventIn in = load_event(ev, e);
+    if (fmin_per_event) {                                   // stand-alone waveform calls: fRef = min of the user's grid,
+        gi.fmin[0] = fmin_per_event[e];
+        gi.fmax[0] = fmin_per_event[n + e];                 // and its max (IMRPhenomNSBH's t0, waveforms.py:2994)
+        gi.fmax_exact = 1;
+    }
+    in.fmax_g = gi.fmax;
+    in.fmax_exact = gi.fmax_exact != 0;
     // gridDim.y = 2: the blocks with blockIdx.y = 0 / 1 compute the two independent halves of every record (IMRPhenomD: phase /
     // amplitude) -- the kernel's duration is the instruction-fetch latency of the code one warp walks through
     const int parts = gridDim.y == 2 ? 1 + (int)blockIdx.y : 3;
@@ -108,15 +138,26 @@ __global__ void __launch_bounds__(128) prologue_kernel(EventsDev ev, long long n
 }
 
 // per-event minimum of a user grid f[res][n] (or the shared f[res])
+// (fmin[e] = min, fmin[n + e] = max)
 __global__ void grid_min_kernel(const double* __restrict__ f, int res, long long n, int f2d, double* __restrict__ fmin) {
     const long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (e >= n) return;
-    double m = f2d ? f[e] : f[0];
+    double m = f2d ? f[e] : f[0], M = m;
     for (int k = 1; k < res; ++k) {
         const double v = f2d ? f[(long long)k * n + e] : f[k];
         m = v < m ? v : m;
+        M = v > M ? v : M;
     }
     fmin[e] = m;
+    fmin[n + e] = M;
+}
+
+// IMRPhenomNSBH: the 200^3 nodes of the xi_tide table (model_nsbh.cuh), one thread per node
+__global__ void __launch_bounds__(128) xitide_table_kernel(double* __restrict__ tab) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= kXiRes * kXiRes * kXiRes) return;
+    const int k = idx % kXiRes, j = (idx / kXiRes) % kXiRes, i = idx / (kXiRes * kXiRes);
+    tab[idx] = xitide_node(xi_node_coord(i, kXiCompMin, kXiCompMax), xi_node_coord(j, kXiQMin, kXiQMax), xi_node_coord(k, kXiChiMin, kXiChiMax));
 }
 
 template <class Rec> struct WaveBlk {
@@ -1136,7 +1177,7 @@ __global__ void __launch_bounds__(256) unpack_gather_kernel(const double* __rest
 // gwf_set_qnm_tables and PSD handles keep a host copy and are uploaded to a device the first time a call runs there.
 struct DeviceCtx {
     int sms = 0;
-    QnmTables qnm = {nullptr, nullptr, nullptr, 0};
+    QnmTables qnm = {nullptr, nullptr, nullptr, 0, nullptr};
     int qnm_version = 0;
     std::unordered_map<const void*, size_t> smem_set;
 };
@@ -1146,7 +1187,8 @@ static std::vector<double> g_qnm_host;       // a | fring | fdamp
 static int g_qnm_n = 0, g_qnm_version = 0;
 
 // context of the current device (needs_qnm: make sure the device copy of the QNM tables is current)
-static int device_ctx(bool needs_qnm, DeviceCtx** out, int* dev_out = nullptr) {
+static int device_ctx(int needs_tables, DeviceCtx** out, int* dev_out = nullptr) {
+    const bool needs_qnm = (needs_tables & 1) != 0;
     int dev = 0;
     GWF_CUDA(cudaGetDevice(&dev));
     if (dev < 0 || dev >= kMaxDevices) return fail(GWF_ERR_ARG, "device index out of range");
@@ -1163,6 +1205,17 @@ static int device_ctx(bool needs_qnm, DeviceCtx** out, int* dev_out = nullptr) {
             c.qnm.a = buf; c.qnm.fring = buf + g_qnm_n; c.qnm.fdamp = buf + 2 * g_qnm_n; c.qnm.n = g_qnm_n;
             c.qnm_version = g_qnm_version;
         }
+    }
+    if ((needs_tables & 2) && !c.qnm.xitide) {
+        // IMRPhenomNSBH: the reference interpolates a 200^3 table of xi_tide that it reads from an HDF5 file or tabulates with numpy.roots
+        // (waveforms.py:3286-3373); here the device solves the 8e6 order-10 polynomials itself, once per device (64 MB of HBM)
+        double* tab = nullptr;
+        const int nodes = kXiRes * kXiRes * kXiRes;
+        GWF_CUDA(cudaMalloc(&tab, sizeof(double) * (size_t)nodes));
+        xitide_table_kernel<<<(nodes + 127) / 128, 128>>>(tab);
+        GWF_CUDA(cudaGetLastError());
+        GWF_CUDA(cudaDeviceSynchronize());
+        c.qnm.xitide = tab;
     }
     *out = &c;
     if (dev_out) *dev_out = dev;
@@ -1230,16 +1283,14 @@ static int run_fisher(const gwf_model* model, const gwf_detector* dets, int ndet
     for (int i = 0; i < GWF_NPARAM_IN; ++i) ev.p[i] = ev_all.p[i] ? ev_all.p[i] + range.lo : nullptr;
     ModelCfg cfg = {model->id, model->flags, model->fcutPar, model->fRef};
     DeviceCtx* ctx = nullptr;
-    if (int rc0 = device_ctx(MODEL == kPhenomD || MODEL == kNRTidalv2, &ctx)) return rc0;
+    if (int rc0 = device_ctx(model_tables<MODEL>(), &ctx)) return rc0;
     NetworkDev net;
     PsdDev pd[kMaxPsd];
     int rc = collect_psds(psds, npsd, pd);
     if (rc) return rc;
     rc = build_network(dets, ndet, pd, npsd, -1, false, net);
     if (rc) return rc;
-    GroupInfo gi;
-    gi.n = net.ngroups;
-    for (int g = 0; g < kMaxGroups; ++g) gi.fmin[g] = net.group_fmin[g];
+    GroupInfo gi = group_info(net);
     // One event per pair of warps (each warp takes every other block of 32 samples): the work unit of the persistent loop is
     // half an event, which shortens its last round (1e4 events on 1184 warps: 8.45 -> 9 rounds of whole events, 16.9 -> 17 of
     // halves; measured 1.36 -> 1.31 ms).  The mapping is fixed per model -- never chosen from n -- so that an event's result
@@ -1348,16 +1399,14 @@ static int run_derivs(const gwf_model* model, const gwf_detector* dets, int ndet
     Rec* recs = reinterpret_cast<Rec*>(ws);
     ModelCfg cfg = {model->id, model->flags, model->fcutPar, model->fRef};
     DeviceCtx* ctx = nullptr;
-    if (int rc0 = device_ctx(MODEL == kPhenomD || MODEL == kNRTidalv2, &ctx)) return rc0;
+    if (int rc0 = device_ctx(model_tables<MODEL>(), &ctx)) return rc0;
     NetworkDev net;
     PsdDev pd[kMaxPsd];
     int rc = collect_psds(psds, npsd, pd);
     if (rc) return rc;
     rc = build_network(dets, ndet, pd, npsd, -1, false, net);
     if (rc) return rc;
-    GroupInfo gi;
-    gi.n = net.ngroups;
-    for (int g = 0; g < kMaxGroups; ++g) gi.fmin[g] = net.group_fmin[g];
+    GroupInfo gi = group_info(net);
     const int pb = 128;
     prologue_kernel<MODEL, NT><<<(unsigned)((n + pb - 1) / pb), pb, 0, st>>>(ev, n, cfg, opts->flags, ctx->qnm, gi, recs);
     GWF_CUDA(cudaGetLastError());
@@ -1388,16 +1437,14 @@ static int run_strain(const gwf_model* model, const gwf_detector* dets, int ndet
     Rec* recs = reinterpret_cast<Rec*>(ws);
     ModelCfg cfg = {model->id, model->flags, model->fcutPar, model->fRef};
     DeviceCtx* ctx = nullptr;
-    if (int rc0 = device_ctx(MODEL == kPhenomD || MODEL == kNRTidalv2, &ctx)) return rc0;
+    if (int rc0 = device_ctx(model_tables<MODEL>(), &ctx)) return rc0;
     NetworkDev net;
     PsdDev pd[kMaxPsd];
     int rc = collect_psds(psds, npsd, pd);
     if (rc) return rc;
     rc = build_network(dets, ndet, pd, npsd, -1, false, net);
     if (rc) return rc;
-    GroupInfo gi;
-    gi.n = net.ngroups;
-    for (int g = 0; g < kMaxGroups; ++g) gi.fmin[g] = net.group_fmin[g];
+    GroupInfo gi = group_info(net);
     const int pb = 128;
     // GWstrain is handed the dict entries as they are (no Fisher re-parametrisation, signal.py:1871)
     prologue_kernel<MODEL, 4><<<(unsigned)((n + pb - 1) / pb), pb, 0, st>>>(ev, n, cfg, 0, ctx->qnm, gi, recs);
@@ -1430,16 +1477,14 @@ static int run_snr(const gwf_model* model, const gwf_detector* dets, int ndet, c
     EventAux* aux = reinterpret_cast<EventAux*>(reinterpret_cast<char*>(ws) + rec_bytes);
     ModelCfg cfg = {model->id, model->flags, model->fcutPar, model->fRef};
     DeviceCtx* ctx = nullptr;
-    if (int rc0 = device_ctx(MODEL == kPhenomD || MODEL == kNRTidalv2, &ctx)) return rc0;
+    if (int rc0 = device_ctx(model_tables<MODEL>(), &ctx)) return rc0;
     NetworkDev net;
     PsdDev pd[kMaxPsd];
     int rc = collect_psds(psds, npsd, pd);
     if (rc) return rc;
     rc = build_network(dets, ndet, pd, npsd, -1, true, net);
     if (rc) return rc;
-    GroupInfo gi;
-    gi.n = net.ngroups;
-    for (int g = 0; g < kMaxGroups; ++g) gi.fmin[g] = net.group_fmin[g];
+    GroupInfo gi = group_info(net);
     const int pb = 128;
     // SNRInteg hands the dict entries straight to the waveform: no Fisher re-parametrisation (signal.py:715-726)
     const int lin = (opts->flags & GWF_OPT_LIN_GRID) ? 1 : 0;
@@ -1491,15 +1536,13 @@ static int run_signal_grid(const gwf_model* model, const gwf_detector* det, doub
                            int f2d, const SignalOut& out, void* ws, size_t ws_bytes, cudaStream_t st) {
     typedef typename ModelTraits<MODEL, 4>::Rec Rec;
     const size_t rec_bytes = (sizeof(Rec) * (size_t)n + 15) & ~(size_t)15;
-    if (ws_bytes < rec_bytes + sizeof(double) * (size_t)n) return fail(GWF_ERR_WORKSPACE, "workspace too small");
+    if (ws_bytes < rec_bytes + 2 * sizeof(double) * (size_t)n) return fail(GWF_ERR_WORKSPACE, "workspace too small");
     Rec* recs = reinterpret_cast<Rec*>(ws);
     double* fmin_ev = reinterpret_cast<double*>(reinterpret_cast<char*>(ws) + rec_bytes);
     ModelCfg cfg = {model->id, model->flags, model->fcutPar, model->fRef};
     DeviceCtx* ctx = nullptr;
-    if (int rc0 = device_ctx(MODEL == kPhenomD || MODEL == kNRTidalv2, &ctx)) return rc0;
-    GroupInfo gi;
-    gi.n = 1;
-    for (int g = 0; g < kMaxGroups; ++g) gi.fmin[g] = 1.0;
+    if (int rc0 = device_ctx(model_tables<MODEL>(), &ctx)) return rc0;
+    GroupInfo gi = group_info_user_grid();
     const int pb = 128;
     const unsigned pg = (unsigned)((n + pb - 1) / pb);
     grid_min_kernel<<<pg, pb, 0, st>>>(f, res, n, f2d, fmin_ev);                 // fRef = min of the user's grid (waveforms.py:1139)
@@ -1524,15 +1567,13 @@ static int run_waveform(const gwf_model* model, const EventsDev& ev, long long n
                         double* tau, double* hphc, double* fcut, void* ws, size_t ws_bytes, cudaStream_t st) {
     typedef typename ModelTraits<MODEL, 4>::Rec Rec;
     const size_t rec_bytes = (sizeof(Rec) * (size_t)n + 15) & ~(size_t)15;
-    if (ws_bytes < rec_bytes + sizeof(double) * (size_t)n) return fail(GWF_ERR_WORKSPACE, "workspace too small");
+    if (ws_bytes < rec_bytes + 2 * sizeof(double) * (size_t)n) return fail(GWF_ERR_WORKSPACE, "workspace too small");
     Rec* recs = reinterpret_cast<Rec*>(ws);
     double* fmin_ev = reinterpret_cast<double*>(reinterpret_cast<char*>(ws) + rec_bytes);
     ModelCfg cfg = {model->id, model->flags, model->fcutPar, model->fRef};
     DeviceCtx* ctx = nullptr;
-    if (int rc0 = device_ctx(MODEL == kPhenomD || MODEL == kNRTidalv2, &ctx)) return rc0;
-    GroupInfo gi;
-    gi.n = 1;
-    for (int g = 0; g < kMaxGroups; ++g) gi.fmin[g] = 1.0;
+    if (int rc0 = device_ctx(model_tables<MODEL>(), &ctx)) return rc0;
+    GroupInfo gi = group_info_user_grid();
     const int pb = 128;
     const unsigned pg = (unsigned)((n + pb - 1) / pb);
     const double* fmin_arg = nullptr;
@@ -1583,10 +1624,11 @@ size_t gwf_workspace_bytes(const gwf_model* model, int64_t n) {
         case GWF_IMRPHENOMD: rec = sizeof(PhenomDRec<4>); break;
         case GWF_IMRPHENOMD_NRTIDALV2: rec = std::max(sizeof(NRTidalRec<4>), sizeof(NRTidalRec<6>)); break;
         case GWF_IMRPHENOMHM: rec = sizeof(HMRec<4>); break;
+        case GWF_IMRPHENOMNSBH: rec = std::max(sizeof(NSBHRec<4>), sizeof(NSBHRec<6>)); break;
         default: rec = 0;
     }
     // records, then the larger of the waveform path's per-event grid minimum and the Fisher path's EventAux
-    return ((rec * (size_t)n + 15) & ~(size_t)15) + std::max(sizeof(double), sizeof(EventAux)) * (size_t)n;
+    return ((rec * (size_t)n + 15) & ~(size_t)15) + std::max(2 * sizeof(double), sizeof(EventAux)) * (size_t)n;
 }
 
 int gwf_psd_create(const double* f, const double* S, int32_t n, gwf_psd** out) {
@@ -1613,6 +1655,14 @@ void gwf_psd_destroy(gwf_psd* psd) {
     delete h;
 }
 
+int gwf_xitide_table(double* table_host) {
+    DeviceCtx* ctx = nullptr;
+    if (int rc0 = device_ctx(2, &ctx)) return rc0;
+    if (table_host)
+        GWF_CUDA(cudaMemcpy(table_host, ctx->qnm.xitide, sizeof(double) * (size_t)kXiRes * kXiRes * kXiRes, cudaMemcpyDeviceToHost));
+    return GWF_OK;
+}
+
 int gwf_set_qnm_tables(const double* a, const double* fring, const double* fdamp, int32_t n) {
     if (!a || !fring || !fdamp || n < 2) return fail(GWF_ERR_ARG, "gwf_set_qnm_tables: bad arguments");
     std::lock_guard<std::mutex> lock(g_mu);
@@ -1632,7 +1682,7 @@ static int check_common(const gwf_model* model, const gwf_detector* dets, const 
     if (opts->res < 2) return fail(GWF_ERR_ARG, "res must be at least 2");
     for (int i = 0; i < 11; ++i)
         if (!events->p[i] && n > 0) return fail(GWF_ERR_ARG, "missing event parameter array");
-    if ((model->id == GWF_IMRPHENOMD || model->id == GWF_IMRPHENOMD_NRTIDALV2) && g_qnm_n == 0)
+    if ((model->id == GWF_IMRPHENOMD || model->id == GWF_IMRPHENOMD_NRTIDALV2 || model->id == GWF_IMRPHENOMNSBH) && g_qnm_n == 0)
         return fail(GWF_ERR_ARG, "QNM tables not set (gwf_set_qnm_tables)");
     return GWF_OK;
 }
@@ -1685,6 +1735,9 @@ static int fisher_dispatch(const gwf_model* model, const gwf_detector* dets, int
             return run_fisher<kNRTidalv2, 6>(model, dets, ndet, psds, npsd, ev, n, range, opts, out, workspace, workspace_bytes, st);
         case GWF_IMRPHENOMHM:
             return run_fisher<kPhenomHM, 4>(model, dets, ndet, psds, npsd, ev, n, range, opts, out, workspace, workspace_bytes, st);
+        case GWF_IMRPHENOMNSBH:
+            if (!ev.p[11] || !ev.p[12]) return fail(GWF_ERR_ARG, "tidal model needs Lambda1, Lambda2");
+            return run_fisher<kNSBH, 6>(model, dets, ndet, psds, npsd, ev, n, range, opts, out, workspace, workspace_bytes, st);
         default:
             return fail(GWF_ERR_UNSUPPORTED, "model not built yet");
     }
@@ -1734,6 +1787,9 @@ int gwf_strain_derivs(const gwf_model* model, const gwf_detector* dets, int32_t 
             return run_derivs<kNRTidalv2, 6>(model, dets, ndet, psds, npsd, ev, n, opts, derivs, workspace, workspace_bytes, st);
         case GWF_IMRPHENOMHM:
             return run_derivs<kPhenomHM, 4>(model, dets, ndet, psds, npsd, ev, n, opts, derivs, workspace, workspace_bytes, st);
+        case GWF_IMRPHENOMNSBH:
+            if (!ev.p[11] || !ev.p[12]) return fail(GWF_ERR_ARG, "tidal model needs Lambda1, Lambda2");
+            return run_derivs<kNSBH, 6>(model, dets, ndet, psds, npsd, ev, n, opts, derivs, workspace, workspace_bytes, st);
         default:
             return fail(GWF_ERR_UNSUPPORTED, "gwf_strain_derivs: model not built");
     }
@@ -1758,6 +1814,8 @@ int gwf_snr(const gwf_model* model, const gwf_detector* dets, int32_t ndet, cons
             return run_snr<kNRTidalv2>(model, dets, ndet, psds, npsd, ev, n, opts, snr2_arm, workspace, workspace_bytes, st);
         case GWF_IMRPHENOMHM:
             return run_snr<kPhenomHM>(model, dets, ndet, psds, npsd, ev, n, opts, snr2_arm, workspace, workspace_bytes, st);
+        case GWF_IMRPHENOMNSBH:
+            return run_snr<kNSBH>(model, dets, ndet, psds, npsd, ev, n, opts, snr2_arm, workspace, workspace_bytes, st);
         default:
             return fail(GWF_ERR_UNSUPPORTED, "model not built yet");
     }
@@ -1784,6 +1842,8 @@ int gwf_strain(const gwf_model* model, const gwf_detector* dets, int32_t ndet, c
             return run_strain<kNRTidalv2>(model, dets, ndet, psds, npsd, ev, n, opts, strain, workspace, workspace_bytes, st);
         case GWF_IMRPHENOMHM:
             return run_strain<kPhenomHM>(model, dets, ndet, psds, npsd, ev, n, opts, strain, workspace, workspace_bytes, st);
+        case GWF_IMRPHENOMNSBH:
+            return run_strain<kNSBH>(model, dets, ndet, psds, npsd, ev, n, opts, strain, workspace, workspace_bytes, st);
         default:
             return fail(GWF_ERR_UNSUPPORTED, "gwf_strain: model not built");
     }
@@ -1909,7 +1969,7 @@ int gwf_waveform(const gwf_model* model, const gwf_events* events, int64_t n, co
     if (n < 0 || res < 0 || (res > 0 && !f)) return fail(GWF_ERR_ARG, "gwf_waveform: bad grid");
     for (int i = 0; i < 11; ++i)
         if (!events->p[i] && n > 0) return fail(GWF_ERR_ARG, "missing event parameter array");
-    if ((model->id == GWF_IMRPHENOMD || model->id == GWF_IMRPHENOMD_NRTIDALV2) && g_qnm_n == 0) return fail(GWF_ERR_ARG, "QNM tables not set (gwf_set_qnm_tables)");
+    if ((model->id == GWF_IMRPHENOMD || model->id == GWF_IMRPHENOMD_NRTIDALV2 || model->id == GWF_IMRPHENOMNSBH) && g_qnm_n == 0) return fail(GWF_ERR_ARG, "QNM tables not set (gwf_set_qnm_tables)");
     if (hphc_out && model->id != GWF_IMRPHENOMHM) return fail(GWF_ERR_UNSUPPORTED, "hphc is only defined for IMRPhenomHM");
     if (n == 0) return GWF_OK;
     EventsDev ev;
@@ -1922,6 +1982,7 @@ int gwf_waveform(const gwf_model* model, const gwf_events* events, int64_t n, co
             if (!ev.p[11] || !ev.p[12]) return fail(GWF_ERR_ARG, "tidal model needs Lambda1, Lambda2");
             return run_waveform<kNRTidalv2>(model, ev, n, f, res, f_is_2d, phi_out, ampl_out, tau_out, hphc_out, fcut_out, workspace, workspace_bytes, st);
         case GWF_IMRPHENOMHM: return run_waveform<kPhenomHM>(model, ev, n, f, res, f_is_2d, phi_out, ampl_out, tau_out, hphc_out, fcut_out, workspace, workspace_bytes, st);
+        case GWF_IMRPHENOMNSBH: return run_waveform<kNSBH>(model, ev, n, f, res, f_is_2d, phi_out, ampl_out, tau_out, hphc_out, fcut_out, workspace, workspace_bytes, st);
         default: return fail(GWF_ERR_ARG, "unknown model");
     }
 }
@@ -1933,7 +1994,7 @@ int gwf_signal_grid(const gwf_model* model, const gwf_detector* det, double rot_
     if (det->shape != 0 && det->shape != 1) return fail(GWF_ERR_ARG, "Enter valid detector configuration");
     for (int i = 0; i < 11; ++i)
         if (!events->p[i] && n > 0) return fail(GWF_ERR_ARG, "missing event parameter array");
-    if ((model->id == GWF_IMRPHENOMD || model->id == GWF_IMRPHENOMD_NRTIDALV2) && g_qnm_n == 0) return fail(GWF_ERR_ARG, "QNM tables not set (gwf_set_qnm_tables)");
+    if ((model->id == GWF_IMRPHENOMD || model->id == GWF_IMRPHENOMD_NRTIDALV2 || model->id == GWF_IMRPHENOMNSBH) && g_qnm_n == 0) return fail(GWF_ERR_ARG, "QNM tables not set (gwf_set_qnm_tables)");
     if (outp->psi && model->id == GWF_IMRPHENOMHM) return fail(GWF_ERR_UNSUPPORTED, "GWPhase is not defined for IMRPhenomHM (its Phi is per mode)");
     if (n == 0) return GWF_OK;
     EventsDev ev;
@@ -1950,6 +2011,7 @@ int gwf_signal_grid(const gwf_model* model, const gwf_detector* det, double rot_
             if (!ev.p[11] || !ev.p[12]) return fail(GWF_ERR_ARG, "tidal model needs Lambda1, Lambda2");
             return run_signal_grid<kNRTidalv2>(model, det, rot_deg, ev, n, f, res, f_is_2d, out, workspace, workspace_bytes, st);
         case GWF_IMRPHENOMHM: return run_signal_grid<kPhenomHM>(model, det, rot_deg, ev, n, f, res, f_is_2d, out, workspace, workspace_bytes, st);
+        case GWF_IMRPHENOMNSBH: return run_signal_grid<kNSBH>(model, det, rot_deg, ev, n, f, res, f_is_2d, out, workspace, workspace_bytes, st);
         default: return fail(GWF_ERR_ARG, "unknown model");
     }
 }

@@ -77,6 +77,7 @@ static int model_nt(const gwf_model& m) {
         case GWF_IMRPHENOMD: return 4;
         case GWF_IMRPHENOMD_NRTIDALV2: return 6;
         case GWF_IMRPHENOMHM: return 4;
+        case GWF_IMRPHENOMNSBH: return 6;
     }
     return -1;
 }

@@ -7,7 +7,7 @@ namespace gwf {
 constexpr int kMaxGroups = 4;   // distinct (fmin, fmax) frequency-grid groups in one network launch
 
 // model ids (gwf_model.id in include/gwfast_b200.h)
-enum ModelId { kTaylorF2 = 0, kPhenomD = 1, kNRTidalv2 = 2, kPhenomHM = 3 };
+enum ModelId { kTaylorF2 = 0, kPhenomD = 1, kNRTidalv2 = 2, kPhenomHM = 3, kNSBH = 4 };
 
 // model option flags (gwf_model.flags)
 enum ModelFlags {
@@ -57,6 +57,10 @@ struct EventIn {
     double Mc, eta, dL, theta, phi, iota, psi, tcoal, Phicoal, chi1z, chi2z, Lambda1, Lambda2;
     double fcut_host, s_host;   // optional host-computed wf_model.fcut and M*GMsun_over_c3 (0 = compute on the device)
     double ecc;                 // orbital eccentricity e0 (eccentric TaylorF2 only)
+    // upper ends of the grid groups' bands in Hz (0 = none), set by the caller of the prologue: IMRPhenomNSBH takes its time shift at
+    // the LAST sample of the event's grid (waveforms.py:2994).  fmax_exact: fmax_g[0] is that sample itself (user grids)
+    const double* fmax_g = nullptr;
+    bool fmax_exact = false;
 };
 
 // intrinsic parameters seeded for differentiation.  Slots: 0,1 = (Mc,eta) or (m1,m2); 2,3 = (chi1z,chi2z) or

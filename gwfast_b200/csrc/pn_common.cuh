@@ -149,6 +149,7 @@ struct QnmTables {
     const double* fring;
     const double* fdamp;
     int n;
+    const double* xitide;   // IMRPhenomNSBH: 200^3 table of xi_tide (model_nsbh.cuh), nullptr until that model runs on the device
 };
 GWF_HD int qnm_segment(const QnmTables& q, double x) {
     int lo = 0, hi = q.n - 1;               // invariant: a[lo] <= x < a[hi] (after clamping)

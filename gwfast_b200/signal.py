@@ -42,8 +42,9 @@ def _engine_events(wf_model, evParams, lambdas=None, use_m1m2=False, exact_cut=F
         ev['Lambda1'], ev['Lambda2'] = L1, L2
     if wf_model.is_eccentric:
         ev['ecc'] = evParams['ecc']              # signal.py:877-880
-    if wf_model.is_HigherModes or (exact_cut and not wf_model.is_tidal and type(wf_model).__name__ != 'TaylorF2_RestrictedPN'):
-        # only IMRPhenomHM needs it at the 1e-9 level (3e-12 for IMRPhenomD); two numpy pow() per event on the host.
+    if wf_model.is_HigherModes or wf_model.objType == 'NSBH' or (exact_cut and not wf_model.is_tidal and type(wf_model).__name__ != 'TaylorF2_RestrictedPN'):
+        # only IMRPhenomHM needs it at the 1e-9 level (3e-12 for IMRPhenomD), and IMRPhenomNSBH, whose d ln A/d Lambda is ~1e2 at the
+        # cut (1e-6 of F[Lambda, Lambda] from that one sample); two numpy pow() per event on the host.
         # exact_cut: the strain-derivative output exposes the last sample itself, so IMRPhenomD asks for it there too
         ev['_fcut'] = wf_model.fcut(**evParams)
         Mc, eta = evParams['Mc'], evParams['eta']

@@ -4,7 +4,7 @@ import numpy as np
 
 from . import gwfastGlobals as glob
 
-SEEDS = {'C1': 20260001, 'C2': 20260002, 'C3': 20260003, 'C4': 20260004, 'C5': 20260005}
+SEEDS = {'C1': 20260001, 'C2': 20260002, 'C3': 20260003, 'C4': 20260004, 'C5': 20260005, 'NSBH': 20260006}
 
 
 def _angles(rng, N):
@@ -31,6 +31,21 @@ def bns_catalog(N, seed, tidal=False):
     ev.update(chi1z=rng.uniform(-0.05, 0.05, N), chi2z=rng.uniform(-0.05, 0.05, N))
     if tidal:
         ev.update(Lambda1=rng.uniform(5, 2000, N), Lambda2=rng.uniform(5, 2000, N))
+    return ev
+
+
+def nsbh_catalog(N, seed):
+    """detector-frame NSBH: m_BH~U(3,12)(1+z), m_NS~U(1.1,2.0)(1+z), z~U(0.01,1.5), chi_BH~U(-0.6,0.9), chi_NS~U(-0.05,0.05),
+    Lambda_NS~U(50,3000) (a tenth of the events below 1: the polynomial branches of the compactness and quadrupole fits), Lambda_BH = 0."""
+    rng = np.random.default_rng(seed)
+    z = rng.uniform(0.01, 1.5, N)
+    m1, m2 = rng.uniform(3., 12., N) * (1 + z), rng.uniform(1.1, 2.0, N) * (1 + z)
+    ev = dict(Mc=(m1 * m2) ** 0.6 / (m1 + m2) ** 0.2, eta=m1 * m2 / (m1 + m2) ** 2, dL=rng.uniform(0.05, 12, N))
+    ev.update(_angles(rng, N))
+    lam = rng.uniform(50., 3000., N)
+    small = rng.uniform(0, 1, N) < 0.1
+    lam[small] = rng.uniform(0.05, 0.95, small.sum())
+    ev.update(chi1z=rng.uniform(-0.6, 0.9, N), chi2z=rng.uniform(-0.05, 0.05, N), Lambda1=np.zeros(N), Lambda2=lam)
     return ev
 
 

@@ -216,6 +216,24 @@ class IMRPhenomHM(WaveFormModel):
         return self._waveform(f, 'hphc', **kwargs)
 
 
+class IMRPhenomNSBH(WaveFormModel):
+    """waveforms.py:2752-3374.  Index 1 is the black hole, 2 the neutron star; ``Lambda1`` is discarded as in the reference.  The
+    xi_tide table the reference reads from ``WFfiles/xiTide_Table_200.h5`` (or tabulates with numpy.roots, :3286-3343) is computed
+    on the device the first time the model runs there (csrc/model_nsbh.cuh)."""
+    _model_id = K.GWF_IMRPHENOMNSBH
+
+    def __init__(self, fRef=None, verbose=True, **kwargs):
+        self.PHI_fJoin_INS = 0.018
+        self.verbose = verbose
+        self.fRef = fRef
+        super().__init__('NSBH', 0.2, is_tidal=True, **kwargs)
+        self.QNMgrid_a, self.QNMgrid_fring, self.QNMgrid_fdamp = _qnm_tables()
+
+    def fcut(self, **kwargs):
+        """waveforms.py:3273-3284."""
+        return self.fcutPar / (kwargs['Mc'] * glob.GMsun_over_c3 / (kwargs['eta'] ** (3. / 5.)))
+
+
 _QNM = None
 
 

@@ -30,8 +30,8 @@ typedef enum {
     GWF_ERR_WORKSPACE = -4   /* workspace too small */
 } gwf_status;
 
-/* waveform models: gwfast/waveforms.py classes at :697, :959, :1339, :1838 */
-typedef enum { GWF_TAYLORF2 = 0, GWF_IMRPHENOMD = 1, GWF_IMRPHENOMD_NRTIDALV2 = 2, GWF_IMRPHENOMHM = 3 } gwf_model_id;
+/* waveform models: gwfast/waveforms.py classes at :697, :959, :1339, :1838, :2752 */
+typedef enum { GWF_TAYLORF2 = 0, GWF_IMRPHENOMD = 1, GWF_IMRPHENOMD_NRTIDALV2 = 2, GWF_IMRPHENOMHM = 3, GWF_IMRPHENOMNSBH = 4 } gwf_model_id;
 
 /* gwf_model.flags -- constructor options of the reference classes that change the arithmetic */
 #define GWF_MODEL_TIDAL 1          /* TaylorF2_RestrictedPN(is_tidal=True)            waveforms.py:850-855 */
@@ -72,6 +72,12 @@ void gwf_psd_destroy(gwf_psd* psd);
 
 /* QNM ringdown tables WFfiles/QNMData_{a,fring,fdamp}.txt (waveforms.py:988-990); host arrays, copied once */
 int gwf_set_qnm_tables(const double* a_host, const double* fring_host, const double* fdamp_host, int32_t n);
+
+/* IMRPhenomNSBH's xi_tide table (waveforms.py:3286-3373: WFfiles/xiTide_Table_200.h5, or IMRPhenomNSBH._tabulate_xiTide with
+ * numpy.roots): 200^3 doubles over (compactness in [0.1, 0.5], q in [1, 100], chi_BH in [-1, 1]), row-major.  The current device
+ * computes its own copy the first time the model runs there; this call makes sure it exists and, if table_host is not NULL,
+ * copies it out (what IMRPhenomNSBH.xiTide_interp tabulates). */
+int gwf_xitide_table(double* table_host);
 
 /* the events dict as device SoA; order of p[]:
  * Mc eta dL theta phi iota psi tcoal Phicoal chi1z chi2z Lambda1 Lambda2 fcut Mtot_sec ecc

@@ -82,6 +82,12 @@ class Dual:
         axes = tuple(range(self.v.ndim))[::-1]
         return Dual(self.v.T, np.transpose(self.d, axes + (self.v.ndim,)))
 
+    def reshape(self, *shape):
+        if len(shape) == 1 and isinstance(shape[0], (tuple, list)):
+            shape = tuple(shape[0])
+        v = self.v.reshape(shape)
+        return Dual(v, self.d.reshape(v.shape + (self.d.shape[-1],)))
+
     def astype(self, dt):
         return Dual(self.v.astype(dt), self.d.astype(dt))
 
@@ -317,6 +323,12 @@ def _interp(x, xp, fp, left=None, right=None, period=None):
     return Dual(v, _ex(slope) * x.d)
 
 
+@_implements(np.searchsorted)
+def _searchsorted(a, v, side='left', sorter=None):
+    # indices are piecewise constant: values only (gwfastUtils.py:1196, RegularGridInterpolator_JAX._find_indices)
+    return np.searchsorted(_val(a), _val(v), side=side, sorter=sorter)
+
+
 @_implements(np.amin)
 def _amin(a, axis=None, **kw):
     i = np.expand_dims(np.argmin(a.v, axis=axis), axis)
@@ -460,6 +472,15 @@ def _vstack(arrs):
 
 
 # ---------------------------------------------------------------- seeding helpers
+def stack0(xs):
+    """np.asarray of a tuple of duals / arrays: stacked along a new leading axis"""
+    like = next(x for x in xs if isinstance(x, Dual))
+    ds = [_as_dual(x, like) for x in xs]
+    shape = np.broadcast_shapes(*[x.v.shape for x in ds])
+    nt = like.d.shape[-1]
+    return Dual(np.stack([np.broadcast_to(x.v, shape) for x in ds]), np.stack([np.broadcast_to(x.d, shape + (nt,)) for x in ds]))
+
+
 def seed(args, argnums):
     """Return ``args`` with those listed in ``argnums`` replaced by identity-seeded duals."""
     nt = len(argnums)

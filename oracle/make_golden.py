@@ -387,7 +387,29 @@ def fx_edge_rest():
     save('edge_lambda_zero_tf2_etsl', cfg, lz, run_network_pool(cfg, lz, chunk=4))
 
 
-ALL = {'init': fx_init, 'c1': fx_c1, 'c1b': fx_c1b, 'c2': fx_c2, 'var': fx_variants, 'c3': fx_c3, 'c4': fx_c4, 'gw170817': fx_gw170817, 'wf': fx_wfvalues, 'newt': fx_newt, 'ecc': fx_ecc, 'c4big': fx_c4big, 'edge': fx_edge, 'edge_eta': fx_edge_eta}
+def fx_nsbh():
+    """IMRPhenomNSBH (waveforms.py:2752-3374) with the xi_tide table tabulated by the reference's own _tabulate_xiTide
+    (oracle/nsbh_table.py): networks + stand-alone Phi / Ampl / tau_star / fcut."""
+    wf, sig, net, utils, glob = reference.load()
+    ev = synthetic.nsbh_catalog(48, synthetic.SEEDS['NSBH'])
+    cfg = dict(model=dict(cls='IMRPhenomNSBH', kw=dict(verbose=False)), network='ET+2CE', rot=True, fmin=2.)
+    save('nsbh_et2ce', cfg, ev, run_network_pool(cfg, ev, chunk=6))
+    sub = take(ev, 12)
+    cfg = dict(model=dict(cls='IMRPhenomNSBH', kw=dict(verbose=False)), network='LVK-O4', rot=False, fmin=10., fmax=512., res=600, fisher_kw=dict(spacing='lin'))
+    save('nsbh_lvk_lin_fmax', cfg, sub, run_network(cfg, sub))
+    cfg = dict(model=dict(cls='IMRPhenomNSBH', kw=dict(verbose=False, fRef=20., apply_fcut=False, is_chi1chi2=False)), network='ET', rot=True, fmin=5.,
+               fisher_kw=dict(use_m1m2=True, use_chi1chi2=False))
+    save('nsbh_et_m1m2_chisa_fref_nocut', cfg, sub, run_network(cfg, sub, want_all=False))
+    cat = take(ev, 8)
+    m = wf.IMRPhenomNSBH(verbose=False)
+    fg = np.geomspace(np.full(8, 5.), 0.97 * m.fcut(**cat), 160)
+    out = {'f': fg, 'fcut': m.fcut(**cat), 'tau': m.tau_star(fg, **cat), 'phi': m.Phi(fg, **cat), 'ampl': m.Ampl(fg, **cat)}
+    fg2 = np.geomspace(np.full(8, 8.), 1.3 * m.fcut(**cat), 120)          # beyond the cut: zeros, and t0 from the grid's own maximum
+    out.update({'f_over': fg2, 'phi_over': m.Phi(fg2, **cat), 'ampl_over': m.Ampl(fg2, **cat)})
+    save('wf_values_nsbh', dict(model=dict(cls='IMRPhenomNSBH')), cat, out)
+
+
+ALL = {'init': fx_init, 'c1': fx_c1, 'c1b': fx_c1b, 'c2': fx_c2, 'var': fx_variants, 'c3': fx_c3, 'c4': fx_c4, 'gw170817': fx_gw170817, 'wf': fx_wfvalues, 'newt': fx_newt, 'ecc': fx_ecc, 'c4big': fx_c4big, 'edge': fx_edge, 'edge_eta': fx_edge_eta, 'nsbh': fx_nsbh}
 
 if __name__ == '__main__':
     warnings.filterwarnings('ignore')

@@ -38,4 +38,6 @@ def load():
         from gwfast import waveforms, signal, network
         from gwfast import gwfastUtils as utils
         from gwfast import gwfastGlobals as glob
+    from oracle import nsbh_table
+    nsbh_table.install(waveforms)             # IMRPhenomNSBH: `time` import and a cache around the reference's own xi_tide tabulation
     return waveforms, signal, network, utils, glob

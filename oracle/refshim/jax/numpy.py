@@ -27,3 +27,15 @@ def fabs(x, *a, **k):
     if _np.iscomplexobj(x):
         x = _np.real(x)
     return _np.fabs(x, *a, **k)
+
+
+def asarray(x, *a, **k):
+    """numpy.asarray that lets dual numbers through.  IMRPhenomNSBH stacks three per-event quantities for its table interpolator with
+    ``np.asarray((np.asarray(Comp), np.asarray(q), np.asarray(chi1))).T`` (gwfast/waveforms.py:3111); jax.numpy.asarray accepts
+    tracers there, numpy.asarray would turn the oracle's Dual objects into an object array."""
+    from oracle.dual import Dual, stack0
+    if isinstance(x, Dual):
+        return x
+    if isinstance(x, (tuple, list)) and True in [isinstance(t, Dual) for t in x]:
+        return stack0(x)
+    return _np.asarray(x, *a, **k)

@@ -8,6 +8,8 @@ netname = sys.argv[1] if len(sys.argv) > 1 else 'ET+2CE'
 mname = sys.argv[2] if len(sys.argv) > 2 else 'IMRPhenomD'
 if mname == 'IMRPhenomD_NRTidalv2':
     ev = synthetic.bns_catalog(n, synthetic.SEEDS['C3'], tidal=True)
+elif mname == 'IMRPhenomNSBH':
+    ev = synthetic.nsbh_catalog(n, synthetic.SEEDS['NSBH'])
 elif mname == 'TaylorF2_RestrictedPN':
     ev = synthetic.bns_catalog(n, synthetic.SEEDS['C1'])
 else:

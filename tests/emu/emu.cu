@@ -18,7 +18,7 @@ struct EmuPsd {
     PsdDev dev;
 };
 
-static QnmTables g_q = {nullptr, nullptr, nullptr, 0};
+static QnmTables g_q = {nullptr, nullptr, nullptr, 0, nullptr};
 static std::vector<double> g_qbuf;
 
 template <int MODEL, int NT, bool SD = false>
@@ -38,6 +38,7 @@ static int emu_run(const gwf_model* model, const gwf_detector* dets, int ndet, c
             in.psi = ev[6][e]; in.tcoal = ev[7][e]; in.Phicoal = ev[8][e]; in.chi1z = ev[9][e]; in.chi2z = ev[10][e];
             in.Lambda1 = ev[11] ? ev[11][e] : 0.; in.Lambda2 = ev[12] ? ev[12][e] : 0.;
             in.fcut_host = ev[13] ? ev[13][e] : 0.; in.s_host = ev[14] ? ev[14][e] : 0.; in.ecc = ev[15] ? ev[15][e] : 0.;
+            in.fmax_g = net.group_fmax;
             Rec rec;
             ModelTraits<MODEL, NT>::prologue(rec, in, cfg, opts->flags, g_q, net.group_fmin, net.ngroups);
             EvGeom geom;
@@ -89,6 +90,7 @@ static int emu_run_snr(const gwf_model* model, const gwf_detector* dets, int nde
         in.psi = ev[6][e]; in.tcoal = ev[7][e]; in.Phicoal = ev[8][e]; in.chi1z = ev[9][e]; in.chi2z = ev[10][e];
         in.Lambda1 = ev[11] ? ev[11][e] : 0.; in.Lambda2 = ev[12] ? ev[12][e] : 0.;
             in.fcut_host = ev[13] ? ev[13][e] : 0.; in.s_host = ev[14] ? ev[14][e] : 0.; in.ecc = ev[15] ? ev[15][e] : 0.;
+        in.fmax_g = net.group_fmax;
         Rec rec;
         ModelTraits<MODEL, 4>::prologue(rec, in, cfg, 0, g_q, net.group_fmin, net.ngroups);
         EvGeom geom;
@@ -130,12 +132,17 @@ static int emu_run_waveform(const gwf_model* model, const double* const* ev, lon
         in.psi = ev[6][e]; in.tcoal = ev[7][e]; in.Phicoal = ev[8][e]; in.chi1z = ev[9][e]; in.chi2z = ev[10][e];
         in.Lambda1 = ev[11] ? ev[11][e] : 0.; in.Lambda2 = ev[12] ? ev[12][e] : 0.;
             in.fcut_host = ev[13] ? ev[13][e] : 0.; in.s_host = ev[14] ? ev[14][e] : 0.; in.ecc = ev[15] ? ev[15][e] : 0.;
-        double fm = 1.0;
+        double fm = 1.0, fM = 0.0;
         if (res > 0) {
-            fm = f2d ? f[e] : f[0];
-            for (int k = 1; k < res; ++k) fm = std::min(fm, f2d ? f[(long long)k * n + e] : f[k]);
+            fm = fM = f2d ? f[e] : f[0];
+            for (int k = 1; k < res; ++k) {
+                fm = std::min(fm, f2d ? f[(long long)k * n + e] : f[k]);
+                fM = std::max(fM, f2d ? f[(long long)k * n + e] : f[k]);
+            }
         }
-        double fmin_g[kMaxGroups] = {fm, fm, fm, fm};
+        double fmin_g[kMaxGroups] = {fm, fm, fm, fm}, fmax_g[kMaxGroups] = {fM, fM, fM, fM};
+        in.fmax_g = fmax_g;
+        in.fmax_exact = true;
         Rec rec;
         ModelTraits<MODEL, 4>::prologue(rec, in, cfg, 0, g_q, fmin_g, 1);
         HMWeights w;
@@ -190,6 +197,7 @@ int emu_waveform(const gwf_model* model, const double* const* ev, long long n, c
         case GWF_IMRPHENOMD: return emu_run_waveform<kPhenomD>(model, ev, n, f, res, f2d, phi, ampl, tau, hphc, fcut);
         case GWF_IMRPHENOMD_NRTIDALV2: return emu_run_waveform<kNRTidalv2>(model, ev, n, f, res, f2d, phi, ampl, tau, hphc, fcut);
         case GWF_IMRPHENOMHM: return emu_run_waveform<kPhenomHM>(model, ev, n, f, res, f2d, phi, ampl, tau, hphc, fcut);
+        case GWF_IMRPHENOMNSBH: return emu_run_waveform<kNSBH>(model, ev, n, f, res, f2d, phi, ampl, tau, hphc, fcut);
     }
     return -2;
 }
@@ -207,6 +215,41 @@ int emu_set_qnm(const double* a, const double* fr, const double* fd, int n) {
     g_qbuf.insert(g_qbuf.end(), fr, fr + n);
     g_qbuf.insert(g_qbuf.end(), fd, fd + n);
     g_q.a = g_qbuf.data(); g_q.fring = g_qbuf.data() + n; g_q.fdamp = g_qbuf.data() + 2 * n; g_q.n = n;
+    return 0;
+}
+
+// IMRPhenomNSBH: use a given 200^3 xi_tide table (nullptr: every node is evaluated on the spot by xitide_node)
+int emu_set_xitide(const double* table) {
+    g_q.xitide = table;
+    return 0;
+}
+// one slab of the xi_tide table: the 200 x 200 nodes (q, chi) of compactness index i, as the device kernel computes them
+int emu_xitide_slab(int i, double* out) {
+    for (int j = 0; j < kXiRes; ++j)
+        for (int k = 0; k < kXiRes; ++k)
+            out[j * kXiRes + k] = xitide_node(xi_node_coord(i, kXiCompMin, kXiCompMax), xi_node_coord(j, kXiQMin, kXiQMax), xi_node_coord(k, kXiChiMin, kXiChiMax));
+    return 0;
+}
+
+// debugging aid: the waveform point (A, d ln A, d Phi; NT = 6 tidal parametrisation) of IMRPhenomNSBH on the samples f[0..res) of one event
+int emu_nsbh_point(const gwf_model* model, const double* evv, double fmin, double fmax, const double* f, int res, double* A, double* lnA_d, double* phi_d) {
+    ModelCfg cfg = {model->id, model->flags, model->fcutPar, model->fRef};
+    EventIn in;
+    in.Mc = evv[0]; in.eta = evv[1]; in.dL = evv[2]; in.theta = evv[3]; in.phi = evv[4]; in.iota = evv[5]; in.psi = evv[6]; in.tcoal = evv[7];
+    in.Phicoal = evv[8]; in.chi1z = evv[9]; in.chi2z = evv[10]; in.Lambda1 = evv[11]; in.Lambda2 = evv[12]; in.fcut_host = 0; in.s_host = 0; in.ecc = 0;
+    double fmin_g[kMaxGroups] = {fmin, fmin, fmin, fmin}, fmax_g[kMaxGroups] = {fmax, fmax, fmax, fmax};
+    in.fmax_g = fmax_g;
+    NSBHRec<6> rec;
+    ModelTraits<kNSBH, 6>::prologue(rec, in, cfg, 0, g_q, fmin_g, 1);
+    for (int k = 0; k < res; ++k) {
+        FreqPoint fp;
+        fp.from_f(f[k]);
+        fp.w = 0.;
+        PointWf<6> w;
+        ModelTraits<kNSBH, 6>::eval(rec, cfg, 0, fp, false, w);
+        A[k] = w.A;
+        for (int j = 0; j < 6; ++j) { lnA_d[k * 6 + j] = w.lnA_d[j]; phi_d[k * 6 + j] = w.phi_d[j]; }
+    }
     return 0;
 }
 
@@ -228,6 +271,7 @@ int emu_fisher(const gwf_model* model, const gwf_detector* dets, int ndet, const
             case GWF_IMRPHENOMD: return emu_run_snr<kPhenomD>(model, dets, ndet, pd, npsd, ev, n, opts, fisher);
             case GWF_IMRPHENOMD_NRTIDALV2: return emu_run_snr<kNRTidalv2>(model, dets, ndet, pd, npsd, ev, n, opts, fisher);
             case GWF_IMRPHENOMHM: return emu_run_snr<kPhenomHM>(model, dets, ndet, pd, npsd, ev, n, opts, fisher);
+            case GWF_IMRPHENOMNSBH: return emu_run_snr<kNSBH>(model, dets, ndet, pd, npsd, ev, n, opts, fisher);
         }
         return -2;
     }
@@ -242,6 +286,7 @@ int emu_fisher(const gwf_model* model, const gwf_detector* dets, int ndet, const
         case GWF_IMRPHENOMD: return emu_run<kPhenomD, 4>(model, dets, ndet, pd, npsd, ev, n, opts, fisher, snr2);
         case GWF_IMRPHENOMD_NRTIDALV2: return emu_run<kNRTidalv2, 6>(model, dets, ndet, pd, npsd, ev, n, opts, fisher, snr2);
         case GWF_IMRPHENOMHM: return emu_run<kPhenomHM, 4>(model, dets, ndet, pd, npsd, ev, n, opts, fisher, snr2);
+        case GWF_IMRPHENOMNSBH: return emu_run<kNSBH, 6>(model, dets, ndet, pd, npsd, ev, n, opts, fisher, snr2);
     }
     return -2;
 }
@@ -269,6 +314,7 @@ int emu_fisher_sd(const gwf_model* model, const gwf_detector* dets, int ndet, co
         case GWF_IMRPHENOMD: return emu_run<kPhenomD, 4>(model, dets, ndet, pd, npsd, ev, n, opts, fisher, snr2, sd);
         case GWF_IMRPHENOMD_NRTIDALV2: return emu_run<kNRTidalv2, 6>(model, dets, ndet, pd, npsd, ev, n, opts, fisher, snr2, sd);
         case GWF_IMRPHENOMHM: return emu_run<kPhenomHM, 4, true>(model, dets, ndet, pd, npsd, ev, n, opts, fisher, snr2, sd);
+        case GWF_IMRPHENOMNSBH: return emu_run<kNSBH, 6>(model, dets, ndet, pd, npsd, ev, n, opts, fisher, snr2, sd);
     }
     return -2;
 }

@@ -48,7 +48,7 @@ def run(model, dets, psds, ev, res=1000, flags=0, per_arm=False, snr_mode=False,
     pn = (C.c_int * len(psds))(*[len(a) for a in pf])
     darr = (K.gwf_detector * len(dets))(*dets)
     opts = K.gwf_opts(res, flags, int(per_arm), 0)
-    nP = {0: (13 if model.flags & K.GWF_MODEL_TIDAL else 11) + (1 if model.flags & K.GWF_MODEL_ECCENTRIC else 0), 1: 11, 2: 13, 3: 11}[model.id]
+    nP = {0: (13 if model.flags & K.GWF_MODEL_TIDAL else 11) + (1 if model.flags & K.GWF_MODEL_ECCENTRIC else 0), 1: 11, 2: 13, 3: 11, 4: 13}[model.id]
     npack = nP * (nP + 1) // 2
     narms = sum(1 if d.shape == 0 else 3 for d in dets)
     if snr_mode:

@@ -154,3 +154,46 @@ def test_emulated_waveform_values_match_reference(has_reference):
         else:
             assert np.max(np.abs(out['phi'][0] - P)) < 1e-8, cls
             assert np.max(np.abs(out['ampl'][0] - A) / np.max(np.abs(A), axis=0)) < 1e-11, cls
+
+
+@pytest.mark.parametrize('name', ['nsbh_et2ce', 'nsbh_lvk_lin_fmax', 'nsbh_et_m1m2_chisa_fref_nocut'])
+def test_emulated_nsbh_matches_reference(name):
+    """IMRPhenomNSBH (13 parameters): PhenomD phase with the NSBH remnant, t0 at the last grid sample of every group, Pade tidal phase,
+    the IMRPhenomC-style amplitude differentiated per sample in dual arithmetic, and xi_tide from the engine's own root finder
+    (no table: the emulation evaluates the eight nodes of an event's cell on the spot) -- against the unmodified reference, whose
+    table was tabulated by its own numpy.roots loop (oracle/nsbh_table.py)."""
+    import emu_driver as E
+    from gwfast_b200 import signal, _capi as K
+    cfg, ev, out = load_golden(name)
+    model, dets, psds = _emu_inputs(cfg)
+    n = min(len(ev['Mc']), 16)
+    sub = {k: v[:n] for k, v in ev.items()}
+    fkw = cfg.get('fisher_kw', {})
+    flags = (K.GWF_OPT_M1M2 if fkw.get('use_m1m2') else 0) | (0 if fkw.get('use_chi1chi2', True) else K.GWF_OPT_CHIS_CHIA) | \
+            (K.GWF_OPT_LIN_GRID if fkw.get('spacing') == 'lin' else 0)
+    res = cfg.get('res', 1000)
+    packed, _ = E.run(model._descriptor(sub), dets, psds, signal._engine_events(model, sub, None, bool(fkw.get('use_m1m2'))), res=res, flags=flags)
+    F = E.unpack(packed, 13)[0]
+    arms, _ = E.run(model._descriptor(sub), dets, psds, signal._engine_events(model, sub), res=res, snr_mode=True)
+    assert snr_err(np.sqrt(arms.sum(axis=0)), out['snr'][:n]) < SNR_RTOL
+    assert fisher_err(F, out['fisher'][..., :n]) < FISHER_TOL
+
+
+def test_emulated_nsbh_waveform_values():
+    """IMRPhenomNSBH.Phi / Ampl / tau_star / fcut on user grids (inside the cut, and running past it: zeros beyond, t0 at the grid's
+    own maximum)."""
+    import emu_driver as E
+    from gwfast_b200 import waveforms as W
+    cfg, ev, out = load_golden('wf_values_nsbh')
+    m = W.IMRPhenomNSBH(verbose=False)
+    for tag in ('', '_over'):
+        fg = out['f' + tag]
+        got = E.waveform(m._descriptor(ev), ev, fg, want=('phi', 'ampl', 'tau'))
+        inside = np.abs(fg / m.fcut(**ev) - 1.) > 1e-9            # a sample ON the cut goes either way in the reference
+        ph, am = out['phi' + tag], out['ampl' + tag]
+        assert np.max((np.abs(got['phi'][0] - ph) / (1. + np.abs(ph)))[inside]) < 1e-9
+        assert np.max((np.abs(got['ampl'][0] - am) / np.max(np.abs(am), axis=0))[inside]) < 1e-10
+        if tag == '':
+            assert np.max(np.abs(got['tau'] / out['tau'] - 1)) < 1e-12
+    assert np.allclose(m.fcut(**ev), out['fcut'], rtol=1e-14)
+    assert np.allclose(got['fcut'], out['fcut'], rtol=1e-13)

@@ -41,9 +41,19 @@ def hm_strain_derivs():
     save('deriv_hm_strain_et', cfg, take(ev, 3), run(cfg, take(ev, 3)))
 
 
+def nsbh_derivs():
+    """IMRPhenomNSBH: 13 rows, the ET triangle with Earth rotation"""
+    cfg = dict(model=dict(cls='IMRPhenomNSBH', kw=dict(verbose=False)), network='ET', rot=True, fmin=2., res=200)
+    ev = take(synthetic.nsbh_catalog(48, synthetic.SEEDS['NSBH']), 4)
+    save('deriv_nsbh', cfg, ev, run(cfg, ev))
+
+
 if __name__ == '__main__':
     if len(sys.argv) > 1 and sys.argv[1] == 'hm':
         hm_strain_derivs()
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == 'nsbh':
+        nsbh_derivs()
         sys.exit(0)
     cfg = dict(model=dict(cls='IMRPhenomD'), network='ET+2CE', rot=True, fmin=2., res=200)
     ev = take(synthetic.bbh_catalog(10000, synthetic.SEEDS['C2']), 6)
@@ -62,3 +72,4 @@ if __name__ == '__main__':
     cfg = dict(model=dict(cls='IMRPhenomD_NRTidalv2'), network='ET', rot=True, fmin=2., res=200)
     ev = take(synthetic.bns_catalog(10000, synthetic.SEEDS['C3'], tidal=True), 4)
     save('deriv_nrtidal', cfg, ev, run(cfg, ev))
+    nsbh_derivs()

@@ -69,9 +69,24 @@ def hm_cases():
     save('wfo_hm_phenomd_et', cfg, ev1, _copy(ev1), run(cfg, ev1, _copy(ev1)))
 
 
+def nsbh_cases():
+    """IMRPhenomNSBH against itself at nearby parameters (ET + 2 CE with rotation) and against IMRPhenomD_NRTidalv2 at the same ones (LVK)"""
+    rng = np.random.default_rng(20260096)
+    nsbh = dict(cls='IMRPhenomNSBH', kw=dict(verbose=False))
+    cfg = dict(model1=nsbh, model2=nsbh, network='ET+2CE', rot=True, fmin=2., res=500)
+    ev1 = take(synthetic.nsbh_catalog(48, synthetic.SEEDS['NSBH']), 5)
+    ev2 = perturb(ev1, rng, rel=1e-4)
+    save('wfo_nsbh_et2ce', cfg, ev1, ev2, run(cfg, ev1, ev2))
+    cfg = dict(model1=nsbh, model2=dict(cls='IMRPhenomD_NRTidalv2'), network='LVK-O4', rot=False, fmin=10., res=400)
+    save('wfo_nsbh_nrtidal_lvk', cfg, take(ev1, 4), _copy(take(ev1, 4)), run(cfg, take(ev1, 4), _copy(take(ev1, 4))))
+
+
 if __name__ == '__main__':
     if len(sys.argv) > 1 and sys.argv[1] == 'hm':
         hm_cases()
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == 'nsbh':
+        nsbh_cases()
         sys.exit(0)
     rng = np.random.default_rng(20260099)
     # same model, nearby parameters, ET triangle + 2 CE with Earth rotation

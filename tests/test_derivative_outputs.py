@@ -31,7 +31,7 @@ def _sd_err(sd, F, ref_sd, ref_F):
 
 
 @pytest.mark.skipif(shutil.which('nvcc') is None, reason='nvcc needed to build the emulation harness')
-@pytest.mark.parametrize('name', ['deriv_c2', 'deriv_tf2tidal', 'deriv_m1m2_lvk', 'deriv_hm_lvk'])
+@pytest.mark.parametrize('name', ['deriv_c2', 'deriv_tf2tidal', 'deriv_m1m2_lvk', 'deriv_hm_lvk', 'deriv_nsbh'])
 def test_emulated_snr_derivatives_match_reference(name):
     import emu_driver as E
     from test_device_math_emulated import _emu_inputs
@@ -54,7 +54,7 @@ def test_emulated_snr_derivatives_match_reference(name):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize('name', ['deriv_c2', 'deriv_tf2tidal', 'deriv_m1m2_lvk', 'deriv_hm_lvk', 'deriv_nrtidal'])
+@pytest.mark.parametrize('name', ['deriv_c2', 'deriv_tf2tidal', 'deriv_m1m2_lvk', 'deriv_hm_lvk', 'deriv_nrtidal', 'deriv_nsbh'])
 def test_engine_snr_derivatives_match_reference(name):
     cfg, ev, out = load_golden(name)
     net = make_network('engine', cfg)
@@ -76,7 +76,7 @@ def test_engine_snr_derivatives_match_reference(name):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize('name', ['deriv_c2', 'deriv_tf2tidal', 'deriv_m1m2_lvk', 'deriv_nrtidal', 'deriv_hm_strain_lvk', 'deriv_hm_strain_et'])
+@pytest.mark.parametrize('name', ['deriv_c2', 'deriv_tf2tidal', 'deriv_m1m2_lvk', 'deriv_nrtidal', 'deriv_hm_strain_lvk', 'deriv_hm_strain_et', 'deriv_nsbh'])
 def test_engine_strain_derivatives_match_reference(name):
     cfg, ev, out = load_golden(name)
     net = make_network('engine', cfg)

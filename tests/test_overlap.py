@@ -16,7 +16,7 @@ import pytest
 from conftest import GOLD, SNR_RTOL, copy_events
 
 OV_TOL = 2e-6
-CASES = ['wfo_phenomd_et2ce', 'wfo_phenomd_tf2_lvk', 'wfo_tidal_etsl_fmax', 'wfo_hm_lvk', 'wfo_hm_phenomd_et']
+CASES = ['wfo_phenomd_et2ce', 'wfo_phenomd_tf2_lvk', 'wfo_tidal_etsl_fmax', 'wfo_hm_lvk', 'wfo_hm_phenomd_et', 'wfo_nsbh_et2ce', 'wfo_nsbh_nrtidal_lvk']
 
 
 def _load(name):

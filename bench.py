@@ -408,9 +408,12 @@ def run_engine(args):
                  ('C4', 'IMRPhenomHM', 'LVK-O4', 'bbh', False, False, 10., 100000, 'strong',
                   'IMRPhenomHM BBH, H1+L1+Virgo+KAGRA (O4), 10^5 events split over the ranks'),
                  ('C5', 'IMRPhenomD', 'ET+2CE', 'bbh', False, True, 2., 1000000, 'strong',
-                  '10^6 IMRPhenomD BBH events, ET+2CE, split over the ranks (north-star target; IMRPhenomXAS is not in the reference)')]
+                  '10^6 IMRPhenomD BBH events, ET+2CE, split over the ranks (north-star target; IMRPhenomXAS is not in the reference)'),
+                 ('NSBH', 'IMRPhenomNSBH', 'ET+2CE', 'nsbh', True, True, 2., EVENTS_PER_GPU * world, 'weak',
+                  'IMRPhenomNSBH, ET+2CE, 13 parameters, 10^4 events/GPU (not a BASELINE.json configuration: no frozen FLOP model, no fraction)')]
         for tag, mname, netname, kind, tidal, rot, fmin, n_tot, scaling, desc in specs:
-            cat = synthetic.bbh_catalog(n_tot, synthetic.SEEDS[tag]) if kind == 'bbh' else synthetic.bns_catalog(n_tot, synthetic.SEEDS[tag], tidal=tidal)
+            cat = (synthetic.bbh_catalog(n_tot, synthetic.SEEDS[tag]) if kind == 'bbh' else
+                   synthetic.nsbh_catalog(n_tot, synthetic.SEEDS[tag]) if kind == 'nsbh' else synthetic.bns_catalog(n_tot, synthetic.SEEDS[tag], tidal=tidal))
             lo, hi = parallel.shard_bounds(n_tot, world, rank)
             sub = {k: np.ascontiguousarray(v[lo:hi]) for k, v in cat.items()}
             m = hi - lo
@@ -457,11 +460,12 @@ def run_engine(args):
             ok = bool(np.all(np.isfinite(r_[0][0] if world > 1 else r_[0])))
             r_ = None
             tk, tm, te = max_over_ranks(tk, tm, te)
-            ach = FLOP_MODEL[tag] * m * osteps / tm / 1e12
+            ach = FLOP_MODEL[tag] * m * osteps / tm / 1e12 if tag in FLOP_MODEL else None
             others[tag] = dict(workload=desc, events_total=n_tot, events_per_gpu=m, scaling=scaling, steps=osteps, value=n_tot * osteps / tk, unit='events/s',
                                ms_per_step=1e3 * tk / osteps, e2e=n_tot * osteps / te, fisher_kernel_ms=1e3 * tm / osteps,
-                               fisher_kernel_ms_per_1e4=1e3 * tm / osteps * 1e4 / m, flop_per_event=FLOP_MODEL[tag], achieved_tflops=ach,
-                               frac=ach / peak_tf if peak_tf > 0 else None, frac_of_nominal=ach / FP64_NOMINAL_TFLOPS, finite=ok,
+                               fisher_kernel_ms_per_1e4=1e3 * tm / osteps * 1e4 / m, flop_per_event=FLOP_MODEL.get(tag), achieved_tflops=ach,
+                               frac=ach / peak_tf if (ach is not None and peak_tf > 0) else None,
+                               frac_of_nominal=ach / FP64_NOMINAL_TFLOPS if ach is not None else None, finite=ok,
                                gather=('fused into the Fisher kernel (NVLink peer stores)' if pgc is not None else ('NCCL all-gather' if gat is not None else 'none'))
                                if world > 1 else 'none (one GPU)')
             c.release()

@@ -528,8 +528,14 @@ struct FisherOut {
 // gathered buffer as soon as the event is done -- 8-byte stores over NVLink spread over the whole lifetime of the kernel, so the
 // exchange step of the path (one all-gather of the Fisher matrices) costs no time of its own.
 __device__ __forceinline__ void forward_row(const PeerSlots& peers, long long e, int npack, int p, double v) {
-#pragma unroll 1
-    for (int q = 0; q < peers.n; ++q) peers.p[q][e * npack + p] = v;
+    // fully unrolled with a predicate per slot: the slot pointers are then read from the kernel's parameter bank at compile-time
+    // offsets.  A loop over peers.n indexed the by-value array dynamically, which made the compiler keep a copy of it in LOCAL memory --
+    // three dependent local loads per slot and event that miss the L1 this kernel's 206 KB of shared memory leaves (measured with local
+    // slots, scripts/forward_probe.py: +10 us per slot and launch of 1e4 events, 8 % at 8 slots)
+    const long long off = e * npack + p;
+#pragma unroll
+    for (int q = 0; q < kMaxPeers; ++q)
+        if (q < peers.n) peers.p[q][off] = v;
 }
 
 template <int MODEL, int NT, int FAST, bool SD, int SHAPE = 0>
@@ -1152,14 +1158,19 @@ __global__ void __launch_bounds__(256) unpack_gather_kernel(const double* __rest
     // the tile's rows are contiguous in the packed array: forward them to the peers as they are
     if (((e0 * npack) & 1) == 0) {
         const double2* s2 = reinterpret_cast<const double2*>(src);
-        for (int q = 0; q < peers.n; ++q) {
+#pragma unroll
+        for (int q = 0; q < kMaxPeers; ++q) {          // unrolled: slot pointers from the parameter bank, not from a local copy (see forward_row)
+            if (q >= peers.n) break;
             double2* d2 = reinterpret_cast<double2*>(peers.p[q] + e0 * npack);
             for (int t = threadIdx.x; t < total / 2; t += blockDim.x) d2[t] = s2[t];
             if ((total & 1) && threadIdx.x == 0) peers.p[q][e0 * npack + total - 1] = src[total - 1];
         }
     } else {
-        for (int q = 0; q < peers.n; ++q)
+#pragma unroll
+        for (int q = 0; q < kMaxPeers; ++q) {
+            if (q >= peers.n) break;
             for (int t = threadIdx.x; t < total; t += blockDim.x) peers.p[q][e0 * npack + t] = src[t];
+        }
     }
     __syncthreads();
     if (full) {

@@ -211,14 +211,12 @@ template <int NT> struct ModelTraits<kNSBH, NT> {
                 w.phi_d[j] += r.kph[1 + j] * R + (r.kph[0] * xRp - t0 * p.x) * d.lam[j] - r.t0[g][1 + j] * p.x;
             NsbhPowers np;
             nsbh_powers(np, p, r.sm76);
-            Dual<NT> c[kNsbhCoef];
+            double F, dF[NT];
+            nsbh_amp_grad<NT>(r.amp, np, d.lam, F, dF);
+            w.A = r.C * F;
+            const double ia = 1.0 / F;
 #pragma unroll
-            for (int k = 0; k < kNsbhCoef; ++k) c[k] = get<NT>(r.amp[k]);
-            const Dual<NT> a = nsbh_amp_shape<Dual<NT>>(c, np, d.lam);
-            w.A = r.C * a.v;
-            const double ia = 1.0 / a.v;
-#pragma unroll
-            for (int j = 0; j < NT; ++j) w.lnA_d[j] = fma(a.d[j], ia, r.lnC_d[j]);
+            for (int j = 0; j < NT; ++j) w.lnA_d[j] = fma(dF[j], ia, r.lnC_d[j]);
         }
         if (need_tau) {
             double tau, dtau[2];
@@ -869,7 +867,7 @@ template <int MODEL, int NT> struct PointFns {
                               bool rot, const FreqPoint& fp, double* __restrict__ acc) {
         amp_phase_point<MODEL, NT>(rec, cfg, geom, net, sc, g, rot, fp, acc);
     }
-    static constexpr bool kHasFast = MODEL != kNSBH;   // IMRPhenomNSBH runs the run-time-bounds form only (one instantiation per kernel)
+    static constexpr bool kHasFast = true;
 #ifdef __CUDA_ARCH__
     template <bool ROT, int SHAPE = 0>
     static __device__ __forceinline__ void fisher_fast(const Rec& rec, const ModelCfg& cfg, const EvGeom& geom, const NetworkDev& net, const EventScratch& sc,

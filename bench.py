@@ -47,7 +47,8 @@ RES = 1000
 FLOP_PER_EVENT = 2.676e6
 FLOP_MODEL = {'C1': 0.674e6, 'C2': 2.676e6, 'C3': 3.444e6, 'C4': 4.176e6, 'C5': 2.676e6}
 FP64_NOMINAL_TFLOPS = 148 * 64 * 2 * 1.965e9 / 1e12
-# DRAM traffic of one fisher_kernel launch of this workload, bytes (ncu --set full, profiles/r02_kernels_ncu.md): 34.70 MB read + 0.32 MB written
+# DRAM traffic of one fisher_kernel launch of this workload, bytes (ncu --set full, profiles/r02d_fisher_d_ncu_raw.csv: 34.70 MB read + 0.32 MB
+# written; the round's last capture, profiles/r02k_fisher_d_ncu_raw.csv, ran without bench.py's L2 flush and read 29.35 MB)
 DRAM_BYTES_PER_LAUNCH = 35.02e6
 
 

@@ -423,36 +423,35 @@ GWF_HD void nsbh_amp_grad(const double (*c)[1 + NT], const NsbhPowers& p, const 
     const double LRD = s2 * iD;
     const double aRD = c[NB_ERD][0] * LRD * p.xm76;
     F = aPN * wPN + aPM * wPM + aRD * wRD;
-    // gradient
+    // gradient, contracted with the coefficient tangents term by term (nothing but the NT sums stays live)
     const double qPN = aPN * wPN;                                   // every ln-derivative of aPN is multiplied by this
     const double hPN = aPN * sPN, hPM = aPM * sPM, hRD = aRD * sRD; // window derivatives d/dz
-    double g[kNsbhCoef];
-    g[NB_XDN] = -0.5 * qPN / c[NB_XDN][0];
-#pragma unroll
-    for (int k = 0; k < 6; ++k) g[NB_XD2 + k] = -0.5 * qPN * iS1 * b1[k];
-    g[NB_AN] = qPN / c[NB_AN][0];
-    const double qS = qPN * S2 * iR2, qT = qPN * T2 * iR2;
-#pragma unroll
-    for (int k = 0; k < 5; ++k) g[i2[k]] = qS * b2[k];
-    g[NB_A5I] = qT * tI;
-    g[NB_GPM] = p.x56 * wPM;
-    g[NB_ERD] = LRD * p.xm76 * wRD;
     const double rd = c[NB_ERD][0] * p.xm76 * wRD * 2. * sg * iD * iD;       // d aRD wRD / d(sig, fring) share this factor
-    g[NB_SIG] = rd * u * u;
-    g[NB_FRING] = rd * sg * u;
-    g[NB_X0PN] = -hPN * iw;
-    g[NB_X0PM] = -hPM * iw;
-    g[NB_X0RD] = -hRD * iw;
-    g[NB_DW] = -(hPN * zPN + hPM * zPM + hRD * zRD) * idw;
     const double gx = qPN * (-0.5 * xS1 * iS1 - 7. / 6. + (S2 * xS2 + T2 * xT2) * iR2) + (5. / 6.) * aPM * wPM +
                       (-rd * sg * u * x - (7. / 6.) * aRD * wRD) + (hPN + hPM + hRD) * x * iw;
 #pragma unroll
-    for (int j = 0; j < NT; ++j) {
-        double a = gx * lam[j];
+    for (int j = 0; j < NT; ++j) dF[j] = gx * lam[j];
+    auto add = [&](int k, double gk) {
 #pragma unroll
-        for (int k = 0; k < kNsbhCoef; ++k) a = fma(g[k], c[k][1 + j], a);
-        dF[j] = a;
-    }
+        for (int j = 0; j < NT; ++j) dF[j] = fma(gk, c[k][1 + j], dF[j]);
+    };
+    add(NB_XDN, -0.5 * qPN / c[NB_XDN][0]);
+    const double q1 = -0.5 * qPN * iS1;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) add(NB_XD2 + k, q1 * b1[k]);
+    add(NB_AN, qPN / c[NB_AN][0]);
+    const double qS = qPN * S2 * iR2, qT = qPN * T2 * iR2;
+#pragma unroll
+    for (int k = 0; k < 5; ++k) add(i2[k], qS * b2[k]);
+    add(NB_A5I, qT * tI);
+    add(NB_GPM, p.x56 * wPM);
+    add(NB_ERD, LRD * p.xm76 * wRD);
+    add(NB_SIG, rd * u * u);
+    add(NB_FRING, rd * sg * u);
+    add(NB_X0PN, -hPN * iw);
+    add(NB_X0PM, -hPM * iw);
+    add(NB_X0RD, -hRD * iw);
+    add(NB_DW, -(hPN * zPN + hPM * zPM + hRD * zRD) * idw);
 }
 
 // ------------------------------------------------------------------------------------------------ record

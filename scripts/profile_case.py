@@ -8,6 +8,8 @@ netname, mname = sys.argv[1], sys.argv[2]
 n = int(sys.argv[3]) if len(sys.argv) > 3 else 10000
 if mname == 'IMRPhenomD_NRTidalv2':
     ev = synthetic.bns_catalog(n, synthetic.SEEDS['C3'], tidal=True)
+elif mname == 'IMRPhenomNSBH':
+    ev = synthetic.nsbh_catalog(n, synthetic.SEEDS['NSBH'])
 elif mname == 'TaylorF2_RestrictedPN':
     ev = synthetic.bns_catalog(n, synthetic.SEEDS['C1'])
 else:

@@ -391,6 +391,11 @@ struct HMX {
     }
 };
 
+#ifndef GWF_HM_UNROLL
+#define GWF_HM_UNROLL 1
+#endif
+constexpr int kHmModeUnroll = GWF_HM_UNROLL;      // the mode loop stays rolled (experiment knob: see DESIGN.md, tried and rejected)
+
 // Amplitude A_lm and phase Phi_lm of the six modes (IMRPhenomHM.Ampl / .Phi, waveforms.py:1874-2254, as vectorised in hphc) at one
 // frequency, with (TAN) d ln A_lm and d Phi_lm w.r.t. the NT intrinsic slots.  Every mode is handed to `sink(m, A, Phi, dlnA, dPhi)`
 // as soon as it is known, so callers that only need sums over the modes keep nothing per mode.  The mode loop is rolled: the six
@@ -407,7 +412,7 @@ GWF_HD void phenomhm_foreach_mode(const HMRec<NT>& r, int g, const FreqPoint& fp
 #pragma unroll
         for (int j = 0; j < NT; ++j) dL0[j] = fma(-fma(r.t0[0], r.lam[j], r.t0[1 + j]), x, r.pc0[g][1 + j]);
     }
-#pragma unroll 1
+#pragma unroll(kHmModeUnroll)
     for (int m = m_begin; m < m_end; ++m) {
         const HMModeRec<NT>& o = r.mode[m];
         const int mm = hm_mm(m);

@@ -48,6 +48,15 @@ __device__ __forceinline__ EventIn load_event(const EventsDev& ev, long long e) 
     return in;
 }
 
+#ifndef GWF_UNR_TF2
+#define GWF_UNR_TF2 1
+#endif
+#ifndef GWF_UNR_D
+#define GWF_UNR_D 1
+#endif
+#ifndef GWF_UNR_NRT
+#define GWF_UNR_NRT 1
+#endif
 #ifndef GWF_FISHER_THREADS
 #define GWF_FISHER_THREADS 256
 #endif
@@ -592,8 +601,12 @@ fisher_kernel(const typename ModelTraits<MODEL, NT>::Rec* __restrict__ recs, con
             // otherwise lanes leave the loop on their own.  Same arithmetic either way; which form the compiler schedules
             // better differs per model (measured per 1e4 events: IMRPhenomD 1.229 -> 1.208 ms, NRTidalv2 3.131 -> 3.287 ms).
             constexpr bool kUniformLoop = MODEL == kPhenomHM || MODEL == kPhenomD;
+            constexpr int kSampleUnroll = MODEL == kTaylorF2 ? GWF_UNR_TF2 : (MODEL == kPhenomD ? GWF_UNR_D : (MODEL == kNRTidalv2 ? GWF_UNR_NRT : 1));
             // kb0 runs over the blocks of `stride` samples; both halves of a pair make the same number of trips (the
             // block barrier below needs every arrival), the half whose block of 32 lies beyond the grid is predicated off
+            // kSampleUnroll = 2 lets the scheduler interleave the Gram of one sample with the serial head (waveform, rotation phase, PSD row,
+            // detector basis) of the next; 1 = rolled (experiment knobs GWF_UNR_*)
+#pragma unroll(kSampleUnroll)
             for (int kb0 = 0; kUniformLoop ? kb0 < res : kb0 + k0 < res; kb0 += stride) {
                 const int k = kb0 + k0;
                 if (!kUniformLoop || k < res) {

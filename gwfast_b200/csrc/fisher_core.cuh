@@ -166,7 +166,7 @@ template <int NT> struct ModelTraits<kNRTidalv2, NT> {
 template <int NT> struct ModelTraits<kNSBH, NT> {
     typedef NSBHRec<NT> Rec;
     static GWF_HD void eval_amp(const Rec& r, const ModelCfg& cfg, const FreqPoint& fp, bool need_tau, double& A, double& tau) {
-        const PhenomDRec<NT>& d = r.d;
+        const PhenomDRec<NT, false>& d = r.d;
         XPow p;
         p.set(d.s, d.sp, fp);
         A = 0.;
@@ -190,7 +190,7 @@ template <int NT> struct ModelTraits<kNSBH, NT> {
         nsbh_prologue(r, p, e.dL, q, fmin_g, e.fmax_g, e.fmax_exact, ng, cfg, e.s_host, e.fcut_host);
     }
     static GWF_HD void eval(const Rec& r, const ModelCfg& cfg, int g, const FreqPoint& fp, bool need_tau, PointWf<NT>& w) {
-        const PhenomDRec<NT>& d = r.d;
+        const PhenomDRec<NT, false>& d = r.d;
         XPow p;
         p.set(d.s, d.sp, fp);
         w.dtn[0] = w.dtn[1] = 0.;

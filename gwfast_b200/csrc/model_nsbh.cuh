@@ -457,7 +457,7 @@ GWF_HD void nsbh_amp_grad(const double (*c)[1 + NT], const NsbhPowers& p, const 
 // ------------------------------------------------------------------------------------------------ record
 template <int NT>
 struct NSBHRec {
-    PhenomDRec<NT> d;                    // phase regions (t0 NOT folded in), s, lam, tau, fcut
+    PhenomDRec<NT, false> d;             // phase regions only (t0 NOT folded in), s, lam, tau, fcut; no IMRPhenomD amplitude rows
     double fcut_hz;                      // 0.2 / s, waveforms.py:3284
     double C, lnC_d[NT];                 // 2 sqrt(5/(64 pi)) M^2 GMsun_c2_Gpc GMsun_c3 / dL, waveforms.py:3256
     double sm76;                         // s^(-7/6)

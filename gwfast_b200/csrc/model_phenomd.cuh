@@ -59,8 +59,16 @@ constexpr int kAInt = 5;    // (x - 0.014)^k, k=0..4
 // rows of the expanded tables are padded to an even number of doubles and 16-byte aligned: the per-frequency evaluation
 // reads a row (value + NT tangents) with 16-byte shared-memory loads
 template <int NT> struct RowLen { static constexpr int v = (NT + 2) & ~1; };
-template <int NT>
-struct PhenomDRec {
+// the amplitude rows: IMRPhenomNSBH reuses the phase half of the record only (its amplitude is a different model) and leaves them out
+// (AMP = false) -- 1.1 KB per staged event, the difference between fitting the PSD windows of ET+2CE into shared memory or not
+template <int NT, bool AMP> struct PhenomDAmpRows {
+    alignas(16) double ains[kAIns][RowLen<NT>::v];
+    alignas(16) double aint[kAInt][RowLen<NT>::v];
+    double amrd[4][1 + NT];   // fring, gamma2/(fdamp gamma3), fdamp*gamma3, fdamp*gamma3*gamma1
+};
+template <int NT> struct PhenomDAmpRows<NT, false> {};
+template <int NT, bool AMP = true>
+struct PhenomDRec : PhenomDAmpRows<NT, AMP> {
     double s;                 // x = s f      (s = M GMsun/c^3)
     ScalePow sp;              // powers of s used to build x^(1/3), x^(-1/3), ln(pi x)/3 from the grid's f-powers
     double lam[NT];           // d ln s / d slot
@@ -73,9 +81,6 @@ struct PhenomDRec {
     alignas(16) double pint[kPInt][RowLen<NT>::v];
     alignas(16) double pmrd[kPMrd][RowLen<NT>::v];
     double atn[3][1 + NT];    // MRD arctan term: alpha4/eta, alpha5*fring, fdamp
-    alignas(16) double ains[kAIns][RowLen<NT>::v];
-    alignas(16) double aint[kAInt][RowLen<NT>::v];
-    double amrd[4][1 + NT];   // fring, gamma2/(fdamp gamma3), fdamp*gamma3, fdamp*gamma3*gamma1
     TauRec tau;
 };
 
@@ -219,13 +224,13 @@ struct PhenomDCore {
 };
 
 // fill the record from the core; xref[g] = dimensionless reference frequency of grid group g
-template <int NT>
-GWF_HD void phenomd_fill(PhenomDRec<NT>& r, const PhenomDCore<NT>& c, const Dual<NT>& M, const Dual<NT>& dL, const double* fmin_g, int ngroups,
+template <int NT, bool AMP>
+GWF_HD void phenomd_fill(PhenomDRec<NT, AMP>& r, const PhenomDCore<NT>& c, const Dual<NT>& M, const Dual<NT>& dL, const double* fmin_g, int ngroups,
                          const ModelCfg& cfg, double s_host = 0.0, double fcut_host = 0.0, int parts = 3) {
     typedef Dual<NT> D;
     D s = M * kGMsunC3;
     if (s_host > 0.0) s.v = s_host;       // the host's M*GMsun_over_c3: x = s f then rounds like the reference's fgrid
-    if (parts & 2) {
+    if constexpr (AMP) if (parts & 2) {
         ScalePow sp;
         sp.set(s.v);
         r.x_peak = c.fpeak_amp.v;
@@ -339,8 +344,8 @@ struct XPow {
 };
 
 // phase tangents (and value) at x; g = grid group.  Returns false beyond the cut (phase/amp identically 0).
-template <int NT>
-GWF_HD void phenomd_phase(const PhenomDRec<NT>& r, int g, const XPow& p, bool apply_cut, double& phi, double* phi_d) {
+template <int NT, bool AMP>
+GWF_HD void phenomd_phase(const PhenomDRec<NT, AMP>& r, int g, const XPow& p, bool apply_cut, double& phi, double* phi_d) {
     const double x = p.x;
     double v = 0., dx = 0., d[NT];
 #pragma unroll

@@ -409,7 +409,14 @@ def fx_nsbh():
     save('wf_values_nsbh', dict(model=dict(cls='IMRPhenomNSBH')), cat, out)
 
 
-ALL = {'init': fx_init, 'c1': fx_c1, 'c1b': fx_c1b, 'c2': fx_c2, 'var': fx_variants, 'c3': fx_c3, 'c4': fx_c4, 'gw170817': fx_gw170817, 'wf': fx_wfvalues, 'newt': fx_newt, 'ecc': fx_ecc, 'c4big': fx_c4big, 'edge': fx_edge, 'edge_eta': fx_edge_eta, 'nsbh': fx_nsbh}
+def fx_nsbhbig():
+    """512 IMRPhenomNSBH events on ET+2CE against the unmodified reference (the size of a parity subset; a second seed)"""
+    cfg = dict(model=dict(cls='IMRPhenomNSBH', kw=dict(verbose=False)), network='ET+2CE', rot=True, fmin=2.)
+    ev = synthetic.nsbh_catalog(512, synthetic.SEEDS['NSBH'] + 1)
+    save('nsbh_et2ce_512', cfg, ev, run_network_pool(cfg, ev, chunk=16))
+
+
+ALL = {'init': fx_init, 'c1': fx_c1, 'c1b': fx_c1b, 'c2': fx_c2, 'var': fx_variants, 'c3': fx_c3, 'c4': fx_c4, 'gw170817': fx_gw170817, 'wf': fx_wfvalues, 'newt': fx_newt, 'ecc': fx_ecc, 'c4big': fx_c4big, 'edge': fx_edge, 'edge_eta': fx_edge_eta, 'nsbh': fx_nsbh, 'nsbhbig': fx_nsbhbig}
 
 if __name__ == '__main__':
     warnings.filterwarnings('ignore')

@@ -1,4 +1,5 @@
-"""h5py stub: only the out-of-scope catalog IO / IMRPhenomNSBH table use it (TEST INFRASTRUCTURE)."""
+"""h5py stub (TEST INFRASTRUCTURE): the reference imports h5py for catalog IO (out of scope) and for IMRPhenomNSBH's xi_tide table, which
+the oracle obtains from the reference's own tabulation instead (oracle/nsbh_table.py) -- the file is never opened."""
 
 
 class File:

@@ -96,7 +96,19 @@ template <int N> GWF_HD Dual<N> chain(const Dual<N>& a, double f, double df) {
     return r;
 }
 GWF_HD double dsqrt(double x) { return sqrt(x); }
-template <int N> GWF_HD Dual<N> dsqrt(const Dual<N>& a) { const double s = sqrt(a.v); return chain(a, s, 0.5 / s); }
+// d sqrt(x) = dx / (2 sqrt(x)); where x = 0 AND dx = 0 exactly the tangent is 0 (not inf * 0 = NaN): what jax returns for a constant
+// zero under a sqrt (the cotangent never meets the infinite factor), and what the oracle's dual does (oracle/dual.py:_sqrt) --
+// e.g. IMRPhenomNSBH at Lambda = 0: compactness 1/2, tidal radius 0 with zero tangent (waveforms.py:3170-3174)
+template <int N> GWF_HD Dual<N> dsqrt(const Dual<N>& a) {
+    const double s = sqrt(a.v);
+    Dual<N> r = chain(a, s, 0.5 / s);
+    if (s == 0.0) {
+#pragma unroll
+        for (int i = 0; i < N; ++i)
+            if (a.d[i] == 0.0) r.d[i] = 0.0;
+    }
+    return r;
+}
 GWF_HD double dlog(double x) { return log(x); }
 template <int N> GWF_HD Dual<N> dlog(const Dual<N>& a) { return chain(a, log(a.v), 1.0 / a.v); }
 GWF_HD double dexp(double x) { return exp(x); }

@@ -416,7 +416,29 @@ def fx_nsbhbig():
     save('nsbh_et2ce_512', cfg, ev, run_network_pool(cfg, ev, chunk=16))
 
 
-ALL = {'init': fx_init, 'c1': fx_c1, 'c1b': fx_c1b, 'c2': fx_c2, 'var': fx_variants, 'c3': fx_c3, 'c4': fx_c4, 'gw170817': fx_gw170817, 'wf': fx_wfvalues, 'newt': fx_newt, 'ecc': fx_ecc, 'c4big': fx_c4big, 'edge': fx_edge, 'edge_eta': fx_edge_eta, 'nsbh': fx_nsbh, 'nsbhbig': fx_nsbhbig}
+def fx_nsbhedge():
+    """IMRPhenomNSBH edge cases: Lambda_NS = 0 exactly (compactness 1/2, quadrupole branch), 1e-6 (below the 1e-5 switch of the quadrupole
+    fit), 1 exactly (switch of the compactness / gamma / delta_2' branches); eta = 0.25; q = 37 .. 93 (towards the upper edge of the
+    xi_tide table, q_max = 100); chi_BH -> +1 (last cell of the table, whose chi = 1 nodes are double roots) and -> -1."""
+    ev = take(synthetic.nsbh_catalog(64, 777), 20)
+    ev = {k: np.array(v) for k, v in ev.items()}
+    ev['Lambda2'][0:4] = 0.0
+    ev['chi1z'][0:4] = [0.3, -0.2, 0.6, -0.7]
+    ev['Lambda2'][4:6] = 1e-6
+    ev['Lambda2'][6:8] = 1.0
+    ev['eta'][8:10] = 0.25
+    m2 = 1.4 * 1.3
+    for i, m1 in zip(range(10, 13), (40., 70., 100.)):
+        m1 = m1 * 1.3
+        ev['Mc'][i] = (m1 * m2) ** 0.6 / (m1 + m2) ** 0.2
+        ev['eta'][i] = m1 * m2 / (m1 + m2) ** 2
+    ev['chi1z'][13:16] = [0.97, 0.992, 0.9999]
+    ev['chi1z'][16:18] = [-0.95, -0.9999]
+    cfg = dict(model=dict(cls='IMRPhenomNSBH', kw=dict(verbose=False)), network='ET+2CE', rot=True, fmin=2.)
+    save('edge_nsbh_et2ce', cfg, ev, run_network_pool(cfg, ev, chunk=5))
+
+
+ALL = {'init': fx_init, 'c1': fx_c1, 'c1b': fx_c1b, 'c2': fx_c2, 'var': fx_variants, 'c3': fx_c3, 'c4': fx_c4, 'gw170817': fx_gw170817, 'wf': fx_wfvalues, 'newt': fx_newt, 'ecc': fx_ecc, 'c4big': fx_c4big, 'edge': fx_edge, 'edge_eta': fx_edge_eta, 'nsbh': fx_nsbh, 'nsbhbig': fx_nsbhbig, 'nsbhedge': fx_nsbhedge}
 
 if __name__ == '__main__':
     warnings.filterwarnings('ignore')

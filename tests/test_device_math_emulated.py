@@ -156,7 +156,7 @@ def test_emulated_waveform_values_match_reference(has_reference):
             assert np.max(np.abs(out['ampl'][0] - A) / np.max(np.abs(A), axis=0)) < 1e-11, cls
 
 
-@pytest.mark.parametrize('name', ['nsbh_et2ce', 'nsbh_lvk_lin_fmax', 'nsbh_et_m1m2_chisa_fref_nocut'])
+@pytest.mark.parametrize('name', ['nsbh_et2ce', 'nsbh_lvk_lin_fmax', 'nsbh_et_m1m2_chisa_fref_nocut', 'edge_nsbh_et2ce'])
 def test_emulated_nsbh_matches_reference(name):
     """IMRPhenomNSBH (13 parameters): PhenomD phase with the NSBH remnant, t0 at the last grid sample of every group, Pade tidal phase,
     the IMRPhenomC-style amplitude differentiated per sample in dual arithmetic, and xi_tide from the engine's own root finder
@@ -166,7 +166,7 @@ def test_emulated_nsbh_matches_reference(name):
     from gwfast_b200 import signal, _capi as K
     cfg, ev, out = load_golden(name)
     model, dets, psds = _emu_inputs(cfg)
-    n = min(len(ev['Mc']), 16)
+    n = min(len(ev['Mc']), 20)
     sub = {k: v[:n] for k, v in ev.items()}
     fkw = cfg.get('fisher_kw', {})
     flags = (K.GWF_OPT_M1M2 if fkw.get('use_m1m2') else 0) | (0 if fkw.get('use_chi1chi2', True) else K.GWF_OPT_CHIS_CHIA) | \
@@ -174,6 +174,7 @@ def test_emulated_nsbh_matches_reference(name):
     res = cfg.get('res', 1000)
     packed, _ = E.run(model._descriptor(sub), dets, psds, signal._engine_events(model, sub, None, bool(fkw.get('use_m1m2'))), res=res, flags=flags)
     F = E.unpack(packed, 13)[0]
+    assert np.all(np.isfinite(F))
     arms, _ = E.run(model._descriptor(sub), dets, psds, signal._engine_events(model, sub), res=res, snr_mode=True)
     assert snr_err(np.sqrt(arms.sum(axis=0)), out['snr'][:n]) < SNR_RTOL
     assert fisher_err(F, out['fisher'][..., :n]) < FISHER_TOL

@@ -19,7 +19,7 @@ from oracle.make_golden import save, REF_PSDS  # noqa: E402
 from gwfast_b200 import synthetic  # noqa: E402
 
 CASES = [('TaylorF2_RestrictedPN', dict(use_3p5PN_SpinHO=True), 'bns', False), ('IMRPhenomD', {}, 'bbh', False),
-         ('IMRPhenomD_NRTidalv2', {}, 'bns', True), ('IMRPhenomHM', {}, 'bbh', False)]
+         ('IMRPhenomD_NRTidalv2', {}, 'bns', True), ('IMRPhenomHM', {}, 'bbh', False), ('IMRPhenomNSBH', dict(verbose=False), 'nsbh', True)]
 DETS = [('ETS', True, False), ('CE1Id', False, False), ('ETSL', False, True)]      # (site, useEarthMotion, noMotion)
 
 
@@ -29,7 +29,8 @@ def main():
     out, evs = {}, {}
     n = 6
     for cls, kw, kind, tidal in CASES:
-        ev = synthetic.bbh_catalog(n, 4100) if kind == 'bbh' else synthetic.bns_catalog(n, 4101, tidal=tidal)
+        ev = (synthetic.bbh_catalog(n, 4100) if kind == 'bbh' else synthetic.nsbh_catalog(n, 4102) if kind == 'nsbh' else
+              synthetic.bns_catalog(n, 4101, tidal=tidal))
         for k, v in ev.items():
             evs['%s__%s' % (cls, k)] = v
         m = getattr(wf, cls)(**kw)

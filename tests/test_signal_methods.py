@@ -25,7 +25,7 @@ def _detector(cls, kw, site, rot_on, nomo):
                            det_long=s['long'], det_xax=s['xax'], verbose=False, useEarthMotion=rot_on, noMotion=nomo, fmin=2.)
 
 
-@pytest.mark.parametrize('case', [0, 1, 2, 3])
+@pytest.mark.parametrize('case', [0, 1, 2, 3, 4])
 def test_amplitudes_phase_and_strain_match_reference(case):
     from gwfast_b200 import gwfastUtils as utils
     cfg, evs, out = load_golden('signal_methods')

@@ -21,7 +21,7 @@ class WaveFormModel(ABC):
                  is_Precessing=False, is_LAL=False, is_prec_ang=False, is_eccentric=False, is_holomorphic=False, apply_fcut=True):
         if is_Precessing or is_LAL:
             raise NotImplementedError('gwfast_b200 builds the non-precessing native models only '
-                                      '(NewtInspiral, TaylorF2_RestrictedPN, IMRPhenomD, IMRPhenomD_NRTidalv2, IMRPhenomHM)')
+                                      '(NewtInspiral, TaylorF2_RestrictedPN, IMRPhenomD, IMRPhenomD_NRTidalv2, IMRPhenomHM, IMRPhenomNSBH)')
         self.objType = objType
         self.fcutPar = fcutPar
         self.is_newtonian = is_newtonian
